@@ -1,0 +1,209 @@
+/*
+ * colq.h -- C ABI of libcolq.so, the B200-native (sm_100a) execution module for the
+ * dgroomes/java-columnar-query-engine `data-system` API.
+ *
+ * The reference has no FFI of its own: its engine is the Java class DataSystemSerialIndices and the
+ * drop-in boundary is the `data-system` interface set.  A sibling Gradle module (`data-system-b200`,
+ * source under java-columnar-query-engine_b200/java/) implements those interfaces and binds exactly
+ * these symbols with java.lang.foreign downcalls.  Every entry point below names
+ * the reference code it stands in for.  Citations are relative to the reference checkout:
+ *   E  = data-system-serial-indices-arrays/src/main/java/dgroomes/data_system_serial_indices_arrays
+ *   M  = data-model-in-memory/src/main/java/dgroomes/in_memory
+ *   DS = data-system/src/main/java/dgroomes/data_system
+ *
+ * Conventions
+ *   - plain C, no torch/CUDA types in any signature; pointers are HOST pointers unless a name ends in
+ *     `_device`; sizes are int64_t; every function returns a colq_status (0 = OK).
+ *   - colq_last_error(ctx) returns the message of the last non-OK status on that context (the text a
+ *     QueryResult.Failure carries, DS/QueryResult.java:7).
+ *   - host buffers are BORROWED for the duration of the call; the library copies them to HBM and owns
+ *     the device memory until colq_destroy.
+ *   - bitmasks use the java.util.BitSet word layout: row i <-> words[i >> 6] & (1L << (i & 63)),
+ *     little-endian uint64, so BitSet.valueOf(LongBuffer) wraps the output directly.
+ *   - one context per process and GPU; calls on one context must not overlap (the Java shim holds a lock).
+ *   - there is NO CPU fallback: if no sm_100-class device is usable, colq_create fails.
+ */
+#ifndef COLQ_H
+#define COLQ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COLQ_ABI_VERSION 1
+
+typedef enum colq_status {
+    COLQ_OK = 0,
+    /* -> QueryResult.Failure(colq_last_error())  (E/DataSystemSerialIndices.java:54-57, E/Verifier.java:62-104) */
+    COLQ_FAILURE = 1,
+    /* -> java.lang.IndexOutOfBoundsException: the reference's unchecked `columns().get(ordinal)` (E/Verifier.java:67,100) */
+    COLQ_THROW_INDEX_OOB = 2,
+    /* -> java.lang.NullPointerException (E/Verifier.java:41-42; M/InMemoryTable.java:70-71 for an association target outside the associated table) */
+    COLQ_THROW_NULL = 3,
+    /* -> java.lang.IllegalStateException (M/InMemoryColumn.java:122-126 and misuse of this ABI) */
+    COLQ_THROW_ILLEGAL_STATE = 4,
+    /* -> java.lang.IllegalArgumentException (DS/Query.java:33-35 duplicate child ordinal; bad enum values) */
+    COLQ_THROW_ILLEGAL_ARG = 5,
+    /* CUDA / NCCL / allocation error; message holds the driver text */
+    COLQ_ERR_DEVICE = 6,
+    /* caller-provided output capacity too small; *out_count still holds the true count */
+    COLQ_ERR_CAPACITY = 7
+} colq_status;
+
+/* where a table's rows live when the context is part of a multi-GPU communicator */
+typedef enum colq_placement {
+    COLQ_REPLICATED = 0,   /* every rank holds all rows (the 51-row states table) */
+    COLQ_SHARDED = 1       /* this rank holds a contiguous row range [global_row_base, +n_rows) (zips, cities) */
+} colq_placement;
+
+/* structured stand-ins for the reference's opaque Predicate<String> lambdas (DS/Criteria.java:17) */
+typedef enum colq_str_op {
+    COLQ_STR_EQ = 0,           /* "X"::equals                (app/.../Runner.java:236) */
+    COLQ_STR_CONTAINS = 1,     /* s -> s.contains("X")       (Runner.java:255,257,259) */
+    COLQ_STR_CMP_GT = 2,       /* s -> s.compareTo("X") > 0  (QueryTest.java:124); UTF-16 code-unit order */
+    COLQ_STR_CMP_LT = 3,       /* s -> s.compareTo("X") < 0  (QueryTest.java:125) */
+    COLQ_STR_CMP_GE = 4,
+    COLQ_STR_CMP_LE = 5,
+    COLQ_STR_NE = 6,
+    COLQ_STR_STARTS_WITH = 7,
+    COLQ_STR_ENDS_WITH = 8
+} colq_str_op;
+
+/* execution strategy knobs (colq_query_set_option) */
+typedef enum colq_option {
+    /* 1 (default): a criteria-free node reached through a to-one foreign key is evaluated lazily, only at
+       the rows its parent still needs (fused FK chain gather); 0: always materialise every node's bitmask. */
+    COLQ_OPT_LAZY_FK = 0,
+    /* 1: record one CUDA event pair per kernel so colq_profile() can report per-stage times (adds launch gaps) */
+    COLQ_OPT_PROFILE = 1,
+    /* 1 (default): replay the query's kernel sequence from a captured CUDA graph when its shape is static */
+    COLQ_OPT_GRAPH = 2
+} colq_option;
+
+typedef struct colq_ctx colq_ctx;       /* one DataSystem instance  (E/DataSystemSerialIndices.java:14-22) */
+typedef struct colq_query colq_query;   /* one Query                (DS/Query.java:17-25) */
+typedef int32_t colq_table;             /* table handle, valid for the owning context */
+
+typedef struct colq_timing {
+    double gpu_ms;          /* CUDA-event time of the whole kernel(+collective) pipeline of the last execute */
+    int32_t kernel_launches;/* kernels of this library launched by the last execute */
+    int32_t collectives;    /* NCCL calls issued by the last execute */
+    int64_t h2d_bytes;      /* bytes copied host->device by the last execute (query constants) */
+    int64_t d2h_bytes;      /* bytes copied device->host by the last execute (count, bitmask, indices) */
+} colq_timing;
+
+typedef struct colq_stage {
+    char name[48];          /* kernel name */
+    double ms;              /* CUDA-event duration (only with COLQ_OPT_PROFILE) */
+    int64_t rows;           /* rows the launch covered */
+    int64_t bytes;          /* ALGORITHMIC bytes of the launch: every input element read once + outputs written */
+} colq_stage;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------ */
+
+int colq_abi_version(void);
+/* new DataSystemSerialIndices() (E/DataSystemSerialIndices.java:20-22). device = CUDA ordinal. */
+colq_status colq_create(int device, colq_ctx **out_ctx);
+colq_status colq_destroy(colq_ctx *ctx);
+const char *colq_last_error(const colq_ctx *ctx);
+/* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores the context's own stream */
+colq_status colq_set_stream(colq_ctx *ctx, void *cuda_stream);
+colq_status colq_get_stream(colq_ctx *ctx, void **out_cuda_stream);
+colq_status colq_synchronize(colq_ctx *ctx);
+
+/* ---- multi-GPU: one process per GPU, host bootstraps the communicator ---------------- */
+
+/* 128-byte ncclUniqueId produced on rank 0; the host ships it to the other ranks by any side channel */
+colq_status colq_comm_unique_id(colq_ctx *ctx, uint8_t out_id[128]);
+colq_status colq_comm_init(colq_ctx *ctx, const uint8_t id[128], int n_ranks, int rank);
+colq_status colq_comm_info(const colq_ctx *ctx, int *out_n_ranks, int *out_rank);
+
+/* ---- tables and columns: InMemoryTable.ofColumns / associateTo (M/InMemoryTable.java:32-35,44-90) --- */
+
+/* n_rows = this rank's rows. For COLQ_SHARDED tables global_row_base is added to emitted row indices. */
+colq_status colq_table_create(colq_ctx *ctx, int64_t n_rows, colq_placement placement, int64_t global_row_base,
+                              colq_table *out_table);
+/* DataSystemSerialIndices.register (E/DataSystemSerialIndices.java:27-29): HashMap.put, the last put wins */
+colq_status colq_register(colq_ctx *ctx, const char *table_name, colq_table table);
+
+/* IntegerColumn(int[] ints) (M/InMemoryColumn.java:46) at `ordinal` (must be the next free ordinal or an unset one) */
+colq_status colq_col_i32(colq_ctx *ctx, colq_table table, int ordinal, const int32_t *values, int64_t n);
+/* StringColumn(String[] strings) (M/InMemoryColumn.java:64) as n+1 shard-relative uint32 offsets + UTF-8 bytes */
+colq_status colq_col_str(colq_ctx *ctx, colq_table table, int ordinal, const uint32_t *offsets, const uint8_t *bytes,
+                         int64_t n, int64_t n_bytes);
+/* BooleanColumn(boolean[] bools) (M/InMemoryColumn.java:28): registered so ordinals line up; any criterion on it
+   is a Failure exactly as in the reference (E/Verifier.java:82-84) */
+colq_status colq_col_bool(colq_ctx *ctx, colq_table table, int ordinal, const uint8_t *values, int64_t n);
+/* zero-copy variants: adopt device buffers the host already owns (e.g. torch tensors). 16-byte aligned; the
+   buffers must outlive the table; `*_capacity` is the allocation size in bytes (the TMA path reads whole
+   16-byte lines inside it). */
+colq_status colq_col_i32_device(colq_ctx *ctx, colq_table table, int ordinal, const void *values_device, int64_t n);
+colq_status colq_col_str_device(colq_ctx *ctx, colq_table table, int ordinal, const void *offsets_device,
+                                int64_t offsets_capacity, const void *bytes_device, int64_t bytes_capacity,
+                                int64_t n, int64_t n_bytes);
+
+/*
+ * x.associateTo(y, associations) (M/InMemoryTable.java:44-90): creates the forward AssociationColumn on x at
+ * x_ordinal AND its reverse (transposed) column on y at y_ordinal, cross-linked (:83-85).  Only the forward data
+ * is stored; hops through the reverse column are executed as a push through the forward data, which is the same
+ * relation because the reference builds the reverse column as the transpose (:55-82).
+ *   _fk : every row is Association.One(fk[i]) or Association.None (fk[i] == -1)        (DS/Association.java:27-43)
+ *   _csr: row i is associated to targets[offsets[i] .. offsets[i+1]) (None / One / Many) (DS/Association.java:27-51)
+ * For two COLQ_SHARDED tables the indices are shard-local. A target outside [0, y.n_rows) is
+ * COLQ_THROW_NULL like the reference's NPE (:70-71).
+ */
+colq_status colq_associate_fk(colq_ctx *ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal,
+                              const int32_t *fk, int64_t n);
+colq_status colq_associate_csr(colq_ctx *ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal,
+                               const int64_t *offsets, const int32_t *targets, int64_t n, int64_t nnz);
+colq_status colq_associate_fk_device(colq_ctx *ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal,
+                                     const void *fk_device, int64_t n);
+
+colq_status colq_table_size(const colq_ctx *ctx, colq_table table, int64_t *out_rows);   /* Table.size()  DS/Table.java:29 */
+colq_status colq_table_width(const colq_ctx *ctx, colq_table table, int *out_columns);   /* Table.width() DS/Table.java:22 */
+
+/* ---- queries: Query / Query.Node / Criteria (DS/Query.java:17-54, DS/Criteria.java:10-20) ----------- */
+
+/* new Query(tableName); node 0 is rootNode. The name is resolved at execute time, like the reference (:54-57). */
+colq_status colq_query_create(colq_ctx *ctx, const char *table_name, colq_query **out_query);
+colq_status colq_query_destroy(colq_query *query);
+/* Query.Node.createChild(ordinal) (DS/Query.java:31-38): COLQ_THROW_ILLEGAL_ARG on a duplicate ordinal */
+colq_status colq_query_child(colq_query *query, int parent_node, int ordinal, int *out_node);
+/* addCriteria(new Criteria.IntCriteria(ordinal, v -> lo <= v && v <= hi)) (DS/Criteria.java:19) */
+colq_status colq_query_criteria_i32_range(colq_query *query, int node, int ordinal, int32_t lo, int32_t hi);
+/* addCriteria(new Criteria.StringCriteria(ordinal, <op needle>)) (DS/Criteria.java:17) */
+colq_status colq_query_criteria_str(colq_query *query, int node, int ordinal, colq_str_op op, const uint8_t *needle,
+                                    int32_t needle_len);
+colq_status colq_query_set_option(colq_query *query, colq_option option, int value);
+
+/*
+ * DataSystemSerialIndices.execute (E/DataSystemSerialIndices.java:53-102): verify/link (E/Verifier.java:40-111),
+ * per-node predicate scan (E/ExecutionContext.java:79-94), leaf-to-root association pruning (:100-122) and the
+ * ascending index half of Table.subset (M/InMemoryTable.java:121-131), all on the device.
+ *   out_bitmask : nullable; receives ceil(rows/64) words of the ROOT node's matching bits (this rank's rows)
+ *   out_indices : nullable; receives the matching row indices, ascending (global indices for a sharded root;
+ *                 with a communicator, rank 0 receives every rank's indices concatenated in rank order)
+ *   out_count   : number of matching rows (this rank's, or the global count on rank 0 after the gather)
+ * Returns COLQ_OK or one of the statuses documented on colq_status.
+ */
+colq_status colq_execute(colq_ctx *ctx, colq_query *query, uint64_t *out_bitmask, int64_t bitmask_capacity_words,
+                         int32_t *out_indices, int64_t indices_capacity, int64_t *out_count, colq_timing *out_timing);
+/*
+ * Same pipeline without any host synchronisation or result copy: kernels are only enqueued on the context's
+ * stream; results stay in HBM until colq_fetch.  Used to time K back-to-back executions with CUDA events.
+ */
+colq_status colq_execute_async(colq_ctx *ctx, colq_query *query);
+colq_status colq_fetch(colq_ctx *ctx, colq_query *query, uint64_t *out_bitmask, int64_t bitmask_capacity_words,
+                       int32_t *out_indices, int64_t indices_capacity, int64_t *out_count, colq_timing *out_timing);
+/* per-kernel stages of the last execute of `query` (times only with COLQ_OPT_PROFILE); returns the stage count */
+colq_status colq_profile(const colq_query *query, colq_stage *out_stages, int capacity, int *out_n_stages);
+/* cardinality of every execution node's bitmask after the last execute, in the reference's node creation (BFS)
+   order; -1 for nodes that were fused away and never materialised. Debug / parity aid. */
+colq_status colq_node_cardinalities(colq_ctx *ctx, const colq_query *query, int64_t *out, int capacity, int *out_n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLQ_H */

@@ -1,0 +1,366 @@
+"""``DataSystemColq`` -- the B200 execution module behind the reference's ``DataSystem`` interface.
+
+Mirrors ``DataSystemSerialIndices`` (``E = data-system-serial-indices-arrays/src/main/java/dgroomes/
+data_system_serial_indices_arrays``): ``register(name, table)`` (E/DataSystemSerialIndices.java:27) and
+``execute(query) -> QueryResult`` (:53).  The host side only (1) ships column arrays to HBM once, (2) translates
+the ``Query`` tree into ``colq_query_*`` downcalls and (3) turns the returned row set into the result ``Table``
+with the registered table's own ``subset`` -- everything else happens in ``libcolq.so`` on the GPU.
+
+Two layers:
+  * ``ColqContext``  -- thin object wrapper of the C ABI (also used by bench.py with device-resident buffers),
+  * ``DataSystemColq`` -- the reference-facing class.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _ffi
+from .data_system import (BitSet, Criteria, DataSystem, IntPredicate, Query, QueryResult, StringPredicate, Table)
+from .in_memory import AssociationColumn, BooleanColumn, IntegerColumn, StringColumn
+
+
+class ColqError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(message)
+        self.status = status
+
+
+def _raise(status: int, message: str):
+    """Map colq_status to the exception class the reference would throw (include/colq.h)."""
+    if status == _ffi.THROW_INDEX_OOB:
+        raise IndexError(message)                      # java.lang.IndexOutOfBoundsException
+    if status == _ffi.THROW_NULL:
+        raise TypeError("NullPointerException: " + message)
+    if status == _ffi.THROW_ILLEGAL_ARG:
+        raise ValueError(message)                      # java.lang.IllegalArgumentException
+    raise ColqError(status, message)                   # IllegalStateException / device errors
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class ExecResult:
+    count: int
+    indices: Optional[np.ndarray]
+    bitmask: Optional[np.ndarray]
+    timing: _ffi.Timing
+
+
+class ColqQuery:
+    def __init__(self, ctx: "ColqContext", table_name: str):
+        self.ctx = ctx
+        self.handle = C.c_void_p()
+        ctx._check(ctx.lib.colq_query_create(ctx.handle, table_name.encode(), C.byref(self.handle)))
+
+    def child(self, parent: int, ordinal: int) -> int:
+        out = C.c_int()
+        self.ctx._check(self.ctx.lib.colq_query_child(self.handle, parent, ordinal, C.byref(out)))
+        return out.value
+
+    def criteria_i32_range(self, node: int, ordinal: int, lo: int, hi: int) -> None:
+        self.ctx._check(self.ctx.lib.colq_query_criteria_i32_range(self.handle, node, ordinal, lo, hi))
+
+    def criteria_str(self, node: int, ordinal: int, op: int, needle: bytes) -> None:
+        buf = (C.c_uint8 * max(len(needle), 1)).from_buffer_copy(needle or b"\0")
+        self.ctx._check(self.ctx.lib.colq_query_criteria_str(self.handle, node, ordinal, op, buf, len(needle)))
+
+    def set_option(self, option: int, value: int) -> None:
+        self.ctx._check(self.ctx.lib.colq_query_set_option(self.handle, option, value))
+
+    def execute(self, want_indices: bool = True, want_bitmask: bool = False, n_rows: int = 0,
+                index_capacity: int = 1 << 20) -> ExecResult:
+        return self.ctx._execute(self, want_indices, want_bitmask, n_rows, index_capacity, fetch_only=False)
+
+    def execute_async(self) -> None:
+        self.ctx._check(self.ctx.lib.colq_execute_async(self.ctx.handle, self.handle))
+
+    def fetch(self, want_indices: bool = True, want_bitmask: bool = False, n_rows: int = 0,
+              index_capacity: int = 1 << 20) -> ExecResult:
+        return self.ctx._execute(self, want_indices, want_bitmask, n_rows, index_capacity, fetch_only=True)
+
+    def profile(self) -> List[Tuple[str, float, int, int]]:
+        stages = (_ffi.Stage * 64)()
+        n = C.c_int()
+        self.ctx._check(self.ctx.lib.colq_profile(self.handle, stages, 64, C.byref(n)))
+        return [(stages[i].name.decode(), stages[i].ms, stages[i].rows, stages[i].bytes) for i in range(min(n.value, 64))]
+
+    def node_cardinalities(self) -> List[int]:
+        out = (C.c_int64 * 64)()
+        n = C.c_int()
+        self.ctx._check(self.ctx.lib.colq_node_cardinalities(self.ctx.handle, self.handle, out, 64, C.byref(n)))
+        return [out[i] for i in range(min(n.value, 64))]
+
+    def close(self) -> None:
+        if self.handle:
+            self.ctx.lib.colq_query_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ColqContext:
+    """Object wrapper of one ``colq_ctx``."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _ffi.load()
+        if self.lib.colq_abi_version() != 1:
+            raise RuntimeError("libcolq.so ABI version mismatch")
+        self.handle = C.c_void_p()
+        st = self.lib.colq_create(device, C.byref(self.handle))
+        if st != _ffi.OK:
+            raise ColqError(st, f"colq_create(device={device}) failed with status {st}: no usable sm_100 GPU "
+                                "(libcolq has no CPU fallback)")
+        self.device = device
+        self._keepalive: List[object] = []
+
+    # -- plumbing
+    def last_error(self) -> str:
+        return (self.lib.colq_last_error(self.handle) or b"").decode("utf-8", "replace")
+
+    def _check(self, status: int) -> None:
+        if status != _ffi.OK:
+            _raise(status, self.last_error())
+
+    def set_stream(self, cuda_stream: int) -> None:
+        self._check(self.lib.colq_set_stream(self.handle, C.c_void_p(cuda_stream)))
+
+    def synchronize(self) -> None:
+        self._check(self.lib.colq_synchronize(self.handle))
+
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        self._check(self.lib.colq_comm_unique_id(self.handle, buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, n_ranks: int, rank: int) -> None:
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self.lib.colq_comm_init(self.handle, buf, n_ranks, rank))
+
+    # -- tables
+    def table_create(self, n_rows: int, placement: int = _ffi.REPLICATED, global_row_base: int = 0) -> int:
+        out = C.c_int32()
+        self._check(self.lib.colq_table_create(self.handle, n_rows, placement, global_row_base, C.byref(out)))
+        return out.value
+
+    def register(self, name: str, table: int) -> None:
+        self._check(self.lib.colq_register(self.handle, name.encode(), table))
+
+    def col_i32(self, table: int, ordinal: int, values: np.ndarray) -> None:
+        v = np.ascontiguousarray(values, dtype=np.int32)
+        self._check(self.lib.colq_col_i32(self.handle, table, ordinal, _ptr(v), v.shape[0]))
+
+    def col_str(self, table: int, ordinal: int, offsets: np.ndarray, data: np.ndarray) -> None:
+        o = np.ascontiguousarray(offsets, dtype=np.uint32)
+        d = np.ascontiguousarray(data, dtype=np.uint8)
+        self._check(self.lib.colq_col_str(self.handle, table, ordinal, _ptr(o), _ptr(d), o.shape[0] - 1, d.shape[0]))
+
+    def col_bool(self, table: int, ordinal: int, values: np.ndarray) -> None:
+        v = np.ascontiguousarray(values, dtype=np.uint8)
+        self._check(self.lib.colq_col_bool(self.handle, table, ordinal, _ptr(v), v.shape[0]))
+
+    def col_i32_device(self, table: int, ordinal: int, dev_ptr: int, n: int, keepalive=None) -> None:
+        self._keepalive.append(keepalive)
+        self._check(self.lib.colq_col_i32_device(self.handle, table, ordinal, C.c_void_p(dev_ptr), n))
+
+    def col_str_device(self, table: int, ordinal: int, off_ptr: int, off_cap: int, bytes_ptr: int, bytes_cap: int, n: int,
+                       n_bytes: int, keepalive=None) -> None:
+        self._keepalive.append(keepalive)
+        self._check(self.lib.colq_col_str_device(self.handle, table, ordinal, C.c_void_p(off_ptr), off_cap,
+                                                 C.c_void_p(bytes_ptr), bytes_cap, n, n_bytes))
+
+    def associate_fk(self, x: int, x_ordinal: int, y: int, y_ordinal: int, fk: np.ndarray) -> None:
+        f = np.ascontiguousarray(fk, dtype=np.int32)
+        self._check(self.lib.colq_associate_fk(self.handle, x, x_ordinal, y, y_ordinal, _ptr(f), f.shape[0]))
+
+    def associate_fk_device(self, x: int, x_ordinal: int, y: int, y_ordinal: int, dev_ptr: int, n: int, keepalive=None) -> None:
+        self._keepalive.append(keepalive)
+        self._check(self.lib.colq_associate_fk_device(self.handle, x, x_ordinal, y, y_ordinal, C.c_void_p(dev_ptr), n))
+
+    def associate_csr(self, x: int, x_ordinal: int, y: int, y_ordinal: int, offsets: np.ndarray, targets: np.ndarray) -> None:
+        o = np.ascontiguousarray(offsets, dtype=np.int64)
+        t = np.ascontiguousarray(targets, dtype=np.int32)
+        self._check(self.lib.colq_associate_csr(self.handle, x, x_ordinal, y, y_ordinal, _ptr(o), _ptr(t), o.shape[0] - 1,
+                                                t.shape[0]))
+
+    def query(self, table_name: str) -> ColqQuery:
+        return ColqQuery(self, table_name)
+
+    def _execute(self, q: ColqQuery, want_indices: bool, want_bitmask: bool, n_rows: int, index_capacity: int,
+                 fetch_only: bool) -> ExecResult:
+        fn = self.lib.colq_fetch if fetch_only else self.lib.colq_execute
+        count = C.c_int64()
+        timing = _ffi.Timing()
+        bitmask = np.zeros((n_rows + 63) // 64, dtype=np.uint64) if want_bitmask else None
+        cap = max(int(index_capacity), 1)
+        while True:
+            idx = np.empty(cap, dtype=np.int32) if want_indices else None
+            st = fn(self.handle, q.handle, _ptr(bitmask), 0 if bitmask is None else bitmask.shape[0], _ptr(idx),
+                    0 if idx is None else cap, C.byref(count), C.byref(timing))
+            if st == _ffi.ERR_CAPACITY and want_indices and count.value > cap:
+                cap = int(count.value)  # the true count was reported: retry the copy with a big enough buffer
+                fn = self.lib.colq_fetch
+                continue
+            self._check(st)
+            break
+        return ExecResult(count.value, None if idx is None else idx[: count.value], bitmask, timing)
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.colq_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DataSystemColq(DataSystem):
+    """The reference-facing engine: same two methods as ``DataSystemSerialIndices``."""
+
+    def __init__(self, device: int = 0, lazy_fk: bool = True, context: Optional[ColqContext] = None):
+        self.ctx = context or ColqContext(device)
+        self.lazy_fk = lazy_fk
+        self._tables: Dict[str, Table] = {}                 # private final Map<String, Table> tables (E/...:18)
+        self._placement: Dict[int, Tuple[int, int]] = {}    # id(table) -> (placement, global_row_base)
+        self._handles: Dict[int, int] = {}                  # id(table) -> colq_table
+        self._uploaded: Dict[int, int] = {}                 # id(table) -> number of columns already on the device
+        self._registered_handle: Dict[str, int] = {}
+        self._pins: List[Table] = []
+        self.last_timing: Optional[_ffi.Timing] = None
+        self.last_query: Optional[ColqQuery] = None
+
+    def register(self, table_name: str, table: Table, placement: int = _ffi.REPLICATED, global_row_base: int = 0) -> None:
+        """E/DataSystemSerialIndices.java:27-29.  Like the reference this only records the reference: the app registers
+        tables BEFORE ``associateTo`` appends their association columns (app/.../Runner.java:107 vs :138), so the
+        device upload happens at the first ``execute`` by walking the table graph."""
+        self._tables[table_name] = table
+        self._placement[id(table)] = (placement, global_row_base)
+        self._pins.append(table)
+
+    # -- ingest: Table graph -> HBM
+    def _sync_tables(self) -> None:
+        # discover every table reachable through association columns (identity-keyed, cycle-safe)
+        todo = list(self._tables.values())
+        seen: Dict[int, Table] = {}
+        while todo:
+            t = todo.pop()
+            if id(t) in seen:
+                continue
+            seen[id(t)] = t
+            for c in t.columns():
+                if isinstance(c, AssociationColumn):
+                    todo.append(c.associated_entity)
+        for tid, t in seen.items():
+            if tid not in self._handles:
+                placement, base = self._placement.get(tid, (_ffi.REPLICATED, 0))
+                self._handles[tid] = self.ctx.table_create(t.size(), placement, base)
+                self._uploaded[tid] = 0
+                self._pins.append(t)
+        # scalar columns first, then associations (both ends must exist)
+        for tid, t in seen.items():
+            h = self._handles[tid]
+            cols = t.columns()
+            for ordinal in range(self._uploaded[tid], len(cols)):
+                c = cols[ordinal]
+                if isinstance(c, IntegerColumn):
+                    self.ctx.col_i32(h, ordinal, c.ints())
+                elif isinstance(c, StringColumn):
+                    self.ctx.col_str(h, ordinal, c.offsets, c.data)
+                elif isinstance(c, BooleanColumn):
+                    self.ctx.col_bool(h, ordinal, c.bools())
+        for tid, t in seen.items():
+            h = self._handles[tid]
+            cols = t.columns()
+            for ordinal in range(self._uploaded[tid], len(cols)):
+                c = cols[ordinal]
+                if isinstance(c, AssociationColumn) and c.is_forward():
+                    y = c.associated_entity
+                    rev = c.reverse_associated_column()
+                    y_ordinal = next(i for i, yc in enumerate(y.columns()) if yc is rev)
+                    fk = c.fk()
+                    if fk is not None:
+                        self.ctx.associate_fk(h, ordinal, self._handles[id(y)], y_ordinal, fk)
+                    else:
+                        _kind, offsets, targets = c.csr()
+                        self.ctx.associate_csr(h, ordinal, self._handles[id(y)], y_ordinal, offsets, targets)
+        for tid, t in seen.items():
+            self._uploaded[tid] = len(t.columns())
+        for name, t in self._tables.items():
+            h = self._handles[id(t)]
+            if self._registered_handle.get(name) != h:
+                self.ctx.register(name, h)
+                self._registered_handle[name] = h
+
+    # -- Query -> colq_query
+    def _translate(self, query: Query) -> Tuple[Optional[ColqQuery], Optional[str]]:
+        cq = self.ctx.query(query.table_name)
+        cq.set_option(_ffi.OPT_LAZY_FK, 1 if self.lazy_fk else 0)
+        stack = [(query.root_node, 0)]
+        while stack:
+            node, nid = stack.pop()
+            for crit in node.get_criteria():
+                if isinstance(crit, Criteria.IntCriteria):
+                    p = crit.integer_predicate
+                    if not isinstance(p, IntPredicate):
+                        cq.close()
+                        return None, ("The criterion on ordinal %d is an opaque IntPredicate lambda; the GPU engine only runs "
+                                      "structured predicates (colq.data_system.int_range & co.) and has no CPU fallback." % crit.ordinal)
+                    cq.criteria_i32_range(nid, crit.ordinal, p.lo, p.hi)
+                elif isinstance(crit, Criteria.StringCriteria):
+                    p = crit.string_predicate
+                    if not isinstance(p, StringPredicate):
+                        cq.close()
+                        return None, ("The criterion on ordinal %d is an opaque Predicate<String> lambda; the GPU engine only runs "
+                                      "structured predicates (colq.data_system.str_equals & co.) and has no CPU fallback." % crit.ordinal)
+                    cq.criteria_str(nid, crit.ordinal, p.op, p.needle)
+                else:
+                    raise TypeError(f"not a Criteria: {crit!r}")
+            for ordinal, child in node.get_children_by_ordinal().items():
+                stack.append((child, cq.child(nid, ordinal)))
+        return cq, None
+
+    def execute(self, query: Query):
+        """E/DataSystemSerialIndices.java:53-102."""
+        if query is None:
+            raise TypeError("NullPointerException: The 'query' argument must not be null")  # E/Verifier.java:41
+        if query.table_name not in self._tables:  # (:54-57)
+            return QueryResult.Failure(f"The query targets the table '{query.table_name}' but that table is not registered")
+        table = self._tables[query.table_name]
+        self._sync_tables()
+        cq, why = self._translate(query)
+        if cq is None:
+            return QueryResult.Failure(why)
+        try:
+            res = cq.execute(want_indices=True, want_bitmask=False, n_rows=table.size())
+        except ColqError as e:
+            cq.close()
+            if e.status == _ffi.FAILURE:
+                return QueryResult.Failure(str(e))
+            raise
+        self.last_timing = res.timing
+        if self.last_query is not None:
+            self.last_query.close()
+        self.last_query = cq
+        placement, base = self._placement.get(id(table), (_ffi.REPLICATED, 0))
+        local = res.indices - base if placement == _ffi.SHARDED else res.indices
+        matching_rows = BitSet.from_indices(local, table.size())
+        # table.subset(executionContext.matchingRows()) (:100): the registered table builds the result itself
+        return QueryResult.Success(table.subset(matching_rows))
+
+    def close(self) -> None:
+        if self.last_query is not None:
+            self.last_query.close()
+            self.last_query = None
+        self.ctx.close()

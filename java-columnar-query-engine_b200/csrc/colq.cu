@@ -1,0 +1,1348 @@
+// colq.cu -- libcolq.so: context, device-resident tables, query verifier, planner/executor and the C ABI.
+//
+// The structure follows the reference's execute() (E/DataSystemSerialIndices.java:53-102):
+//   verify/link (E/Verifier.java:40-111)  ->  per-node self filter (E/ExecutionContext.java:79-94)
+//   ->  leaf-to-root association pruning (:100-122)  ->  ascending subset indices (M/InMemoryTable.java:121-131)
+// but evaluates the node tree bottom-up in ONE post-order pass (the reference's repeated leaf-to-root walks reach
+// the same fixed point because every step is a monotone AND), and fuses work across nodes:
+//   * a hop through a forward to-one column is PULLED (parent row tests its child's bit) inside the parent's scan,
+//   * chains of criteria-free to-one hops are walked lazily only for rows that survived the parent's predicates,
+//   * a hop through a reverse column is PUSHED by the epilogue of the child's own scan kernel,
+//   * in a multi-GPU communicator a push from a sharded child into a replicated parent is followed by the only
+//     data-path collective: an all-gather of the (tiny) parent mask that the next kernel ORs together.
+// There is no CPU fallback anywhere in this file.
+//
+// E = data-system-serial-indices-arrays/src/main/java/dgroomes/data_system_serial_indices_arrays
+// M = data-model-in-memory/src/main/java/dgroomes/in_memory, DS = data-system/src/main/java/dgroomes/data_system
+#include "../../include/colq.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "colq_kernels.cuh"
+#include "colq_nccl.h"
+
+using namespace colq;
+
+// =====================================================================================================
+// internal types
+// =====================================================================================================
+
+namespace {
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    bool owned = false;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept { *this = std::move(o); }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            ptr = o.ptr; bytes = o.bytes; owned = o.owned;
+            o.ptr = nullptr; o.bytes = 0; o.owned = false;
+        }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() {
+        if (owned && ptr) cudaFree(ptr);
+        ptr = nullptr; bytes = 0; owned = false;
+    }
+};
+
+enum ColKind { COL_UNSET = 0, COL_I32, COL_STR, COL_BOOL, COL_ASSOC };
+
+struct Column {
+    ColKind kind = COL_UNSET;
+    int64_t n = 0;
+    DevBuf data;      // i32 values | string bytes | to-one fk
+    DevBuf offsets;   // string offsets (u32, n+1) | CSR offsets (i64, n+1)
+    DevBuf targets;   // CSR targets
+    int64_t n_bytes = 0;         // string payload bytes
+    int64_t bytes_capacity = 0;  // usable allocation of `data` for strings (multiple of 16)
+    // association columns (M/InMemoryColumn.java:85-138)
+    bool forward = false;  // true: this column owns the data; false: reverse column = transpose of the peer
+    bool is_fk = false;    // forward data is a dense to-one array (else CSR)
+    int peer_table = -1;   // associatedEntity
+    int peer_ordinal = -1; // reverseAssociatedColumn
+};
+
+struct Table {
+    int64_t n_rows = 0;
+    colq_placement placement = COLQ_REPLICATED;
+    int64_t row_base = 0;
+    std::vector<Column> cols;
+};
+
+struct Crit {
+    int ordinal = 0;
+    bool is_str = false;
+    int32_t lo = 0, hi = 0;
+    int op = 0;
+    std::vector<uint8_t> needle;
+    DevBuf needle_dev;
+};
+
+struct QNode {
+    std::vector<Crit> crit;
+    std::vector<std::pair<int, int>> children;  // (ordinal, node)
+};
+
+// one kernel launch (or collective / memset) of a planned query
+enum OpKind { K_SCAN_ROWS, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT };
+
+struct Op {
+    OpKind kind;
+    int node = -1;
+    int np = 0, ng = 0;
+    bool eager = false;
+    bool never = false;  // an empty int interval: the launch degenerates to clearing the mask
+    ScanRowsParams rows{};
+    ScanStrParams str{};
+    CsrPullParams csr{};
+    PushBitsParams pushb{};
+    // generic
+    u32* dst = nullptr;
+    const u32* src = nullptr;
+    int64_t n_words = 0, n_rows = 0, n_alloc_words = 0;
+    u32* gathered = nullptr;
+    u32* block_counts = nullptr;
+    u64* block_offsets = nullptr;
+    u64* total = nullptr;
+    int32_t* out_idx = nullptr;
+    int64_t capacity = 0, row_base = 0, n_blocks = 0;
+    // launch shape for scan_str
+    int grid = 0;
+    size_t smem = 0;
+    // accounting
+    const char* name = "";
+    int64_t acct_rows = 0, acct_bytes = 0;
+};
+
+struct XNode {
+    int table = -1;
+    int parent = -1;
+    int parent_ordinal = -1;
+    std::vector<const Crit*> preds;
+    std::vector<std::pair<int, int>> children;  // (ordinal on this table, xnode)
+    u32* bits = nullptr;   // final bitmask if materialised
+    bool all_ones = false;
+    bool fused = false;    // folded into a lazy FK chain, never materialised
+};
+
+struct Pool {
+    std::vector<DevBuf> bufs;
+    size_t cursor = 0;
+    void reset() { cursor = 0; }
+};
+
+}  // namespace
+
+struct colq_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::vector<Table> tables;
+    std::map<std::string, int> registry;
+    std::string err;
+    // communicator
+    NcclApi nccl;
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1, rank = 0;
+    bool str_attr_set = false;
+    std::map<size_t, int> str_occupancy;  // dynamic smem bytes -> resident CTAs per SM
+};
+
+struct colq_query {
+    colq_ctx* ctx = nullptr;
+    std::string table_name;
+    std::vector<QNode> nodes;
+    int opt_lazy = 1, opt_profile = 0, opt_graph = 1;
+    // execution state
+    Pool pool;
+    std::vector<XNode> xnodes;
+    std::vector<Op> ops;
+    int root_table = -1;
+    u32* root_bits = nullptr;
+    u64* d_total = nullptr;
+    u64* d_all_counts = nullptr;  // per-rank counts after the count all-gather
+    int32_t* d_idx = nullptr;
+    int64_t idx_capacity = 0;
+    int64_t want_idx_capacity = 1 << 20;
+    DevBuf idx_buf;       // grows on demand, outside the pool
+    DevBuf gather_buf;    // rank 0: concatenated indices of all ranks
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    std::vector<cudaEvent_t> stage_ev;
+    std::vector<colq_stage> stages;
+    colq_timing timing{};
+    bool executed = false;
+    // captured CUDA graph of the op sequence
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<Op> graph_ops;
+};
+
+namespace {
+
+// =====================================================================================================
+// error helpers
+// =====================================================================================================
+
+colq_status fail(colq_ctx* ctx, colq_status st, const char* fmt, ...) {
+    char buf[768];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return st;
+}
+
+#define CU(ctx, expr)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            return fail((ctx), COLQ_ERR_DEVICE, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, \
+                        __LINE__, cudaGetErrorString(_e));                                                    \
+    } while (0)
+
+#define NC(ctx, expr)                                                                                   \
+    do {                                                                                                \
+        ncclResult_t _r = (expr);                                                                       \
+        if (_r != 0)                                                                                    \
+            return fail((ctx), COLQ_ERR_DEVICE, "NCCL error %d at %s:%d: %s", _r, __FILE__, __LINE__,   \
+                        (ctx)->nccl.GetErrorString ? (ctx)->nccl.GetErrorString(_r) : "?");             \
+    } while (0)
+
+#define ST(expr)                              \
+    do {                                      \
+        colq_status _s = (expr);              \
+        if (_s != COLQ_OK) return _s;         \
+    } while (0)
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// bitmask allocation: whole compaction blocks (32768 rows) so every kernel can store / vector-load full lines
+inline int64_t bitmap_alloc_words(int64_t n_rows) { return round_up(std::max<int64_t>(n_rows, 1), 32768) / 32; }
+inline int64_t bitmap_words(int64_t n_rows) { return (n_rows + 31) / 32; }
+
+colq_status dev_alloc(colq_ctx* ctx, DevBuf& b, size_t bytes) {
+    b.release();
+    void* p = nullptr;
+    CU(ctx, cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+    b.ptr = p; b.bytes = std::max<size_t>(bytes, 16); b.owned = true;
+    return COLQ_OK;
+}
+
+colq_status pool_alloc(colq_query* q, size_t bytes, void** out) {
+    Pool& pl = q->pool;
+    if (pl.cursor == pl.bufs.size()) pl.bufs.emplace_back();
+    DevBuf& b = pl.bufs[pl.cursor++];
+    if (b.bytes < bytes) ST(dev_alloc(q->ctx, b, bytes));
+    *out = b.ptr;
+    return COLQ_OK;
+}
+
+Table* get_table(colq_ctx* ctx, colq_table t) {
+    if (t < 0 || (size_t)t >= ctx->tables.size()) return nullptr;
+    return &ctx->tables[t];
+}
+
+colq_status slot_for(colq_ctx* ctx, colq_table t, int ordinal, int64_t n, Column** out) {
+    Table* tb = get_table(ctx, t);
+    if (!tb) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "unknown table handle %d", t);
+    if (ordinal < 0) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "negative column ordinal %d", ordinal);
+    if (n != tb->n_rows)
+        return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "column height %lld does not match the table's %lld rows", (long long)n,
+                    (long long)tb->n_rows);
+    if ((size_t)ordinal >= tb->cols.size()) tb->cols.resize(ordinal + 1);
+    if (tb->cols[ordinal].kind != COL_UNSET)
+        return fail(ctx, COLQ_THROW_ILLEGAL_STATE, "column %d of table %d is already set", ordinal, t);
+    *out = &tb->cols[ordinal];
+    return COLQ_OK;
+}
+
+const char* java_class_name(ColKind k) {
+    switch (k) {
+        case COL_I32: return "dgroomes.in_memory.InMemoryColumn$IntegerColumn";
+        case COL_STR: return "dgroomes.in_memory.InMemoryColumn$StringColumn";
+        case COL_BOOL: return "dgroomes.in_memory.InMemoryColumn$BooleanColumn";
+        default: return "dgroomes.in_memory.InMemoryColumn$AssociationColumn";
+    }
+}
+
+// =====================================================================================================
+// verify: E/Verifier.java:40-111 (same traversal order, same messages)
+// =====================================================================================================
+
+colq_status verify(colq_query* q) {
+    colq_ctx* ctx = q->ctx;
+    auto it = ctx->registry.find(q->table_name);
+    if (it == ctx->registry.end())  // E/DataSystemSerialIndices.java:54-57
+        return fail(ctx, COLQ_FAILURE, "The query targets the table '%s' but that table is not registered",
+                    q->table_name.c_str());
+    q->root_table = it->second;
+    q->xnodes.clear();
+    q->xnodes.reserve(q->nodes.size());
+    std::deque<std::pair<int, int>> to_visit;  // (query node, execution node): add = tail, pop = head (:49-54)
+    q->xnodes.emplace_back();
+    q->xnodes[0].table = q->root_table;
+    to_visit.emplace_back(0, 0);
+    while (!to_visit.empty()) {
+        auto [qi, xi] = to_visit.front();
+        to_visit.pop_front();
+        const QNode& qn = q->nodes[qi];
+        const Table& tb = ctx->tables[q->xnodes[xi].table];
+        const int width = (int)tb.cols.size();
+        for (const Crit& c : qn.crit) {
+            if (width < c.ordinal)  // sic: `<` (:62); ordinal == width falls through to columns().get()
+                return fail(ctx, COLQ_FAILURE, "The query ordinal '%d' is out of bounds for the table with %d columns",
+                            c.ordinal, width);
+            if (c.ordinal < 0 || c.ordinal >= width)  // columns().get(ordinal) (:67)
+                return fail(ctx, COLQ_THROW_INDEX_OOB, "Index %d out of bounds for length %d", c.ordinal, width);
+            const Column& col = tb.cols[c.ordinal];
+            switch (col.kind) {  // switch (column.filterableType()) (:71-90)
+                case COL_STR:
+                    if (!c.is_str)
+                        return fail(ctx, COLQ_FAILURE, "The column is a string column but the criterion is not a string predicate.");
+                    break;
+                case COL_I32:
+                    if (c.is_str)
+                        return fail(ctx, COLQ_FAILURE, "The column is an integer column but the criterion is not an integer predicate.");
+                    break;
+                case COL_BOOL:
+                    return fail(ctx, COLQ_FAILURE, "Boolean columns are not supported yet.");
+                case COL_ASSOC:
+                    return fail(ctx, COLQ_FAILURE, "Association columns can't be matched on with a scalar criteria.");
+                default:
+                    return fail(ctx, COLQ_THROW_ILLEGAL_STATE, "column %d was never set", c.ordinal);
+            }
+            q->xnodes[xi].preds.push_back(&c);  // addColumnPredicate (:92)
+        }
+        for (auto [ordinal, child_q] : qn.children) {  // Map.copyOf iteration order is unspecified; results are order-free
+            if (ordinal < 0 || ordinal >= width)       // columns().get(ordinal), unchecked (:100)
+                return fail(ctx, COLQ_THROW_INDEX_OOB, "Index %d out of bounds for length %d", ordinal, width);
+            const Column& col = tb.cols[ordinal];
+            if (col.kind != COL_ASSOC)  // (:102-104)
+                return fail(ctx, COLQ_FAILURE, "The column at ordinal %d is not an association column. It is a %s", ordinal,
+                            java_class_name(col.kind));
+            // createChildNode: Node(assoc.associatedEntity(), this, assoc.reverseAssociatedColumn()) (E/ExecutionContext.java:64-68)
+            XNode cx;
+            cx.table = col.peer_table;
+            cx.parent = xi;
+            cx.parent_ordinal = ordinal;
+            q->xnodes.push_back(cx);
+            int ci = (int)q->xnodes.size() - 1;
+            q->xnodes[xi].children.emplace_back(ordinal, ci);
+            to_visit.emplace_back(child_q, ci);
+        }
+    }
+    return COLQ_OK;
+}
+
+// =====================================================================================================
+// planner: post-order evaluation of the execution-node tree into a linear op list
+// =====================================================================================================
+
+struct Consume {
+    bool push = false;          // false: the parent needs this node's bitmask materialised
+    const Column* fwd = nullptr;  // forward column on THIS node's table pointing at the parent's rows
+    u32* reach = nullptr;
+    int64_t n_parent = 0;
+};
+
+struct NodeBits {
+    u32* bits = nullptr;
+    bool all_ones = false;
+};
+
+struct Planner {
+    colq_query* q;
+    colq_ctx* ctx;
+
+    colq_status alloc_bitmap(int64_t n_rows, u32** out) {
+        void* p;
+        ST(pool_alloc(q, (size_t)bitmap_alloc_words(n_rows) * 4, &p));
+        *out = (u32*)p;
+        return COLQ_OK;
+    }
+
+    bool sharded(const Table& t) const { return ctx->n_ranks > 1 && t.placement == COLQ_SHARDED; }
+
+    bool lazy_eligible(int xi) const {
+        const XNode& x = q->xnodes[xi];
+        if (!q->opt_lazy || !x.preds.empty() || x.children.size() != 1) return false;
+        const Table& t = ctx->tables[x.table];
+        const Column& col = t.cols[x.children[0].first];
+        if (!(col.forward && col.is_fk)) return false;
+        const Table& ct = ctx->tables[col.peer_table];
+        if (!sharded(t) && sharded(ct)) return false;
+        return true;
+    }
+
+    colq_status eval(int xi, const Consume& consume, NodeBits* out) {
+        XNode& x = q->xnodes[xi];
+        const Table& T = ctx->tables[x.table];
+        const int64_t n = T.n_rows;
+        const size_t first_op = q->ops.size();
+
+        std::vector<GatherD> gathers;
+        struct CsrIn { const Column* col; NodeBits child; int64_t n_child; };
+        std::vector<CsrIn> csrs;
+        u32* cur = nullptr;  // null: every row still matches
+
+        for (auto [ordinal, ci] : std::vector<std::pair<int, int>>(x.children)) {
+            const Column& col = T.cols[ordinal];
+            const Table& CT = ctx->tables[col.peer_table];
+            if (col.forward) {
+                if (!sharded(T) && sharded(CT))
+                    return fail(ctx, COLQ_FAILURE, "unsupported placement: a replicated table holds an association into a sharded table");
+                if (col.is_fk) {
+                    GatherD g{};
+                    g.fk[0] = (const int32_t*)col.data.ptr;
+                    g.n[0] = CT.n_rows;
+                    g.depth = 1;
+                    int cj = ci;
+                    while (g.depth < GATHER_MAX_DEPTH && lazy_eligible(cj)) {
+                        XNode& c = q->xnodes[cj];
+                        const Column& ccol = ctx->tables[c.table].cols[c.children[0].first];
+                        g.fk[g.depth] = (const int32_t*)ccol.data.ptr;
+                        g.n[g.depth] = ctx->tables[ccol.peer_table].n_rows;
+                        g.depth++;
+                        c.fused = true;
+                        cj = c.children[0].second;
+                    }
+                    NodeBits nb;
+                    ST(eval(cj, Consume{}, &nb));
+                    g.bits = nb.all_ones ? nullptr : nb.bits;
+                    gathers.push_back(g);
+                } else {
+                    NodeBits nb;
+                    ST(eval(ci, Consume{}, &nb));
+                    csrs.push_back({&col, nb, CT.n_rows});
+                }
+            } else {
+                // reverse side: the data is the child's forward column; the child pushes into `reach`
+                const Column& f = CT.cols[col.peer_ordinal];
+                if (sharded(T) && !sharded(CT))
+                    return fail(ctx, COLQ_FAILURE, "unsupported placement: a replicated table holds an association into a sharded table");
+                u32* reach;
+                ST(alloc_bitmap(n, &reach));
+                Op z{};
+                z.kind = K_ZERO; z.node = xi; z.dst = reach; z.n_alloc_words = bitmap_alloc_words(n); z.name = "memset_reach";
+                q->ops.push_back(z);
+                Consume cc;
+                cc.push = true; cc.fwd = &f; cc.reach = reach; cc.n_parent = n;
+                NodeBits nb;
+                ST(eval(ci, cc, &nb));
+                if (sharded(CT) && !sharded(T)) {
+                    // the only data-path collective: OR-allreduce of the replicated parent's mask
+                    Op g{};
+                    g.kind = K_ALLGATHER_OR; g.node = xi; g.dst = reach; g.n_words = bitmap_words(n);
+                    void* gb;
+                    ST(pool_alloc(q, (size_t)g.n_words * 4 * ctx->n_ranks, &gb));
+                    g.gathered = (u32*)gb;
+                    g.name = "allgather_or_mask";
+                    g.acct_bytes = g.n_words * 4 * ctx->n_ranks;
+                    q->ops.push_back(g);
+                }
+                if (cur == nullptr) cur = reach;
+                else {
+                    Op a{};
+                    a.kind = K_AND; a.node = xi; a.dst = cur; a.src = reach; a.n_words = bitmap_words(n); a.name = "and_words";
+                    a.acct_rows = n; a.acct_bytes = a.n_words * 12;
+                    q->ops.push_back(a);
+                }
+            }
+        }
+
+        XNode& xr = q->xnodes[xi];  // (children evals may not reallocate xnodes, but re-bind for clarity)
+        u32* own = nullptr;         // this node's bitmask buffer, allocated on first use
+        auto out_buf = [&](u32** p) -> colq_status {
+            if (!own) ST(alloc_bitmap(n, &own));
+            *p = own;
+            return COLQ_OK;
+        };
+
+        // ---- string criteria: one TMA-staged scan each
+        for (const Crit* c : xr.preds) {
+            if (!c->is_str) continue;
+            const Column& col = T.cols[c->ordinal];
+            Op o{};
+            o.kind = K_SCAN_STR; o.node = xi; o.name = "scan_str";
+            ScanStrParams& P = o.str;
+            P.n = n;
+            P.offsets = (const u32*)col.offsets.ptr;
+            P.bytes = (const uint8_t*)col.data.ptr;
+            P.bytes_capacity = col.bytes_capacity;
+            P.needle = (const uint8_t*)c->needle_dev.ptr;
+            P.needle_len = (int)c->needle.size();
+            P.op = c->op;
+            double avg = n > 0 ? (double)col.n_bytes / (double)n : 0.0;
+            int64_t cap = (int64_t)(2.0 * avg * ST_ROWS) + 256;
+            cap = std::min<int64_t>(std::max<int64_t>(cap, 4096), 40960);
+            P.cap = (int)round_up(cap, 16);
+            P.n_tiles = (n + ST_ROWS - 1) / ST_ROWS;
+            P.in_bits = cur;
+            u32* ob;
+            ST(out_buf(&ob));
+            P.out_bits = ob;
+            o.smem = (size_t)ST_STAGES * (ST_OFF_BYTES + P.cap + 16) + ST_MAX_NEEDLE + 16 + ST_STAGES * 8 +
+                     ST_STAGES * sizeof(StrTileMeta) + PUSH_SMEM_WORDS * 4;
+            o.acct_rows = n;
+            o.acct_bytes = (n + 1) * 4 + col.n_bytes + bitmap_words(n) * 4;
+            q->ops.push_back(o);
+            cur = ob;
+        }
+
+        // ---- int criteria + forward to-one hops: fused row scans, at most 2 predicates and 2 chains per launch
+        std::vector<const Crit*> ints;
+        for (const Crit* c : xr.preds)
+            if (!c->is_str) ints.push_back(c);
+        size_t pi = 0, gi = 0;
+        while (pi < ints.size() || gi < gathers.size()) {
+            Op o{};
+            o.kind = K_SCAN_ROWS; o.node = xi; o.name = "scan_rows";
+            ScanRowsParams& P = o.rows;
+            P.n = n;
+            P.in_bits = cur;
+            int64_t bytes = 0;
+            while (pi < ints.size() && o.np < SR_MAX_PRED) {
+                const Crit* c = ints[pi++];
+                const Column& col = T.cols[c->ordinal];
+                IntPredD& d = P.pred[o.np++];
+                d.col = (const int32_t*)col.data.ptr;
+                if (c->lo > c->hi) {  // empty closed interval: no value satisfies it
+                    o.never = true;
+                    d.lo = 0; d.span = 0;
+                } else {
+                    d.lo = c->lo;
+                    d.span = (u32)((int64_t)c->hi - (int64_t)c->lo);
+                }
+                bytes += n * 4;
+            }
+            while (gi < gathers.size() && o.ng < SR_MAX_GATHER) {
+                P.gather[o.ng++] = gathers[gi++];
+            }
+            o.eager = (o.np == 0 && cur == nullptr);
+            if (o.eager) bytes += (int64_t)o.ng * n * 4;
+            u32* ob;
+            ST(out_buf(&ob));
+            P.out_bits = ob;
+            o.acct_rows = n;
+            o.acct_bytes = bytes + bitmap_words(n) * 4;
+            q->ops.push_back(o);
+            cur = ob;
+        }
+
+        // ---- forward to-many hops
+        for (const CsrIn& ci : csrs) {
+            Op o{};
+            o.kind = K_CSR_PULL; o.node = xi; o.name = "csr_pull";
+            CsrPullParams& P = o.csr;
+            P.n = n;
+            P.offsets = (const int64_t*)ci.col->offsets.ptr;
+            P.targets = (const int32_t*)ci.col->targets.ptr;
+            P.child_bits = ci.child.all_ones ? nullptr : ci.child.bits;
+            P.n_child = ci.n_child;
+            P.in_bits = cur;
+            u32* ob;
+            ST(out_buf(&ob));
+            P.out_bits = ob;
+            o.acct_rows = n;
+            o.acct_bytes = (n + 1) * 8 + (int64_t)(ci.col->targets.bytes) + bitmap_words(n) * 4;
+            q->ops.push_back(o);
+            cur = ob;
+        }
+
+        // ---- hand the result to the consumer
+        if (consume.push) {
+            Op* last = nullptr;
+            if (q->ops.size() > first_op) {
+                Op& l = q->ops.back();
+                if (l.node == xi && (l.kind == K_SCAN_ROWS || l.kind == K_SCAN_STR || l.kind == K_CSR_PULL)) last = &l;
+            }
+            if (last && last->never) {
+                // no row of this node matches: nothing to push, and nobody else reads the mask
+                last->rows.out_bits = nullptr;
+                xr.bits = nullptr; xr.all_ones = false; xr.fused = true;
+            } else if (last && consume.fwd->is_fk) {
+                PushD pd{(const int32_t*)consume.fwd->data.ptr, consume.reach, consume.n_parent};
+                if (last->kind == K_SCAN_ROWS) { last->rows.push = pd; last->rows.out_bits = nullptr; }
+                else if (last->kind == K_SCAN_STR) { last->str.push = pd; last->str.out_bits = nullptr; }
+                else { last->csr.push = pd; last->csr.out_bits = nullptr; }
+                // out_bits dropped: nobody else reads this node's mask (debug cardinality reports -1)
+                xr.bits = nullptr;
+                xr.all_ones = false;
+                xr.fused = true;
+            } else {
+                Op o{};
+                o.kind = K_PUSH_BITS; o.node = xi; o.name = "push_bits";
+                PushBitsParams& P = o.pushb;
+                P.n_child = n;
+                P.child_bits = cur;
+                if (consume.fwd->is_fk) P.fk = (const int32_t*)consume.fwd->data.ptr;
+                else {
+                    P.offsets = (const int64_t*)consume.fwd->offsets.ptr;
+                    P.targets = (const int32_t*)consume.fwd->targets.ptr;
+                }
+                P.reach = consume.reach;
+                P.n_parent = consume.n_parent;
+                o.acct_rows = n;
+                o.acct_bytes = bitmap_words(n) * 4 + (consume.fwd->is_fk ? n * 4 : (int64_t)consume.fwd->targets.bytes);
+                q->ops.push_back(o);
+                xr.bits = cur;
+                xr.all_ones = (cur == nullptr);
+            }
+            if (out) *out = NodeBits{};
+            return COLQ_OK;
+        }
+        xr.bits = cur;
+        xr.all_ones = (cur == nullptr);
+        if (out) { out->bits = cur; out->all_ones = (cur == nullptr); }
+        return COLQ_OK;
+    }
+};
+
+// =====================================================================================================
+// launch
+// =====================================================================================================
+
+template <int NP, int NG>
+void launch_scan_rows_e(const Op& o, cudaStream_t s) {
+    int grid = (int)((o.rows.n + SR_BLOCK_ROWS - 1) / SR_BLOCK_ROWS);
+    if (grid == 0) return;
+    if (o.eager) scan_rows_kernel<NP, NG, true><<<grid, SR_THREADS, 0, s>>>(o.rows);
+    else scan_rows_kernel<NP, NG, false><<<grid, SR_THREADS, 0, s>>>(o.rows);
+}
+
+void launch_scan_rows(const Op& o, cudaStream_t s) {
+    switch (o.np * 3 + o.ng) {
+        case 0: launch_scan_rows_e<0, 0>(o, s); break;
+        case 1: launch_scan_rows_e<0, 1>(o, s); break;
+        case 2: launch_scan_rows_e<0, 2>(o, s); break;
+        case 3: launch_scan_rows_e<1, 0>(o, s); break;
+        case 4: launch_scan_rows_e<1, 1>(o, s); break;
+        case 5: launch_scan_rows_e<1, 2>(o, s); break;
+        case 6: launch_scan_rows_e<2, 0>(o, s); break;
+        case 7: launch_scan_rows_e<2, 1>(o, s); break;
+        case 8: launch_scan_rows_e<2, 2>(o, s); break;
+    }
+}
+
+inline int grid_for(int64_t work_items, int threads, int sm_count, int per_sm) {
+    int64_t g = (work_items + threads - 1) / threads;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)sm_count * per_sm));
+}
+
+colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = false) {
+    colq_ctx* ctx = q->ctx;
+    (void)count_only;
+    switch (o.kind) {
+        case K_SCAN_ROWS:
+            if (o.never) {  // an empty int interval: no row matches
+                if (o.rows.out_bits)
+                    CU(ctx, cudaMemsetAsync(o.rows.out_bits, 0, (size_t)bitmap_alloc_words(o.rows.n) * 4, s));
+            } else {
+                launch_scan_rows(o, s);
+                q->timing.kernel_launches++;
+            }
+            break;
+        case K_SCAN_STR: {
+            if (o.str.n_tiles == 0) break;
+            if (o.grid == 0) {
+                if (!ctx->str_attr_set) {
+                    CU(ctx, cudaFuncSetAttribute(scan_str_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    ctx->str_attr_set = true;
+                }
+                auto it = ctx->str_occupancy.find(o.smem);
+                if (it == ctx->str_occupancy.end()) {
+                    int occ = 0;
+                    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_str_kernel, ST_THREADS, o.smem));
+                    if (occ < 1) return fail(ctx, COLQ_ERR_DEVICE, "scan_str_kernel does not fit on an SM (smem %zu)", o.smem);
+                    it = ctx->str_occupancy.emplace(o.smem, occ).first;
+                }
+                o.grid = (int)std::min<int64_t>(o.str.n_tiles, (int64_t)ctx->sm_count * it->second);
+            }
+            scan_str_kernel<<<o.grid, ST_THREADS, o.smem, s>>>(o.str);
+            q->timing.kernel_launches++;
+            break;
+        }
+        case K_CSR_PULL: {
+            int grid = (int)((o.csr.n + 255) / 256);
+            if (grid == 0) break;
+            csr_pull_kernel<<<grid, 256, 0, s>>>(o.csr);
+            q->timing.kernel_launches++;
+            break;
+        }
+        case K_PUSH_BITS:
+            if (o.pushb.n_child == 0) break;
+            push_bits_kernel<<<grid_for(o.pushb.n_child, 256, ctx->sm_count, 8), 256, 0, s>>>(o.pushb);
+            q->timing.kernel_launches++;
+            break;
+        case K_AND:
+            and_words_kernel<<<grid_for(o.n_words, 256, ctx->sm_count, 8), 256, 0, s>>>(o.dst, o.src, o.n_words);
+            q->timing.kernel_launches++;
+            break;
+        case K_FILL:
+            fill_ones_kernel<<<grid_for(o.n_alloc_words, 256, ctx->sm_count, 8), 256, 0, s>>>(o.dst, o.n_rows, o.n_alloc_words);
+            q->timing.kernel_launches++;
+            break;
+        case K_ZERO:
+            CU(ctx, cudaMemsetAsync(o.dst, 0, (size_t)o.n_alloc_words * 4, s));
+            break;
+        case K_ALLGATHER_OR:
+            NC(ctx, ctx->nccl.AllGather(o.dst, o.gathered, (size_t)o.n_words, kNcclUint32, ctx->comm, (void*)s));
+            q->timing.collectives++;
+            or_ranks_kernel<<<grid_for(o.n_words, 256, ctx->sm_count, 8), 256, 0, s>>>(o.dst, o.gathered, o.n_words, ctx->n_ranks);
+            q->timing.kernel_launches++;
+            break;
+        case K_POPC:
+            popc_blocks_kernel<<<(int)o.n_blocks, CP_THREADS, 0, s>>>(o.src, o.n_words, o.block_counts);
+            q->timing.kernel_launches++;
+            break;
+        case K_SCAN_COUNTS:
+            scan_counts_kernel<<<1, 1024, 0, s>>>(o.block_counts, o.n_blocks, o.block_offsets, o.total);
+            q->timing.kernel_launches++;
+            break;
+        case K_COMPACT:
+            compact_kernel<<<(int)o.n_blocks, CP_THREADS, 0, s>>>(o.src, o.n_words, o.block_offsets, o.out_idx, o.capacity, o.row_base);
+            q->timing.kernel_launches++;
+            break;
+    }
+    CU(ctx, cudaGetLastError());
+    return COLQ_OK;
+}
+
+colq_status ensure_idx_capacity(colq_query* q, int64_t want) {
+    if (q->idx_buf.bytes < (size_t)want * 4) ST(dev_alloc(q->ctx, q->idx_buf, (size_t)want * 4));
+    q->d_idx = (int32_t*)q->idx_buf.ptr;
+    q->idx_capacity = (int64_t)(q->idx_buf.bytes / 4);
+    return COLQ_OK;
+}
+
+// verify + plan + enqueue. No host synchronisation.
+colq_status run_pipeline(colq_query* q) {
+    colq_ctx* ctx = q->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    ST(verify(q));
+    q->pool.reset();
+    q->ops.clear();
+    q->timing = colq_timing{};
+    Planner pl{q, ctx};
+    NodeBits root;
+    ST(pl.eval(0, Consume{}, &root));
+
+    const Table& RT = ctx->tables[q->root_table];
+    const int64_t n = RT.n_rows;
+    if (root.all_ones) {  // matchingBits.set(0, size) (E/ExecutionContext.java:83-87)
+        u32* b;
+        ST(pl.alloc_bitmap(n, &b));
+        Op f{};
+        f.kind = K_FILL; f.node = 0; f.dst = b; f.n_rows = n; f.n_alloc_words = bitmap_alloc_words(n); f.name = "fill_ones";
+        f.acct_rows = n; f.acct_bytes = bitmap_words(n) * 4;
+        q->ops.push_back(f);
+        root.bits = b;
+        q->xnodes[0].bits = b;
+    }
+    q->root_bits = root.bits;
+
+    // ---- compaction of the root mask (M/InMemoryTable.java:121-131)
+    const int64_t n_words = bitmap_words(n);
+    const int64_t n_blocks = std::max<int64_t>(1, (n_words + CP_WORDS_PER_BLOCK - 1) / CP_WORDS_PER_BLOCK);
+    void *bc, *bo, *tot;
+    ST(pool_alloc(q, (size_t)n_blocks * 4, &bc));
+    ST(pool_alloc(q, (size_t)n_blocks * 8, &bo));
+    ST(pool_alloc(q, 64 + 8 * (size_t)std::max(ctx->n_ranks, 1), &tot));
+    q->d_total = (u64*)tot;
+    q->d_all_counts = (u64*)tot + 8;
+    ST(ensure_idx_capacity(q, std::max<int64_t>(q->want_idx_capacity, 1)));
+    {
+        Op p{};
+        p.kind = K_POPC; p.node = 0; p.src = root.bits; p.n_words = n_words; p.n_blocks = n_blocks; p.block_counts = (u32*)bc;
+        p.name = "popc_blocks"; p.acct_rows = n; p.acct_bytes = n_words * 4;
+        q->ops.push_back(p);
+        Op sc{};
+        sc.kind = K_SCAN_COUNTS; sc.node = 0; sc.block_counts = (u32*)bc; sc.n_blocks = n_blocks; sc.block_offsets = (u64*)bo;
+        sc.total = q->d_total; sc.name = "scan_counts"; sc.acct_bytes = n_blocks * 12;
+        q->ops.push_back(sc);
+        Op c{};
+        c.kind = K_COMPACT; c.node = 0; c.src = root.bits; c.n_words = n_words; c.n_blocks = n_blocks; c.block_offsets = (u64*)bo;
+        c.out_idx = q->d_idx; c.capacity = q->idx_capacity;
+        c.row_base = (ctx->n_ranks > 1 && RT.placement == COLQ_SHARDED) ? RT.row_base : RT.row_base;
+        c.name = "compact"; c.acct_rows = n; c.acct_bytes = n_words * 4;
+        q->ops.push_back(c);
+    }
+
+    // ---- enqueue
+    cudaStream_t s = ctx->stream;
+    if (!q->ev_start) {
+        CU(ctx, cudaEventCreate(&q->ev_start));
+        CU(ctx, cudaEventCreate(&q->ev_stop));
+    }
+    const bool prof = q->opt_profile != 0;
+    if (prof) {
+        while (q->stage_ev.size() < q->ops.size() + 1) {
+            cudaEvent_t e;
+            CU(ctx, cudaEventCreate(&e));
+            q->stage_ev.push_back(e);
+        }
+    }
+    CU(ctx, cudaEventRecord(q->ev_start, s));
+    if (prof) CU(ctx, cudaEventRecord(q->stage_ev[0], s));
+    for (size_t i = 0; i < q->ops.size(); ++i) {
+        ST(launch_op(q, q->ops[i], s));
+        if (prof) CU(ctx, cudaEventRecord(q->stage_ev[i + 1], s));
+    }
+    CU(ctx, cudaEventRecord(q->ev_stop, s));
+    q->executed = true;
+    return COLQ_OK;
+}
+
+// count D2H, (multi-GPU) final gather to rank 0, result copies. Synchronises the stream.
+colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_cap, int32_t* out_idx, int64_t idx_cap,
+                          int64_t* out_count, colq_timing* out_timing) {
+    colq_ctx* ctx = q->ctx;
+    if (!q->executed) return fail(ctx, COLQ_THROW_ILLEGAL_STATE, "colq_fetch before colq_execute_async");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const Table& RT = ctx->tables[q->root_table];
+    u64 local = 0;
+    CU(ctx, cudaMemcpyAsync(&local, q->d_total, 8, cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    q->timing.d2h_bytes += 8;
+    float ms = 0;
+    CU(ctx, cudaEventElapsedTime(&ms, q->ev_start, q->ev_stop));
+    q->timing.gpu_ms = ms;
+
+    if ((int64_t)local > q->idx_capacity) {
+        // index buffer was too small: grow it and redo only the ordered write (the mask is still resident)
+        q->want_idx_capacity = (int64_t)local;
+        ST(ensure_idx_capacity(q, (int64_t)local));
+        for (Op& o : q->ops)
+            if (o.kind == K_COMPACT) {
+                o.out_idx = q->d_idx;
+                o.capacity = q->idx_capacity;
+                ST(launch_op(q, o, s));
+            }
+        CU(ctx, cudaStreamSynchronize(s));
+    }
+
+    int64_t count = (int64_t)local;
+    const int32_t* src_idx = q->d_idx;
+    const bool gather = ctx->n_ranks > 1 && RT.placement == COLQ_SHARDED;
+    if (gather) {
+        // final gather of matched indices to rank 0: all-gather the counts, then variable-size send/recv
+        NC(ctx, ctx->nccl.AllGather(q->d_total, q->d_all_counts, 1, kNcclUint64, ctx->comm, (void*)s));
+        q->timing.collectives++;
+        std::vector<u64> counts(ctx->n_ranks);
+        CU(ctx, cudaMemcpyAsync(counts.data(), q->d_all_counts, 8 * (size_t)ctx->n_ranks, cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaStreamSynchronize(s));
+        q->timing.d2h_bytes += 8 * ctx->n_ranks;
+        int64_t total = 0;
+        for (u64 c : counts) total += (int64_t)c;
+        if (ctx->rank == 0) {
+            if (q->gather_buf.bytes < (size_t)std::max<int64_t>(total, 1) * 4)
+                ST(dev_alloc(ctx, q->gather_buf, (size_t)std::max<int64_t>(total, 1) * 4));
+            int32_t* g = (int32_t*)q->gather_buf.ptr;
+            CU(ctx, cudaMemcpyAsync(g, q->d_idx, (size_t)local * 4, cudaMemcpyDeviceToDevice, s));
+            NC(ctx, ctx->nccl.GroupStart());
+            int64_t off = (int64_t)counts[0];
+            for (int r = 1; r < ctx->n_ranks; ++r) {
+                if (counts[r]) NC(ctx, ctx->nccl.Recv(g + off, (size_t)counts[r], kNcclInt32, r, ctx->comm, (void*)s));
+                off += (int64_t)counts[r];
+            }
+            NC(ctx, ctx->nccl.GroupEnd());
+            q->timing.collectives++;
+            src_idx = g;
+            count = total;
+        } else {
+            NC(ctx, ctx->nccl.GroupStart());
+            if (local) NC(ctx, ctx->nccl.Send(q->d_idx, (size_t)local, kNcclInt32, 0, ctx->comm, (void*)s));
+            NC(ctx, ctx->nccl.GroupEnd());
+            q->timing.collectives++;
+        }
+        CU(ctx, cudaStreamSynchronize(s));
+    }
+
+    if (out_count) *out_count = count;
+    colq_status rc = COLQ_OK;
+    if (out_bitmask) {
+        int64_t words64 = (RT.n_rows + 63) / 64;
+        if (bitmask_cap < words64) rc = fail(ctx, COLQ_ERR_CAPACITY, "bitmask capacity %lld < %lld words", (long long)bitmask_cap, (long long)words64);
+        else {
+            CU(ctx, cudaMemcpyAsync(out_bitmask, q->root_bits, (size_t)words64 * 8, cudaMemcpyDeviceToHost, s));
+            q->timing.d2h_bytes += words64 * 8;
+        }
+    }
+    if (out_idx && (ctx->rank == 0 || !gather)) {
+        if (idx_cap < count) rc = fail(ctx, COLQ_ERR_CAPACITY, "index capacity %lld < %lld matches", (long long)idx_cap, (long long)count);
+        else if (count > 0) {
+            CU(ctx, cudaMemcpyAsync(out_idx, src_idx, (size_t)count * 4, cudaMemcpyDeviceToHost, s));
+            q->timing.d2h_bytes += count * 4;
+        }
+    }
+    CU(ctx, cudaStreamSynchronize(s));
+
+    // per-stage profile
+    q->stages.clear();
+    for (size_t i = 0; i < q->ops.size(); ++i) {
+        const Op& o = q->ops[i];
+        if (o.kind == K_ZERO) continue;
+        colq_stage st{};
+        snprintf(st.name, sizeof st.name, "%s", o.name);
+        if (o.kind == K_SCAN_ROWS) snprintf(st.name, sizeof st.name, "scan_rows<%d,%d,%s>%s", o.np, o.ng, o.eager ? "eager" : "lazy", o.rows.push.fk ? "+push" : "");
+        if (o.kind == K_SCAN_STR) snprintf(st.name, sizeof st.name, "scan_str<op%d>%s", o.str.op, o.str.push.fk ? "+push" : "");
+        st.rows = o.acct_rows;
+        st.bytes = o.acct_bytes;
+        st.ms = -1.0;
+        if (q->opt_profile && q->stage_ev.size() > i + 1) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, q->stage_ev[i], q->stage_ev[i + 1]) == cudaSuccess) st.ms = t;
+        }
+        q->stages.push_back(st);
+    }
+    if (out_timing) *out_timing = q->timing;
+    return rc;
+}
+
+colq_status upload(colq_ctx* ctx, DevBuf& b, const void* host, size_t bytes, size_t alloc_bytes) {
+    ST(dev_alloc(ctx, b, alloc_bytes));
+    if (alloc_bytes > bytes) CU(ctx, cudaMemsetAsync((char*)b.ptr + bytes, 0, alloc_bytes - bytes, ctx->stream));
+    if (bytes) CU(ctx, cudaMemcpyAsync(b.ptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return COLQ_OK;
+}
+
+colq_status check_fk_range(colq_ctx* ctx, const int32_t* d_fk, int64_t n, int64_t n_target) {
+    if (n == 0) return COLQ_OK;
+    DevBuf mm;
+    ST(dev_alloc(ctx, mm, 8));
+    int32_t init[2] = {INT32_MAX, INT32_MIN};
+    CU(ctx, cudaMemcpyAsync(mm.ptr, init, 8, cudaMemcpyHostToDevice, ctx->stream));
+    fk_minmax_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_fk, n, (int32_t*)mm.ptr, (int32_t*)mm.ptr + 1);
+    CU(ctx, cudaGetLastError());
+    int32_t got[2];
+    CU(ctx, cudaMemcpyAsync(got, mm.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (got[0] < -1 || got[1] >= n_target)  // M/InMemoryTable.java:70-71: yIndexToXAssociations.get(yIndex) is null -> NPE
+        return fail(ctx, COLQ_THROW_NULL, "association target outside the associated table (min %d, max %d, size %lld)", got[0],
+                    got[1], (long long)n_target);
+    return COLQ_OK;
+}
+
+colq_status link_assoc(colq_ctx* ctx, colq_table x, int xo, colq_table y, int yo, bool is_fk, Column** fwd_out) {
+    Table* X = get_table(ctx, x);
+    Table* Y = get_table(ctx, y);
+    if (!X || !Y) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "unknown table handle");
+    if (x == y && xo == yo) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "forward and reverse column need distinct ordinals");
+    Column *f, *r;
+    ST(slot_for(ctx, x, xo, X->n_rows, &f));
+    f->kind = COL_ASSOC;  // claim before asking for the second slot (x may equal y)
+    colq_status st = slot_for(ctx, y, yo, Y->n_rows, &r);
+    f = &ctx->tables[x].cols[xo];  // slot_for may have grown the vector
+    if (st != COLQ_OK) { f->kind = COL_UNSET; return st; }
+    f->n = X->n_rows; f->forward = true; f->is_fk = is_fk; f->peer_table = y; f->peer_ordinal = yo;
+    r->kind = COL_ASSOC; r->n = Y->n_rows; r->forward = false; r->is_fk = false; r->peer_table = x; r->peer_ordinal = xo;
+    *fwd_out = f;
+    return COLQ_OK;
+}
+
+void unlink_assoc(colq_ctx* ctx, colq_table x, int xo, colq_table y, int yo) {
+    ctx->tables[x].cols[xo] = Column();
+    ctx->tables[y].cols[yo] = Column();
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+
+extern "C" {
+
+int colq_abi_version(void) { return COLQ_ABI_VERSION; }
+
+colq_status colq_create(int device, colq_ctx** out_ctx) {
+    if (!out_ctx) return COLQ_THROW_NULL;
+    *out_ctx = nullptr;
+    std::unique_ptr<colq_ctx> ctx(new colq_ctx());
+    ctx->device = device;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        // no CPU fallback: the module is useless without its GPU (north_star)
+        fprintf(stderr, "colq_create: no usable CUDA device %d (%s)\n", device, e != cudaSuccess ? cudaGetErrorString(e) : "device count");
+        return COLQ_ERR_DEVICE;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return COLQ_ERR_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return COLQ_ERR_DEVICE;
+    if (prop.major < 10) {
+        fprintf(stderr, "colq_create: device %d is sm_%d%d; libcolq is built for sm_100a only\n", device, prop.major, prop.minor);
+        return COLQ_ERR_DEVICE;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return COLQ_ERR_DEVICE;
+    ctx->stream = ctx->own_stream;
+    *out_ctx = ctx.release();
+    return COLQ_OK;
+}
+
+colq_status colq_destroy(colq_ctx* ctx) {
+    if (!ctx) return COLQ_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
+    ctx->tables.clear();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return COLQ_OK;
+}
+
+const char* colq_last_error(const colq_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+colq_status colq_set_stream(colq_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return COLQ_THROW_NULL;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return COLQ_OK;
+}
+
+colq_status colq_get_stream(colq_ctx* ctx, void** out) {
+    if (!ctx || !out) return COLQ_THROW_NULL;
+    *out = (void*)ctx->stream;
+    return COLQ_OK;
+}
+
+colq_status colq_synchronize(colq_ctx* ctx) {
+    if (!ctx) return COLQ_THROW_NULL;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return COLQ_OK;
+}
+
+colq_status colq_comm_unique_id(colq_ctx* ctx, uint8_t out_id[128]) {
+    if (!ctx || !out_id) return COLQ_THROW_NULL;
+    std::string err;
+    if (!ctx->nccl.load(err)) return fail(ctx, COLQ_ERR_DEVICE, "%s", err.c_str());
+    ncclUniqueId id;
+    NC(ctx, ctx->nccl.GetUniqueId(&id));
+    memcpy(out_id, id.internal, 128);
+    return COLQ_OK;
+}
+
+colq_status colq_comm_init(colq_ctx* ctx, const uint8_t id_bytes[128], int n_ranks, int rank) {
+    if (!ctx || !id_bytes) return COLQ_THROW_NULL;
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "bad rank %d of %d", rank, n_ranks);
+    if (ctx->comm) return fail(ctx, COLQ_THROW_ILLEGAL_STATE, "communicator already initialised");
+    std::string err;
+    if (!ctx->nccl.load(err)) return fail(ctx, COLQ_ERR_DEVICE, "%s", err.c_str());
+    CU(ctx, cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(id.internal, id_bytes, 128);
+    NC(ctx, ctx->nccl.CommInitRank(&ctx->comm, n_ranks, id, rank));
+    ctx->n_ranks = n_ranks;
+    ctx->rank = rank;
+    return COLQ_OK;
+}
+
+colq_status colq_comm_info(const colq_ctx* ctx, int* out_n_ranks, int* out_rank) {
+    if (!ctx) return COLQ_THROW_NULL;
+    if (out_n_ranks) *out_n_ranks = ctx->n_ranks;
+    if (out_rank) *out_rank = ctx->rank;
+    return COLQ_OK;
+}
+
+colq_status colq_table_create(colq_ctx* ctx, int64_t n_rows, colq_placement placement, int64_t global_row_base, colq_table* out) {
+    if (!ctx || !out) return COLQ_THROW_NULL;
+    if (n_rows < 0 || n_rows > INT32_MAX) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "row count %lld outside [0, 2^31)", (long long)n_rows);
+    if (placement != COLQ_REPLICATED && placement != COLQ_SHARDED) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "bad placement %d", (int)placement);
+    Table t;
+    t.n_rows = n_rows; t.placement = placement; t.row_base = global_row_base;
+    ctx->tables.push_back(std::move(t));
+    *out = (colq_table)ctx->tables.size() - 1;
+    return COLQ_OK;
+}
+
+colq_status colq_register(colq_ctx* ctx, const char* name, colq_table table) {
+    if (!ctx || !name) return COLQ_THROW_NULL;
+    if (!get_table(ctx, table)) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "unknown table handle %d", table);
+    ctx->registry[name] = table;  // HashMap.put (E/DataSystemSerialIndices.java:28)
+    return COLQ_OK;
+}
+
+colq_status colq_col_i32(colq_ctx* ctx, colq_table table, int ordinal, const int32_t* values, int64_t n) {
+    if (!ctx || (!values && n > 0)) return COLQ_THROW_NULL;
+    CU(ctx, cudaSetDevice(ctx->device));
+    Column* c;
+    ST(slot_for(ctx, table, ordinal, n, &c));
+    ST(upload(ctx, c->data, values, (size_t)n * 4, (size_t)round_up(n * 4 + 16, 16)));
+    c->kind = COL_I32; c->n = n;
+    return COLQ_OK;
+}
+
+colq_status colq_col_i32_device(colq_ctx* ctx, colq_table table, int ordinal, const void* values_device, int64_t n) {
+    if (!ctx || (!values_device && n > 0)) return COLQ_THROW_NULL;
+    if ((uintptr_t)values_device & 15) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "device column must be 16-byte aligned");
+    Column* c;
+    ST(slot_for(ctx, table, ordinal, n, &c));
+    c->data.ptr = const_cast<void*>(values_device); c->data.bytes = (size_t)n * 4; c->data.owned = false;
+    c->kind = COL_I32; c->n = n;
+    return COLQ_OK;
+}
+
+static colq_status finish_str(colq_ctx* ctx, Column* c, int64_t n, int64_t n_bytes) {
+    c->kind = COL_STR; c->n = n; c->n_bytes = n_bytes;
+    (void)ctx;
+    return COLQ_OK;
+}
+
+colq_status colq_col_str(colq_ctx* ctx, colq_table table, int ordinal, const uint32_t* offsets, const uint8_t* bytes, int64_t n,
+                         int64_t n_bytes) {
+    if (!ctx || !offsets || (!bytes && n_bytes > 0)) return COLQ_THROW_NULL;
+    if (n_bytes < 0 || n_bytes > (int64_t)0xfffffff0ll) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "string payload of %lld bytes exceeds the uint32 offset range", (long long)n_bytes);
+    if (offsets[0] != 0 || (int64_t)offsets[n] != n_bytes) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "offsets must start at 0 and end at n_bytes");
+    CU(ctx, cudaSetDevice(ctx->device));
+    Column* c;
+    ST(slot_for(ctx, table, ordinal, n, &c));
+    ST(upload(ctx, c->offsets, offsets, (size_t)(n + 1) * 4, (size_t)round_up((n + 1) * 4, 16) + 16));
+    size_t cap = (size_t)round_up(n_bytes, 16) + 16;
+    ST(upload(ctx, c->data, bytes, (size_t)n_bytes, cap));
+    c->bytes_capacity = (int64_t)cap;
+    return finish_str(ctx, c, n, n_bytes);
+}
+
+colq_status colq_col_str_device(colq_ctx* ctx, colq_table table, int ordinal, const void* offsets_device, int64_t offsets_capacity,
+                                const void* bytes_device, int64_t bytes_capacity, int64_t n, int64_t n_bytes) {
+    if (!ctx || !offsets_device || (!bytes_device && n_bytes > 0)) return COLQ_THROW_NULL;
+    if (((uintptr_t)offsets_device & 15) || ((uintptr_t)bytes_device & 15)) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "device buffers must be 16-byte aligned");
+    if (n_bytes < 0 || n_bytes > (int64_t)0xfffffff0ll) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "string payload of %lld bytes exceeds the uint32 offset range", (long long)n_bytes);
+    CU(ctx, cudaSetDevice(ctx->device));
+    Column* c;
+    ST(slot_for(ctx, table, ordinal, n, &c));
+    const int64_t need_off = round_up((n + 1) * 4, 16), need_bytes = round_up(n_bytes, 16) + 16;
+    if (offsets_capacity >= need_off) {
+        c->offsets.ptr = const_cast<void*>(offsets_device); c->offsets.bytes = (size_t)offsets_capacity; c->offsets.owned = false;
+    } else {  // too tight for whole-line TMA reads: keep a padded private copy
+        ST(dev_alloc(ctx, c->offsets, (size_t)need_off + 16));
+        CU(ctx, cudaMemsetAsync(c->offsets.ptr, 0, c->offsets.bytes, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(c->offsets.ptr, offsets_device, (size_t)(n + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (bytes_capacity >= need_bytes) {
+        c->data.ptr = const_cast<void*>(bytes_device); c->data.bytes = (size_t)bytes_capacity; c->data.owned = false;
+        c->bytes_capacity = bytes_capacity & ~(int64_t)15;
+    } else {
+        ST(dev_alloc(ctx, c->data, (size_t)need_bytes));
+        CU(ctx, cudaMemsetAsync(c->data.ptr, 0, c->data.bytes, ctx->stream));
+        if (n_bytes) CU(ctx, cudaMemcpyAsync(c->data.ptr, bytes_device, (size_t)n_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        c->bytes_capacity = need_bytes;
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return finish_str(ctx, c, n, n_bytes);
+}
+
+colq_status colq_col_bool(colq_ctx* ctx, colq_table table, int ordinal, const uint8_t* values, int64_t n) {
+    if (!ctx || (!values && n > 0)) return COLQ_THROW_NULL;
+    CU(ctx, cudaSetDevice(ctx->device));
+    Column* c;
+    ST(slot_for(ctx, table, ordinal, n, &c));
+    ST(upload(ctx, c->data, values, (size_t)n, (size_t)round_up(n + 16, 16)));
+    c->kind = COL_BOOL; c->n = n;
+    return COLQ_OK;
+}
+
+colq_status colq_associate_fk(colq_ctx* ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal, const int32_t* fk, int64_t n) {
+    if (!ctx || (!fk && n > 0)) return COLQ_THROW_NULL;
+    CU(ctx, cudaSetDevice(ctx->device));
+    Column* f;
+    ST(link_assoc(ctx, x, x_ordinal, y, y_ordinal, true, &f));
+    if (n != f->n) { unlink_assoc(ctx, x, x_ordinal, y, y_ordinal); return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "association height %lld != table rows", (long long)n); }
+    colq_status st = upload(ctx, f->data, fk, (size_t)n * 4, (size_t)round_up(n * 4 + 16, 16));
+    if (st == COLQ_OK) st = check_fk_range(ctx, (const int32_t*)f->data.ptr, n, ctx->tables[y].n_rows);
+    if (st != COLQ_OK) unlink_assoc(ctx, x, x_ordinal, y, y_ordinal);
+    return st;
+}
+
+colq_status colq_associate_fk_device(colq_ctx* ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal, const void* fk_device,
+                                     int64_t n) {
+    if (!ctx || (!fk_device && n > 0)) return COLQ_THROW_NULL;
+    if ((uintptr_t)fk_device & 15) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "device column must be 16-byte aligned");
+    CU(ctx, cudaSetDevice(ctx->device));
+    Column* f;
+    ST(link_assoc(ctx, x, x_ordinal, y, y_ordinal, true, &f));
+    if (n != f->n) { unlink_assoc(ctx, x, x_ordinal, y, y_ordinal); return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "association height %lld != table rows", (long long)n); }
+    f->data.ptr = const_cast<void*>(fk_device); f->data.bytes = (size_t)n * 4; f->data.owned = false;
+    colq_status st = check_fk_range(ctx, (const int32_t*)fk_device, n, ctx->tables[y].n_rows);
+    if (st != COLQ_OK) unlink_assoc(ctx, x, x_ordinal, y, y_ordinal);
+    return st;
+}
+
+colq_status colq_associate_csr(colq_ctx* ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal, const int64_t* offsets,
+                               const int32_t* targets, int64_t n, int64_t nnz) {
+    if (!ctx || !offsets || (!targets && nnz > 0)) return COLQ_THROW_NULL;
+    CU(ctx, cudaSetDevice(ctx->device));
+    Table* Y = get_table(ctx, y);
+    if (!Y) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "unknown table handle %d", y);
+    if (offsets[0] != 0 || offsets[n] != nnz) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "CSR offsets must start at 0 and end at nnz");
+    for (int64_t i = 0; i < n; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "CSR offsets must be non-decreasing");
+    for (int64_t e = 0; e < nnz; ++e)  // M/InMemoryTable.java:70-71
+        if (targets[e] < 0 || targets[e] >= Y->n_rows)
+            return fail(ctx, COLQ_THROW_NULL, "association target %d outside the associated table (size %lld)", targets[e], (long long)Y->n_rows);
+    Column* f;
+    ST(link_assoc(ctx, x, x_ordinal, y, y_ordinal, false, &f));
+    if (n != f->n) { unlink_assoc(ctx, x, x_ordinal, y, y_ordinal); return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "association height %lld != table rows", (long long)n); }
+    colq_status st = upload(ctx, f->offsets, offsets, (size_t)(n + 1) * 8, (size_t)(n + 1) * 8 + 16);
+    if (st == COLQ_OK) st = upload(ctx, f->targets, targets, (size_t)nnz * 4, (size_t)nnz * 4 + 16);
+    if (st != COLQ_OK) unlink_assoc(ctx, x, x_ordinal, y, y_ordinal);
+    return st;
+}
+
+colq_status colq_table_size(const colq_ctx* ctx, colq_table table, int64_t* out_rows) {
+    if (!ctx || !out_rows) return COLQ_THROW_NULL;
+    if (table < 0 || (size_t)table >= ctx->tables.size()) return COLQ_THROW_ILLEGAL_ARG;
+    *out_rows = ctx->tables[table].n_rows;
+    return COLQ_OK;
+}
+
+colq_status colq_table_width(const colq_ctx* ctx, colq_table table, int* out_columns) {
+    if (!ctx || !out_columns) return COLQ_THROW_NULL;
+    if (table < 0 || (size_t)table >= ctx->tables.size()) return COLQ_THROW_ILLEGAL_ARG;
+    *out_columns = (int)ctx->tables[table].cols.size();
+    return COLQ_OK;
+}
+
+colq_status colq_query_create(colq_ctx* ctx, const char* table_name, colq_query** out_query) {
+    if (!ctx || !table_name || !out_query) return COLQ_THROW_NULL;
+    colq_query* q = new colq_query();
+    q->ctx = ctx;
+    q->table_name = table_name;
+    q->nodes.emplace_back();  // rootNode (DS/Query.java:22-25)
+    *out_query = q;
+    return COLQ_OK;
+}
+
+colq_status colq_query_destroy(colq_query* q) {
+    if (!q) return COLQ_OK;
+    cudaSetDevice(q->ctx->device);
+    cudaStreamSynchronize(q->ctx->stream);
+    if (q->graph_exec) cudaGraphExecDestroy(q->graph_exec);
+    if (q->ev_start) cudaEventDestroy(q->ev_start);
+    if (q->ev_stop) cudaEventDestroy(q->ev_stop);
+    for (cudaEvent_t e : q->stage_ev) cudaEventDestroy(e);
+    delete q;
+    return COLQ_OK;
+}
+
+colq_status colq_query_child(colq_query* q, int parent_node, int ordinal, int* out_node) {
+    if (!q || !out_node) return COLQ_THROW_NULL;
+    if (parent_node < 0 || (size_t)parent_node >= q->nodes.size()) return fail(q->ctx, COLQ_THROW_ILLEGAL_ARG, "unknown query node %d", parent_node);
+    for (auto& ch : q->nodes[parent_node].children)
+        if (ch.first == ordinal)  // DS/Query.java:33-35
+            return fail(q->ctx, COLQ_THROW_ILLEGAL_ARG, "A child already exists at ordinal %d", ordinal);
+    q->nodes.emplace_back();
+    int id = (int)q->nodes.size() - 1;
+    q->nodes[parent_node].children.emplace_back(ordinal, id);
+    *out_node = id;
+    return COLQ_OK;
+}
+
+colq_status colq_query_criteria_i32_range(colq_query* q, int node, int ordinal, int32_t lo, int32_t hi) {
+    if (!q) return COLQ_THROW_NULL;
+    if (node < 0 || (size_t)node >= q->nodes.size()) return fail(q->ctx, COLQ_THROW_ILLEGAL_ARG, "unknown query node %d", node);
+    Crit c;
+    c.ordinal = ordinal; c.is_str = false; c.lo = lo; c.hi = hi;
+    q->nodes[node].crit.push_back(std::move(c));
+    return COLQ_OK;
+}
+
+colq_status colq_query_criteria_str(colq_query* q, int node, int ordinal, colq_str_op op, const uint8_t* needle, int32_t len) {
+    if (!q || (!needle && len > 0)) return COLQ_THROW_NULL;
+    colq_ctx* ctx = q->ctx;
+    if (node < 0 || (size_t)node >= q->nodes.size()) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "unknown query node %d", node);
+    if ((int)op < 0 || (int)op > (int)COLQ_STR_ENDS_WITH) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "unknown string operator %d", (int)op);
+    if (len < 0 || len > ST_MAX_NEEDLE) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "needle length %d outside [0, %d]", len, ST_MAX_NEEDLE);
+    CU(ctx, cudaSetDevice(ctx->device));
+    Crit c;
+    c.ordinal = ordinal; c.is_str = true; c.op = (int)op;
+    c.needle.assign(needle, needle + len);
+    ST(upload(ctx, c.needle_dev, needle, (size_t)len, (size_t)round_up(len + 16, 16)));
+    q->nodes[node].crit.push_back(std::move(c));
+    return COLQ_OK;
+}
+
+colq_status colq_query_set_option(colq_query* q, colq_option option, int value) {
+    if (!q) return COLQ_THROW_NULL;
+    switch (option) {
+        case COLQ_OPT_LAZY_FK: q->opt_lazy = value; break;
+        case COLQ_OPT_PROFILE: q->opt_profile = value; break;
+        case COLQ_OPT_GRAPH: q->opt_graph = value; break;
+        default: return fail(q->ctx, COLQ_THROW_ILLEGAL_ARG, "unknown option %d", (int)option);
+    }
+    return COLQ_OK;
+}
+
+colq_status colq_execute_async(colq_ctx* ctx, colq_query* q) {
+    if (!ctx || !q) return COLQ_THROW_NULL;
+    if (q->ctx != ctx) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "query belongs to another context");
+    return run_pipeline(q);
+}
+
+colq_status colq_fetch(colq_ctx* ctx, colq_query* q, uint64_t* out_bitmask, int64_t bitmask_capacity_words, int32_t* out_indices,
+                       int64_t indices_capacity, int64_t* out_count, colq_timing* out_timing) {
+    if (!ctx || !q) return COLQ_THROW_NULL;
+    if (q->ctx != ctx) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "query belongs to another context");
+    return fetch_results(q, out_bitmask, bitmask_capacity_words, out_indices, indices_capacity, out_count, out_timing);
+}
+
+colq_status colq_execute(colq_ctx* ctx, colq_query* q, uint64_t* out_bitmask, int64_t bitmask_capacity_words, int32_t* out_indices,
+                         int64_t indices_capacity, int64_t* out_count, colq_timing* out_timing) {
+    if (!ctx || !q) return COLQ_THROW_NULL;
+    if (q->ctx != ctx) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "query belongs to another context");
+    if (indices_capacity > q->want_idx_capacity && out_indices) q->want_idx_capacity = std::min<int64_t>(indices_capacity, (int64_t)1 << 28);
+    ST(run_pipeline(q));
+    return fetch_results(q, out_bitmask, bitmask_capacity_words, out_indices, indices_capacity, out_count, out_timing);
+}
+
+colq_status colq_profile(const colq_query* q, colq_stage* out_stages, int capacity, int* out_n_stages) {
+    if (!q || !out_n_stages) return COLQ_THROW_NULL;
+    *out_n_stages = (int)q->stages.size();
+    for (int i = 0; i < capacity && i < (int)q->stages.size(); ++i) out_stages[i] = q->stages[i];
+    return COLQ_OK;
+}
+
+colq_status colq_node_cardinalities(colq_ctx* ctx, const colq_query* q, int64_t* out, int capacity, int* out_n) {
+    if (!ctx || !q || !out_n) return COLQ_THROW_NULL;
+    if (!q->executed) return fail(ctx, COLQ_THROW_ILLEGAL_STATE, "query was never executed");
+    CU(ctx, cudaSetDevice(ctx->device));
+    *out_n = (int)q->xnodes.size();
+    DevBuf acc;
+    ST(dev_alloc(ctx, acc, 8));
+    for (int i = 0; i < capacity && i < (int)q->xnodes.size(); ++i) {
+        const XNode& x = q->xnodes[i];
+        const int64_t n = ctx->tables[x.table].n_rows;
+        if (x.fused && !x.bits) { out[i] = -1; continue; }
+        if (x.all_ones || !x.bits) { out[i] = x.all_ones ? n : -1; continue; }
+        CU(ctx, cudaMemsetAsync(acc.ptr, 0, 8, ctx->stream));
+        popc_total_kernel<<<grid_for(bitmap_words(n), 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(x.bits, bitmap_words(n), (u64*)acc.ptr);
+        u64 c = 0;
+        CU(ctx, cudaMemcpyAsync(&c, acc.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        out[i] = (int64_t)c;
+    }
+    return COLQ_OK;
+}
+
+}  // extern "C"

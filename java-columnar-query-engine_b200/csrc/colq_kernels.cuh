@@ -1,0 +1,808 @@
+// colq_kernels.cuh -- hand-written sm_100a kernels of the query hot path.
+//
+// Each kernel names the reference loop it replaces.  Citations are relative to the reference checkout:
+//   E = data-system-serial-indices-arrays/src/main/java/dgroomes/data_system_serial_indices_arrays
+//   M = data-model-in-memory/src/main/java/dgroomes/in_memory
+//
+// Everything here is HBM-bound integer / byte work: the design rules are coalesced 128-bit loads,
+// TMA (cp.async.bulk) staging for the variable-length string column, many loads in flight per SM and
+// grids sized from the SM count.  There is no GEMM-shaped work, hence no tcgen05.
+//
+// Bitmask layout everywhere: java.util.BitSet words, row i <-> bit (i & 63) of uint64 word (i >> 6).
+// Kernels address the same memory as little-endian uint32 halves (row i <-> bit (i & 31) of u32 word (i >> 5)).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace colq {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+constexpr u32 FULL_MASK = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+
+// streaming 128-bit load: read-only path, do not allocate in L1 (every input element is touched once)
+__device__ __forceinline__ int4 ldg_stream_v4(const int32_t* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_stream_v4u(const u32* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+// dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ bool bit_test(const u32* bits, int64_t i) { return (bits[i >> 5] >> (i & 31)) & 1u; }
+
+// ---------------------------------------------------------------------------------------------
+// push epilogue: ExecutionContext.Node.filterParent for a to-one association (E/ExecutionContext.java:100-122,
+// Association.One branch :114).  A matching child row sets the bit of its parent row in `reach`.
+// Small parents (<= PUSH_SMEM_BITS rows, e.g. the 51-row states table) are accumulated in shared memory and
+// flushed once per CTA so that same-address atomics do not serialise in L2.
+// ---------------------------------------------------------------------------------------------
+
+constexpr int PUSH_SMEM_BITS = 4096;
+constexpr int PUSH_SMEM_WORDS = PUSH_SMEM_BITS / 32;
+
+struct PushD {
+    const int32_t* fk;  // forward to-one column on the CHILD table (child row -> parent row, -1 = None); null = no push
+    u32* reach;         // parent-sized bitmask, zero-initialised
+    int64_t n_parent;
+};
+
+__device__ __forceinline__ void push_init(const PushD& ps, u32* s_reach) {
+    if (ps.fk != nullptr && ps.n_parent <= PUSH_SMEM_BITS) {
+        for (int i = threadIdx.x; i < PUSH_SMEM_WORDS; i += blockDim.x) s_reach[i] = 0;
+    }
+}
+__device__ __forceinline__ void push_row(const PushD& ps, u32* s_reach, int64_t row) {
+    int32_t t = ps.fk[row];
+    if (t < 0 || t >= ps.n_parent) return;  // None, or (never via associateTo) out of range: vanishes at the AND
+    u32 m = 1u << (t & 31);
+    if (ps.n_parent <= PUSH_SMEM_BITS) {
+        if (!(s_reach[t >> 5] & m)) atomicOr(&s_reach[t >> 5], m);
+    } else {
+        if (!(ps.reach[t >> 5] & m)) atomicOr(&ps.reach[t >> 5], m);
+    }
+}
+// call after a __syncthreads()
+__device__ __forceinline__ void push_flush(const PushD& ps, const u32* s_reach) {
+    if (ps.fk != nullptr && ps.n_parent <= PUSH_SMEM_BITS) {
+        int words = (int)((ps.n_parent + 31) >> 5);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) {
+            u32 w = s_reach[i];
+            if (w) atomicOr(&ps.reach[i], w);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1  scan_rows: int32 range predicates + foreign-key chain gathers -> bitmask
+//
+// Replaces ExecutionContext.Node.filterSelf (E/ExecutionContext.java:79-94) over IntegerColumn.where
+// (M/InMemoryColumn.java:53-56) and, fused into the same pass, the to-one branch of filterParent for every
+// child reached through a forward foreign key (pull form: parent row r keeps its bit iff the child row fk[r]
+// matches; equals the reference's push through the transposed reverse column, M/InMemoryTable.java:55-85).
+//
+// Mapping: one warp owns 512 consecutive rows per tile (4 x 128-bit loads per lane and column, all issued
+// before first use), a 256-thread CTA owns 4096 rows.  Lane l of vector j holds rows base + 128 j + 4 l .. +3;
+// its 4 result bits are merged into u32 words with an 8-lane shuffle butterfly and the warp stores its 16 words
+// (64 B) with one coalesced instruction.
+// ---------------------------------------------------------------------------------------------
+
+constexpr int SR_THREADS = 256;
+constexpr int SR_V = 4;                                  // 128-bit vectors per lane per column
+constexpr int SR_WARP_ROWS = 128 * SR_V;                 // 512
+constexpr int SR_BLOCK_ROWS = SR_WARP_ROWS * (SR_THREADS / 32);  // 4096
+constexpr int SR_MAX_PRED = 2;
+constexpr int SR_MAX_GATHER = 2;
+constexpr int GATHER_MAX_DEPTH = 3;
+
+struct IntPredD {
+    const int32_t* col;
+    int32_t lo;
+    u32 span;  // row passes iff (u32)(v - lo) <= span, i.e. lo <= v <= lo + span (closed interval, no overflow)
+};
+
+// A chain of to-one hops r0 -fk[0]-> r1 -fk[1]-> ... ending in a bitmask test.
+struct GatherD {
+    const int32_t* fk[GATHER_MAX_DEPTH];
+    int64_t n[GATHER_MAX_DEPTH];  // n[d] = rows of the table that fk[d]'s values index into
+    int depth;
+    const u32* bits;  // final test; null = every row of the last table matches
+};
+
+struct ScanRowsParams {
+    int64_t n;
+    const u32* in_bits;  // nullable: AND-in (bits of this node computed so far)
+    u32* out_bits;       // nullable when only the push epilogue consumes the result
+    IntPredD pred[SR_MAX_PRED];
+    GatherD gather[SR_MAX_GATHER];
+    PushD push;
+};
+
+__device__ __forceinline__ bool gather_eval(const GatherD& g, int64_t r, int level) {
+    for (int d = level; d < g.depth; ++d) {
+        int32_t t = g.fk[d][r];
+        if (t < 0 || t >= g.n[d]) return false;  // Association.None, or a target that vanishes at the AND
+        r = t;
+    }
+    return g.bits == nullptr ? true : bit_test(g.bits, r);
+}
+
+__device__ __forceinline__ u32 range4(const int4& v, int32_t lo, u32 span) {
+    u32 m = 0;
+    m |= ((u32)(v.x - lo) <= span) ? 1u : 0u;
+    m |= ((u32)(v.y - lo) <= span) ? 2u : 0u;
+    m |= ((u32)(v.z - lo) <= span) ? 4u : 0u;
+    m |= ((u32)(v.w - lo) <= span) ? 8u : 0u;
+    return m;
+}
+
+// NP predicates, NG gather chains.  EAGER: the first hop of every chain is loaded with coalesced 128-bit loads
+// for all rows (right when no selective predicate precedes it); otherwise chains are walked lazily, only for rows
+// that survived the predicates (the 0.16 %-selective population filter skips almost every FK sector).
+template <int NP, int NG, bool EAGER>
+__global__ void __launch_bounds__(SR_THREADS) scan_rows_kernel(const ScanRowsParams P) {
+    __shared__ u32 s_reach[PUSH_SMEM_WORDS];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int64_t wbase = (int64_t)blockIdx.x * SR_BLOCK_ROWS + (int64_t)warp * SR_WARP_ROWS;
+    const bool do_push = P.push.fk != nullptr;
+    if (do_push) {
+        push_init(P.push, s_reach);
+        __syncthreads();
+    }
+
+    if (wbase < P.n) {
+        u32 nib[SR_V];
+        int4 fkv[NG > 0 && EAGER ? NG : 1][SR_V];
+        const bool full = wbase + SR_WARP_ROWS <= P.n;
+        if (full) {
+            // ---- fast path: every vector is inside the column; issue all loads first
+            int4 v[NP > 0 ? NP : 1][SR_V];
+#pragma unroll
+            for (int p = 0; p < NP; ++p)
+#pragma unroll
+                for (int j = 0; j < SR_V; ++j) v[p][j] = ldg_stream_v4(P.pred[p].col + wbase + j * 128 + lane * 4);
+            if (EAGER) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+#pragma unroll
+                    for (int j = 0; j < SR_V; ++j)
+                        fkv[g][j] = ldg_stream_v4(P.gather[g].fk[0] + wbase + j * 128 + lane * 4);
+            }
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) {
+                u32 m = 0xFu;
+#pragma unroll
+                for (int p = 0; p < NP; ++p) m &= range4(v[p][j], P.pred[p].lo, P.pred[p].span);
+                nib[j] = m;
+            }
+        } else {
+            // ---- tail warp: scalar guarded loads
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) {
+                u32 m = 0;
+                int32_t f[NG > 0 ? NG : 1][4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    int64_t r = wbase + j * 128 + lane * 4 + e;
+                    bool ok = r < P.n;
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        if (ok) {
+                            int32_t x = P.pred[p].col[r];
+                            ok = (u32)(x - P.pred[p].lo) <= P.pred[p].span;
+                        }
+                    }
+                    if (EAGER) {
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) f[g][e] = (r < P.n) ? P.gather[g].fk[0][r] : -1;
+                    }
+                    m |= ok ? (1u << e) : 0u;
+                }
+                if (EAGER) {
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) fkv[g][j] = make_int4(f[g][0], f[g][1], f[g][2], f[g][3]);
+                }
+                nib[j] = m;
+            }
+        }
+
+        // ---- AND-in the bits this node already has
+        if (P.in_bits != nullptr) {
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) {
+                u32 w = P.in_bits[((wbase + j * 128) >> 5) + (lane >> 3)];
+                nib[j] &= (w >> ((lane & 7) * 4)) & 0xFu;
+            }
+        }
+
+        // ---- association hops through forward foreign keys
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) {
+                u32 m = nib[j];
+                if (m == 0) continue;
+                const int64_t r0 = wbase + j * 128 + lane * 4;
+                if (EAGER) {
+                    const int32_t f[4] = {fkv[g][j].x, fkv[g][j].y, fkv[g][j].z, fkv[g][j].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (m & (1u << e)) {
+                            bool ok = f[e] >= 0 && f[e] < P.gather[g].n[0] && gather_eval(P.gather[g], f[e], 1);
+                            if (!ok) m &= ~(1u << e);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (m & (1u << e)) {
+                            if (!gather_eval(P.gather[g], r0 + e, 0)) m &= ~(1u << e);
+                        }
+                    }
+                }
+                nib[j] = m;
+            }
+        }
+
+        // ---- push epilogue (this node is the child of a reverse-side hop)
+        if (do_push) {
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) {
+                u32 m = nib[j];
+                while (m) {
+                    int e = __ffs(m) - 1;
+                    m &= m - 1;
+                    push_row(P.push, s_reach, wbase + j * 128 + lane * 4 + e);
+                }
+            }
+        }
+
+        // ---- pack nibbles into u32 words and store 64 B per warp
+        if (P.out_bits != nullptr) {
+            u32 y[SR_V];
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) {
+                u32 x = nib[j] << ((lane & 7) * 4);
+                x |= __shfl_xor_sync(FULL_MASK, x, 1);
+                x |= __shfl_xor_sync(FULL_MASK, x, 2);
+                x |= __shfl_xor_sync(FULL_MASK, x, 4);
+                y[j] = __shfl_sync(FULL_MASK, x, (lane & 3) * 8);  // lane gets word (lane & 3) of vector j
+            }
+            u32 out = y[0];
+#pragma unroll
+            for (int j = 1; j < SR_V; ++j) out = ((lane >> 2) == j) ? y[j] : out;
+            if (lane < 4 * SR_V) P.out_bits[(wbase >> 5) + lane] = out;
+        }
+    }
+
+    if (do_push) {
+        __syncthreads();
+        push_flush(P.push, s_reach);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2  scan_str: string predicate over an (offsets, bytes) column -> bitmask, TMA-staged
+//
+// Replaces ExecutionContext.Node.filterSelf (E/ExecutionContext.java:79-94) over StringColumn.where
+// (M/InMemoryColumn.java:71-74) with "X"::equals / s.contains("X") / s.compareTo("X") predicates
+// (app/.../Runner.java:236,255-259; QueryTest.java:124-125).
+//
+// Persistent CTAs (grid = SMs x CTAs/SM) walk row tiles round-robin.  For each tile one elected thread issues
+// two TMA bulk copies (the tile's offsets slice and its contiguous byte range, both widened to 16-byte lines)
+// into a STAGES-deep shared-memory ring guarded by mbarriers, so HBM reads are long, perfectly coalesced
+// bursts regardless of row lengths; all threads then test one row each out of shared memory and a warp ballot
+// emits the bitmask word.  A tile whose bytes do not fit the ring slot is read straight from global memory.
+// ---------------------------------------------------------------------------------------------
+
+constexpr int ST_THREADS = 256;
+constexpr int ST_ROWS = 1024;  // rows per tile (multiple of 32 and 4)
+constexpr int ST_STAGES = 4;
+constexpr int ST_OFF_BYTES = (ST_ROWS + 4) * 4;  // offsets slice incl. the closing offset, padded to 16 B
+constexpr int ST_MAX_NEEDLE = 1024;
+
+enum StrOp : int {
+    OP_EQ = 0, OP_CONTAINS = 1, OP_CMP_GT = 2, OP_CMP_LT = 3, OP_CMP_GE = 4, OP_CMP_LE = 5, OP_NE = 6,
+    OP_STARTS_WITH = 7, OP_ENDS_WITH = 8
+};
+
+struct ScanStrParams {
+    int64_t n;
+    const u32* offsets;   // n + 1 entries, allocation padded to a 16-byte multiple past entry n
+    const uint8_t* bytes;
+    int64_t bytes_capacity;  // allocation size (multiple of 16)
+    const uint8_t* needle;   // device copy of the needle
+    int needle_len;
+    int op;
+    int cap;                 // bytes slot size of one ring stage (multiple of 16)
+    int64_t n_tiles;
+    const u32* in_bits;
+    u32* out_bits;
+    PushD push;
+};
+
+// 4 bytes starting at byte position pos of a little-endian word array (pos need not be aligned)
+__device__ __forceinline__ u32 extract32(const u32* words, u32 pos) {
+    u32 i = pos >> 2;
+    u32 lo = words[i], hi = words[i + 1];
+    return __funnelshift_r(lo, hi, (pos & 3) * 8);
+}
+__device__ __forceinline__ u32 low_mask(int nbytes) { return nbytes >= 4 ? 0xffffffffu : ((1u << (nbytes * 8)) - 1u); }
+
+// bytes [pos, pos+len) of `hay` equal needle[0, len)
+__device__ __forceinline__ bool bytes_equal(const u32* hay, u32 pos, const u32* needle_w, int len) {
+    for (int c = 0; c < len; c += 4) {
+        u32 h = extract32(hay, pos + c);
+        u32 m = low_mask(len - c);
+        if ((h ^ needle_w[c >> 2]) & m) return false;
+    }
+    return true;
+}
+
+// String.compareTo sign (UTF-16 code-unit order on UTF-8 bytes; see oracle/colq_oracle.c java_compare_to)
+__device__ __forceinline__ int utf16_key(u32 b) { return b >= 0xF0u ? 0xED * 2 + 1 : (int)b * 2; }
+__device__ __forceinline__ int compare_to(const u32* hay, u32 pos, int len, const u32* needle_w, int nlen) {
+    int m = len < nlen ? len : nlen;
+    for (int c = 0; c < m; c += 4) {
+        u32 h = extract32(hay, pos + c);
+        u32 d = (h ^ needle_w[c >> 2]) & low_mask(m - c);
+        if (d) {
+            int bi = (__ffs(d) - 1) >> 3;
+            u32 hb = (h >> (bi * 8)) & 0xffu, nb = (needle_w[c >> 2] >> (bi * 8)) & 0xffu;
+            return utf16_key(hb) < utf16_key(nb) ? -1 : 1;
+        }
+    }
+    return len < nlen ? -1 : (len > nlen ? 1 : 0);
+}
+
+__device__ __forceinline__ bool contains(const u32* hay, u32 pos, int len, const u32* needle_w, int nlen) {
+    if (nlen == 0) return true;
+    if (len < nlen) return false;
+    const u32 first_mask = low_mask(nlen);
+    const u32 first = needle_w[0] & first_mask;
+    // rolling window over aligned words: one shared-memory load per 4 candidate positions
+    u32 wi = pos >> 2;
+    u32 cur = hay[wi], nxt = hay[wi + 1];
+    int sh = (int)(pos & 3);
+    const int last = len - nlen;  // last candidate start
+    for (int p = 0; p <= last; ++p) {
+        u32 h = __funnelshift_r(cur, nxt, sh * 8);
+        if (((h ^ first) & first_mask) == 0) {
+            if (nlen <= 4 || bytes_equal(hay, pos + p + 4, needle_w + 1, nlen - 4)) return true;
+        }
+        if (++sh == 4) {
+            sh = 0;
+            ++wi;
+            cur = nxt;
+            nxt = hay[wi + 1];
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ bool str_test(int op, const u32* hay, u32 pos, int len, const u32* needle_w, int nlen) {
+    switch (op) {
+        case OP_EQ: return len == nlen && bytes_equal(hay, pos, needle_w, nlen);
+        case OP_NE: return !(len == nlen && bytes_equal(hay, pos, needle_w, nlen));
+        case OP_CONTAINS: return contains(hay, pos, len, needle_w, nlen);
+        case OP_CMP_GT: return compare_to(hay, pos, len, needle_w, nlen) > 0;
+        case OP_CMP_LT: return compare_to(hay, pos, len, needle_w, nlen) < 0;
+        case OP_CMP_GE: return compare_to(hay, pos, len, needle_w, nlen) >= 0;
+        case OP_CMP_LE: return compare_to(hay, pos, len, needle_w, nlen) <= 0;
+        case OP_STARTS_WITH: return len >= nlen && bytes_equal(hay, pos, needle_w, nlen);
+        case OP_ENDS_WITH: return len >= nlen && bytes_equal(hay, pos + (u32)(len - nlen), needle_w, nlen);
+    }
+    return false;
+}
+
+struct StrTileMeta {
+    u32 a0_lo, a0_hi;  // 16-byte-aligned global byte offset the staged slice starts at
+    u32 fast;          // 1: bytes were staged in shared memory, 0: read them from global memory
+    u32 pad;
+};
+
+__global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // layout: [stage0 offsets | stage0 bytes(cap+16)] ... | needle words | mbarriers | metas | reach
+    const int stage_bytes = ST_OFF_BYTES + P.cap + 16;
+    u32* s_needle = reinterpret_cast<u32*>(smem + (size_t)ST_STAGES * stage_bytes);
+    u64* s_full = reinterpret_cast<u64*>(reinterpret_cast<uint8_t*>(s_needle) + ST_MAX_NEEDLE + 16);
+    StrTileMeta* s_meta = reinterpret_cast<StrTileMeta*>(s_full + ST_STAGES);
+    u32* s_reach = reinterpret_cast<u32*>(s_meta + ST_STAGES);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool do_push = P.push.fk != nullptr;
+
+    for (int i = tid; i < (ST_MAX_NEEDLE + 16) / 4; i += ST_THREADS) {
+        u32 w = 0;
+        for (int b = 0; b < 4; ++b) {
+            int k = i * 4 + b;
+            if (k < P.needle_len) w |= (u32)P.needle[k] << (8 * b);
+        }
+        s_needle[i] = w;
+    }
+    if (do_push) push_init(P.push, s_reach);
+    if (tid == 0) {
+        for (int s = 0; s < ST_STAGES; ++s) mbar_init(&s_full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int64_t first_tile = blockIdx.x;
+    const int64_t tile_stride = gridDim.x;
+    const int64_t my_tiles = first_tile < P.n_tiles ? (P.n_tiles - first_tile + tile_stride - 1) / tile_stride : 0;
+
+    // producer (thread 0): issue the TMA copies of local tile k into ring slot k % STAGES
+    auto issue = [&](int64_t k, u32 gb0, u32 gb1) {
+        const int s = (int)(k % ST_STAGES);
+        const int64_t r0 = (first_tile + k * tile_stride) * ST_ROWS;
+        const int nr = (int)((P.n - r0) < ST_ROWS ? (P.n - r0) : ST_ROWS);
+        uint8_t* base = smem + (size_t)s * stage_bytes;
+        const u64 a0 = (u64)gb0 & ~(u64)15;
+        const u64 a1 = ((u64)gb1 + 15) & ~(u64)15;
+        const u64 sz = a1 - a0;
+        const u32 off_bytes = (u32)(((nr + 1) * 4 + 15) & ~15);
+        const bool fast = sz <= (u64)P.cap && (int64_t)a1 <= P.bytes_capacity;
+        s_meta[s].a0_lo = (u32)a0;
+        s_meta[s].a0_hi = (u32)(a0 >> 32);
+        s_meta[s].fast = fast ? 1u : 0u;
+        mbar_arrive_expect_tx(&s_full[s], off_bytes + (fast ? (u32)sz : 0u));
+        tma_bulk_g2s(base, P.offsets + r0, off_bytes, &s_full[s]);
+        if (fast && sz > 0) tma_bulk_g2s(base + ST_OFF_BYTES, P.bytes + a0, (u32)sz, &s_full[s]);
+    };
+    auto tile_bounds = [&](int64_t k, u32& gb0, u32& gb1) {
+        const int64_t r0 = (first_tile + k * tile_stride) * ST_ROWS;
+        const int64_t r1 = (r0 + ST_ROWS) < P.n ? (r0 + ST_ROWS) : P.n;
+        gb0 = __ldg(P.offsets + r0);
+        gb1 = __ldg(P.offsets + r1);
+    };
+
+    u32 nb0 = 0, nb1 = 0;  // prefetched byte bounds of the next tile to issue (thread 0 only)
+    if (tid == 0) {
+        for (int64_t k = 0; k < ST_STAGES - 1 && k < my_tiles; ++k) {
+            u32 a, b;
+            tile_bounds(k, a, b);
+            issue(k, a, b);
+        }
+        if (ST_STAGES - 1 < my_tiles) tile_bounds(ST_STAGES - 1, nb0, nb1);
+    }
+
+    for (int64_t k = 0; k < my_tiles; ++k) {
+        const int s = (int)(k % ST_STAGES);
+        if (tid == 0) {
+            const int64_t kn = k + ST_STAGES - 1;
+            if (kn < my_tiles) {
+                issue(kn, nb0, nb1);  // slot (k-1) % STAGES was released by the __syncthreads closing iteration k-1
+                if (kn + 1 < my_tiles) tile_bounds(kn + 1, nb0, nb1);
+            }
+        }
+        mbar_wait(&s_full[s], (u32)((k / ST_STAGES) & 1));
+
+        const uint8_t* base = smem + (size_t)s * stage_bytes;
+        const u32* so = reinterpret_cast<const u32*>(base);
+        const int64_t r0 = (first_tile + k * tile_stride) * ST_ROWS;
+        const int nr = (int)((P.n - r0) < ST_ROWS ? (P.n - r0) : ST_ROWS);
+        const bool fast = s_meta[s].fast != 0;
+        const u64 a0 = ((u64)s_meta[s].a0_hi << 32) | s_meta[s].a0_lo;
+        const u32* hay = fast ? reinterpret_cast<const u32*>(base + ST_OFF_BYTES) : reinterpret_cast<const u32*>(P.bytes);
+
+#pragma unroll
+        for (int p = 0; p < ST_ROWS / ST_THREADS; ++p) {
+            const int row = p * ST_THREADS + tid;
+            bool match = false;
+            if (row < nr) {
+                const u32 b0 = so[row], b1 = so[row + 1];
+                const int len = (int)(b1 - b0);
+                // staged: position relative to the slot; not staged: absolute position in the column (< 4 GiB)
+                const u32 pos = fast ? (u32)((u64)b0 - a0) : b0;
+                match = str_test(P.op, hay, pos, len, s_needle, P.needle_len);
+            }
+            u32 word = __ballot_sync(FULL_MASK, match);
+            const int64_t wi = (r0 + p * ST_THREADS + warp * 32) >> 5;
+            if (P.in_bits != nullptr) word &= P.in_bits[wi];  // warp-uniform address: one broadcast load
+            if (do_push) {
+                if ((word >> lane) & 1u) push_row(P.push, s_reach, r0 + row);
+            }
+            if (lane == 0 && P.out_bits != nullptr && (r0 + p * ST_THREADS + warp * 32) < ((P.n + 63) & ~(int64_t)63)) P.out_bits[wi] = word;
+        }
+        __syncthreads();  // every thread is done with slot s before thread 0 refills it next iteration
+    }
+
+    if (do_push) {
+        __syncthreads();
+        push_flush(P.push, s_reach);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4b  csr_pull: to-many association hop on the forward side
+//
+// Replaces ExecutionContext.Node.filterParent, Association.Many branch (E/ExecutionContext.java:111-113), in pull
+// form: parent row r keeps its bit iff any of its targets matches in the child.  Used for the 51-row state
+// adjacency (219 edges) and the QueryTest garden grid.
+// ---------------------------------------------------------------------------------------------
+
+struct CsrPullParams {
+    int64_t n;               // parent rows
+    const int64_t* offsets;  // n + 1
+    const int32_t* targets;
+    const u32* child_bits;   // null = every child row matches
+    int64_t n_child;
+    const u32* in_bits;      // nullable
+    u32* out_bits;
+    PushD push;
+};
+
+__global__ void __launch_bounds__(256) csr_pull_kernel(const CsrPullParams P) {
+    __shared__ u32 s_reach[PUSH_SMEM_WORDS];
+    const bool do_push = P.push.fk != nullptr;
+    if (do_push) {
+        push_init(P.push, s_reach);
+        __syncthreads();
+    }
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool ok = false;
+    if (r < P.n) {
+        for (int64_t e = P.offsets[r]; e < P.offsets[r + 1] && !ok; ++e) {
+            int32_t t = P.targets[e];
+            if (t >= 0 && t < P.n_child) ok = P.child_bits == nullptr ? true : bit_test(P.child_bits, t);
+        }
+    }
+    u32 word = __ballot_sync(FULL_MASK, ok);
+    const int64_t wbase = r - lane;  // first row of this warp
+    if (wbase < ((P.n + 63) & ~(int64_t)63)) {
+        if (P.in_bits != nullptr) word &= P.in_bits[wbase >> 5];
+        if (do_push && ((word >> lane) & 1u)) push_row(P.push, s_reach, r);
+        if (lane == 0 && P.out_bits != nullptr) P.out_bits[wbase >> 5] = word;
+    }
+    if (do_push) {
+        __syncthreads();
+        push_flush(P.push, s_reach);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4a/K4c  push from a materialised child bitmask (reverse-side hop whose child was not fused), AND, fill
+// Replaces the One / Many / None switch of filterParent (E/ExecutionContext.java:105-119) and BitSet.and (:121).
+// ---------------------------------------------------------------------------------------------
+
+struct PushBitsParams {
+    int64_t n_child;
+    const u32* child_bits;   // null = all child rows
+    const int32_t* fk;       // to-one forward column on the child, or null when CSR
+    const int64_t* offsets;  // CSR forward column on the child
+    const int32_t* targets;
+    u32* reach;
+    int64_t n_parent;
+};
+
+__global__ void __launch_bounds__(256) push_bits_kernel(const PushBitsParams P) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n_child; r += stride) {
+        if (P.child_bits != nullptr && !bit_test(P.child_bits, r)) continue;
+        if (P.fk != nullptr) {
+            int32_t t = P.fk[r];
+            if (t >= 0 && t < P.n_parent) {
+                u32 m = 1u << (t & 31);
+                if (!(P.reach[t >> 5] & m)) atomicOr(&P.reach[t >> 5], m);
+            }
+        } else {
+            for (int64_t e = P.offsets[r]; e < P.offsets[r + 1]; ++e) {
+                int32_t t = P.targets[e];
+                if (t >= 0 && t < P.n_parent) {
+                    u32 m = 1u << (t & 31);
+                    if (!(P.reach[t >> 5] & m)) atomicOr(&P.reach[t >> 5], m);
+                }
+            }
+        }
+    }
+}
+
+// dst &= src  (BitSet.and, E/ExecutionContext.java:121)
+__global__ void __launch_bounds__(256) and_words_kernel(u32* dst, const u32* src, int64_t n_words) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) dst[i] &= src[i];
+}
+
+// matchingBits.set(0, table.size()) (E/ExecutionContext.java:83-87); words past n stay zero
+__global__ void __launch_bounds__(256) fill_ones_kernel(u32* dst, int64_t n_rows, int64_t n_words_alloc) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words_alloc; i += stride) {
+        int64_t lo = i << 5;
+        u32 w = 0;
+        if (lo + 32 <= n_rows) w = 0xffffffffu;
+        else if (lo < n_rows) w = (1u << (n_rows - lo)) - 1u;
+        dst[i] = w;
+    }
+}
+
+// dst[w] = OR over ranks of gathered[rank * n_words + w]: the consumer half of the state-mask OR-allreduce
+__global__ void __launch_bounds__(256) or_ranks_kernel(u32* dst, const u32* gathered, int64_t n_words, int n_ranks) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
+        u32 w = 0;
+        for (int r = 0; r < n_ranks; ++r) w |= gathered[(int64_t)r * n_words + i];
+        dst[i] = w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3  stream compaction: bitmask -> ascending row indices
+//
+// Replaces the index half of InMemoryTable.subset (M/InMemoryTable.java:121-131: cardinality(), then an ordered
+// copy).  Three launches: per-block popcount, single-block exclusive scan of block counts, ordered write with a
+// warp-shuffle scan inside each block.  Output order is ascending by construction.
+// ---------------------------------------------------------------------------------------------
+
+constexpr int CP_THREADS = 256;
+constexpr int CP_WORDS_PER_BLOCK = CP_THREADS * 4;  // one 128-bit load per thread: 32768 rows per block
+
+__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* s_warp, u32& block_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 t = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0;
+        u32 wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u32 t = __shfl_up_sync(FULL_MASK, wi, d);
+            if (lane >= d) wi += t;
+        }
+        if (lane < (int)(blockDim.x >> 5)) s_warp[lane] = wi - w;
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    block_total = s_warp[32];
+    return s_warp[warp] + incl - v;
+}
+
+__device__ __forceinline__ uint4 load_words4(const u32* bits, int64_t w0, int64_t n_words) {
+    // bitmask allocations are padded to whole compaction blocks, so the vector load is always in bounds
+    uint4 v = *reinterpret_cast<const uint4*>(bits + w0);
+    if (w0 + 0 >= n_words) v.x = 0;
+    if (w0 + 1 >= n_words) v.y = 0;
+    if (w0 + 2 >= n_words) v.z = 0;
+    if (w0 + 3 >= n_words) v.w = 0;
+    return v;
+}
+
+__global__ void __launch_bounds__(CP_THREADS) popc_blocks_kernel(const u32* bits, int64_t n_words, u32* block_counts) {
+    __shared__ u32 s_warp[33];
+    const int64_t w0 = ((int64_t)blockIdx.x * CP_THREADS + threadIdx.x) * 4;
+    uint4 v = load_words4(bits, w0, n_words);
+    u32 c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    u32 total;
+    block_exclusive_scan(c, s_warp, total);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of block_counts -> block_offsets, total -> *out_total
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const u32* block_counts, int64_t n_blocks, u64* block_offsets,
+                                                          u64* out_total) {
+    __shared__ u32 s_warp[33];
+    __shared__ u64 s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_blocks; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        u32 v = i < n_blocks ? block_counts[i] : 0;
+        u32 total;
+        u32 ex = block_exclusive_scan(v, s_warp, total);
+        const u64 carry = s_carry;
+        if (i < n_blocks) block_offsets[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out_total = s_carry;
+}
+
+__global__ void __launch_bounds__(CP_THREADS) compact_kernel(const u32* bits, int64_t n_words, const u64* block_offsets,
+                                                            int32_t* out_idx, int64_t capacity, int64_t row_base) {
+    __shared__ u32 s_warp[33];
+    const int64_t w0 = ((int64_t)blockIdx.x * CP_THREADS + threadIdx.x) * 4;
+    uint4 v = load_words4(bits, w0, n_words);
+    u32 c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    u32 total;
+    u32 ex = block_exclusive_scan(c, s_warp, total);
+    if (total == 0 || c == 0) return;
+    int64_t pos = (int64_t)block_offsets[blockIdx.x] + ex;
+    const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        u32 m = w[k];
+        const int64_t rb = row_base + ((w0 + k) << 5);
+        while (m) {
+            int b = __ffs(m) - 1;
+            m &= m - 1;
+            if (pos < capacity) out_idx[pos] = (int32_t)(rb + b);
+            ++pos;
+        }
+    }
+}
+
+// popcount of a whole bitmask into one u64 (node cardinalities; not on the timed path)
+__global__ void __launch_bounds__(256) popc_total_kernel(const u32* bits, int64_t n_words, u64* out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    u64 c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) c += __popc(bits[i]);
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(FULL_MASK, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd((unsigned long long*)out, (unsigned long long)c);
+}
+
+// association ingest check: min / max of a to-one column (M/InMemoryTable.java:70-71 would NPE on a bad target)
+__global__ void __launch_bounds__(256) fk_minmax_kernel(const int32_t* fk, int64_t n, int32_t* out_min, int32_t* out_max) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int32_t lo = INT32_MAX, hi = INT32_MIN;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int32_t v = fk[i];
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        int32_t a = __shfl_down_sync(FULL_MASK, lo, d), b = __shfl_down_sync(FULL_MASK, hi, d);
+        lo = a < lo ? a : lo;
+        hi = b > hi ? b : hi;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out_min, lo);
+        atomicMax(out_max, hi);
+    }
+}
+
+}  // namespace colq

@@ -1,0 +1,25 @@
+import json
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (ROOT, ROOT / "java-columnar-query-engine_b200", ROOT / "oracle", ROOT / "tests"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with `-m gpu` on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def expected():
+    return json.loads((ROOT / "tests" / "golden" / "expected.json").read_text())
+
+
+@pytest.fixture(scope="session")
+def base_geography():
+    from colq import geography
+    return geography.load_base()
