@@ -125,7 +125,7 @@ def int_equals(x: int) -> IntPredicate:
     return IntPredicate(x, x)
 
 
-# operator codes shared with include/colq.h (colq_str_op) and oracle/colq_oracle.h
+# operator codes: the colq_str_op enum of include/colq.h
 STR_EQ, STR_CONTAINS, STR_CMP_GT, STR_CMP_LT, STR_CMP_GE, STR_CMP_LE, STR_NE, STR_STARTS_WITH, STR_ENDS_WITH = range(9)
 
 

@@ -499,7 +499,7 @@ struct Planner {
             u32* ob;
             ST(out_buf(&ob));
             P.out_bits = ob;
-            o.smem = (size_t)ST_STAGES * (ST_OFF_BYTES + P.cap + 16) + ST_MAX_NEEDLE + 16 + ST_STAGES * 8 +
+            o.smem = (size_t)ST_STAGES * (ST_OFF_BYTES + P.cap + 16) + st_needle_region(P.needle_len) + ST_STAGES * 8 +
                      ST_STAGES * sizeof(StrTileMeta) + PUSH_SMEM_WORDS * 4;
             o.acct_rows = n;
             o.acct_bytes = (n + 1) * 4 + col.n_bytes + bitmap_words(n) * 4;

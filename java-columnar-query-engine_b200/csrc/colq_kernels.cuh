@@ -346,7 +346,8 @@ constexpr int ST_THREADS = 256;
 constexpr int ST_ROWS = 1024;  // rows per tile (multiple of 32 and 4)
 constexpr int ST_STAGES = 4;
 constexpr int ST_OFF_BYTES = (ST_ROWS + 4) * 4;  // offsets slice incl. the closing offset, padded to 16 B
-constexpr int ST_MAX_NEEDLE = 1024;
+constexpr int ST_MAX_NEEDLE = 16384;  // needle bytes are staged in shared memory next to the ring
+__host__ __device__ inline int st_needle_region(int needle_len) { return (needle_len + 16 + 15) & ~15; }
 
 enum StrOp : int {
     OP_EQ = 0, OP_CONTAINS = 1, OP_CMP_GT = 2, OP_CMP_LT = 3, OP_CMP_GE = 4, OP_CMP_LE = 5, OP_NE = 6,
@@ -453,14 +454,15 @@ __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParam
     // layout: [stage0 offsets | stage0 bytes(cap+16)] ... | needle words | mbarriers | metas | reach
     const int stage_bytes = ST_OFF_BYTES + P.cap + 16;
     u32* s_needle = reinterpret_cast<u32*>(smem + (size_t)ST_STAGES * stage_bytes);
-    u64* s_full = reinterpret_cast<u64*>(reinterpret_cast<uint8_t*>(s_needle) + ST_MAX_NEEDLE + 16);
+    const int needle_region = st_needle_region(P.needle_len);
+    u64* s_full = reinterpret_cast<u64*>(reinterpret_cast<uint8_t*>(s_needle) + needle_region);
     StrTileMeta* s_meta = reinterpret_cast<StrTileMeta*>(s_full + ST_STAGES);
     u32* s_reach = reinterpret_cast<u32*>(s_meta + ST_STAGES);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool do_push = P.push.fk != nullptr;
 
-    for (int i = tid; i < (ST_MAX_NEEDLE + 16) / 4; i += ST_THREADS) {
+    for (int i = tid; i < needle_region / 4; i += ST_THREADS) {
         u32 w = 0;
         for (int b = 0; b < 4; ++b) {
             int k = i * 4 + b;

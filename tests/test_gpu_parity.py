@@ -1,0 +1,279 @@
+"""GPU suite (-m gpu): libcolq.so on a B200, called through the C ABI, bit-exact against the CPU oracle."""
+import numpy as np
+import pytest
+
+import tck
+from colq import (Association, Criteria, InMemoryTable, Query, QueryResult, geography as G, int_range, of_columns,
+                  of_ints, of_strings)
+from colq.data_system import StringPredicate
+from colq.in_memory import IntegerColumn, StringColumn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engines():
+    from colq.engine import DataSystemColq
+    from oracle_system import OracleDataSystem
+    made = []
+
+    def new_gpu(lazy_fk=True):
+        ds = DataSystemColq(0, lazy_fk=lazy_fk)
+        made.append(ds)
+        return ds
+
+    yield new_gpu, OracleDataSystem
+    for ds in made:
+        ds.close()
+
+
+def both(engines, build, queries, lazy_modes=(True, False)):
+    """Build the same tables for the oracle and the GPU engine, run each query on both, compare row sets bit for bit."""
+    new_gpu, new_oracle = engines
+    oracle = new_oracle()
+    build(oracle)
+    want = []
+    for q in queries:
+        r = oracle.execute(q())
+        assert isinstance(r, QueryResult.Success), getattr(r, "message", None)
+        want.append((oracle.last_indices.copy(), oracle.last_words.copy(), oracle.node_cardinalities()))
+    for lazy in lazy_modes:
+        gpu = new_gpu(lazy)
+        build(gpu)
+        for q, (idx, words, cards) in zip(queries, want):
+            r = gpu.execute(q())
+            assert isinstance(r, QueryResult.Success), getattr(r, "message", None)
+            cq = gpu.last_query
+            got = cq.fetch(want_indices=True, want_bitmask=True, n_rows=words.shape[0] * 64)
+            assert got.count == idx.shape[0]
+            assert np.array_equal(got.indices, idx), "row index set differs from the oracle"
+            assert np.array_equal(got.bitmask[: words.shape[0]], words), "BitSet words differ from the oracle"
+            gc = cq.node_cardinalities()
+            assert len(gc) == len(cards)
+            for a, b in zip(gc, cards):
+                assert a == -1 or a == b, (gc, cards)   # -1: node fused away, never materialised
+            if not lazy:
+                assert gc[0] == cards[0]
+        gpu.close()
+
+
+# ------------------------------------------------------------------ the reference's own tests + failure paths
+@pytest.mark.parametrize("lazy", [True, False])
+@pytest.mark.parametrize("case", tck.REFERENCE_TESTS + tck.FAILURE_TESTS + tck.EXTRA_TESTS, ids=lambda f: f.__name__)
+def test_tck(engines, case, lazy):
+    new_gpu, _ = engines
+    case(lambda: new_gpu(lazy))
+
+
+def test_headline_queries_one_universe(engines, expected, base_geography):
+    new_gpu, _ = engines
+    tck.plymouth(new_gpu, expected, base_geography)
+    tck.north_south_north(new_gpu, expected, base_geography)
+    tck.plymouth(lambda: new_gpu(False), expected, base_geography)
+
+
+def test_opaque_lambda_is_a_failure_not_a_fallback(engines):
+    new_gpu, _ = engines
+    ds = new_gpu()
+    ds.register("ints", of_columns(of_ints(1, 2, 3)))
+    q = Query("ints")
+    q.root_node.add_criteria(Criteria.IntCriteria(0, lambda i: i > 1))
+    r = ds.execute(q)
+    assert isinstance(r, QueryResult.Failure) and "no CPU fallback" in r.message
+
+
+# ------------------------------------------------------------------ int scans: sizes around every tile boundary
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 127, 128, 129, 511, 512, 513, 4095, 4096, 4097, 32767, 32768, 32769,
+                               100_003, (1 << 20) + 7])
+def test_int_range_scan_sizes(engines, n):
+    rng = np.random.default_rng(n)
+    a = rng.integers(-50, 50, size=n, dtype=np.int32)
+    b = rng.integers(np.iinfo(np.int32).min, np.iinfo(np.int32).max, size=n, dtype=np.int32, endpoint=True)
+
+    def build(ds):
+        ds.register("t", InMemoryTable.of_columns(IntegerColumn(a), IntegerColumn(b), IntegerColumn(a[::-1].copy())))
+
+    def q1():
+        q = Query("t"); q.root_node.add_criteria(Criteria.IntCriteria(0, int_range(-3, 7))); return q
+
+    def q2():  # two predicates on two columns, extremes of the int range
+        q = Query("t")
+        q.root_node.add_criteria(Criteria.IntCriteria(0, int_range(-50, 49)))
+        q.root_node.add_criteria(Criteria.IntCriteria(1, int_range(-(2 ** 31), 0)))
+        return q
+
+    def q3():  # three predicates: needs two fused launches
+        q = Query("t")
+        for o, (lo, hi) in enumerate([(-10, 30), (-(2 ** 30), 2 ** 31 - 1), (-40, 10)]):
+            q.root_node.add_criteria(Criteria.IntCriteria(o, int_range(lo, hi)))
+        return q
+
+    def q4():  # empty interval and no criteria at all
+        q = Query("t"); q.root_node.add_criteria(Criteria.IntCriteria(0, int_range(5, 4))); return q
+
+    def q5():
+        return Query("t")
+
+    both(engines, build, [q1, q2, q3, q4, q5], lazy_modes=(True,))
+
+
+# ------------------------------------------------------------------ string scans: every operator, ragged lengths
+def random_strings(rng, n, max_len, alphabet):
+    lens = rng.integers(0, max_len + 1, size=n)
+    return ["".join(rng.choice(alphabet, size=l)) for l in lens]
+
+
+@pytest.mark.parametrize("n,max_len", [(0, 4), (1, 4), (1023, 6), (1024, 6), (1025, 6), (5000, 40), (70_000, 12),
+                                      (400_000, 9), (3000, 300)])
+def test_string_ops(engines, n, max_len):
+    rng = np.random.default_rng(n * 31 + max_len)
+    alphabet = np.array(list("abAB "))
+    strings = random_strings(rng, n, max_len, alphabet)
+    if n > 10:
+        strings[3] = ""
+        strings[7] = "é😀ﬁ"          # multi-byte UTF-8, incl. a supplementary code point
+        strings[9] = "ab" * 700                 # longer than any ring slot: read from global memory
+    col = StringColumn(strings)
+    needles = ["", "a", "ab", "aB a", "abABa", "b" * 9, "é", "😀", "ﬁ", "ab" * 700]
+
+    def build(ds):
+        ds.register("s", InMemoryTable.of_columns(col))
+
+    queries = []
+    for op in range(9):
+        for nd in needles:
+            def mk(op=op, nd=nd):
+                q = Query("s")
+                q.root_node.add_criteria(Criteria.StringCriteria(0, StringPredicate(op, nd)))
+                return q
+            queries.append(mk)
+    both(engines, build, queries, lazy_modes=(True,))
+
+
+def test_two_string_criteria_and_int_on_one_node(engines):
+    rng = np.random.default_rng(5)
+    n = 9000
+    s = StringColumn(random_strings(rng, n, 7, np.array(list("xyz"))))
+    v = IntegerColumn(rng.integers(0, 100, size=n, dtype=np.int32))
+
+    def build(ds):
+        ds.register("t", InMemoryTable.of_columns(s, v))
+
+    def q():
+        qq = Query("t")
+        qq.root_node.add_criteria(Criteria.StringCriteria(0, StringPredicate(1, "xy")))
+        qq.root_node.add_criteria(Criteria.IntCriteria(1, int_range(10, 60)))
+        qq.root_node.add_criteria(Criteria.StringCriteria(0, StringPredicate(2, "xz")))
+        return qq
+
+    both(engines, build, [q], lazy_modes=(True,))
+
+
+# ------------------------------------------------------------------ associations: random graphs, forward and reverse hops
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_association_graphs(engines, seed):
+    rng = np.random.default_rng(seed)
+    na, nb, nc = 20_011, 3_001, 97
+    a_val = rng.integers(0, 1000, size=na, dtype=np.int32)
+    b_val = rng.integers(0, 1000, size=nb, dtype=np.int32)
+    c_val = rng.integers(0, 1000, size=nc, dtype=np.int32)
+    a_to_b = rng.integers(-1, nb, size=na, dtype=np.int32)          # to-one with Nones
+    b_to_c = rng.integers(-1, nc, size=nb, dtype=np.int32)
+    deg = rng.integers(0, 5, size=nc)
+    c_off = np.zeros(nc + 1, dtype=np.int64); np.cumsum(deg, out=c_off[1:])
+    c_tgt = rng.integers(0, nc, size=int(c_off[-1]), dtype=np.int32)  # to-many self association on c
+    deg2 = rng.integers(0, 3, size=nb)
+    bm_off = np.zeros(nb + 1, dtype=np.int64); np.cumsum(deg2, out=bm_off[1:])
+    bm_tgt = rng.integers(0, na, size=int(bm_off[-1]), dtype=np.int32)  # to-many b -> a
+
+    def build(ds):
+        A = InMemoryTable.of_columns(IntegerColumn(a_val))
+        B = InMemoryTable.of_columns(IntegerColumn(b_val))
+        Cc = InMemoryTable.of_columns(IntegerColumn(c_val))
+        A.associate_to(B, fk=a_to_b)            # A.1 -> B ; B.1 <- A
+        B.associate_to(Cc, fk=b_to_c)           # B.2 -> C ; C.1 <- B
+        Cc.associate_to(Cc, csr=(c_off, c_tgt))  # C.2 -> C ; C.3 <- C
+        B.associate_to(A, csr=(bm_off, bm_tgt))  # B.3 -> A (many) ; A.2 <- B
+        ds.register("A", A); ds.register("B", B); ds.register("C", Cc)
+
+    def chain_down():   # A -> B -> C -> C (forward fk, fk, csr) with criteria at root and leaf
+        q = Query("A")
+        q.root_node.add_criteria(Criteria.IntCriteria(0, int_range(0, 300)))
+        q.root_node.create_child(1).create_child(2).create_child(2).add_criteria(Criteria.IntCriteria(0, int_range(0, 200)))
+        return q
+
+    def chain_down_no_root_pred():   # eager first hop
+        q = Query("A")
+        q.root_node.create_child(1).create_child(2).add_criteria(Criteria.IntCriteria(0, int_range(0, 500)))
+        return q
+
+    def chain_up():     # C <- B <- A through the reverse columns
+        q = Query("C")
+        q.root_node.create_child(1).create_child(1).add_criteria(Criteria.IntCriteria(0, int_range(0, 20)))
+        return q
+
+    def mid_criteria():  # criteria on every level, reverse csr hop C.3
+        q = Query("C")
+        q.root_node.add_criteria(Criteria.IntCriteria(0, int_range(100, 900)))
+        n = q.root_node.create_child(3); n.add_criteria(Criteria.IntCriteria(0, int_range(0, 700)))
+        n.create_child(1).add_criteria(Criteria.IntCriteria(0, int_range(0, 100)))
+        return q
+
+    def two_children():  # B has a to-one child and a to-many child and a reverse child
+        q = Query("B")
+        q.root_node.create_child(2).add_criteria(Criteria.IntCriteria(0, int_range(0, 600)))
+        q.root_node.create_child(3).add_criteria(Criteria.IntCriteria(0, int_range(0, 400)))
+        q.root_node.create_child(1).add_criteria(Criteria.IntCriteria(0, int_range(500, 999)))
+        return q
+
+    def reverse_of_many():  # A.2 is the reverse of the to-many B.3
+        q = Query("A")
+        q.root_node.create_child(2).add_criteria(Criteria.IntCriteria(0, int_range(0, 50)))
+        return q
+
+    def no_criteria_anywhere():
+        q = Query("A")
+        q.root_node.create_child(1).create_child(2)
+        return q
+
+    both(engines, build, [chain_down, chain_down_no_root_pred, chain_up, mid_criteria, two_children, reverse_of_many,
+                          no_criteria_anywhere])
+
+
+# ------------------------------------------------------------------ parallel universes
+@pytest.mark.parametrize("U", [3, 40])
+def test_plymouth_universes_match_oracle(engines, base_geography, U):
+    geo = G.build_tables(U, base=base_geography)
+
+    def build(ds):
+        G.register_geography(ds, geo)
+
+    both(engines, build, [G.plymouth_query, G.north_south_north_query])
+
+
+def test_plymouth_full_size_properties(base_geography, expected):
+    """BASELINE config 4 at full size (10k universes, 293.5 M ZIP rows) generated in HBM: the result must be exactly
+    {u * 29353 + r} for the 31 one-universe rows r, ascending, for both execution strategies."""
+    import torch
+    from colq.device_data import build_geography_on_device, plymouth_colq_query
+    from colq.engine import ColqContext
+    from oracle_system import OracleDataSystem
+    oracle = OracleDataSystem()
+    G.register_geography(oracle, G.build_tables(1, base=base_geography))
+    oracle.execute(G.plymouth_query())
+    rows1 = oracle.last_indices.astype(np.int64)
+    U = 10_000
+    ctx = ColqContext(0)
+    geo = build_geography_on_device(ctx, U, base=base_geography)
+    want = (np.arange(U, dtype=np.int64)[:, None] * G.N_ZIPS + rows1[None, :]).reshape(-1)
+    for lazy in (True, False):
+        q = plymouth_colq_query(ctx, lazy_fk=lazy)
+        res = q.execute(want_indices=True, want_bitmask=True, n_rows=geo.n_zip_rows, index_capacity=31 * U)
+        assert res.count == 31 * U
+        assert np.array_equal(res.indices.astype(np.int64), want)
+        words = res.bitmask
+        assert int(np.unpackbits(words.view(np.uint8)).sum()) == 31 * U   # checksum of the mask agrees with the list
+        q.close()
+    del geo
+    ctx.close()
+    torch.cuda.empty_cache()

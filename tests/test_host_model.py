@@ -1,0 +1,75 @@
+"""CPU suite: the host-side mirror of the data-system / in-memory model (no GPU, no oracle)."""
+import numpy as np
+import pytest
+
+from colq import (NONE, Association, BitSet, InMemoryTable, Many, One, Query, of_columns, of_ints, of_strings,
+                  str_compare_gt, str_contains, str_equals)
+from colq import geography as G
+
+
+def test_association_add_follows_reference():
+    # Association.java:27-51
+    a = Association.to_none().add(3)
+    assert a == One(3)
+    b = a.add(5)
+    assert b == Many((3, 5))
+    assert b.add(7) == Many((3, 5, 7))
+    assert NONE.targets() == ()
+
+
+def test_associate_to_builds_transposed_reverse_column():
+    x = of_columns(of_strings("x0", "x1", "x2", "x3"))
+    y = of_columns(of_strings("y0", "y1", "y2"))
+    fwd = x.associate_to(y, Association.to_one(1), Association.to_many(0, 1), Association.to_none(), Association.to_one(1))
+    assert x.width() == 2 and y.width() == 2            # InMemoryTable.java:48,88
+    rev = y.columns()[1]
+    assert fwd.reverse_associated_column() is rev and rev.reverse_associated_column() is fwd
+    assert rev.associations_for_index(0) == One(1)       # InMemoryTable.java:75-82
+    assert rev.associations_for_index(1) == Many((0, 1, 3))   # x ascending (:61)
+    assert rev.associations_for_index(2) is NONE
+    with pytest.raises(TypeError):                       # NPE at :70-71
+        x.associate_to(y, Association.to_one(3), NONE, NONE, NONE)
+
+
+def test_subset_keeps_all_columns_ascending_and_unremapped():
+    t = of_columns(of_strings("a", "bb", "", "dddd"), of_ints(1, 2, 3, 4))
+    u = of_columns(of_ints(9, 8))
+    t.associate_to(u, Association.to_one(1), Association.to_none(), Association.to_one(0), Association.to_one(1))
+    s = t.subset(BitSet.from_indices(np.array([3, 0]), 4))
+    assert s.size() == 2 and s.width() == 3             # InMemoryTable.java:106-159
+    assert s.columns()[0].strings() == ["a", "dddd"]
+    assert s.columns()[1].ints().tolist() == [1, 4]
+    assert s.columns()[2].associations_for_index(1) == One(1)   # indices are not remapped (:143-154)
+
+
+def test_bitset_layout_is_java_util_bitset():
+    b = BitSet.from_indices(np.array([0, 63, 64, 130]), 131)
+    assert b.words.tolist() == [(1 << 63) | 1, 1, 4]
+    assert b.to_indices().tolist() == [0, 63, 64, 130]
+    assert b.cardinality() == 4 and b.get(64) and not b.get(65)
+
+
+def test_query_duplicate_child_ordinal_throws():
+    q = Query("t")
+    q.root_node.create_child(2)
+    with pytest.raises(ValueError):                      # Query.java:33-35
+        q.root_node.create_child(2)
+
+
+def test_structured_predicates_are_callables():
+    assert str_equals("PLYMOUTH")("PLYMOUTH") and not str_equals("PLYMOUTH")("NEW PLYMOUTH")
+    assert str_contains("North")("North Dakota") and not str_contains("North")("north")
+    assert str_compare_gt("a")("b") and not str_compare_gt("a")("a")
+
+
+def test_universe_replication_shapes(base_geography):
+    geo = G.build_tables(3, base=base_geography)
+    assert geo.zips.size() == 3 * G.N_ZIPS and geo.cities.size() == 3 * G.N_CITIES and geo.states.size() == G.N_STATES
+    fk = geo.zips.columns()[2].fk()
+    assert fk[G.N_ZIPS] == base_geography["zip_city"][0] + G.N_CITIES
+    names = geo.cities.columns()[0]
+    assert names.get(G.N_CITIES + 5) == names.get(5)
+    assert [G.universe_range(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    shard = G.build_tables(10, n_ranks=4, rank=2, base=base_geography)
+    assert shard.n_universes == 2 and shard.zip_row_base == 6 * G.N_ZIPS
+    assert int(shard.zips.columns()[2].fk().max()) < shard.cities.size()   # keys are shard-local
