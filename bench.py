@@ -1,0 +1,416 @@
+#!/usr/bin/env python3
+"""bench.py -- the Plymouth-adjacency query at 10k synthetic universes (BASELINE.json configs[3]) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libcolq.so)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference engine's CPU algorithm (oracle port)
+
+One "step" = one execution of the query (app/src/main/java/dgroomes/app/Runner.java:230-236) over the whole
+workload: 293,530,000 ZIP rows / 257,010,000 city rows, sharded by universe range over the N ranks (strong scaling),
+state table replicated.  metric = root-table (ZIP) rows per second, whole job.
+
+  value     K steps timed with CUDA events on the launching stream, tables resident in HBM, max over ranks.
+            Every step enqueues all kernels, the state-mask all-gather and the final index gather (N>1).
+  e2e       the same query through the C ABI with HOST buffers: per step all columns are copied from pinned host
+            memory into HBM (colq_col_* / colq_associate_*), the query runs, the matched indices are read back.
+  roofline  the dominant kernel (the TMA-staged city-name scan), timed per launch with CUDA events inside libcolq
+            (COLQ_OPT_PROFILE) in separate profiled steps; algorithmic bytes = offsets + name bytes + mask out.
+  cpu_baseline  the oracle port (oracle/colq_oracle.c), single thread like the serial reference, bounded sample.
+
+Inputs are far larger than L2 (6.6 GB touched per step on one GPU, 0.82 GB per GPU on eight; L2 is 126 MB), so no
+explicit flush between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT / "java-columnar-query-engine_b200", ROOT / "oracle"):
+    sys.path.insert(0, str(p))
+
+import numpy as np  # noqa: E402
+
+N_ZIPS, N_CITIES = 29_353, 25_701
+METRIC = "plymouth_query_zip_rows_per_sec"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="colq", choices=["colq", "reference"])
+    ap.add_argument("--universes", type=int, default=10_000)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--profile-steps", type=int, default=10)
+    ap.add_argument("--cpu-universes", type=int, default=1000, help="bounded sample for the CPU baseline legs")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="disable the lazy FK chain (materialise every node)")
+    return ap.parse_args()
+
+
+def workload_config(U, world, lazy=True):
+    return {
+        "workload": "plymouth_adjacency_query_10k_universes" if U == 10_000 else f"plymouth_adjacency_query_{U}_universes",
+        "source": "BASELINE.json configs[3]; app/.../Runner.java:230-236",
+        "universes": U, "zip_rows": U * N_ZIPS, "city_rows": U * N_CITIES, "state_rows": 51,
+        "sharding": f"universe ranges over {world} rank(s); states replicated",
+        "l2_policy": "inputs larger than L2 (no flush)",
+        "strategy": "lazy_fk_chain" if lazy else "materialise_all_nodes",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.005):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+            nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = get_reasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+        return {
+            "sm_mhz": statistics.median(self.samples) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+def measured_peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel_prefix: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    f = ROOT / "profiles" / "roofline_traffic.json"
+    if f.exists():
+        try:
+            d = json.loads(f.read_text())
+            for k, v in d.get("kernels", {}).items():
+                if kernel_prefix.startswith(k):
+                    return v.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    return None
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+def oracle_run(U, n_threads, repeats):
+    """Times orc_execute (tables already resident in host memory, like the reference's execute) on U universes."""
+    from colq import geography as G
+    from oracle_system import OracleDataSystem
+    geo = G.build_tables(U)
+    ds = OracleDataSystem(n_threads=n_threads)
+    G.register_geography(ds, geo)
+    q = G.plymouth_query()
+    times = []
+    for _ in range(repeats):
+        r = ds.execute(q)
+        assert r.result_set.size() == 31 * U
+        times.append(ds.last_execute_seconds)
+    ds.close()
+    return times
+
+
+def run_reference(args, rank, world):
+    """The reference arm: the reference engine's own algorithm on the host cores.  The reference is Java and neither
+    this image nor the GPU box has a JVM, so this times the C port of it (oracle/colq_oracle.c) with
+    all host threads on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    U = args.cpu_universes
+    times = oracle_run(U, cores, args.warmup + args.steps)[args.warmup:]
+    sec = statistics.mean(times)
+    value = U * N_ZIPS / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": dict(workload_config(args.universes, 1), sample_universes=U, sample_zip_rows=U * N_ZIPS),
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port",
+                         "sample": f"{U} of {args.universes} universes ({U * N_ZIPS} ZIP rows) per step; C port of the serial-indices "
+                                   f"engine with its row loops split over {cores} OpenMP threads; Java engine not timed: no JVM in image"},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_colq(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from colq import _ffi
+    from colq import geography as G
+    from colq.device_data import build_geography_on_device, plymouth_colq_query
+    from colq.engine import ColqContext
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    ctx = ColqContext(local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    U = args.universes
+    base = G.load_base()
+    geo = build_geography_on_device(ctx, U, world, rank, base=base, device=dev, sharded=world > 1)
+    q = plymouth_colq_query(ctx, lazy_fk=not args.eager)
+
+    # ---- correctness gate before any number: the result must be exactly {u * 29353 + r}
+    from oracle_system import OracleDataSystem
+    one = OracleDataSystem()
+    G.register_geography(one, G.build_tables(1, base=base))
+    one.execute(G.plymouth_query())
+    rows1 = one.last_indices.astype(np.int64)
+    one.close()
+    want = (np.arange(U, dtype=np.int64)[:, None] * N_ZIPS + rows1[None, :]).reshape(-1)
+    res = q.execute(want_indices=True, index_capacity=31 * U + 16)
+    if res.count != 31 * U or not np.array_equal(res.indices.astype(np.int64), want):
+        raise SystemExit(f"rank {rank}: GPU result differs from the oracle-derived expectation (count {res.count} vs {31 * U})")
+    launches_per_step = int(res.timing.kernel_launches)
+    collectives_per_step = int(res.timing.collectives)
+
+    # ---- value: K steps, resident tables, CUDA events on the launching stream, max over ranks
+    sampler = ClockSampler(local_rank)
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            q.execute_async()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.start()
+        e0.record(stream)
+        for _ in range(args.steps):
+            q.execute_async()
+        e1.record(stream)
+        stream.synchronize()
+        clocks = sampler.stop()
+        barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    res = q.fetch(want_indices=True, index_capacity=31 * U + 16)
+    assert res.count == 31 * U and np.array_equal(res.indices.astype(np.int64), want)
+    rows = U * N_ZIPS
+    value = rows / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events inside libcolq, separate profiled steps
+    q.set_option(_ffi.OPT_PROFILE, 1)
+    acc = {}
+    for _ in range(args.profile_steps):
+        q.execute(want_indices=False)
+        for name, ms, r, b in q.profile():
+            if ms >= 0:
+                a = acc.setdefault(name, [0.0, 0, r, b])
+                a[0] += ms
+                a[1] += 1
+    q.set_option(_ffi.OPT_PROFILE, 0)
+    stages = {k: {"ms": v[0] / v[1], "rows": v[2], "algorithmic_bytes": v[3]} for k, v in acc.items() if v[1]}
+    dom = max(stages, key=lambda k: stages[k]["ms"])
+    peak, peak_src = measured_peak()
+    achieved = stages[dom]["algorithmic_bytes"] / (stages[dom]["ms"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(dom), "peak_source": peak_src, "ms_per_launch": stages[dom]["ms"],
+                "algorithmic_bytes_per_launch": stages[dom]["algorithmic_bytes"],
+                "share_of_step": stages[dom]["ms"] / sum(s["ms"] for s in stages.values())}
+
+    # whole-query algorithmic bytes for the HBM GB/s half of BASELINE's metric
+    algo_bytes = 4 * geo.n_zip_rows * 2 + 4 * (geo.n_city_rows + 1) + geo.name_bytes + 4 * geo.n_city_rows + 4 * 31 * geo.n_universes
+    algo_total = algo_bytes
+    if world > 1:
+        t = torch.tensor([float(algo_bytes)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        algo_total = float(t.item())
+    query_gbs = algo_total / (ms_step * 1e-3) / 1e9
+
+    # ---- e2e_resident: the public call with resident tables, matched indices read back every step
+    barrier()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        n_res = max(5, min(args.steps, 50))
+        for _ in range(n_res):
+            r2 = q.execute(want_indices=True, index_capacity=31 * U + 16)
+        e1.record(stream)
+        stream.synchronize()
+    ms_res = max_over_ranks(e0.elapsed_time(e1)) / n_res
+    d2h_res = int(r2.timing.d2h_bytes)
+
+    # ---- e2e: HOST buffers in, matched indices out, every step (columns re-uploaded from pinned memory)
+    e2e = None
+    if not args.no_e2e:
+        host = {}
+        for k, t in geo.tensors.items():
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t)
+            host[k] = h.numpy()
+        torch.cuda.synchronize(dev)
+        nz, nc, nb = geo.n_zip_rows, geo.n_city_rows, geo.name_bytes
+        sharded = world > 1
+        place = _ffi.SHARDED if sharded else _ffi.REPLICATED
+        h2d = 4 * nz * 3 + 4 * (nc + 1) + nb + 4 * nc + int(base["state_code_bytes"].size + base["state_name_bytes"].size) + 4 * 104 + 8 * 52 + 4 * 219
+        # free the resident copy first so that both never coexist (keeps the e2e leg honest about allocation cost too)
+        q.close()
+        for tb in (geo.zips, geo.cities, geo.states):
+            ctx.table_destroy(tb)
+        geo.tensors.clear()
+        ctx._keepalive.clear()
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            states = ctx.table_create(51, _ffi.REPLICATED, 0)
+            cities = ctx.table_create(nc, place, geo.u0 * N_CITIES)
+            zips = ctx.table_create(nz, place, geo.u0 * N_ZIPS)
+            ctx.col_str(states, 0, base["state_code_offsets"], base["state_code_bytes"])
+            ctx.col_str(states, 1, base["state_name_offsets"], base["state_name_bytes"])
+            ctx.col_str(cities, 0, host["city_name_offsets"][: nc + 1].view(np.uint32), host["city_name_bytes"][:nb])
+            ctx.associate_fk(cities, 1, states, 2, host["city_state"][:nc])
+            ctx.col_i32(zips, 0, host["zip_code"][:nz])
+            ctx.col_i32(zips, 1, host["zip_pop"][:nz])
+            ctx.associate_fk(zips, 2, cities, 2, host["zip_city"][:nz])
+            ctx.associate_csr(states, 3, states, 4, base["adj_offsets"].astype(np.int64), base["adj_targets"])
+            for name, tb in (("states", states), ("cities", cities), ("zips", zips)):
+                ctx.register(name, tb)
+            qq = plymouth_colq_query(ctx, lazy_fk=not args.eager)
+            r = qq.execute(want_indices=True, index_capacity=31 * U + 16)
+            qq.close()
+            for tb in (zips, cities, states):
+                ctx.table_destroy(tb)
+            return r
+
+        r3 = e2e_step()  # warm-up (also first-touch of the pinned pages)
+        assert r3.count == 31 * U and np.array_equal(r3.indices.astype(np.int64), want)
+        barrier()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(args.e2e_steps):
+                r3 = e2e_step()
+            e1.record(stream)
+            stream.synchronize()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.e2e_steps
+        assert r3.count == 31 * U
+        e2e = {"value": rows / (ms_e2e * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(r3.timing.d2h_bytes), "ms_per_step": ms_e2e, "steps": args.e2e_steps,
+               "what": "colq_table_create + colq_col_*/colq_associate_* from pinned host memory + colq_execute with index read-back + colq_table_destroy, per step, per rank"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the serial port, like the serial reference engine
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        Uc = args.cpu_universes
+        times = oracle_run(Uc, 1, 4)[1:]
+        sec = statistics.mean(times)
+        cpu = {"value": Uc * N_ZIPS / sec, "unit": "rows/s", "cores": 1, "kind": "port",
+               "sample": f"{Uc} of {U} universes ({Uc * N_ZIPS} ZIP rows), 3 timed runs of orc_execute, single thread "
+                         "(the reference engine is serial); Java engine not timed: no JVM in image",
+               "ms_per_sample": sec * 1e3}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "config": workload_config(U, world, not args.eager),
+            "hbm_gbs_query_algorithmic": query_gbs, "query_algorithmic_bytes": algo_total,
+            "roofline": roofline, "stages_ms": {k: round(v["ms"], 5) for k, v in stages.items()},
+            "cpu_baseline": cpu, "e2e": e2e,
+            "e2e_resident": {"value": rows / (ms_res * 1e-3), "unit": "rows/s", "ms_per_step": ms_res, "h2d_bytes_per_step": 0,
+                             "d2h_bytes_per_step": d2h_res, "what": "colq_execute with resident tables, matched indices read back every step"},
+            "clocks": clocks, "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+            "collectives_per_step": collectives_per_step,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus:
+        if args.gpus == 1 and world == 1:
+            pass
+        else:
+            raise SystemExit(f"--gpus {args.gpus} needs WORLD_SIZE={args.gpus} (launch with torch.distributed.run); got {world}")
+    run_colq(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

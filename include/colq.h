@@ -161,6 +161,9 @@ colq_status colq_associate_csr(colq_ctx *ctx, colq_table x, int x_ordinal, colq_
 colq_status colq_associate_fk_device(colq_ctx *ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal,
                                      const void *fk_device, int64_t n);
 
+/* Release a table's device memory and its registrations (the reference leaves this to the garbage collector).
+   Association columns of other tables that pointed at it become unset. The handle stays reserved. */
+colq_status colq_table_destroy(colq_ctx *ctx, colq_table table);
 colq_status colq_table_size(const colq_ctx *ctx, colq_table table, int64_t *out_rows);   /* Table.size()  DS/Table.java:29 */
 colq_status colq_table_width(const colq_ctx *ctx, colq_table table, int *out_columns);   /* Table.width() DS/Table.java:22 */
 
@@ -184,15 +187,16 @@ colq_status colq_query_set_option(colq_query *query, colq_option option, int val
  * ascending index half of Table.subset (M/InMemoryTable.java:121-131), all on the device.
  *   out_bitmask : nullable; receives ceil(rows/64) words of the ROOT node's matching bits (this rank's rows)
  *   out_indices : nullable; receives the matching row indices, ascending (global indices for a sharded root;
- *                 with a communicator, rank 0 receives every rank's indices concatenated in rank order)
- *   out_count   : number of matching rows (this rank's, or the global count on rank 0 after the gather)
+ *                 with a communicator, every rank receives all ranks' indices concatenated in rank order)
+ *   out_count   : number of matching rows (global count when the root table is sharded over a communicator)
  * Returns COLQ_OK or one of the statuses documented on colq_status.
  */
 colq_status colq_execute(colq_ctx *ctx, colq_query *query, uint64_t *out_bitmask, int64_t bitmask_capacity_words,
                          int32_t *out_indices, int64_t indices_capacity, int64_t *out_count, colq_timing *out_timing);
 /*
- * Same pipeline without any host synchronisation or result copy: kernels are only enqueued on the context's
- * stream; results stay in HBM until colq_fetch.  Used to time K back-to-back executions with CUDA events.
+ * Same pipeline without any host synchronisation or result copy: kernels and collectives (including the final
+ * gather of matched indices) are only enqueued on the context's stream; results stay in HBM until colq_fetch.
+ * Used to time K back-to-back executions with CUDA events.
  */
 colq_status colq_execute_async(colq_ctx *ctx, colq_query *query);
 colq_status colq_fetch(colq_ctx *ctx, colq_query *query, uint64_t *out_bitmask, int64_t bitmask_capacity_words,

@@ -155,6 +155,9 @@ class ColqContext:
     def register(self, name: str, table: int) -> None:
         self._check(self.lib.colq_register(self.handle, name.encode(), table))
 
+    def table_destroy(self, table: int) -> None:
+        self._check(self.lib.colq_table_destroy(self.handle, table))
+
     def col_i32(self, table: int, ordinal: int, values: np.ndarray) -> None:
         v = np.ascontiguousarray(values, dtype=np.int32)
         self._check(self.lib.colq_col_i32(self.handle, table, ordinal, _ptr(v), v.shape[0]))

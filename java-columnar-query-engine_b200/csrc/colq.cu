@@ -101,7 +101,7 @@ struct QNode {
 };
 
 // one kernel launch (or collective / memset) of a planned query
-enum OpKind { K_SCAN_ROWS, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT };
+enum OpKind { K_SCAN_ROWS, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER };
 
 struct Op {
     OpKind kind;
@@ -177,13 +177,15 @@ struct colq_query {
     std::vector<Op> ops;
     int root_table = -1;
     u32* root_bits = nullptr;
+    // result block in HBM: [u64 count | 8 B pad | idx_capacity int32 row indices]; grows on demand, outside the pool
+    DevBuf idx_buf;
     u64* d_total = nullptr;
-    u64* d_all_counts = nullptr;  // per-rank counts after the count all-gather
     int32_t* d_idx = nullptr;
     int64_t idx_capacity = 0;
-    int64_t want_idx_capacity = 1 << 20;
-    DevBuf idx_buf;       // grows on demand, outside the pool
-    DevBuf gather_buf;    // rank 0: concatenated indices of all ranks
+    int64_t want_idx_capacity = 0;  // 0 = pick a default at first execute
+    // multi-GPU final gather: all ranks' result blocks, then their valid prefixes concatenated in rank order
+    bool gathered = false;
+    DevBuf gather_buf, gout_buf, ginfo_buf;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     std::vector<cudaEvent_t> stage_ev;
     std::vector<colq_stage> stages;
@@ -721,15 +723,25 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
             compact_kernel<<<(int)o.n_blocks, CP_THREADS, 0, s>>>(o.src, o.n_words, o.block_offsets, o.out_idx, o.capacity, o.row_base);
             q->timing.kernel_launches++;
             break;
+        case K_GATHER:
+            NC(ctx, ctx->nccl.AllGather(q->idx_buf.ptr, q->gather_buf.ptr, (size_t)(o.capacity + GATHER_HEADER_WORDS), kNcclInt32,
+                                        ctx->comm, (void*)s));
+            q->timing.collectives++;
+            unpack_gather_kernel<<<grid_for(o.capacity * ctx->n_ranks, 256, ctx->sm_count, 4), 256, 0, s>>>(
+                (const int32_t*)q->gather_buf.ptr, ctx->n_ranks, o.capacity, (int32_t*)q->gout_buf.ptr, (u64*)q->ginfo_buf.ptr);
+            q->timing.kernel_launches++;
+            break;
     }
     CU(ctx, cudaGetLastError());
     return COLQ_OK;
 }
 
 colq_status ensure_idx_capacity(colq_query* q, int64_t want) {
-    if (q->idx_buf.bytes < (size_t)want * 4) ST(dev_alloc(q->ctx, q->idx_buf, (size_t)want * 4));
-    q->d_idx = (int32_t*)q->idx_buf.ptr;
-    q->idx_capacity = (int64_t)(q->idx_buf.bytes / 4);
+    const size_t need = (size_t)(want + GATHER_HEADER_WORDS) * 4;
+    if (q->idx_buf.bytes < need) ST(dev_alloc(q->ctx, q->idx_buf, need));
+    q->d_total = (u64*)q->idx_buf.ptr;
+    q->d_idx = (int32_t*)q->idx_buf.ptr + GATHER_HEADER_WORDS;
+    q->idx_capacity = (int64_t)(q->idx_buf.bytes / 4) - GATHER_HEADER_WORDS;
     return COLQ_OK;
 }
 
@@ -762,13 +774,12 @@ colq_status run_pipeline(colq_query* q) {
     // ---- compaction of the root mask (M/InMemoryTable.java:121-131)
     const int64_t n_words = bitmap_words(n);
     const int64_t n_blocks = std::max<int64_t>(1, (n_words + CP_WORDS_PER_BLOCK - 1) / CP_WORDS_PER_BLOCK);
-    void *bc, *bo, *tot;
+    void *bc, *bo;
     ST(pool_alloc(q, (size_t)n_blocks * 4, &bc));
     ST(pool_alloc(q, (size_t)n_blocks * 8, &bo));
-    ST(pool_alloc(q, 64 + 8 * (size_t)std::max(ctx->n_ranks, 1), &tot));
-    q->d_total = (u64*)tot;
-    q->d_all_counts = (u64*)tot + 8;
-    ST(ensure_idx_capacity(q, std::max<int64_t>(q->want_idx_capacity, 1)));
+    q->gathered = ctx->n_ranks > 1 && RT.placement == COLQ_SHARDED;
+    if (q->want_idx_capacity <= 0) q->want_idx_capacity = q->gathered ? (1 << 16) : (1 << 20);
+    ST(ensure_idx_capacity(q, q->want_idx_capacity));
     {
         Op p{};
         p.kind = K_POPC; p.node = 0; p.src = root.bits; p.n_words = n_words; p.n_blocks = n_blocks; p.block_counts = (u32*)bc;
@@ -781,9 +792,22 @@ colq_status run_pipeline(colq_query* q) {
         Op c{};
         c.kind = K_COMPACT; c.node = 0; c.src = root.bits; c.n_words = n_words; c.n_blocks = n_blocks; c.block_offsets = (u64*)bo;
         c.out_idx = q->d_idx; c.capacity = q->idx_capacity;
-        c.row_base = (ctx->n_ranks > 1 && RT.placement == COLQ_SHARDED) ? RT.row_base : RT.row_base;
+        c.row_base = RT.row_base;  // global row index = shard-local index + the shard's base
         c.name = "compact"; c.acct_rows = n; c.acct_bytes = n_words * 4;
         q->ops.push_back(c);
+    }
+    if (q->gathered) {
+        // final gather of matched indices, entirely on the device: one all-gather of fixed-size
+        // result blocks, then a kernel that concatenates their valid prefixes in rank order
+        const int64_t cap = q->idx_capacity;
+        const size_t block_bytes = (size_t)(cap + GATHER_HEADER_WORDS) * 4;
+        if (q->gather_buf.bytes < block_bytes * ctx->n_ranks) ST(dev_alloc(ctx, q->gather_buf, block_bytes * ctx->n_ranks));
+        if (q->gout_buf.bytes < (size_t)cap * 4 * ctx->n_ranks) ST(dev_alloc(ctx, q->gout_buf, (size_t)cap * 4 * ctx->n_ranks));
+        if (!q->ginfo_buf.ptr) ST(dev_alloc(ctx, q->ginfo_buf, 64));
+        Op g{};
+        g.kind = K_GATHER; g.node = 0; g.capacity = cap; g.name = "allgather_indices";
+        g.acct_bytes = (int64_t)block_bytes * ctx->n_ranks;
+        q->ops.push_back(g);
     }
 
     // ---- enqueue
@@ -820,59 +844,39 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
     cudaStream_t s = ctx->stream;
     const Table& RT = ctx->tables[q->root_table];
     u64 local = 0;
+    u64 ginfo[4] = {0, 0, 0, 0};
+    const bool gather = q->gathered;
     CU(ctx, cudaMemcpyAsync(&local, q->d_total, 8, cudaMemcpyDeviceToHost, s));
+    if (gather) CU(ctx, cudaMemcpyAsync(ginfo, q->ginfo_buf.ptr, 32, cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaStreamSynchronize(s));
-    q->timing.d2h_bytes += 8;
+    q->timing.d2h_bytes += gather ? 40 : 8;
     float ms = 0;
     CU(ctx, cudaEventElapsedTime(&ms, q->ev_start, q->ev_stop));
     q->timing.gpu_ms = ms;
 
-    if ((int64_t)local > q->idx_capacity) {
+    int64_t count = (int64_t)local;
+    const int32_t* src_idx = q->d_idx;
+    if (gather) {
+        if ((int64_t)ginfo[1] > q->idx_capacity) {
+            // some rank found more rows than a result block holds: every rank sees the same gathered counts, so all
+            // of them grow the block and run the query again
+            q->want_idx_capacity = (int64_t)ginfo[1] + (int64_t)ginfo[1] / 4 + 1024;
+            ST(run_pipeline(q));
+            return fetch_results(q, out_bitmask, bitmask_cap, out_idx, idx_cap, out_count, out_timing);
+        }
+        count = (int64_t)ginfo[2];
+        src_idx = (const int32_t*)q->gout_buf.ptr;
+    } else if ((int64_t)local > q->idx_capacity) {
         // index buffer was too small: grow it and redo only the ordered write (the mask is still resident)
         q->want_idx_capacity = (int64_t)local;
         ST(ensure_idx_capacity(q, (int64_t)local));
-        for (Op& o : q->ops)
+        for (Op& o : q->ops) {
+            if (o.kind == K_SCAN_COUNTS) { o.total = q->d_total; ST(launch_op(q, o, s)); }
             if (o.kind == K_COMPACT) {
                 o.out_idx = q->d_idx;
                 o.capacity = q->idx_capacity;
                 ST(launch_op(q, o, s));
             }
-        CU(ctx, cudaStreamSynchronize(s));
-    }
-
-    int64_t count = (int64_t)local;
-    const int32_t* src_idx = q->d_idx;
-    const bool gather = ctx->n_ranks > 1 && RT.placement == COLQ_SHARDED;
-    if (gather) {
-        // final gather of matched indices to rank 0: all-gather the counts, then variable-size send/recv
-        NC(ctx, ctx->nccl.AllGather(q->d_total, q->d_all_counts, 1, kNcclUint64, ctx->comm, (void*)s));
-        q->timing.collectives++;
-        std::vector<u64> counts(ctx->n_ranks);
-        CU(ctx, cudaMemcpyAsync(counts.data(), q->d_all_counts, 8 * (size_t)ctx->n_ranks, cudaMemcpyDeviceToHost, s));
-        CU(ctx, cudaStreamSynchronize(s));
-        q->timing.d2h_bytes += 8 * ctx->n_ranks;
-        int64_t total = 0;
-        for (u64 c : counts) total += (int64_t)c;
-        if (ctx->rank == 0) {
-            if (q->gather_buf.bytes < (size_t)std::max<int64_t>(total, 1) * 4)
-                ST(dev_alloc(ctx, q->gather_buf, (size_t)std::max<int64_t>(total, 1) * 4));
-            int32_t* g = (int32_t*)q->gather_buf.ptr;
-            CU(ctx, cudaMemcpyAsync(g, q->d_idx, (size_t)local * 4, cudaMemcpyDeviceToDevice, s));
-            NC(ctx, ctx->nccl.GroupStart());
-            int64_t off = (int64_t)counts[0];
-            for (int r = 1; r < ctx->n_ranks; ++r) {
-                if (counts[r]) NC(ctx, ctx->nccl.Recv(g + off, (size_t)counts[r], kNcclInt32, r, ctx->comm, (void*)s));
-                off += (int64_t)counts[r];
-            }
-            NC(ctx, ctx->nccl.GroupEnd());
-            q->timing.collectives++;
-            src_idx = g;
-            count = total;
-        } else {
-            NC(ctx, ctx->nccl.GroupStart());
-            if (local) NC(ctx, ctx->nccl.Send(q->d_idx, (size_t)local, kNcclInt32, 0, ctx->comm, (void*)s));
-            NC(ctx, ctx->nccl.GroupEnd());
-            q->timing.collectives++;
         }
         CU(ctx, cudaStreamSynchronize(s));
     }
@@ -887,7 +891,7 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
             q->timing.d2h_bytes += words64 * 8;
         }
     }
-    if (out_idx && (ctx->rank == 0 || !gather)) {
+    if (out_idx) {
         if (idx_cap < count) rc = fail(ctx, COLQ_ERR_CAPACITY, "index capacity %lld < %lld matches", (long long)idx_cap, (long long)count);
         else if (count > 0) {
             CU(ctx, cudaMemcpyAsync(out_idx, src_idx, (size_t)count * 4, cudaMemcpyDeviceToHost, s));
@@ -1045,7 +1049,7 @@ colq_status colq_comm_unique_id(colq_ctx* ctx, uint8_t out_id[128]) {
 
 colq_status colq_comm_init(colq_ctx* ctx, const uint8_t id_bytes[128], int n_ranks, int rank) {
     if (!ctx || !id_bytes) return COLQ_THROW_NULL;
-    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "bad rank %d of %d", rank, n_ranks);
+    if (n_ranks < 1 || n_ranks > MAX_RANKS || rank < 0 || rank >= n_ranks) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "bad rank %d of %d", rank, n_ranks);
     if (ctx->comm) return fail(ctx, COLQ_THROW_ILLEGAL_STATE, "communicator already initialised");
     std::string err;
     if (!ctx->nccl.load(err)) return fail(ctx, COLQ_ERR_DEVICE, "%s", err.c_str());
@@ -1210,6 +1214,23 @@ colq_status colq_associate_csr(colq_ctx* ctx, colq_table x, int x_ordinal, colq_
     return st;
 }
 
+colq_status colq_table_destroy(colq_ctx* ctx, colq_table table) {
+    if (!ctx) return COLQ_THROW_NULL;
+    Table* t = get_table(ctx, table);
+    if (!t) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "unknown table handle %d", table);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto it = ctx->registry.begin(); it != ctx->registry.end();)
+        it = (it->second == table) ? ctx->registry.erase(it) : std::next(it);
+    // association columns of OTHER tables that point here become unset (their peer is gone)
+    for (Table& o : ctx->tables)
+        for (Column& c : o.cols)
+            if (c.kind == COL_ASSOC && c.peer_table == table && &o != t) c = Column();
+    t->cols.clear();
+    t->n_rows = 0;
+    return COLQ_OK;
+}
+
 colq_status colq_table_size(const colq_ctx* ctx, colq_table table, int64_t* out_rows) {
     if (!ctx || !out_rows) return COLQ_THROW_NULL;
     if (table < 0 || (size_t)table >= ctx->tables.size()) return COLQ_THROW_ILLEGAL_ARG;
@@ -1311,7 +1332,8 @@ colq_status colq_execute(colq_ctx* ctx, colq_query* q, uint64_t* out_bitmask, in
                          int64_t indices_capacity, int64_t* out_count, colq_timing* out_timing) {
     if (!ctx || !q) return COLQ_THROW_NULL;
     if (q->ctx != ctx) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "query belongs to another context");
-    if (indices_capacity > q->want_idx_capacity && out_indices) q->want_idx_capacity = std::min<int64_t>(indices_capacity, (int64_t)1 << 28);
+    if (indices_capacity > q->want_idx_capacity && out_indices && !(ctx->n_ranks > 1))
+        q->want_idx_capacity = std::min<int64_t>(indices_capacity, (int64_t)1 << 28);
     ST(run_pipeline(q));
     return fetch_results(q, out_bitmask, bitmask_capacity_words, out_indices, indices_capacity, out_count, out_timing);
 }

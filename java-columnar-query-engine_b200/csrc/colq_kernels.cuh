@@ -778,6 +778,46 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(const u32* bits, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// final gather (multi-GPU): every rank contributes one fixed-size block [u64 count | pad | cap indices]; after the
+// all-gather this kernel concatenates the valid prefixes in rank order (= ascending global row order, because
+// ranks own ascending universe ranges).  info[0] = rows written, info[1] = largest per-rank count (overflow check),
+// info[2] = true total.
+// ---------------------------------------------------------------------------------------------
+constexpr int GATHER_HEADER_WORDS = 4;
+constexpr int MAX_RANKS = 64;
+
+__global__ void __launch_bounds__(256) unpack_gather_kernel(const int32_t* blocks, int n_ranks, int64_t cap, int32_t* out,
+                                                          u64* info) {
+    __shared__ int64_t s_off[MAX_RANKS + 1];
+    const int64_t stride_words = cap + GATHER_HEADER_WORDS;
+    if (threadIdx.x == 0) {
+        int64_t off = 0;
+        u64 maxc = 0, total = 0;
+        for (int r = 0; r < n_ranks; ++r) {
+            u64 c = *reinterpret_cast<const u64*>(blocks + r * stride_words);
+            s_off[r] = off;
+            off += (int64_t)(c < (u64)cap ? c : (u64)cap);
+            maxc = c > maxc ? c : maxc;
+            total += c;
+        }
+        s_off[n_ranks] = off;
+        if (blockIdx.x == 0) {
+            info[0] = (u64)off;
+            info[1] = maxc;
+            info[2] = total;
+        }
+    }
+    __syncthreads();
+    const int64_t n = s_off[n_ranks];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int r = 0;
+        while (r + 1 < n_ranks && i >= s_off[r + 1]) ++r;
+        out[i] = blocks[r * stride_words + GATHER_HEADER_WORDS + (i - s_off[r])];
+    }
+}
+
 // popcount of a whole bitmask into one u64 (node cardinalities; not on the timed path)
 __global__ void __launch_bounds__(256) popc_total_kernel(const u32* bits, int64_t n_words, u64* out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;

@@ -10,6 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import subprocess
 import sys
+import time
 from pathlib import Path
 from typing import Dict, List, Optional
 
@@ -87,6 +88,7 @@ class OracleDataSystem:
         self._registered: Dict[str, int] = {}
         self.last_indices: Optional[np.ndarray] = None
         self.last_words: Optional[np.ndarray] = None
+        self.last_execute_seconds = 0.0   # wall time of the last orc_execute call alone (tables already resident)
 
     def register(self, table_name: str, table: Table, **_placement) -> None:
         self._tables[table_name] = table
@@ -189,7 +191,9 @@ class OracleDataSystem:
         words, idx = C.c_void_p(), C.c_void_p()
         nwords, count = C.c_int64(), C.c_int64()
         try:
+            t0 = time.perf_counter()
             rc = self.lib.orc_execute(self.sys, q, self.n_threads, C.byref(words), C.byref(nwords), C.byref(idx), C.byref(count))
+            self.last_execute_seconds = time.perf_counter() - t0
             msg = self.lib.orc_last_message(self.sys).decode()
             if rc == FAILURE:
                 return QueryResult.Failure(msg)
