@@ -163,7 +163,7 @@ struct colq_ctx {
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
     bool str_attr_set = false;
-    std::map<size_t, int> str_occupancy;  // dynamic smem bytes -> resident CTAs per SM
+    std::map<std::pair<int, size_t>, int> str_occupancy;  // (kernel mode, dynamic smem bytes) -> resident CTAs per SM
 };
 
 struct colq_query {
@@ -501,7 +501,7 @@ struct Planner {
             u32* ob;
             ST(out_buf(&ob));
             P.out_bits = ob;
-            o.smem = (size_t)ST_STAGES * (ST_OFF_BYTES + P.cap + 16) + st_needle_region(P.needle_len) + ST_STAGES * 8 +
+            o.smem = (size_t)ST_STAGES * st_stage_bytes(P.cap) + st_needle_region(P.needle_len) + 2 * ST_STAGES * 8 +
                      ST_STAGES * sizeof(StrTileMeta) + PUSH_SMEM_WORDS * 4;
             o.acct_rows = n;
             o.acct_bytes = (n + 1) * 4 + col.n_bytes + bitmap_words(n) * 4;
@@ -664,21 +664,39 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
             break;
         case K_SCAN_STR: {
             if (o.str.n_tiles == 0) break;
+            // fixed family: EQ / NE / STARTS_WITH / ENDS_WITH with a needle of 1..16 bytes; generic family otherwise
+            const int nl = o.str.needle_len, op = o.str.op;
+            const bool fixed = (op == OP_EQ || op == OP_NE || op == OP_STARTS_WITH || op == OP_ENDS_WITH) && nl >= 1 && nl <= 16;
+            const int mode = fixed ? -((nl + 3) / 4) : op;
+            void (*kern)(const ScanStrParams) = nullptr;
+            switch (mode) {
+                case -1: kern = scan_str_kernel<-1>; break;
+                case -2: kern = scan_str_kernel<-2>; break;
+                case -3: kern = scan_str_kernel<-3>; break;
+                case -4: kern = scan_str_kernel<-4>; break;
+                case OP_EQ: kern = scan_str_kernel<OP_EQ>; break;
+                case OP_CONTAINS: kern = scan_str_kernel<OP_CONTAINS>; break;
+                case OP_CMP_GT: kern = scan_str_kernel<OP_CMP_GT>; break;
+                case OP_CMP_LT: kern = scan_str_kernel<OP_CMP_LT>; break;
+                case OP_CMP_GE: kern = scan_str_kernel<OP_CMP_GE>; break;
+                case OP_CMP_LE: kern = scan_str_kernel<OP_CMP_LE>; break;
+                case OP_NE: kern = scan_str_kernel<OP_NE>; break;
+                case OP_STARTS_WITH: kern = scan_str_kernel<OP_STARTS_WITH>; break;
+                default: kern = scan_str_kernel<OP_ENDS_WITH>; break;
+            }
             if (o.grid == 0) {
-                if (!ctx->str_attr_set) {
-                    CU(ctx, cudaFuncSetAttribute(scan_str_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    ctx->str_attr_set = true;
-                }
-                auto it = ctx->str_occupancy.find(o.smem);
+                const std::pair<int, size_t> key(mode, o.smem);
+                auto it = ctx->str_occupancy.find(key);
                 if (it == ctx->str_occupancy.end()) {
+                    CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
                     int occ = 0;
-                    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_str_kernel, ST_THREADS, o.smem));
+                    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, ST_THREADS, o.smem));
                     if (occ < 1) return fail(ctx, COLQ_ERR_DEVICE, "scan_str_kernel does not fit on an SM (smem %zu)", o.smem);
-                    it = ctx->str_occupancy.emplace(o.smem, occ).first;
+                    it = ctx->str_occupancy.emplace(key, occ).first;
                 }
                 o.grid = (int)std::min<int64_t>(o.str.n_tiles, (int64_t)ctx->sm_count * it->second);
             }
-            scan_str_kernel<<<o.grid, ST_THREADS, o.smem, s>>>(o.str);
+            kern<<<o.grid, ST_THREADS, o.smem, s>>>(o.str);
             q->timing.kernel_launches++;
             break;
         }
@@ -1122,7 +1140,7 @@ colq_status colq_col_str(colq_ctx* ctx, colq_table table, int ordinal, const uin
     Column* c;
     ST(slot_for(ctx, table, ordinal, n, &c));
     ST(upload(ctx, c->offsets, offsets, (size_t)(n + 1) * 4, (size_t)round_up((n + 1) * 4, 16) + 16));
-    size_t cap = (size_t)round_up(n_bytes, 16) + 16;
+    size_t cap = (size_t)round_up(n_bytes, 16) + ST_SLACK;
     ST(upload(ctx, c->data, bytes, (size_t)n_bytes, cap));
     c->bytes_capacity = (int64_t)cap;
     return finish_str(ctx, c, n, n_bytes);
@@ -1136,7 +1154,7 @@ colq_status colq_col_str_device(colq_ctx* ctx, colq_table table, int ordinal, co
     CU(ctx, cudaSetDevice(ctx->device));
     Column* c;
     ST(slot_for(ctx, table, ordinal, n, &c));
-    const int64_t need_off = round_up((n + 1) * 4, 16), need_bytes = round_up(n_bytes, 16) + 16;
+    const int64_t need_off = round_up((n + 1) * 4, 16), need_bytes = round_up(n_bytes, 16) + ST_SLACK;
     if (offsets_capacity >= need_off) {
         c->offsets.ptr = const_cast<void*>(offsets_device); c->offsets.bytes = (size_t)offsets_capacity; c->offsets.owned = false;
     } else {  // too tight for whole-line TMA reads: keep a padded private copy

@@ -53,6 +53,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(u64* bar, u32 bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
     asm volatile(
         "{\n\t"
@@ -329,25 +332,37 @@ __global__ void __launch_bounds__(SR_THREADS) scan_rows_kernel(const ScanRowsPar
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2  scan_str: string predicate over an (offsets, bytes) column -> bitmask, TMA-staged
+// K2  scan_str: string predicate over an (offsets, bytes) column -> bitmask, TMA-staged, warp-specialised
 //
 // Replaces ExecutionContext.Node.filterSelf (E/ExecutionContext.java:79-94) over StringColumn.where
 // (M/InMemoryColumn.java:71-74) with "X"::equals / s.contains("X") / s.compareTo("X") predicates
 // (app/.../Runner.java:236,255-259; QueryTest.java:124-125).
 //
-// Persistent CTAs (grid = SMs x CTAs/SM) walk row tiles round-robin.  For each tile one elected thread issues
-// two TMA bulk copies (the tile's offsets slice and its contiguous byte range, both widened to 16-byte lines)
-// into a STAGES-deep shared-memory ring guarded by mbarriers, so HBM reads are long, perfectly coalesced
-// bursts regardless of row lengths; all threads then test one row each out of shared memory and a warp ballot
-// emits the bitmask word.  A tile whose bytes do not fit the ring slot is read straight from global memory.
+// Persistent CTAs (grid = SMs x CTAs/SM) walk 1024-row tiles round-robin.  One PRODUCER warp (one elected lane)
+// issues, per tile, two TMA bulk copies -- the tile's offsets slice and its contiguous byte range, both widened to
+// 16-byte lines -- into a STAGES-deep shared-memory ring; "full" mbarriers carry the transaction bytes, "empty"
+// mbarriers hand slots back.  Eight CONSUMER warps never touch global memory for input: each thread takes 4
+// consecutive rows (one 128-bit + one 32-bit shared load for its 5 offsets), tests them out of shared memory, and the
+// warp merges the 4-bit results into bitmask words with a shuffle butterfly.  HBM therefore only sees long, perfectly
+// coalesced bursts whatever the row lengths are.  A tile whose bytes do not fit a ring slot is read from global
+// memory instead (correct, slower).
+//
+// Two instantiation families keep the per-row instruction count low:
+//   scan_str_fixed<NW>   EQ / NE / STARTS_WITH / ENDS_WITH with a needle of at most 4*NW <= 16 bytes: branch-free,
+//                        every row does NW+1 shared loads, NW funnel shifts and NW xors, no divergence
+//   scan_str_generic<OP> everything else (contains, compareTo, long needles): per-row loops
 // ---------------------------------------------------------------------------------------------
 
-constexpr int ST_THREADS = 256;
-constexpr int ST_ROWS = 1024;  // rows per tile (multiple of 32 and 4)
+constexpr int ST_CONSUMER_WARPS = 8;
+constexpr int ST_CONSUMER_THREADS = ST_CONSUMER_WARPS * 32;  // 256
+constexpr int ST_THREADS = ST_CONSUMER_THREADS + 32;         // + 1 producer warp
+constexpr int ST_ROWS = 4 * ST_CONSUMER_THREADS;             // 1024 rows per tile
 constexpr int ST_STAGES = 4;
 constexpr int ST_OFF_BYTES = (ST_ROWS + 4) * 4;  // offsets slice incl. the closing offset, padded to 16 B
-constexpr int ST_MAX_NEEDLE = 16384;  // needle bytes are staged in shared memory next to the ring
+constexpr int ST_SLACK = 32;                     // readable bytes behind the staged byte range
+constexpr int ST_MAX_NEEDLE = 16384;             // needle bytes are staged in shared memory next to the ring
 __host__ __device__ inline int st_needle_region(int needle_len) { return (needle_len + 16 + 15) & ~15; }
+__host__ __device__ inline int st_stage_bytes(int cap) { return ST_OFF_BYTES + cap + ST_SLACK; }
 
 enum StrOp : int {
     OP_EQ = 0, OP_CONTAINS = 1, OP_CMP_GT = 2, OP_CMP_LT = 3, OP_CMP_GE = 4, OP_CMP_LE = 5, OP_NE = 6,
@@ -356,9 +371,9 @@ enum StrOp : int {
 
 struct ScanStrParams {
     int64_t n;
-    const u32* offsets;   // n + 1 entries, allocation padded to a 16-byte multiple past entry n
+    const u32* offsets;      // n + 1 entries, allocation padded to a 16-byte multiple past entry n
     const uint8_t* bytes;
-    int64_t bytes_capacity;  // allocation size (multiple of 16)
+    int64_t bytes_capacity;  // usable allocation size (multiple of 16, >= n_bytes + ST_SLACK)
     const uint8_t* needle;   // device copy of the needle
     int needle_len;
     int op;
@@ -369,27 +384,49 @@ struct ScanStrParams {
     PushD push;
 };
 
-// 4 bytes starting at byte position pos of a little-endian word array (pos need not be aligned)
-__device__ __forceinline__ u32 extract32(const u32* words, u32 pos) {
-    u32 i = pos >> 2;
-    u32 lo = words[i], hi = words[i + 1];
-    return __funnelshift_r(lo, hi, (pos & 3) * 8);
-}
+struct StrTileMeta {
+    u32 a0;    // 16-byte-aligned global byte offset the staged slice starts at (offsets are uint32)
+    u32 fast;  // 1: bytes were staged in shared memory, 0: read them from global memory
+};
+
+// ---- word loaders: the same row tests run over the staged slice (ld.shared) or the column itself (ld.global)
+struct SmemWords {
+    u32 base;  // shared-state-space address of word 0
+    __device__ __forceinline__ u32 operator()(u32 word_index) const {
+        u32 v;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(base + word_index * 4));
+        return v;
+    }
+};
+struct GlobalWords {
+    const u32* base;
+    __device__ __forceinline__ u32 operator()(u32 word_index) const { return __ldg(base + word_index); }
+};
+
 __device__ __forceinline__ u32 low_mask(int nbytes) { return nbytes >= 4 ? 0xffffffffu : ((1u << (nbytes * 8)) - 1u); }
 
-// bytes [pos, pos+len) of `hay` equal needle[0, len)
-__device__ __forceinline__ bool bytes_equal(const u32* hay, u32 pos, const u32* needle_w, int len) {
+// 4 bytes starting at byte position pos (any alignment) of a little-endian word array
+template <class W>
+__device__ __forceinline__ u32 extract32(const W& words, u32 pos) {
+    u32 i = pos >> 2;
+    return __funnelshift_r(words(i), words(i + 1), (pos & 3) * 8);
+}
+
+// bytes [pos, pos+len) equal needle[0, len)
+template <class W>
+__device__ __forceinline__ bool bytes_equal(const W& hay, u32 pos, const u32* needle_w, int len) {
     for (int c = 0; c < len; c += 4) {
         u32 h = extract32(hay, pos + c);
-        u32 m = low_mask(len - c);
-        if ((h ^ needle_w[c >> 2]) & m) return false;
+        if ((h ^ needle_w[c >> 2]) & low_mask(len - c)) return false;
     }
     return true;
 }
 
-// String.compareTo sign (UTF-16 code-unit order on UTF-8 bytes; see oracle/colq_oracle.c java_compare_to)
+// String.compareTo sign (UTF-16 code-unit order on UTF-8 bytes; a supplementary code point, lead byte >= 0xF0, sorts
+// below U+E000..U+FFFF, lead bytes 0xEE/0xEF; a differing continuation byte implies equal lead bytes)
 __device__ __forceinline__ int utf16_key(u32 b) { return b >= 0xF0u ? 0xED * 2 + 1 : (int)b * 2; }
-__device__ __forceinline__ int compare_to(const u32* hay, u32 pos, int len, const u32* needle_w, int nlen) {
+template <class W>
+__device__ __forceinline__ int compare_to(const W& hay, u32 pos, int len, const u32* needle_w, int nlen) {
     int m = len < nlen ? len : nlen;
     for (int c = 0; c < m; c += 4) {
         u32 h = extract32(hay, pos + c);
@@ -403,14 +440,15 @@ __device__ __forceinline__ int compare_to(const u32* hay, u32 pos, int len, cons
     return len < nlen ? -1 : (len > nlen ? 1 : 0);
 }
 
-__device__ __forceinline__ bool contains(const u32* hay, u32 pos, int len, const u32* needle_w, int nlen) {
+template <class W>
+__device__ __forceinline__ bool contains(const W& hay, u32 pos, int len, const u32* needle_w, int nlen) {
     if (nlen == 0) return true;
     if (len < nlen) return false;
     const u32 first_mask = low_mask(nlen);
     const u32 first = needle_w[0] & first_mask;
-    // rolling window over aligned words: one shared-memory load per 4 candidate positions
+    // rolling window over aligned words: one load per 4 candidate positions
     u32 wi = pos >> 2;
-    u32 cur = hay[wi], nxt = hay[wi + 1];
+    u32 cur = hay(wi), nxt = hay(wi + 1);
     int sh = (int)(pos & 3);
     const int last = len - nlen;  // last candidate start
     for (int p = 0; p <= last; ++p) {
@@ -422,41 +460,73 @@ __device__ __forceinline__ bool contains(const u32* hay, u32 pos, int len, const
             sh = 0;
             ++wi;
             cur = nxt;
-            nxt = hay[wi + 1];
+            nxt = hay(wi + 1);
         }
     }
     return false;
 }
 
-__device__ __forceinline__ bool str_test(int op, const u32* hay, u32 pos, int len, const u32* needle_w, int nlen) {
-    switch (op) {
-        case OP_EQ: return len == nlen && bytes_equal(hay, pos, needle_w, nlen);
-        case OP_NE: return !(len == nlen && bytes_equal(hay, pos, needle_w, nlen));
-        case OP_CONTAINS: return contains(hay, pos, len, needle_w, nlen);
-        case OP_CMP_GT: return compare_to(hay, pos, len, needle_w, nlen) > 0;
-        case OP_CMP_LT: return compare_to(hay, pos, len, needle_w, nlen) < 0;
-        case OP_CMP_GE: return compare_to(hay, pos, len, needle_w, nlen) >= 0;
-        case OP_CMP_LE: return compare_to(hay, pos, len, needle_w, nlen) <= 0;
-        case OP_STARTS_WITH: return len >= nlen && bytes_equal(hay, pos, needle_w, nlen);
-        case OP_ENDS_WITH: return len >= nlen && bytes_equal(hay, pos + (u32)(len - nlen), needle_w, nlen);
-    }
+template <int OP, class W>
+__device__ __forceinline__ bool str_test(const W& hay, u32 pos, int len, const u32* needle_w, int nlen) {
+    if (OP == OP_EQ) return len == nlen && bytes_equal(hay, pos, needle_w, nlen);
+    if (OP == OP_NE) return !(len == nlen && bytes_equal(hay, pos, needle_w, nlen));
+    if (OP == OP_CONTAINS) return contains(hay, pos, len, needle_w, nlen);
+    if (OP == OP_CMP_GT) return compare_to(hay, pos, len, needle_w, nlen) > 0;
+    if (OP == OP_CMP_LT) return compare_to(hay, pos, len, needle_w, nlen) < 0;
+    if (OP == OP_CMP_GE) return compare_to(hay, pos, len, needle_w, nlen) >= 0;
+    if (OP == OP_CMP_LE) return compare_to(hay, pos, len, needle_w, nlen) <= 0;
+    if (OP == OP_STARTS_WITH) return len >= nlen && bytes_equal(hay, pos, needle_w, nlen);
+    if (OP == OP_ENDS_WITH) return len >= nlen && bytes_equal(hay, pos + (u32)(len - nlen), needle_w, nlen);
     return false;
 }
 
-struct StrTileMeta {
-    u32 a0_lo, a0_hi;  // 16-byte-aligned global byte offset the staged slice starts at
-    u32 fast;          // 1: bytes were staged in shared memory, 0: read them from global memory
-    u32 pad;
-};
+// out-of-line copy of every operator for tiles that were not staged (one instance per kernel keeps the code small)
+__device__ __noinline__ bool slow_row_test(int op, GlobalWords hay, u32 pos, int len, const u32* needle_w, int nlen) {
+    switch (op) {
+        case OP_EQ: return str_test<OP_EQ>(hay, pos, len, needle_w, nlen);
+        case OP_CONTAINS: return str_test<OP_CONTAINS>(hay, pos, len, needle_w, nlen);
+        case OP_CMP_GT: return str_test<OP_CMP_GT>(hay, pos, len, needle_w, nlen);
+        case OP_CMP_LT: return str_test<OP_CMP_LT>(hay, pos, len, needle_w, nlen);
+        case OP_CMP_GE: return str_test<OP_CMP_GE>(hay, pos, len, needle_w, nlen);
+        case OP_CMP_LE: return str_test<OP_CMP_LE>(hay, pos, len, needle_w, nlen);
+        case OP_NE: return str_test<OP_NE>(hay, pos, len, needle_w, nlen);
+        case OP_STARTS_WITH: return str_test<OP_STARTS_WITH>(hay, pos, len, needle_w, nlen);
+        default: return str_test<OP_ENDS_WITH>(hay, pos, len, needle_w, nlen);
+    }
+}
 
+// branch-free test of one row against a needle of at most 4*NW bytes (EQ / NE / STARTS_WITH / ENDS_WITH)
+template <int NW, class W>
+__device__ __forceinline__ bool fixed_test(const W& hay, u32 pos, int len, const u32 (&needle)[NW], u32 last_mask, int nlen,
+                                          int op) {
+    const bool len_ok = (op == OP_EQ || op == OP_NE) ? (len == nlen) : (len >= nlen);
+    u32 p = pos;
+    if (op == OP_ENDS_WITH) p += (u32)(len >= nlen ? len - nlen : 0);
+    const u32 wi = p >> 2, sh = (p & 3) * 8;
+    u32 w[NW + 1];
+#pragma unroll
+    for (int i = 0; i <= NW; ++i) w[i] = hay(wi + i);
+    u32 diff = 0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        u32 h = __funnelshift_r(w[i], w[i + 1], sh);
+        diff |= (h ^ needle[i]) & (i == NW - 1 ? last_mask : 0xffffffffu);
+    }
+    const bool m = len_ok && diff == 0;
+    return op == OP_NE ? !m : m;
+}
+
+// MODE >= 0: generic path for operator MODE.  MODE < 0: fixed path with NW = -MODE needle words.
+template <int MODE>
 __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
-    // layout: [stage0 offsets | stage0 bytes(cap+16)] ... | needle words | mbarriers | metas | reach
-    const int stage_bytes = ST_OFF_BYTES + P.cap + 16;
-    u32* s_needle = reinterpret_cast<u32*>(smem + (size_t)ST_STAGES * stage_bytes);
+    // layout: [stage: offsets | bytes(cap + slack)] x STAGES | needle words | full[] | empty[] | metas | reach
+    const int stage_bytes = st_stage_bytes(P.cap);
     const int needle_region = st_needle_region(P.needle_len);
+    u32* s_needle = reinterpret_cast<u32*>(smem + (size_t)ST_STAGES * stage_bytes);
     u64* s_full = reinterpret_cast<u64*>(reinterpret_cast<uint8_t*>(s_needle) + needle_region);
-    StrTileMeta* s_meta = reinterpret_cast<StrTileMeta*>(s_full + ST_STAGES);
+    u64* s_empty = s_full + ST_STAGES;
+    StrTileMeta* s_meta = reinterpret_cast<StrTileMeta*>(s_empty + ST_STAGES);
     u32* s_reach = reinterpret_cast<u32*>(s_meta + ST_STAGES);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -472,7 +542,10 @@ __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParam
     }
     if (do_push) push_init(P.push, s_reach);
     if (tid == 0) {
-        for (int s = 0; s < ST_STAGES; ++s) mbar_init(&s_full[s], 1);
+        for (int s = 0; s < ST_STAGES; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], ST_CONSUMER_WARPS);
+        }
         mbar_fence_init();
     }
     __syncthreads();
@@ -481,80 +554,119 @@ __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParam
     const int64_t tile_stride = gridDim.x;
     const int64_t my_tiles = first_tile < P.n_tiles ? (P.n_tiles - first_tile + tile_stride - 1) / tile_stride : 0;
 
-    // producer (thread 0): issue the TMA copies of local tile k into ring slot k % STAGES
-    auto issue = [&](int64_t k, u32 gb0, u32 gb1) {
-        const int s = (int)(k % ST_STAGES);
-        const int64_t r0 = (first_tile + k * tile_stride) * ST_ROWS;
-        const int nr = (int)((P.n - r0) < ST_ROWS ? (P.n - r0) : ST_ROWS);
-        uint8_t* base = smem + (size_t)s * stage_bytes;
-        const u64 a0 = (u64)gb0 & ~(u64)15;
-        const u64 a1 = ((u64)gb1 + 15) & ~(u64)15;
-        const u64 sz = a1 - a0;
-        const u32 off_bytes = (u32)(((nr + 1) * 4 + 15) & ~15);
-        const bool fast = sz <= (u64)P.cap && (int64_t)a1 <= P.bytes_capacity;
-        s_meta[s].a0_lo = (u32)a0;
-        s_meta[s].a0_hi = (u32)(a0 >> 32);
-        s_meta[s].fast = fast ? 1u : 0u;
-        mbar_arrive_expect_tx(&s_full[s], off_bytes + (fast ? (u32)sz : 0u));
-        tma_bulk_g2s(base, P.offsets + r0, off_bytes, &s_full[s]);
-        if (fast && sz > 0) tma_bulk_g2s(base + ST_OFF_BYTES, P.bytes + a0, (u32)sz, &s_full[s]);
-    };
-    auto tile_bounds = [&](int64_t k, u32& gb0, u32& gb1) {
-        const int64_t r0 = (first_tile + k * tile_stride) * ST_ROWS;
-        const int64_t r1 = (r0 + ST_ROWS) < P.n ? (r0 + ST_ROWS) : P.n;
-        gb0 = __ldg(P.offsets + r0);
-        gb1 = __ldg(P.offsets + r1);
-    };
-
-    u32 nb0 = 0, nb1 = 0;  // prefetched byte bounds of the next tile to issue (thread 0 only)
-    if (tid == 0) {
-        for (int64_t k = 0; k < ST_STAGES - 1 && k < my_tiles; ++k) {
-            u32 a, b;
-            tile_bounds(k, a, b);
-            issue(k, a, b);
-        }
-        if (ST_STAGES - 1 < my_tiles) tile_bounds(ST_STAGES - 1, nb0, nb1);
-    }
-
-    for (int64_t k = 0; k < my_tiles; ++k) {
-        const int s = (int)(k % ST_STAGES);
-        if (tid == 0) {
-            const int64_t kn = k + ST_STAGES - 1;
-            if (kn < my_tiles) {
-                issue(kn, nb0, nb1);  // slot (k-1) % STAGES was released by the __syncthreads closing iteration k-1
-                if (kn + 1 < my_tiles) tile_bounds(kn + 1, nb0, nb1);
+    if (warp == ST_CONSUMER_WARPS) {
+        // =========================== producer warp: one lane drives the TMA ring ===========================
+        if (lane == 0) {
+            u32 nb0 = 0, nb1 = 0;
+            auto tile_bounds = [&](int64_t k, u32& gb0, u32& gb1) {
+                const int64_t r0 = (first_tile + k * tile_stride) * ST_ROWS;
+                const int64_t r1 = (r0 + ST_ROWS) < P.n ? (r0 + ST_ROWS) : P.n;
+                gb0 = __ldg(P.offsets + r0);
+                gb1 = __ldg(P.offsets + r1);
+            };
+            if (my_tiles > 0) tile_bounds(0, nb0, nb1);
+            for (int64_t k = 0; k < my_tiles; ++k) {
+                const int s = (int)(k % ST_STAGES);
+                const u32 gb0 = nb0, gb1 = nb1;
+                if (k + 1 < my_tiles) tile_bounds(k + 1, nb0, nb1);  // in flight while we wait for the slot
+                if (k >= ST_STAGES) mbar_wait(&s_empty[s], (u32)(((k / ST_STAGES) - 1) & 1));
+                const int64_t r0 = (first_tile + k * tile_stride) * ST_ROWS;
+                const int nr = (int)((P.n - r0) < ST_ROWS ? (P.n - r0) : ST_ROWS);
+                uint8_t* base = smem + (size_t)s * stage_bytes;
+                const u64 a0 = (u64)gb0 & ~(u64)15;
+                const u64 a1 = ((u64)gb1 + 15) & ~(u64)15;
+                const u64 sz = a1 - a0;
+                const u32 off_bytes = (u32)(((nr + 1) * 4 + 15) & ~15);
+                const bool fast = sz <= (u64)P.cap && (int64_t)a1 <= P.bytes_capacity;
+                s_meta[s].a0 = (u32)a0;
+                s_meta[s].fast = fast ? 1u : 0u;
+                mbar_arrive_expect_tx(&s_full[s], off_bytes + (fast ? (u32)sz : 0u));
+                tma_bulk_g2s(base, P.offsets + r0, off_bytes, &s_full[s]);
+                if (fast && sz > 0) tma_bulk_g2s(base + ST_OFF_BYTES, P.bytes + a0, (u32)sz, &s_full[s]);
             }
         }
-        mbar_wait(&s_full[s], (u32)((k / ST_STAGES) & 1));
-
-        const uint8_t* base = smem + (size_t)s * stage_bytes;
-        const u32* so = reinterpret_cast<const u32*>(base);
-        const int64_t r0 = (first_tile + k * tile_stride) * ST_ROWS;
-        const int nr = (int)((P.n - r0) < ST_ROWS ? (P.n - r0) : ST_ROWS);
-        const bool fast = s_meta[s].fast != 0;
-        const u64 a0 = ((u64)s_meta[s].a0_hi << 32) | s_meta[s].a0_lo;
-        const u32* hay = fast ? reinterpret_cast<const u32*>(base + ST_OFF_BYTES) : reinterpret_cast<const u32*>(P.bytes);
-
+    } else {
+        // =========================== consumer warps ===========================
+        // needle words of the fixed path live in registers
+        constexpr int NW = MODE < 0 ? -MODE : 1;
+        u32 needle_r[NW];
 #pragma unroll
-        for (int p = 0; p < ST_ROWS / ST_THREADS; ++p) {
-            const int row = p * ST_THREADS + tid;
-            bool match = false;
-            if (row < nr) {
-                const u32 b0 = so[row], b1 = so[row + 1];
-                const int len = (int)(b1 - b0);
-                // staged: position relative to the slot; not staged: absolute position in the column (< 4 GiB)
-                const u32 pos = fast ? (u32)((u64)b0 - a0) : b0;
-                match = str_test(P.op, hay, pos, len, s_needle, P.needle_len);
+        for (int i = 0; i < NW; ++i) needle_r[i] = s_needle[i];
+        const int nlen = P.needle_len;
+        const u32 last_mask = low_mask(nlen - 4 * (NW - 1));
+        const int op = P.op;
+
+        for (int64_t k = 0; k < my_tiles; ++k) {
+            const int s = (int)(k % ST_STAGES);
+            mbar_wait(&s_full[s], (u32)((k / ST_STAGES) & 1));
+
+            const uint8_t* base = smem + (size_t)s * stage_bytes;
+            const u32 so = smem_u32(base);
+            const int64_t r0 = (first_tile + k * tile_stride) * ST_ROWS;
+            const int nr = (int)((P.n - r0) < ST_ROWS ? (P.n - r0) : ST_ROWS);
+            const bool fast = s_meta[s].fast != 0;
+            const u32 a0 = s_meta[s].a0;
+
+            // this thread's 4 consecutive rows: offsets o[0..4]
+            u32 o[5];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3])
+                         : "r"(so + tid * 16));
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(o[4]) : "r"(so + tid * 16 + 16));
+
+            u32 nib = 0;
+            if (fast) {
+                const SmemWords hay{so + ST_OFF_BYTES};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool valid = tid * 4 + j < nr;
+                    const u32 pos = valid ? o[j] - a0 : 0u;
+                    const int len = valid ? (int)(o[j + 1] - o[j]) : -1;
+                    bool m;
+                    if (MODE < 0) m = fixed_test<NW>(hay, pos, len, needle_r, last_mask, nlen, op);
+                    else m = str_test<(MODE < 0 ? 0 : MODE)>(hay, pos, len, s_needle, nlen);
+                    nib |= (valid && m) ? (1u << j) : 0u;
+                }
+            } else {
+                const GlobalWords hay{reinterpret_cast<const u32*>(P.bytes)};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool valid = tid * 4 + j < nr;
+                    if (!valid) continue;
+                    const u32 pos = o[j];  // absolute byte position in the column (< 4 GiB)
+                    const int len = (int)(o[j + 1] - o[j]);
+                    const bool m = slow_row_test(op, hay, pos, len, s_needle, nlen);
+                    nib |= m ? (1u << j) : 0u;
+                }
             }
-            u32 word = __ballot_sync(FULL_MASK, match);
-            const int64_t wi = (r0 + p * ST_THREADS + warp * 32) >> 5;
-            if (P.in_bits != nullptr) word &= P.in_bits[wi];  // warp-uniform address: one broadcast load
+            // all shared-memory reads of this slot are done: hand it back to the producer
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[s]);
+
+            // this warp owns rows [r0 + 128 warp, +128) = 4 bitmask words
+            const int64_t w0 = (r0 >> 5) + warp * 4;
+            if (P.in_bits != nullptr) {
+                u32 w = P.in_bits[w0 + (lane >> 3)];
+                nib &= (w >> ((lane & 7) * 4)) & 0xFu;
+            }
             if (do_push) {
-                if ((word >> lane) & 1u) push_row(P.push, s_reach, r0 + row);
+                u32 m = nib;
+                while (m) {
+                    int e = __ffs(m) - 1;
+                    m &= m - 1;
+                    push_row(P.push, s_reach, r0 + tid * 4 + e);
+                }
             }
-            if (lane == 0 && P.out_bits != nullptr && (r0 + p * ST_THREADS + warp * 32) < ((P.n + 63) & ~(int64_t)63)) P.out_bits[wi] = word;
+            if (P.out_bits != nullptr) {
+                u32 x = nib << ((lane & 7) * 4);
+                x |= __shfl_xor_sync(FULL_MASK, x, 1);
+                x |= __shfl_xor_sync(FULL_MASK, x, 2);
+                x |= __shfl_xor_sync(FULL_MASK, x, 4);
+                u32 y = __shfl_sync(FULL_MASK, x, (lane & 3) * 8);  // lane l < 4 gets word l
+                // write every word that overlaps the table, rounded up to whole 64-row BitSet words
+                if (lane < 4 && ((w0 + lane) << 5) < ((P.n + 63) & ~(int64_t)63)) P.out_bits[w0 + lane] = y;
+            }
         }
-        __syncthreads();  // every thread is done with slot s before thread 0 refills it next iteration
     }
 
     if (do_push) {
