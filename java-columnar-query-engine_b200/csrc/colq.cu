@@ -667,13 +667,17 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
             // fixed family: EQ / NE / STARTS_WITH / ENDS_WITH with a needle of 1..16 bytes; generic family otherwise
             const int nl = o.str.needle_len, op = o.str.op;
             const bool fixed = (op == OP_EQ || op == OP_NE || op == OP_STARTS_WITH || op == OP_ENDS_WITH) && nl >= 1 && nl <= 16;
-            const int mode = fixed ? -((nl + 3) / 4) : op;
+            const int mode = fixed ? -((nl + 3) / 4) - (op == OP_EQ ? 0 : 4) : op;
             void (*kern)(const ScanStrParams) = nullptr;
             switch (mode) {
                 case -1: kern = scan_str_kernel<-1>; break;
                 case -2: kern = scan_str_kernel<-2>; break;
                 case -3: kern = scan_str_kernel<-3>; break;
                 case -4: kern = scan_str_kernel<-4>; break;
+                case -5: kern = scan_str_kernel<-5>; break;
+                case -6: kern = scan_str_kernel<-6>; break;
+                case -7: kern = scan_str_kernel<-7>; break;
+                case -8: kern = scan_str_kernel<-8>; break;
                 case OP_EQ: kern = scan_str_kernel<OP_EQ>; break;
                 case OP_CONTAINS: kern = scan_str_kernel<OP_CONTAINS>; break;
                 case OP_CMP_GT: kern = scan_str_kernel<OP_CMP_GT>; break;

@@ -495,13 +495,19 @@ __device__ __noinline__ bool slow_row_test(int op, GlobalWords hay, u32 pos, int
     }
 }
 
-// branch-free test of one row against a needle of at most 4*NW bytes (EQ / NE / STARTS_WITH / ENDS_WITH)
-template <int NW, class W>
+// branch-free test of one row against a needle of at most 4*NW bytes.  EQ_ONLY: "X"::equals; otherwise the operator
+// (EQ / NE / STARTS_WITH / ENDS_WITH) is a run-time, warp-uniform value.
+template <int NW, bool EQ_ONLY, class W>
 __device__ __forceinline__ bool fixed_test(const W& hay, u32 pos, int len, const u32 (&needle)[NW], u32 last_mask, int nlen,
                                           int op) {
-    const bool len_ok = (op == OP_EQ || op == OP_NE) ? (len == nlen) : (len >= nlen);
     u32 p = pos;
-    if (op == OP_ENDS_WITH) p += (u32)(len >= nlen ? len - nlen : 0);
+    bool len_ok;
+    if (EQ_ONLY) {
+        len_ok = len == nlen;
+    } else {
+        len_ok = (op == OP_EQ || op == OP_NE) ? (len == nlen) : (len >= nlen);
+        if (op == OP_ENDS_WITH) p += (u32)(len >= nlen ? len - nlen : 0);
+    }
     const u32 wi = p >> 2, sh = (p & 3) * 8;
     u32 w[NW + 1];
 #pragma unroll
@@ -513,10 +519,11 @@ __device__ __forceinline__ bool fixed_test(const W& hay, u32 pos, int len, const
         diff |= (h ^ needle[i]) & (i == NW - 1 ? last_mask : 0xffffffffu);
     }
     const bool m = len_ok && diff == 0;
-    return op == OP_NE ? !m : m;
+    return (!EQ_ONLY && op == OP_NE) ? !m : m;
 }
 
-// MODE >= 0: generic path for operator MODE.  MODE < 0: fixed path with NW = -MODE needle words.
+// MODE >= 0: generic path for operator MODE.  MODE in -1..-4: fixed path, EQ only, NW = -MODE needle words.
+// MODE in -5..-8: fixed path, run-time operator (EQ / NE / STARTS_WITH / ENDS_WITH), NW = -MODE - 4.
 template <int MODE>
 __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -588,22 +595,28 @@ __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParam
     } else {
         // =========================== consumer warps ===========================
         // needle words of the fixed path live in registers
-        constexpr int NW = MODE < 0 ? -MODE : 1;
+        constexpr int NW = MODE < -4 ? -MODE - 4 : (MODE < 0 ? -MODE : 1);
+        constexpr bool EQ_ONLY = MODE >= -4;
         u32 needle_r[NW];
 #pragma unroll
         for (int i = 0; i < NW; ++i) needle_r[i] = s_needle[i];
         const int nlen = P.needle_len;
         const u32 last_mask = low_mask(nlen - 4 * (NW - 1));
         const int op = P.op;
+        const u32* in_bits = P.in_bits;
+        u32* out_bits = P.out_bits;
+        const u32 n_words_out = (u32)(((P.n + 63) >> 6) << 1);  // whole 64-row BitSet words, as u32 halves
 
-        for (int64_t k = 0; k < my_tiles; ++k) {
-            const int s = (int)(k % ST_STAGES);
-            mbar_wait(&s_full[s], (u32)((k / ST_STAGES) & 1));
+        const u32 n_my = (u32)my_tiles;
+        u32 tile = (u32)first_tile;  // global tile index; tile * 1024 < 2^31 because n < 2^31
+        u32 s = 0, parity = 0;
+        for (u32 k = 0; k < n_my; ++k, tile += (u32)tile_stride) {
+            mbar_wait(&s_full[s], parity);
 
-            const uint8_t* base = smem + (size_t)s * stage_bytes;
-            const u32 so = smem_u32(base);
-            const int64_t r0 = (first_tile + k * tile_stride) * ST_ROWS;
-            const int nr = (int)((P.n - r0) < ST_ROWS ? (P.n - r0) : ST_ROWS);
+            const u32 so = smem_u32(smem) + s * (u32)stage_bytes;
+            const u32 r0 = tile * ST_ROWS;
+            const u32 rem = (u32)P.n - r0;
+            const int nr = rem < (u32)ST_ROWS ? (int)rem : ST_ROWS;
             const bool fast = s_meta[s].fast != 0;
             const u32 a0 = s_meta[s].a0;
 
@@ -615,7 +628,19 @@ __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParam
             asm volatile("ld.shared.b32 %0, [%1];" : "=r"(o[4]) : "r"(so + tid * 16 + 16));
 
             u32 nib = 0;
-            if (fast) {
+            if (fast && nr == ST_ROWS) {
+                // full staged tile: no per-row validity checks
+                const SmemWords hay{so + ST_OFF_BYTES};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const u32 pos = o[j] - a0;
+                    const int len = (int)(o[j + 1] - o[j]);
+                    bool m;
+                    if (MODE < 0) m = fixed_test<NW, EQ_ONLY>(hay, pos, len, needle_r, last_mask, nlen, op);
+                    else m = str_test<(MODE < 0 ? 0 : MODE)>(hay, pos, len, s_needle, nlen);
+                    nib |= m ? (1u << j) : 0u;
+                }
+            } else if (fast) {
                 const SmemWords hay{so + ST_OFF_BYTES};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -623,7 +648,7 @@ __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParam
                     const u32 pos = valid ? o[j] - a0 : 0u;
                     const int len = valid ? (int)(o[j + 1] - o[j]) : -1;
                     bool m;
-                    if (MODE < 0) m = fixed_test<NW>(hay, pos, len, needle_r, last_mask, nlen, op);
+                    if (MODE < 0) m = fixed_test<NW, EQ_ONLY>(hay, pos, len, needle_r, last_mask, nlen, op);
                     else m = str_test<(MODE < 0 ? 0 : MODE)>(hay, pos, len, s_needle, nlen);
                     nib |= (valid && m) ? (1u << j) : 0u;
                 }
@@ -644,9 +669,9 @@ __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParam
             if (lane == 0) mbar_arrive(&s_empty[s]);
 
             // this warp owns rows [r0 + 128 warp, +128) = 4 bitmask words
-            const int64_t w0 = (r0 >> 5) + warp * 4;
-            if (P.in_bits != nullptr) {
-                u32 w = P.in_bits[w0 + (lane >> 3)];
+            const u32 w0 = (r0 >> 5) + warp * 4;
+            if (in_bits != nullptr) {
+                u32 w = in_bits[w0 + (lane >> 3)];
                 nib &= (w >> ((lane & 7) * 4)) & 0xFu;
             }
             if (do_push) {
@@ -654,17 +679,21 @@ __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParam
                 while (m) {
                     int e = __ffs(m) - 1;
                     m &= m - 1;
-                    push_row(P.push, s_reach, r0 + tid * 4 + e);
+                    push_row(P.push, s_reach, (int64_t)r0 + tid * 4 + e);
                 }
             }
-            if (P.out_bits != nullptr) {
+            if (out_bits != nullptr) {
                 u32 x = nib << ((lane & 7) * 4);
                 x |= __shfl_xor_sync(FULL_MASK, x, 1);
                 x |= __shfl_xor_sync(FULL_MASK, x, 2);
                 x |= __shfl_xor_sync(FULL_MASK, x, 4);
                 u32 y = __shfl_sync(FULL_MASK, x, (lane & 3) * 8);  // lane l < 4 gets word l
                 // write every word that overlaps the table, rounded up to whole 64-row BitSet words
-                if (lane < 4 && ((w0 + lane) << 5) < ((P.n + 63) & ~(int64_t)63)) P.out_bits[w0 + lane] = y;
+                if (lane < 4 && (w0 + lane) < n_words_out) out_bits[w0 + lane] = y;
+            }
+            if (++s == ST_STAGES) {
+                s = 0;
+                parity ^= 1;
             }
         }
     }
