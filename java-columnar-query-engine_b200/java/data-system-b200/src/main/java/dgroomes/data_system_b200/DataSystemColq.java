@@ -1,0 +1,277 @@
+package dgroomes.data_system_b200;
+
+import dgroomes.data_system.Association;
+import dgroomes.data_system.AssociationColumn;
+import dgroomes.data_system.Column;
+import dgroomes.data_system.Criteria;
+import dgroomes.data_system.DataSystem;
+import dgroomes.data_system.Query;
+import dgroomes.data_system.QueryResult;
+import dgroomes.data_system.Table;
+import dgroomes.in_memory.InMemoryColumn;
+
+import java.lang.foreign.Arena;
+import java.lang.foreign.MemorySegment;
+import java.nio.ByteOrder;
+import java.nio.charset.StandardCharsets;
+import java.util.ArrayDeque;
+import java.util.BitSet;
+import java.util.HashMap;
+import java.util.IdentityHashMap;
+import java.util.List;
+import java.util.Map;
+import java.util.Objects;
+
+import static dgroomes.data_system_b200.ColqLibrary.*;
+import static java.lang.foreign.ValueLayout.ADDRESS;
+import static java.lang.foreign.ValueLayout.JAVA_BYTE;
+import static java.lang.foreign.ValueLayout.JAVA_INT;
+import static java.lang.foreign.ValueLayout.JAVA_LONG;
+
+/**
+ * The B200 execution module behind the reference's {@link DataSystem} interface: same two methods as
+ * {@code DataSystemSerialIndices} (data-system-serial-indices-arrays/.../DataSystemSerialIndices.java:27,53).
+ * <p>
+ * Host work is limited to (1) flattening the registered {@link Table} graph into off-heap {@link MemorySegment}
+ * column buffers and handing them to libcolq.so once, (2) translating the {@link Query} tree into
+ * {@code colq_query_*} downcalls, (3) turning the returned BitSet words into the result table with the registered
+ * table's own {@code subset}. Everything else happens on the GPU. There is no CPU fallback.
+ * <p>
+ * NOTE: written against JDK 22 and never compiled in the build image (no JVM there); the ctypes twin of this class,
+ * colq/engine.py, is the one exercised by the test suite through the very same C ABI.
+ */
+public final class DataSystemColq implements DataSystem, AutoCloseable {
+
+    private final Map<String, Table> tables = new HashMap<>();
+    private final IdentityHashMap<Table, Integer> handles = new IdentityHashMap<>();
+    private final IdentityHashMap<Table, Integer> uploadedColumns = new IdentityHashMap<>();
+    private final Map<String, Integer> registeredHandle = new HashMap<>();
+    private final Arena arena = Arena.ofShared();
+    private final MemorySegment ctx;
+
+    public DataSystemColq() {
+        this(0);
+    }
+
+    public DataSystemColq(int device) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment out = a.allocate(ADDRESS);
+            int st = (int) colq_create.invokeExact(device, out);
+            if (st != OK) throw new IllegalStateException("colq_create failed (" + st + "): no usable sm_100 GPU; libcolq has no CPU fallback");
+            ctx = out.get(ADDRESS, 0);
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new IllegalStateException(t);
+        }
+    }
+
+    /** DataSystemSerialIndices.register (:27-29): only records the reference; upload happens at the first execute. */
+    public synchronized void register(String tableName, Table table) {
+        tables.put(tableName, table);
+    }
+
+    @Override
+    public synchronized QueryResult execute(Query query) {
+        Objects.requireNonNull(query, "The 'query' argument must not be null");
+        if (!tables.containsKey(query.tableName)) {
+            return new QueryResult.Failure("The query targets the table '%s' but that table is not registered".formatted(query.tableName));
+        }
+        Table table = tables.get(query.tableName);
+        try (Arena call = Arena.ofConfined()) {
+            syncTables(call);
+            MemorySegment qOut = call.allocate(ADDRESS);
+            check((int) colq_query_create.invokeExact(ctx, call.allocateFrom(query.tableName), qOut));
+            MemorySegment q = qOut.get(ADDRESS, 0);
+            try {
+                String opaque = translate(call, q, query);
+                if (opaque != null) return new QueryResult.Failure(opaque);
+                long words = (table.size() + 63L) / 64L;
+                MemorySegment mask = call.allocate(JAVA_LONG, Math.max(words, 1));
+                MemorySegment count = call.allocate(JAVA_LONG);
+                int st = (int) colq_execute.invokeExact(ctx, q, mask, words, MemorySegment.NULL, 0L, count, MemorySegment.NULL);
+                if (st == FAILURE) return new QueryResult.Failure(lastError());
+                check(st);
+                // BitSet.valueOf(LongBuffer): libcolq writes java.util.BitSet words directly
+                BitSet matchingRows = BitSet.valueOf(mask.asSlice(0, words * 8).asByteBuffer().order(ByteOrder.LITTLE_ENDIAN).asLongBuffer());
+                return new QueryResult.Success(table.subset(matchingRows));   // DataSystemSerialIndices.java:100
+            } finally {
+                int ignored = (int) colq_query_destroy.invokeExact(q);
+            }
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new IllegalStateException(t);
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------ Query -> colq_query
+    private String translate(Arena call, MemorySegment q, Query query) throws Throwable {
+        record Pending(Query.Node node, int id) {}
+        var stack = new ArrayDeque<Pending>();
+        stack.push(new Pending(query.rootNode, 0));
+        while (!stack.isEmpty()) {
+            Pending p = stack.pop();
+            for (Criteria c : p.node().getCriteria()) {
+                switch (c) {
+                    case Criteria.IntCriteria(int ordinal, var pred) -> {
+                        if (!(pred instanceof Predicates.IntRange(int lo, int hi)))
+                            return "The criterion on ordinal %d is an opaque IntPredicate lambda; the GPU engine only runs structured predicates (dgroomes.data_system_b200.Predicates) and has no CPU fallback.".formatted(ordinal);
+                        check((int) colq_query_criteria_i32_range.invokeExact(q, p.id(), ordinal, lo, hi));
+                    }
+                    case Criteria.StringCriteria(int ordinal, var pred) -> {
+                        if (!(pred instanceof Predicates.StringOp op))
+                            return "The criterion on ordinal %d is an opaque Predicate<String> lambda; the GPU engine only runs structured predicates (dgroomes.data_system_b200.Predicates) and has no CPU fallback.".formatted(ordinal);
+                        byte[] needle = op.needle();
+                        MemorySegment n = call.allocate(Math.max(needle.length, 1));
+                        MemorySegment.copy(needle, 0, n, JAVA_BYTE, 0, needle.length);
+                        check((int) colq_query_criteria_str.invokeExact(q, p.id(), ordinal, op.op().ordinal(), n, needle.length));
+                    }
+                }
+            }
+            for (Map.Entry<Integer, Query.Node> e : p.node().getChildrenByOrdinal().entrySet()) {
+                MemorySegment out = call.allocate(JAVA_INT);
+                check((int) colq_query_child.invokeExact(q, p.id(), (int) e.getKey(), out));
+                stack.push(new Pending(e.getValue(), out.get(JAVA_INT, 0)));
+            }
+        }
+        return null;
+    }
+
+    // ------------------------------------------------------------------------------------------ Table graph -> HBM
+    private void syncTables(Arena call) throws Throwable {
+        // discover every table reachable through association columns (identity-keyed, cycle-safe): the app registers
+        // tables BEFORE associateTo appends their association columns (Runner.java:107 vs :138,165,195)
+        var seen = new IdentityHashMap<Table, Boolean>();
+        var todo = new ArrayDeque<>(tables.values());
+        while (!todo.isEmpty()) {
+            Table t = todo.pop();
+            if (seen.put(t, true) != null) continue;
+            for (Column c : t.columns()) if (c instanceof AssociationColumn ac) todo.push(ac.associatedEntity());
+        }
+        for (Table t : seen.keySet()) {
+            if (handles.containsKey(t)) continue;
+            MemorySegment out = call.allocate(JAVA_INT);
+            check((int) colq_table_create.invokeExact(ctx, (long) t.size(), REPLICATED, 0L, out));
+            handles.put(t, out.get(JAVA_INT, 0));
+            uploadedColumns.put(t, 0);
+        }
+        for (Table t : seen.keySet()) {   // scalar columns
+            int h = handles.get(t);
+            List<? extends Column> cols = t.columns();
+            for (int ordinal = uploadedColumns.get(t); ordinal < cols.size(); ordinal++) {
+                switch (cols.get(ordinal)) {
+                    case InMemoryColumn.IntegerColumn(int[] ints) -> {
+                        MemorySegment seg = call.allocate(JAVA_INT, Math.max(ints.length, 1));
+                        MemorySegment.copy(ints, 0, seg, JAVA_INT, 0, ints.length);
+                        check((int) colq_col_i32.invokeExact(ctx, h, ordinal, seg, (long) ints.length));
+                    }
+                    case InMemoryColumn.StringColumn(String[] strings) -> {
+                        // offsets + UTF-8 bytes: byte equality == String.equals, byte substring == String.contains
+                        byte[][] enc = new byte[strings.length][];
+                        long total = 0;
+                        for (int i = 0; i < strings.length; i++) { enc[i] = strings[i].getBytes(StandardCharsets.UTF_8); total += enc[i].length; }
+                        MemorySegment off = call.allocate(JAVA_INT, strings.length + 1L);
+                        MemorySegment bytes = call.allocate(Math.max(total, 1));
+                        long pos = 0;
+                        for (int i = 0; i < strings.length; i++) {
+                            off.setAtIndex(JAVA_INT, i, (int) pos);
+                            MemorySegment.copy(enc[i], 0, bytes, JAVA_BYTE, pos, enc[i].length);
+                            pos += enc[i].length;
+                        }
+                        off.setAtIndex(JAVA_INT, strings.length, (int) pos);
+                        check((int) colq_col_str.invokeExact(ctx, h, ordinal, off, bytes, (long) strings.length, total));
+                    }
+                    case InMemoryColumn.BooleanColumn(boolean[] bools) -> {
+                        MemorySegment seg = call.allocate(Math.max(bools.length, 1));
+                        for (int i = 0; i < bools.length; i++) seg.set(JAVA_BYTE, i, (byte) (bools[i] ? 1 : 0));
+                        check((int) colq_col_bool.invokeExact(ctx, h, ordinal, seg, (long) bools.length));
+                    }
+                    default -> { /* association columns below */ }
+                }
+            }
+        }
+        for (Table t : seen.keySet()) {   // association pairs, declared from their to-one (or smaller) side
+            int h = handles.get(t);
+            List<? extends Column> cols = t.columns();
+            for (int ordinal = uploadedColumns.get(t); ordinal < cols.size(); ordinal++) {
+                if (!(cols.get(ordinal) instanceof InMemoryColumn.AssociationColumn ac)) continue;
+                var rev = ac.reverseAssociatedColumn();
+                Table y = ac.associatedEntity();
+                int yOrdinal = identityIndexOf(y.columns(), rev);
+                // each pair is uploaded once: from the side that comes first in (table handle, ordinal) order
+                int hy = handles.get(y);
+                if (hy < h || (hy == h && yOrdinal < ordinal)) continue;
+                uploadAssociation(call, h, ordinal, hy, yOrdinal, ac.associations);
+            }
+        }
+        for (Table t : seen.keySet()) uploadedColumns.put(t, t.columns().size());
+        for (var e : tables.entrySet()) {
+            int h = handles.get(e.getValue());
+            if (!Integer.valueOf(h).equals(registeredHandle.get(e.getKey()))) {
+                check((int) colq_register.invokeExact(ctx, call.allocateFrom(e.getKey()), h));
+                registeredHandle.put(e.getKey(), h);
+            }
+        }
+    }
+
+    /** Association[] (None | One | Many, Association.java:27-51) -> dense fk (-1 = None) or CSR. */
+    private void uploadAssociation(Arena call, int x, int xOrdinal, int y, int yOrdinal, Association[] assoc) throws Throwable {
+        boolean toOne = true;
+        long nnz = 0;
+        for (Association a : assoc) {
+            if (a instanceof Association.Many(int[] idx)) { toOne = false; nnz += idx.length; }
+            else if (a instanceof Association.One) nnz++;
+        }
+        if (toOne) {
+            MemorySegment fk = call.allocate(JAVA_INT, Math.max(assoc.length, 1));
+            for (int i = 0; i < assoc.length; i++) fk.setAtIndex(JAVA_INT, i, assoc[i] instanceof Association.One(int idx) ? idx : -1);
+            check((int) colq_associate_fk.invokeExact(ctx, x, xOrdinal, y, yOrdinal, fk, (long) assoc.length));
+        } else {
+            MemorySegment off = call.allocate(JAVA_LONG, assoc.length + 1L);
+            MemorySegment tgt = call.allocate(JAVA_INT, Math.max(nnz, 1));
+            long pos = 0;
+            for (int i = 0; i < assoc.length; i++) {
+                off.setAtIndex(JAVA_LONG, i, pos);
+                switch (assoc[i]) {
+                    case Association.Many(int[] idx) -> { for (int v : idx) tgt.setAtIndex(JAVA_INT, pos++, v); }
+                    case Association.One(int idx) -> tgt.setAtIndex(JAVA_INT, pos++, idx);
+                    case Association.None ignored -> { }
+                }
+            }
+            off.setAtIndex(JAVA_LONG, assoc.length, pos);
+            check((int) colq_associate_csr.invokeExact(ctx, x, xOrdinal, y, yOrdinal, off, tgt, (long) assoc.length, nnz));
+        }
+    }
+
+    private static int identityIndexOf(List<? extends Column> cols, Object col) {
+        for (int i = 0; i < cols.size(); i++) if (cols.get(i) == col) return i;
+        throw new IllegalStateException("reverse association column is not a column of its table");
+    }
+
+    private String lastError() throws Throwable {
+        MemorySegment p = (MemorySegment) colq_last_error.invokeExact(ctx);
+        return p.reinterpret(1024).getString(0);
+    }
+
+    /** colq_status -> the exception class the reference would throw (include/colq.h). */
+    private void check(int status) throws Throwable {
+        switch (status) {
+            case OK -> { }
+            case THROW_INDEX_OOB -> throw new IndexOutOfBoundsException(lastError());
+            case THROW_NULL -> throw new NullPointerException(lastError());
+            case THROW_ILLEGAL_ARG -> throw new IllegalArgumentException(lastError());
+            default -> throw new IllegalStateException("libcolq status " + status + ": " + lastError());
+        }
+    }
+
+    @Override
+    public synchronized void close() {
+        try {
+            int ignored = (int) colq_destroy.invokeExact(ctx);
+        } catch (Throwable t) {
+            throw new IllegalStateException(t);
+        }
+        arena.close();
+    }
+}
