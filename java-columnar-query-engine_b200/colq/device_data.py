@@ -112,3 +112,80 @@ def north_south_north_colq_query(ctx: ColqContext):
     n = q.child(n, 3)
     q.criteria_str(n, 1, 1, b"North")
     return q
+
+
+# ------------------------------------------------------------------------------------------------ configs 2 and 5
+def _lsr(z: torch.Tensor, k: int) -> torch.Tensor:
+    """Logical shift right of int64 bit patterns (torch has no uint64 arithmetic)."""
+    return (z >> k) & ((1 << (64 - k)) - 1)
+
+
+def _wrap(v: int) -> int:
+    """Python int -> the int64 with the same low 64 bits."""
+    v &= (1 << 64) - 1
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def splitmix64_mod_device(seed: int, start: int, n: int, m: int, device) -> torch.Tensor:
+    """``splitmix64(seed, i) mod m`` for i in [start, start+n) -- bit-identical to ``geography.splitmix64`` (int64
+    multiplication wraps exactly like uint64)."""
+    i = torch.arange(start, start + n, device=device, dtype=torch.int64)
+    z = (i + 1) * _wrap(0x9E3779B97F4A7C15) + _wrap(seed)
+    z = (z ^ _lsr(z, 30)) * _wrap(0xBF58476D1CE4E5B9)
+    z = (z ^ _lsr(z, 27)) * _wrap(0x94D049BB133111EB)
+    z = z ^ _lsr(z, 31)
+    hi, lo = _lsr(z, 32), z & 0xFFFFFFFF
+    return ((hi % m) * ((1 << 32) % m) + lo % m) % m
+
+
+def build_int_scan_on_device(ctx: ColqContext, n_rows: int, base=None, seed: int = 42, chunk: int = 1 << 26):
+    """BASELINE config 2: ``v[i] = pops[splitmix64(42, i) mod 29353]`` as a one-column table registered as "ints"."""
+    base = base or load_base()
+    device = torch.device("cuda", ctx.device)
+    pops = torch.from_numpy(base["zip_pop"]).to(device)
+    col = torch.zeros(n_rows + 16, dtype=torch.int32, device=device)
+    for s in range(0, n_rows, chunk):
+        c = min(chunk, n_rows - s)
+        col[s:s + c] = pops[splitmix64_mod_device(seed, s, c, N_ZIPS, device)]
+    torch.cuda.synchronize(device)
+    t = ctx.table_create(n_rows, _ffi.REPLICATED, 0)
+    ctx.col_i32_device(t, 0, col.data_ptr(), n_rows, keepalive=col)
+    ctx.register("ints", t)
+    return t, col
+
+
+def build_name_scan_on_device(ctx: ColqContext, n_rows: int, base=None, seed: int = 42, chunk: int = 1 << 23):
+    """BASELINE config 5: ``name[i] = cityNames[splitmix64(42, i) mod 25701]`` as offsets + bytes, registered as
+    "names".  Returns (table, offsets tensor, bytes tensor, idx tensor of the drawn base rows)."""
+    base = base or load_base()
+    device = torch.device("cuda", ctx.device)
+    boff = torch.from_numpy(base["city_name_offsets"].astype(np.int64)).to(device)
+    bbytes = torch.from_numpy(base["city_name_bytes"]).to(device)
+    blen = boff[1:] - boff[:-1]
+    idx = torch.empty(n_rows, dtype=torch.int32, device=device)
+    off = torch.zeros(n_rows + 1 + 16, dtype=torch.int64, device=device)
+    for s in range(0, n_rows, 1 << 26):
+        c = min(1 << 26, n_rows - s)
+        idx[s:s + c] = splitmix64_mod_device(seed, s, c, N_CITIES, device).to(torch.int32)
+    for s in range(0, n_rows, 1 << 26):
+        c = min(1 << 26, n_rows - s)
+        off[s + 1:s + c + 1] = torch.cumsum(blen[idx[s:s + c].long()], 0) + off[s]
+    total = int(off[n_rows].item())
+    assert total < 2 ** 32 - 64
+    data = torch.zeros(total + 64, dtype=torch.uint8, device=device)
+    for s in range(0, n_rows, chunk):
+        c = min(chunk, n_rows - s)
+        ii = idx[s:s + c].long()
+        lens = blen[ii]
+        o0 = off[s:s + c]
+        nb = int((off[s + c] - off[s]).item())
+        row = torch.repeat_interleave(torch.arange(c, device=device), lens, output_size=nb)
+        within = torch.arange(nb, device=device) - (o0 - off[s])[row]
+        data[int(off[s].item()):int(off[s].item()) + nb] = bbytes[boff[ii][row] + within]
+    off32 = ((off + 2 ** 31) % 2 ** 32 - 2 ** 31).to(torch.int32)  # uint32 bit pattern in an int32 tensor
+    del off
+    torch.cuda.synchronize(device)
+    t = ctx.table_create(n_rows, _ffi.REPLICATED, 0)
+    ctx.col_str_device(t, 0, off32.data_ptr(), off32.numel() * 4, data.data_ptr(), data.numel(), n_rows, total, keepalive=(off32, data))
+    ctx.register("names", t)
+    return t, off32, data, idx, total
