@@ -79,7 +79,12 @@ typedef enum colq_option {
     /* 1: record one CUDA event pair per kernel so colq_profile() can report per-stage times (adds launch gaps) */
     COLQ_OPT_PROFILE = 1,
     /* 1 (default): replay the query's kernel sequence from a captured CUDA graph when its shape is static */
-    COLQ_OPT_GRAPH = 2
+    COLQ_OPT_GRAPH = 2,
+    /* 1 (default): multi-GPU exchanges (state-mask OR, final index gather) run as own kernels that store into the
+       peers' HBM over NVLink (CUDA-IPC mailboxes); 0: NCCL all-gathers */
+    COLQ_OPT_PEER_EXCHANGE = 3,
+    /* 1 (default): one cooperative compaction launch; 0: popcount / scan / write as three launches */
+    COLQ_OPT_FUSED_COMPACT = 4
 } colq_option;
 
 typedef struct colq_ctx colq_ctx;       /* one DataSystem instance  (E/DataSystemSerialIndices.java:14-22) */

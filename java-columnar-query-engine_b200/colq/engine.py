@@ -232,9 +232,11 @@ class ColqContext:
 class DataSystemColq(DataSystem):
     """The reference-facing engine: same two methods as ``DataSystemSerialIndices``."""
 
-    def __init__(self, device: int = 0, lazy_fk: bool = True, context: Optional[ColqContext] = None):
+    def __init__(self, device: int = 0, lazy_fk: bool = True, context: Optional[ColqContext] = None,
+                 options: Optional[Dict[int, int]] = None):
         self.ctx = context or ColqContext(device)
         self.lazy_fk = lazy_fk
+        self.options = dict(options or {})   # colq_option -> value, applied to every query
         self._tables: Dict[str, Table] = {}                 # private final Map<String, Table> tables (E/...:18)
         self._placement: Dict[int, Tuple[int, int]] = {}    # id(table) -> (placement, global_row_base)
         self._handles: Dict[int, int] = {}                  # id(table) -> colq_table
@@ -310,6 +312,8 @@ class DataSystemColq(DataSystem):
     def _translate(self, query: Query) -> Tuple[Optional[ColqQuery], Optional[str]]:
         cq = self.ctx.query(query.table_name)
         cq.set_option(_ffi.OPT_LAZY_FK, 1 if self.lazy_fk else 0)
+        for opt, val in self.options.items():
+            cq.set_option(opt, val)
         stack = [(query.root_node, 0)]
         while stack:
             node, nid = stack.pop()

@@ -101,7 +101,7 @@ struct QNode {
 };
 
 // one kernel launch (or collective / memset) of a planned query
-enum OpKind { K_SCAN_ROWS, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER };
+enum OpKind { K_SCAN_ROWS, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER, K_COMPACT_FUSED, K_PEER_MASK_OR, K_PEER_GATHER };
 
 struct Op {
     OpKind kind;
@@ -123,6 +123,9 @@ struct Op {
     u64* total = nullptr;
     int32_t* out_idx = nullptr;
     int64_t capacity = 0, row_base = 0, n_blocks = 0;
+    CompactFusedParams cfused{};
+    PeerMaskParams pmask{};
+    PeerGatherParams pgather{};
     // launch shape for scan_str
     int grid = 0;
     size_t smem = 0;
@@ -163,6 +166,20 @@ struct colq_ctx {
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
     bool str_attr_set = false;
+    // peer-memory mailboxes (CUDA IPC over NVLink); ok == false -> NCCL collectives on the data path
+    struct PeerBox {
+        bool ok = false;
+        void* local = nullptr;
+        size_t bytes = 0;
+        void* peer_ptr[MAX_RANKS] = {};
+        uint8_t** d_peers = nullptr;
+        u32* d_done = nullptr;
+        u32* d_status = nullptr;
+        u64 mask_epoch = 0, gather_epoch = 0;
+        int64_t slot_cap = 0;
+        size_t slot_bytes = 0;
+    } peer;
+    int compact_grid = 0;  // co-resident grid of compact_fused_kernel
     std::map<std::pair<int, size_t>, int> str_occupancy;  // (kernel mode, dynamic smem bytes) -> resident CTAs per SM
 };
 
@@ -170,7 +187,9 @@ struct colq_query {
     colq_ctx* ctx = nullptr;
     std::string table_name;
     std::vector<QNode> nodes;
-    int opt_lazy = 1, opt_profile = 0, opt_graph = 1;
+    int opt_lazy = 1, opt_profile = 0, opt_graph = 1, opt_peer = 1, opt_fused_compact = 1;
+    DevBuf barrier_buf;
+    u32 barrier_count = 0;
     // execution state
     Pool pool;
     std::vector<XNode> xnodes;
@@ -452,12 +471,20 @@ struct Planner {
                 if (sharded(CT) && !sharded(T)) {
                     // the only data-path collective: OR-allreduce of the replicated parent's mask
                     Op g{};
-                    g.kind = K_ALLGATHER_OR; g.node = xi; g.dst = reach; g.n_words = bitmap_words(n);
-                    void* gb;
-                    ST(pool_alloc(q, (size_t)g.n_words * 4 * ctx->n_ranks, &gb));
-                    g.gathered = (u32*)gb;
-                    g.name = "allgather_or_mask";
-                    g.acct_bytes = g.n_words * 4 * ctx->n_ranks;
+                    g.node = xi; g.dst = reach; g.n_words = bitmap_words(n);
+                    if (ctx->peer.ok && q->opt_peer && g.n_words <= MASK_WORDS_MAX) {
+                        g.kind = K_PEER_MASK_OR; g.name = "peer_mask_or";
+                        PeerMaskParams& P = g.pmask;
+                        P.reach = reach; P.n_words = (int)g.n_words; P.n_ranks = ctx->n_ranks; P.rank = ctx->rank;
+                        P.peers = ctx->peer.d_peers; P.status = ctx->peer.d_status;
+                        g.acct_bytes = g.n_words * 4 * ctx->n_ranks;
+                    } else {
+                        g.kind = K_ALLGATHER_OR; g.name = "allgather_or_mask";
+                        void* gb;
+                        ST(pool_alloc(q, (size_t)g.n_words * 4 * ctx->n_ranks, &gb));
+                        g.gathered = (u32*)gb;
+                        g.acct_bytes = g.n_words * 4 * ctx->n_ranks;
+                    }
                     q->ops.push_back(g);
                 }
                 if (cur == nullptr) cur = reach;
@@ -745,6 +772,29 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
             compact_kernel<<<(int)o.n_blocks, CP_THREADS, 0, s>>>(o.src, o.n_words, o.block_offsets, o.out_idx, o.capacity, o.row_base);
             q->timing.kernel_launches++;
             break;
+        case K_COMPACT_FUSED: {
+            if ((uint64_t)q->barrier_count + (uint64_t)o.grid > 0x7fffffffull) {  // keep the barrier counter far from wrapping
+                CU(ctx, cudaMemsetAsync(q->barrier_buf.ptr, 0, 64, s));
+                q->barrier_count = 0;
+            }
+            q->barrier_count += (u32)o.grid;
+            o.cfused.barrier_target = q->barrier_count;
+            void* args[] = {(void*)&o.cfused};
+            CU(ctx, cudaLaunchCooperativeKernel((const void*)compact_fused_kernel, dim3(o.grid), dim3(CP_THREADS), args, 0, s));
+            q->timing.kernel_launches++;
+            break;
+        }
+        case K_PEER_MASK_OR:
+            o.pmask.epoch = ++ctx->peer.mask_epoch;
+            peer_mask_or_kernel<<<1, 256, 0, s>>>(o.pmask);
+            q->timing.kernel_launches++;
+            break;
+        case K_PEER_GATHER:
+            o.pgather.epoch = ++ctx->peer.gather_epoch;
+            peer_gather_send_kernel<<<ctx->n_ranks * o.pgather.blocks_per_peer, 256, 0, s>>>(o.pgather);
+            peer_gather_recv_kernel<<<grid_for(o.capacity * ctx->n_ranks / 4, 256, ctx->sm_count, 2), 256, 0, s>>>(o.pgather);
+            q->timing.kernel_launches += 2;
+            break;
         case K_GATHER:
             NC(ctx, ctx->nccl.AllGather(q->idx_buf.ptr, q->gather_buf.ptr, (size_t)(o.capacity + GATHER_HEADER_WORDS), kNcclInt32,
                                         ctx->comm, (void*)s));
@@ -800,9 +850,30 @@ colq_status run_pipeline(colq_query* q) {
     ST(pool_alloc(q, (size_t)n_blocks * 4, &bc));
     ST(pool_alloc(q, (size_t)n_blocks * 8, &bo));
     q->gathered = ctx->n_ranks > 1 && RT.placement == COLQ_SHARDED;
-    if (q->want_idx_capacity <= 0) q->want_idx_capacity = q->gathered ? (1 << 16) : (1 << 20);
+    const bool peer_gather = q->gathered && ctx->peer.ok && q->opt_peer;
+    if (q->want_idx_capacity <= 0) q->want_idx_capacity = (q->gathered && !peer_gather) ? (1 << 16) : (1 << 20);
     ST(ensure_idx_capacity(q, q->want_idx_capacity));
-    {
+    if (q->opt_fused_compact) {
+        // one cooperative launch: per-tile popcount, grid barrier, ordered write
+        if (ctx->compact_grid == 0) {
+            int occ = 0;
+            CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, compact_fused_kernel, CP_THREADS, 0));
+            ctx->compact_grid = ctx->sm_count * std::max(1, std::min(occ, 8));
+        }
+        if (!q->barrier_buf.ptr) {
+            ST(dev_alloc(ctx, q->barrier_buf, 64));
+            CU(ctx, cudaMemsetAsync(q->barrier_buf.ptr, 0, 64, ctx->stream));
+            q->barrier_count = 0;
+        }
+        Op f{};
+        f.kind = K_COMPACT_FUSED; f.node = 0; f.name = "compact_fused"; f.acct_rows = n; f.acct_bytes = n_words * 8;
+        CompactFusedParams& P = f.cfused;
+        P.bits = root.bits; P.n_words = n_words; P.n_tiles = n_blocks; P.tile_counts = (u32*)bc;
+        P.barrier = (u32*)q->barrier_buf.ptr; P.total = q->d_total; P.out_idx = q->d_idx; P.capacity = q->idx_capacity;
+        P.row_base = RT.row_base;  // global row index = shard-local index + the shard's base
+        f.grid = (int)std::min<int64_t>(n_blocks, ctx->compact_grid);
+        q->ops.push_back(f);
+    } else {
         Op p{};
         p.kind = K_POPC; p.node = 0; p.src = root.bits; p.n_words = n_words; p.n_blocks = n_blocks; p.block_counts = (u32*)bc;
         p.name = "popc_blocks"; p.acct_rows = n; p.acct_bytes = n_words * 4;
@@ -814,22 +885,36 @@ colq_status run_pipeline(colq_query* q) {
         Op c{};
         c.kind = K_COMPACT; c.node = 0; c.src = root.bits; c.n_words = n_words; c.n_blocks = n_blocks; c.block_offsets = (u64*)bo;
         c.out_idx = q->d_idx; c.capacity = q->idx_capacity;
-        c.row_base = RT.row_base;  // global row index = shard-local index + the shard's base
+        c.row_base = RT.row_base;
         c.name = "compact"; c.acct_rows = n; c.acct_bytes = n_words * 4;
         q->ops.push_back(c);
     }
     if (q->gathered) {
-        // final gather of matched indices, entirely on the device: one all-gather of fixed-size
-        // result blocks, then a kernel that concatenates their valid prefixes in rank order
-        const int64_t cap = q->idx_capacity;
-        const size_t block_bytes = (size_t)(cap + GATHER_HEADER_WORDS) * 4;
-        if (q->gather_buf.bytes < block_bytes * ctx->n_ranks) ST(dev_alloc(ctx, q->gather_buf, block_bytes * ctx->n_ranks));
-        if (q->gout_buf.bytes < (size_t)cap * 4 * ctx->n_ranks) ST(dev_alloc(ctx, q->gout_buf, (size_t)cap * 4 * ctx->n_ranks));
+        // final gather of matched indices, entirely on the device
         if (!q->ginfo_buf.ptr) ST(dev_alloc(ctx, q->ginfo_buf, 64));
-        Op g{};
-        g.kind = K_GATHER; g.node = 0; g.capacity = cap; g.name = "allgather_indices";
-        g.acct_bytes = (int64_t)block_bytes * ctx->n_ranks;
-        q->ops.push_back(g);
+        if (peer_gather) {
+            // own kernels over NVLink peer memory: every rank stores its indices into every peer's mailbox slot
+            const int64_t cap = std::min<int64_t>(q->idx_capacity, ctx->peer.slot_cap);
+            if (q->gout_buf.bytes < (size_t)cap * 4 * ctx->n_ranks) ST(dev_alloc(ctx, q->gout_buf, (size_t)cap * 4 * ctx->n_ranks));
+            Op g{};
+            g.kind = K_PEER_GATHER; g.node = 0; g.name = "peer_gather_indices"; g.capacity = cap;
+            PeerGatherParams& P = g.pgather;
+            P.count = q->d_total; P.idx = q->d_idx; P.idx_capacity = q->idx_capacity; P.slot_cap = ctx->peer.slot_cap;
+            P.slot_bytes = ctx->peer.slot_bytes; P.n_ranks = ctx->n_ranks; P.rank = ctx->rank; P.peers = ctx->peer.d_peers;
+            P.done = ctx->peer.d_done; P.blocks_per_peer = std::max(1, std::min(32, 2 * ctx->sm_count / ctx->n_ranks)); P.status = ctx->peer.d_status;
+            P.out = (int32_t*)q->gout_buf.ptr; P.info = (u64*)q->ginfo_buf.ptr;
+            q->ops.push_back(g);
+        } else {
+            // NCCL: one all-gather of fixed-size result blocks, then a kernel that concatenates their valid prefixes
+            const int64_t cap = q->idx_capacity;
+            const size_t block_bytes = (size_t)(cap + GATHER_HEADER_WORDS) * 4;
+            if (q->gather_buf.bytes < block_bytes * ctx->n_ranks) ST(dev_alloc(ctx, q->gather_buf, block_bytes * ctx->n_ranks));
+            if (q->gout_buf.bytes < (size_t)cap * 4 * ctx->n_ranks) ST(dev_alloc(ctx, q->gout_buf, (size_t)cap * 4 * ctx->n_ranks));
+            Op g{};
+            g.kind = K_GATHER; g.node = 0; g.capacity = cap; g.name = "allgather_indices";
+            g.acct_bytes = (int64_t)block_bytes * ctx->n_ranks;
+            q->ops.push_back(g);
+        }
     }
 
     // ---- enqueue
@@ -876,31 +961,34 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
     CU(ctx, cudaEventElapsedTime(&ms, q->ev_start, q->ev_stop));
     q->timing.gpu_ms = ms;
 
+    if (ctx->peer.ok) {
+        u32 status = 0;
+        CU(ctx, cudaMemcpyAsync(&status, ctx->peer.d_status, 4, cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaStreamSynchronize(s));
+        if (status != 0) return fail(ctx, COLQ_ERR_DEVICE, "peer-memory exchange timed out waiting for another rank");
+    }
     int64_t count = (int64_t)local;
     const int32_t* src_idx = q->d_idx;
     if (gather) {
-        if ((int64_t)ginfo[1] > q->idx_capacity) {
+        bool peer_gather = false;
+        int64_t block_cap = q->idx_capacity;
+        for (const Op& o : q->ops)
+            if (o.kind == K_PEER_GATHER) { peer_gather = true; block_cap = o.capacity; }
+        if ((int64_t)ginfo[1] > block_cap) {
             // some rank found more rows than a result block holds: every rank sees the same gathered counts, so all
-            // of them grow the block and run the query again
+            // of them grow the block (or leave the fixed-size mailbox path) and run the query again
             q->want_idx_capacity = (int64_t)ginfo[1] + (int64_t)ginfo[1] / 4 + 1024;
+            if (peer_gather && q->want_idx_capacity > ctx->peer.slot_cap) q->opt_peer = 0;
             ST(run_pipeline(q));
             return fetch_results(q, out_bitmask, bitmask_cap, out_idx, idx_cap, out_count, out_timing);
         }
         count = (int64_t)ginfo[2];
         src_idx = (const int32_t*)q->gout_buf.ptr;
     } else if ((int64_t)local > q->idx_capacity) {
-        // index buffer was too small: grow it and redo only the ordered write (the mask is still resident)
-        q->want_idx_capacity = (int64_t)local;
-        ST(ensure_idx_capacity(q, (int64_t)local));
-        for (Op& o : q->ops) {
-            if (o.kind == K_SCAN_COUNTS) { o.total = q->d_total; ST(launch_op(q, o, s)); }
-            if (o.kind == K_COMPACT) {
-                o.out_idx = q->d_idx;
-                o.capacity = q->idx_capacity;
-                ST(launch_op(q, o, s));
-            }
-        }
-        CU(ctx, cudaStreamSynchronize(s));
+        // index buffer was too small: grow it and run again (happens once per query, the capacity sticks)
+        q->want_idx_capacity = (int64_t)local + (int64_t)local / 8 + 1024;
+        ST(run_pipeline(q));
+        return fetch_results(q, out_bitmask, bitmask_cap, out_idx, idx_cap, out_count, out_timing);
     }
 
     if (out_count) *out_count = count;
@@ -991,6 +1079,85 @@ void unlink_assoc(colq_ctx* ctx, colq_table x, int xo, colq_table y, int yo) {
     ctx->tables[y].cols[yo] = Column();
 }
 
+// CUDA-IPC mailboxes for the peer-memory exchange kernels.  Collective over the freshly created NCCL communicator
+// (used here only to ship the 64-byte IPC handles and to agree on success).  Any failure leaves peer.ok == false and
+// the data path falls back to NCCL all-gathers.
+colq_status setup_peerbox(colq_ctx* ctx) {
+    auto& pb = ctx->peer;
+    const char* env = getenv("COLQ_PEER");
+    if (ctx->n_ranks < 2 || (env && env[0] == '0')) return COLQ_OK;
+    cudaStream_t s = ctx->stream;
+    const char* cap_env = getenv("COLQ_PEER_SLOT_CAP");
+    pb.slot_cap = cap_env ? std::max<int64_t>(1024, atoll(cap_env)) : ((int64_t)1 << 20);
+    pb.slot_bytes = (size_t)GATHER_SLOT_HEADER + (size_t)pb.slot_cap * 4;
+    pb.bytes = PEER_GATHER_AREA_OFFSET + (size_t)2 * ctx->n_ranks * pb.slot_bytes;
+    struct Msg { cudaIpcMemHandle_t handle; int ok; int pad[15]; };
+    static_assert(sizeof(Msg) == 128, "message layout");
+    Msg mine{};
+    mine.ok = 1;
+    if (cudaMalloc(&pb.local, pb.bytes) != cudaSuccess) { mine.ok = 0; pb.local = nullptr; }
+    if (mine.ok && cudaMemset(pb.local, 0, pb.bytes) != cudaSuccess) mine.ok = 0;
+    if (mine.ok && cudaIpcGetMemHandle(&mine.handle, pb.local) != cudaSuccess) mine.ok = 0;
+    cudaGetLastError();
+    DevBuf send, recv;
+    ST(dev_alloc(ctx, send, sizeof(Msg)));
+    ST(dev_alloc(ctx, recv, sizeof(Msg) * ctx->n_ranks));
+    std::vector<Msg> all(ctx->n_ranks);
+    auto exchange = [&]() -> colq_status {
+        CU(ctx, cudaMemcpyAsync(send.ptr, &mine, sizeof(Msg), cudaMemcpyHostToDevice, s));
+        NC(ctx, ctx->nccl.AllGather(send.ptr, recv.ptr, sizeof(Msg), kNcclUint8, ctx->comm, (void*)s));
+        CU(ctx, cudaMemcpyAsync(all.data(), recv.ptr, sizeof(Msg) * ctx->n_ranks, cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaStreamSynchronize(s));
+        return COLQ_OK;
+    };
+    ST(exchange());
+    bool all_ok = true;
+    for (const Msg& m : all) all_ok = all_ok && m.ok;
+    if (all_ok) {
+        for (int r = 0; r < ctx->n_ranks; ++r) {
+            if (r == ctx->rank) { pb.peer_ptr[r] = pb.local; continue; }
+            if (cudaIpcOpenMemHandle(&pb.peer_ptr[r], all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                pb.peer_ptr[r] = nullptr;
+                mine.ok = 0;
+                cudaGetLastError();
+            }
+        }
+    } else {
+        mine.ok = 0;
+    }
+    ST(exchange());  // second round: did every rank map every mailbox?
+    all_ok = true;
+    for (const Msg& m : all) all_ok = all_ok && m.ok;
+    if (!all_ok) {
+        for (int r = 0; r < ctx->n_ranks; ++r)
+            if (r != ctx->rank && pb.peer_ptr[r]) cudaIpcCloseMemHandle(pb.peer_ptr[r]);
+        if (pb.local) cudaFree(pb.local);
+        pb = colq_ctx::PeerBox();
+        cudaGetLastError();
+        return COLQ_OK;
+    }
+    void* p;
+    CU(ctx, cudaMalloc(&p, sizeof(void*) * MAX_RANKS));
+    pb.d_peers = (uint8_t**)p;
+    CU(ctx, cudaMemcpy(pb.d_peers, pb.peer_ptr, sizeof(void*) * MAX_RANKS, cudaMemcpyHostToDevice));
+    CU(ctx, cudaMalloc(&p, sizeof(u32) * (MAX_RANKS + 16)));
+    CU(ctx, cudaMemset(p, 0, sizeof(u32) * (MAX_RANKS + 16)));
+    pb.d_done = (u32*)p;
+    pb.d_status = pb.d_done + MAX_RANKS;
+    pb.ok = true;
+    return COLQ_OK;
+}
+
+void destroy_peerbox(colq_ctx* ctx) {
+    auto& pb = ctx->peer;
+    for (int r = 0; r < ctx->n_ranks; ++r)
+        if (r != ctx->rank && pb.peer_ptr[r]) cudaIpcCloseMemHandle(pb.peer_ptr[r]);
+    if (pb.local) cudaFree(pb.local);
+    if (pb.d_peers) cudaFree(pb.d_peers);
+    if (pb.d_done) cudaFree(pb.d_done);
+    pb = colq_ctx::PeerBox();
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -1031,6 +1198,7 @@ colq_status colq_destroy(colq_ctx* ctx) {
     if (!ctx) return COLQ_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    destroy_peerbox(ctx);
     if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
     ctx->tables.clear();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1081,7 +1249,7 @@ colq_status colq_comm_init(colq_ctx* ctx, const uint8_t id_bytes[128], int n_ran
     NC(ctx, ctx->nccl.CommInitRank(&ctx->comm, n_ranks, id, rank));
     ctx->n_ranks = n_ranks;
     ctx->rank = rank;
-    return COLQ_OK;
+    return setup_peerbox(ctx);
 }
 
 colq_status colq_comm_info(const colq_ctx* ctx, int* out_n_ranks, int* out_rank) {
@@ -1332,6 +1500,8 @@ colq_status colq_query_set_option(colq_query* q, colq_option option, int value) 
         case COLQ_OPT_LAZY_FK: q->opt_lazy = value; break;
         case COLQ_OPT_PROFILE: q->opt_profile = value; break;
         case COLQ_OPT_GRAPH: q->opt_graph = value; break;
+        case COLQ_OPT_PEER_EXCHANGE: q->opt_peer = value; break;
+        case COLQ_OPT_FUSED_COMPACT: q->opt_fused_compact = value; break;
         default: return fail(q->ctx, COLQ_THROW_ILLEGAL_ARG, "unknown option %d", (int)option);
     }
     return COLQ_OK;

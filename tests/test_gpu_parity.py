@@ -251,6 +251,27 @@ def test_plymouth_universes_match_oracle(engines, base_geography, U):
     both(engines, build, [G.plymouth_query, G.north_south_north_query])
 
 
+def test_three_launch_compaction_path_matches(engines, base_geography):
+    """COLQ_OPT_FUSED_COMPACT=0 keeps the popcount / scan / write launches; both paths must agree with the oracle."""
+    from colq import _ffi
+    from colq.engine import DataSystemColq
+    _, new_oracle = engines
+    geo = G.build_tables(5, base=base_geography)
+    oracle = new_oracle()
+    G.register_geography(oracle, geo)
+    oracle.execute(G.plymouth_query())
+    for fused in (0, 1):
+        ds = DataSystemColq(0, options={_ffi.OPT_FUSED_COMPACT: fused})
+        G.register_geography(ds, geo)
+        r = ds.execute(G.plymouth_query())
+        assert isinstance(r, QueryResult.Success)
+        got = ds.last_query.fetch(want_indices=True)
+        assert np.array_equal(got.indices, oracle.last_indices)
+        names = [n for n, *_ in ds.last_query.profile()]
+        assert ("compact_fused" in names) == bool(fused)
+        ds.close()
+
+
 def test_plymouth_full_size_properties(base_geography, expected):
     """BASELINE config 4 at full size (10k universes, 293.5 M ZIP rows) generated in HBM: the result must be exactly
     {u * 29353 + r} for the 31 one-universe rows r, ascending, for both execution strategies."""
