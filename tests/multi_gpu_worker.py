@@ -1,0 +1,83 @@
+"""Worker for tests/test_gpu_multi.py: run under torchrun with one rank per GPU.
+
+Checks, through the reference-facing Python mirror over the C ABI, that the sharded execution (universe ranges per
+rank, replicated states, mask exchange, final gather) returns exactly the unsharded oracle result -- for the exact-copy
+workload, for the perturbed workload where only the last rank holds PLYMOUTH rows, with peer-memory and NCCL exchanges.
+"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (ROOT / "java-columnar-query-engine_b200", ROOT / "oracle"):
+    sys.path.insert(0, str(p))
+
+from colq import _ffi, geography as G  # noqa: E402
+from colq.engine import ColqContext, DataSystemColq  # noqa: E402
+from oracle_system import OracleDataSystem  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = ColqContext(local)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank)
+
+    U = 4 * world + 1   # uneven split on purpose
+    checked = 0
+    for perturbed in (False, True):
+        # the unsharded expectation from the oracle (exact copies: the perturbation moves no result row)
+        oracle = OracleDataSystem()
+        G.register_geography(oracle, G.build_tables(U))
+        oracle.execute(G.plymouth_query())
+        want = oracle.last_indices.copy()
+        oracle.execute(G.north_south_north_query())
+        want_nsn = oracle.last_indices.copy()
+        oracle.close()
+
+        geo = G.build_tables(U, n_ranks=world, rank=rank, rename_plymouth_except_last_rank=perturbed)
+        for peer in (1, 0):
+            for lazy in (True, False):
+                ds = DataSystemColq(context=ctx, lazy_fk=lazy, options={_ffi.OPT_PEER_EXCHANGE: peer})
+                ds._tables.clear()
+                G.register_geography(ds, geo, sharded=True)
+                ds._sync_tables()
+                cq, why = ds._translate(G.plymouth_query())
+                assert cq is not None, why
+                res = cq.execute(want_indices=True, index_capacity=64)   # small on purpose: exercises the regrow path
+                assert res.count == want.shape[0], (rank, perturbed, peer, lazy, res.count, want.shape[0])
+                assert np.array_equal(res.indices, want), (rank, perturbed, peer, lazy)
+                names = [n for n, *_ in cq.profile()]
+                if peer and os.environ.get("COLQ_PEER", "1") != "0":
+                    assert "peer_mask_or" in names and "peer_gather_indices" in names, names
+                else:
+                    assert "allgather_or_mask" in names and "allgather_indices" in names, names
+                cq.close()
+                # a query on the replicated table alone: no collective, same answer on every rank
+                cq, _ = ds._translate(G.north_south_north_query())
+                res = cq.execute(want_indices=True)
+                assert np.array_equal(res.indices, want_nsn)
+                cq.close()
+                # drop this engine's tables so the next variant re-registers under the same names
+                for h in set(ds._handles.values()):
+                    ctx.table_destroy(h)
+                checked += 1
+    dist.barrier()
+    if rank == 0:
+        print(f"MULTI_GPU_OK world={world} variants={checked}")
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
