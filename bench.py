@@ -47,12 +47,17 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="colq", choices=["colq", "reference"])
     ap.add_argument("--universes", type=int, default=10_000)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--profile-steps", type=int, default=10)
     ap.add_argument("--cpu-universes", type=int, default=1000, help="bounded sample for the CPU baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="disable the lazy FK chain (materialise every node)")
+    ap.add_argument("--workload", default="plymouth", choices=["plymouth", "int_scan", "str_eq"],
+                    help="plymouth = BASELINE configs[3] (the headline); int_scan = configs[1] (1B-row int range scan + "
+                         "compaction); str_eq = configs[4] (city-name equality, one GPU's 62.5M-row shard). The last two are "
+                         "single-GPU kernel benchmarks for DESIGN.md, not the driver's bench line.")
+    ap.add_argument("--rows", type=int, default=0, help="row count override for int_scan / str_eq")
     return ap.parse_args()
 
 
@@ -309,6 +314,8 @@ def run_colq(args, rank, local_rank, world):
     ms_res = max_over_ranks(e0.elapsed_time(e1)) / n_res
     d2h_res = int(r2.timing.d2h_bytes)
 
+    small = small_query_latency(base) if world == 1 else None
+
     # ---- e2e: HOST buffers in, matched indices out, every step (columns re-uploaded from pinned memory)
     e2e = None
     if not args.no_e2e:
@@ -387,6 +394,7 @@ def run_colq(args, rank, local_rank, world):
             "cpu_baseline": cpu, "e2e": e2e,
             "e2e_resident": {"value": rows / (ms_res * 1e-3), "unit": "rows/s", "ms_per_step": ms_res, "h2d_bytes_per_step": 0,
                              "d2h_bytes_per_step": d2h_res, "what": "colq_execute with resident tables, matched indices read back every step"},
+            "small_query_latency": small,
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "collectives_per_step": collectives_per_step,
         }
@@ -396,6 +404,113 @@ def run_colq(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def small_query_latency(base):
+    """BASELINE configs[0] and configs[2] on the GPU: 29k / 51 rows are launch-latency bound, so report microseconds
+    per colq_execute call (host wall clock, result read back), not a roofline fraction."""
+    from colq.device_data import build_geography_on_device, north_south_north_colq_query, plymouth_colq_query
+    from colq.engine import ColqContext
+    ctx = ColqContext(0)
+    build_geography_on_device(ctx, 1, base=base)
+    out = {}
+    for name, make, want in (("plymouth_1_universe", plymouth_colq_query, 31), ("north_south_north", north_south_north_colq_query, 2)):
+        q = make(ctx)
+        for _ in range(20):
+            r = q.execute(want_indices=True)
+        assert r.count == want
+        ts = []
+        for _ in range(300):
+            t0 = time.perf_counter()
+            q.execute(want_indices=True)
+            ts.append((time.perf_counter() - t0) * 1e6)
+        out[name] = {"median_us": statistics.median(ts), "p10_us": sorted(ts)[30], "kernel_launches": int(r.timing.kernel_launches)}
+        q.close()
+    ctx.close()
+    return out
+
+
+def run_single_table(args):
+    """int_scan / str_eq: one column, one predicate, one GPU (BASELINE configs[1] and configs[4])."""
+    import torch
+    from colq import _ffi
+    from colq import geography as G
+    from colq.device_data import build_int_scan_on_device, build_name_scan_on_device
+    from colq.engine import ColqContext
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(device=dev)
+    ctx = ColqContext(0)
+    ctx.set_stream(stream.cuda_stream)
+    base = G.load_base()
+    if args.workload == "int_scan":
+        n = args.rows or 1_000_000_000
+        _t, col = build_int_scan_on_device(ctx, n, base=base)
+        q = ctx.query("ints")
+        q.criteria_i32_range(0, 0, 10_000, 10_099)
+        v = col[:n]
+        expect = int(((v >= 10_000) & (v <= 10_099)).sum().item())
+        workload = {"workload": "int_range_scan_plus_compaction", "source": "BASELINE.json configs[1]", "rows": n,
+                    "predicate": "[10000, 10099]", "generator": "pops[splitmix64(42, i) mod 29353]"}
+        metric = "int_range_scan_rows_per_sec"
+        algo = lambda m: 4 * n + 4 * m  # noqa: E731  (SURVEY.md 8d config 2)
+    else:
+        n = args.rows or 62_500_000
+        _t, off32, data, idx, total = build_name_scan_on_device(ctx, n, base=base)
+        q = ctx.query("names")
+        q.criteria_str(0, 0, 0, b"PLYMOUTH")
+        names = [bytes(base["city_name_bytes"][base["city_name_offsets"][i]:base["city_name_offsets"][i + 1]]) for i in range(G.N_CITIES)]
+        ply = torch.tensor([i for i, s_ in enumerate(names) if s_ == b"PLYMOUTH"], device=dev, dtype=torch.int32)
+        expect = int(torch.isin(idx, ply).sum().item())
+        workload = {"workload": "city_name_equality_scan", "source": "BASELINE.json configs[4] (one GPU's shard of 500M rows)",
+                    "rows": n, "name_bytes": total, "generator": "cityNames[splitmix64(42, i) mod 25701]"}
+        metric = "string_equality_scan_rows_per_sec"
+        algo = lambda m: 4 * (n + 1) + total + n // 8  # noqa: E731  (SURVEY.md 8d config 5)
+    res = q.execute(want_indices=True, index_capacity=max(expect, 1) + 16)
+    if res.count != expect:
+        raise SystemExit(f"GPU count {res.count} != independent expectation {expect}")
+    launches = int(res.timing.kernel_launches)
+    sampler = ClockSampler(0)
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            q.execute_async()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.start()
+        e0.record(stream)
+        for _ in range(args.steps):
+            q.execute_async()
+        e1.record(stream)
+        stream.synchronize()
+        clocks = sampler.stop()
+    ms_step = e0.elapsed_time(e1) / args.steps
+    q.set_option(_ffi.OPT_PROFILE, 1)
+    acc = {}
+    for _ in range(args.profile_steps):
+        q.execute(want_indices=False)
+        for name, ms, r, b in q.profile():
+            if ms >= 0:
+                a = acc.setdefault(name, [0.0, 0, r, b])
+                a[0] += ms
+                a[1] += 1
+    stages = {k: {"ms": v[0] / v[1], "algorithmic_bytes": v[3]} for k, v in acc.items() if v[1]}
+    dom = max(stages, key=lambda k: stages[k]["ms"])
+    peak, peak_src = measured_peak()
+    achieved = stages[dom]["algorithmic_bytes"] / (stages[dom]["ms"] * 1e-3) / 1e9
+    line = {
+        "metric": metric, "value": n / (ms_step * 1e-3), "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32" if args.workload == "int_scan" else "u8", "data": "synthetic",
+        "config": dict(workload, l2_policy="inputs larger than L2 (no flush)", matches=expect),
+        "hbm_gbs_query_algorithmic": algo(expect) / (ms_step * 1e-3) / 1e9, "query_algorithmic_bytes": algo(expect),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "ms_per_launch": stages[dom]["ms"],
+                     "algorithmic_bytes_per_launch": stages[dom]["algorithmic_bytes"]},
+        "stages_ms": {k: round(v["ms"], 5) for k, v in stages.items()},
+        "cpu_baseline": None, "e2e": None, "clocks": clocks, "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+    }
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -403,6 +518,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload != "plymouth":
+        if world != 1:
+            raise SystemExit("--workload int_scan / str_eq are single-GPU kernel benchmarks")
+        run_single_table(args)
         return
     if world != args.gpus:
         if args.gpus == 1 and world == 1:

@@ -78,7 +78,7 @@ typedef enum colq_option {
     COLQ_OPT_LAZY_FK = 0,
     /* 1: record one CUDA event pair per kernel so colq_profile() can report per-stage times (adds launch gaps) */
     COLQ_OPT_PROFILE = 1,
-    /* 1 (default): replay the query's kernel sequence from a captured CUDA graph when its shape is static */
+    /* reserved: CUDA-graph replay of the op list (accepted and ignored in this version) */
     COLQ_OPT_GRAPH = 2,
     /* 1 (default): multi-GPU exchanges (state-mask OR, final index gather) run as own kernels that store into the
        peers' HBM over NVLink (CUDA-IPC mailboxes); 0: NCCL all-gathers */

@@ -188,8 +188,7 @@ struct colq_query {
     std::string table_name;
     std::vector<QNode> nodes;
     int opt_lazy = 1, opt_profile = 0, opt_graph = 1, opt_peer = 1, opt_fused_compact = 1;
-    DevBuf barrier_buf;
-    u32 barrier_count = 0;
+    DevBuf barrier_buf;  // {arrival count, generation} of the cooperative compaction kernel
     // execution state
     Pool pool;
     std::vector<XNode> xnodes;
@@ -255,8 +254,8 @@ colq_status fail(colq_ctx* ctx, colq_status st, const char* fmt, ...) {
 
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
-// bitmask allocation: whole compaction blocks (32768 rows) so every kernel can store / vector-load full lines
-inline int64_t bitmap_alloc_words(int64_t n_rows) { return round_up(std::max<int64_t>(n_rows, 1), 32768) / 32; }
+// bitmask allocation: whole compaction tiles (131072 rows) so every kernel can store / vector-load full lines
+inline int64_t bitmap_alloc_words(int64_t n_rows) { return round_up(std::max<int64_t>(n_rows, 1), 32 * CF_WORDS_PER_TILE) / 32; }
 inline int64_t bitmap_words(int64_t n_rows) { return (n_rows + 31) / 32; }
 
 colq_status dev_alloc(colq_ctx* ctx, DevBuf& b, size_t bytes) {
@@ -773,12 +772,6 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
             q->timing.kernel_launches++;
             break;
         case K_COMPACT_FUSED: {
-            if ((uint64_t)q->barrier_count + (uint64_t)o.grid > 0x7fffffffull) {  // keep the barrier counter far from wrapping
-                CU(ctx, cudaMemsetAsync(q->barrier_buf.ptr, 0, 64, s));
-                q->barrier_count = 0;
-            }
-            q->barrier_count += (u32)o.grid;
-            o.cfused.barrier_target = q->barrier_count;
             void* args[] = {(void*)&o.cfused};
             CU(ctx, cudaLaunchCooperativeKernel((const void*)compact_fused_kernel, dim3(o.grid), dim3(CP_THREADS), args, 0, s));
             q->timing.kernel_launches++;
@@ -863,15 +856,15 @@ colq_status run_pipeline(colq_query* q) {
         if (!q->barrier_buf.ptr) {
             ST(dev_alloc(ctx, q->barrier_buf, 64));
             CU(ctx, cudaMemsetAsync(q->barrier_buf.ptr, 0, 64, ctx->stream));
-            q->barrier_count = 0;
         }
         Op f{};
         f.kind = K_COMPACT_FUSED; f.node = 0; f.name = "compact_fused"; f.acct_rows = n; f.acct_bytes = n_words * 8;
         CompactFusedParams& P = f.cfused;
-        P.bits = root.bits; P.n_words = n_words; P.n_tiles = n_blocks; P.tile_counts = (u32*)bc;
+        const int64_t n_tiles = std::max<int64_t>(1, (n_words + CF_WORDS_PER_TILE - 1) / CF_WORDS_PER_TILE);
+        P.bits = root.bits; P.n_words = n_words; P.n_tiles = n_tiles; P.tile_counts = (u32*)bc;
         P.barrier = (u32*)q->barrier_buf.ptr; P.total = q->d_total; P.out_idx = q->d_idx; P.capacity = q->idx_capacity;
         P.row_base = RT.row_base;  // global row index = shard-local index + the shard's base
-        f.grid = (int)std::min<int64_t>(n_blocks, ctx->compact_grid);
+        f.grid = (int)std::min<int64_t>(n_tiles, ctx->compact_grid);
         q->ops.push_back(f);
     } else {
         Op p{};

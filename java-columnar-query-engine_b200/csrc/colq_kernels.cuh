@@ -1127,44 +1127,66 @@ __global__ void __launch_bounds__(256) peer_gather_recv_kernel(const PeerGatherP
 // the grid is sized to be co-resident (cudaLaunchCooperativeKernel) so the hand-rolled barrier cannot deadlock.
 // ---------------------------------------------------------------------------------------------
 
+constexpr int CF_VEC = 4;                                   // 128-bit loads per thread per tile
+constexpr int CF_WORDS_PER_TILE = CP_THREADS * 4 * CF_VEC;  // 4096 words = 131072 rows
+
 struct CompactFusedParams {
     const u32* bits;
     int64_t n_words;
-    int64_t n_tiles;       // tiles of CP_WORDS_PER_BLOCK words
+    int64_t n_tiles;       // tiles of CF_WORDS_PER_TILE words
     u32* tile_counts;      // [n_tiles]
-    u32* barrier;          // one counter, monotonically increasing across launches
-    u32 barrier_target;    // value the counter reaches when every block of THIS launch has arrived
+    u32* barrier;          // {arrival count, generation}: self-resetting, no host-side state
     u64* total;
     int32_t* out_idx;
     int64_t capacity;
     int64_t row_base;
 };
 
+// thread t of a tile owns words [16 t, 16 t + 16): four consecutive 128-bit loads
+__device__ __forceinline__ u32 cf_load(const CompactFusedParams& P, int64_t tile, uint4 (&v)[CF_VEC]) {
+    const int64_t w0 = tile * CF_WORDS_PER_TILE + (int64_t)threadIdx.x * 4 * CF_VEC;
+    u32 c = 0;
+#pragma unroll
+    for (int k = 0; k < CF_VEC; ++k) {
+        v[k] = load_words4(P.bits, w0 + 4 * k, P.n_words);
+        c += __popc(v[k].x) + __popc(v[k].y) + __popc(v[k].z) + __popc(v[k].w);
+    }
+    return c;
+}
+
 __global__ void __launch_bounds__(CP_THREADS) compact_fused_kernel(const CompactFusedParams P) {
     __shared__ u32 s_warp[33];
     __shared__ u64 s_base;
-    // phase 1: popcount my tiles
-    for (int64_t t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
-        const int64_t w0 = (t * CP_THREADS + threadIdx.x) * 4;
-        uint4 v = load_words4(P.bits, w0, P.n_words);
-        u32 c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
-        u32 total;
-        block_exclusive_scan(c, s_warp, total);
-        if (threadIdx.x == 0) P.tile_counts[t] = total;
+    uint4 v[CF_VEC];
+    {
+        // phase 1: popcount my tiles
+        for (int64_t t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
+            u32 c = cf_load(P, t, v);
+            u32 total;
+            block_exclusive_scan(c, s_warp, total);
+            if (threadIdx.x == 0) P.tile_counts[t] = total;
+            __syncthreads();
+        }
+        // grid barrier (sense reversal on a generation word; the grid is co-resident by cooperative launch)
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            volatile u32* gen = P.barrier + 1;
+            const u32 my_gen = *gen;
+            if (atomicAdd(P.barrier, 1u) == gridDim.x - 1) {
+                P.barrier[0] = 0;
+                __threadfence();
+                atomicAdd(P.barrier + 1, 1u);
+            } else {
+                while (*gen == my_gen) {}
+            }
+            __threadfence();
+        }
         __syncthreads();
     }
-    // grid barrier (release my counts, wait for everybody's)
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        atomicAdd(P.barrier, 1u);
-        while (*reinterpret_cast<volatile u32*>(P.barrier) < P.barrier_target) {}
-        __threadfence();
-    }
-    __syncthreads();
-    // phase 2: for each of my tiles, prefix = sum of the counts of all earlier tiles (block-wide reduction), then write
+    // phase 2: prefix of each of my tiles = sum of the counts of all earlier tiles (carried forward), then write
     int64_t prev_tile = 0;
-    u64 running = 0;  // exclusive prefix at prev_tile, carried forward so each count is read once per block
+    u64 running = 0;
     for (int64_t t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
         u32 part = 0;
         for (int64_t i = prev_tile + threadIdx.x; i < t; i += CP_THREADS) part += P.tile_counts[i];
@@ -1174,24 +1196,25 @@ __global__ void __launch_bounds__(CP_THREADS) compact_fused_kernel(const Compact
         __syncthreads();
         running = s_base;
         prev_tile = t;
-        const u32 my_tile_count = P.tile_counts[t];
-        if (my_tile_count != 0) {
-            const int64_t w0 = (t * CP_THREADS + threadIdx.x) * 4;
-            uint4 v = load_words4(P.bits, w0, P.n_words);
-            u32 c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        if (P.tile_counts[t] != 0) {
+            u32 c = cf_load(P, t, v);
             u32 total;
             u32 ex = block_exclusive_scan(c, s_warp, total);
             int64_t pos = (int64_t)running + ex;
-            const u32 w[4] = {v.x, v.y, v.z, v.w};
+            const int64_t w0 = t * CF_WORDS_PER_TILE + (int64_t)threadIdx.x * 4 * CF_VEC;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                u32 m = w[k];
-                const int64_t rb = P.row_base + ((w0 + k) << 5);
-                while (m) {
-                    int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    if (pos < P.capacity) P.out_idx[pos] = (int32_t)(rb + b);
-                    ++pos;
+            for (int k = 0; k < CF_VEC; ++k) {
+                const u32 w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    u32 m = w[j];
+                    const int64_t rb = P.row_base + ((w0 + 4 * k + j) << 5);
+                    while (m) {
+                        int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        if (pos < P.capacity) P.out_idx[pos] = (int32_t)(rb + b);
+                        ++pos;
+                    }
                 }
             }
         }
