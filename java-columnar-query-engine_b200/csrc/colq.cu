@@ -72,6 +72,7 @@ struct Column {
     DevBuf targets;   // CSR targets
     int64_t n_bytes = 0;         // string payload bytes
     int64_t bytes_capacity = 0;  // usable allocation of `data` for strings (multiple of 16)
+    int64_t max_tile_bytes = 0;  // largest payload of a 1024-row scan tile (sizes the TMA ring slot)
     // association columns (M/InMemoryColumn.java:85-138)
     bool forward = false;  // true: this column owns the data; false: reverse column = transpose of the peer
     bool is_fk = false;    // forward data is a dense to-one array (else CSR)
@@ -518,17 +519,21 @@ struct Planner {
             P.needle = (const uint8_t*)c->needle_dev.ptr;
             P.needle_len = (int)c->needle.size();
             P.op = c->op;
-            double avg = n > 0 ? (double)col.n_bytes / (double)n : 0.0;
-            int64_t cap = (int64_t)(2.0 * avg * ST_ROWS) + 256;
-            cap = std::min<int64_t>(std::max<int64_t>(cap, 4096), 40960);
+            // ring geometry: a slot holds the column's largest tile payload (measured at ingest) plus the two 16-byte
+            // alignment margins, so every tile is staged unless it exceeds the 40 KB limit (then it is read from global
+            // memory); 3 slots per CTA leave room for 4-5 resident CTAs per SM, which is what saturates HBM (r01 sweep
+            // in profiles/r01_scan_str_ring_sweep.txt)
+            static const int stages_env = getenv("COLQ_STR_STAGES") ? atoi(getenv("COLQ_STR_STAGES")) : 3;
+            int64_t cap = std::min<int64_t>(std::max<int64_t>(col.max_tile_bytes + 48, 2048), 40960);
             P.cap = (int)round_up(cap, 16);
+            P.stages = std::max(2, std::min(stages_env, (int)ST_MAX_STAGES));
             P.n_tiles = (n + ST_ROWS - 1) / ST_ROWS;
             P.in_bits = cur;
             u32* ob;
             ST(out_buf(&ob));
             P.out_bits = ob;
-            o.smem = (size_t)ST_STAGES * st_stage_bytes(P.cap) + st_needle_region(P.needle_len) + 2 * ST_STAGES * 8 +
-                     ST_STAGES * sizeof(StrTileMeta) + PUSH_SMEM_WORDS * 4;
+            o.smem = (size_t)P.stages * st_stage_bytes(P.cap) + st_needle_region(P.needle_len) + 2 * ST_MAX_STAGES * 8 +
+                     ST_MAX_STAGES * sizeof(StrTileMeta) + PUSH_SMEM_WORDS * 4;
             o.acct_rows = n;
             o.acct_bytes = (n + 1) * 4 + col.n_bytes + bitmap_words(n) * 4;
             q->ops.push_back(o);
@@ -1292,7 +1297,19 @@ colq_status colq_col_i32_device(colq_ctx* ctx, colq_table table, int ordinal, co
 
 static colq_status finish_str(colq_ctx* ctx, Column* c, int64_t n, int64_t n_bytes) {
     c->kind = COL_STR; c->n = n; c->n_bytes = n_bytes;
-    (void)ctx;
+    c->max_tile_bytes = 0;
+    if (n > 0) {
+        DevBuf mx;
+        ST(dev_alloc(ctx, mx, 4));
+        CU(ctx, cudaMemsetAsync(mx.ptr, 0, 4, ctx->stream));
+        const int64_t n_tiles = (n + ST_ROWS - 1) / ST_ROWS;
+        tile_payload_max_kernel<<<grid_for(n_tiles, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>((const u32*)c->offsets.ptr, n, (u32*)mx.ptr);
+        CU(ctx, cudaGetLastError());
+        u32 got = 0;
+        CU(ctx, cudaMemcpyAsync(&got, mx.ptr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        c->max_tile_bytes = got;
+    }
     return COLQ_OK;
 }
 

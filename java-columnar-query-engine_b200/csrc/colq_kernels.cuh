@@ -357,7 +357,7 @@ constexpr int ST_CONSUMER_WARPS = 8;
 constexpr int ST_CONSUMER_THREADS = ST_CONSUMER_WARPS * 32;  // 256
 constexpr int ST_THREADS = ST_CONSUMER_THREADS + 32;         // + 1 producer warp
 constexpr int ST_ROWS = 4 * ST_CONSUMER_THREADS;             // 1024 rows per tile
-constexpr int ST_STAGES = 4;
+constexpr int ST_MAX_STAGES = 8;  // ring depth is a launch parameter (ScanStrParams::stages)
 constexpr int ST_OFF_BYTES = (ST_ROWS + 4) * 4;  // offsets slice incl. the closing offset, padded to 16 B
 constexpr int ST_SLACK = 32;                     // readable bytes behind the staged byte range
 constexpr int ST_MAX_NEEDLE = 16384;             // needle bytes are staged in shared memory next to the ring
@@ -378,6 +378,7 @@ struct ScanStrParams {
     int needle_len;
     int op;
     int cap;                 // bytes slot size of one ring stage (multiple of 16)
+    int stages;              // ring depth, 2..ST_MAX_STAGES
     int64_t n_tiles;
     const u32* in_bits;
     u32* out_bits;
@@ -530,11 +531,12 @@ __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParam
     // layout: [stage: offsets | bytes(cap + slack)] x STAGES | needle words | full[] | empty[] | metas | reach
     const int stage_bytes = st_stage_bytes(P.cap);
     const int needle_region = st_needle_region(P.needle_len);
-    u32* s_needle = reinterpret_cast<u32*>(smem + (size_t)ST_STAGES * stage_bytes);
+    const int n_stages = P.stages;
+    u32* s_needle = reinterpret_cast<u32*>(smem + (size_t)n_stages * stage_bytes);
     u64* s_full = reinterpret_cast<u64*>(reinterpret_cast<uint8_t*>(s_needle) + needle_region);
-    u64* s_empty = s_full + ST_STAGES;
-    StrTileMeta* s_meta = reinterpret_cast<StrTileMeta*>(s_empty + ST_STAGES);
-    u32* s_reach = reinterpret_cast<u32*>(s_meta + ST_STAGES);
+    u64* s_empty = s_full + ST_MAX_STAGES;
+    StrTileMeta* s_meta = reinterpret_cast<StrTileMeta*>(s_empty + ST_MAX_STAGES);
+    u32* s_reach = reinterpret_cast<u32*>(s_meta + ST_MAX_STAGES);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool do_push = P.push.fk != nullptr;
@@ -549,7 +551,7 @@ __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParam
     }
     if (do_push) push_init(P.push, s_reach);
     if (tid == 0) {
-        for (int s = 0; s < ST_STAGES; ++s) {
+        for (int s = 0; s < n_stages; ++s) {
             mbar_init(&s_full[s], 1);
             mbar_init(&s_empty[s], ST_CONSUMER_WARPS);
         }
@@ -572,11 +574,12 @@ __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParam
                 gb1 = __ldg(P.offsets + r1);
             };
             if (my_tiles > 0) tile_bounds(0, nb0, nb1);
+            int s = 0;
+            u32 round = 0;  // how many times the ring has wrapped
             for (int64_t k = 0; k < my_tiles; ++k) {
-                const int s = (int)(k % ST_STAGES);
                 const u32 gb0 = nb0, gb1 = nb1;
                 if (k + 1 < my_tiles) tile_bounds(k + 1, nb0, nb1);  // in flight while we wait for the slot
-                if (k >= ST_STAGES) mbar_wait(&s_empty[s], (u32)(((k / ST_STAGES) - 1) & 1));
+                if (round > 0) mbar_wait(&s_empty[s], (round - 1) & 1);
                 const int64_t r0 = (first_tile + k * tile_stride) * ST_ROWS;
                 const int nr = (int)((P.n - r0) < ST_ROWS ? (P.n - r0) : ST_ROWS);
                 uint8_t* base = smem + (size_t)s * stage_bytes;
@@ -590,6 +593,10 @@ __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParam
                 mbar_arrive_expect_tx(&s_full[s], off_bytes + (fast ? (u32)sz : 0u));
                 tma_bulk_g2s(base, P.offsets + r0, off_bytes, &s_full[s]);
                 if (fast && sz > 0) tma_bulk_g2s(base + ST_OFF_BYTES, P.bytes + a0, (u32)sz, &s_full[s]);
+                if (++s == n_stages) {
+                    s = 0;
+                    ++round;
+                }
             }
         }
     } else {
@@ -691,7 +698,7 @@ __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParam
                 // write every word that overlaps the table, rounded up to whole 64-row BitSet words
                 if (lane < 4 && (w0 + lane) < n_words_out) out_bits[w0 + lane] = y;
             }
-            if (++s == ST_STAGES) {
+            if (++s == (u32)n_stages) {
                 s = 0;
                 parity ^= 1;
             }
@@ -1231,6 +1238,20 @@ __global__ void __launch_bounds__(256) popc_total_kernel(const u32* bits, int64_
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) c += __popc(bits[i]);
     for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(FULL_MASK, c, d);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd((unsigned long long*)out, (unsigned long long)c);
+}
+
+// string ingest: the largest byte payload of any 1024-row scan tile; sizes the TMA ring slots of scan_str exactly
+__global__ void __launch_bounds__(256) tile_payload_max_kernel(const u32* offsets, int64_t n, u32* out_max) {
+    const int64_t n_tiles = (n + ST_ROWS - 1) / ST_ROWS;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    u32 m = 0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += stride) {
+        const int64_t r0 = t * ST_ROWS, r1 = (r0 + ST_ROWS) < n ? (r0 + ST_ROWS) : n;
+        const u32 b = offsets[r1] - offsets[r0];
+        m = b > m ? b : m;
+    }
+    m = __reduce_max_sync(FULL_MASK, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out_max, m);
 }
 
 // association ingest check: min / max of a to-one column (M/InMemoryTable.java:70-71 would NPE on a bad target)
