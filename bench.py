@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--cpu-universes", type=int, default=1000, help="bounded sample for the CPU baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-small-queries", action="store_true", help="skip the 1-universe latency measurements (keeps ncu launch lists clean)")
     ap.add_argument("--eager", action="store_true", help="disable the lazy FK chain (materialise every node)")
     ap.add_argument("--workload", default="plymouth", choices=["plymouth", "int_scan", "str_eq"],
                     help="plymouth = BASELINE configs[3] (the headline); int_scan = configs[1] (1B-row int range scan + "
@@ -314,7 +315,7 @@ def run_colq(args, rank, local_rank, world):
     ms_res = max_over_ranks(e0.elapsed_time(e1)) / n_res
     d2h_res = int(r2.timing.d2h_bytes)
 
-    small = small_query_latency(base) if world == 1 else None
+    small = small_query_latency(base) if (world == 1 and not args.no_small_queries) else None
 
     # ---- e2e: HOST buffers in, matched indices out, every step (columns re-uploaded from pinned memory)
     e2e = None
