@@ -111,6 +111,7 @@ typedef struct colq_stage {
 int colq_abi_version(void);
 /* new DataSystemSerialIndices() (E/DataSystemSerialIndices.java:20-22). device = CUDA ordinal. */
 colq_status colq_create(int device, colq_ctx **out_ctx);
+/* also destroys every query still alive on the context */
 colq_status colq_destroy(colq_ctx *ctx);
 const char *colq_last_error(const colq_ctx *ctx);
 /* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores the context's own stream */

@@ -13,6 +13,7 @@ Two layers:
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -57,6 +58,7 @@ class ColqQuery:
         self.ctx = ctx
         self.handle = C.c_void_p()
         ctx._check(ctx.lib.colq_query_create(ctx.handle, table_name.encode(), C.byref(self.handle)))
+        ctx._queries.add(self)
 
     def child(self, parent: int, ordinal: int) -> int:
         out = C.c_int()
@@ -97,9 +99,9 @@ class ColqQuery:
         return [out[i] for i in range(min(n.value, 64))]
 
     def close(self) -> None:
-        if self.handle:
+        if self.handle and self.ctx.handle:
             self.ctx.lib.colq_query_destroy(self.handle)
-            self.handle = C.c_void_p()
+        self.handle = C.c_void_p()
 
     def __del__(self):  # pragma: no cover
         try:
@@ -122,6 +124,7 @@ class ColqContext:
                                 "(libcolq has no CPU fallback)")
         self.device = device
         self._keepalive: List[object] = []
+        self._queries = weakref.WeakSet()   # colq_destroy frees a context's queries: close them first
 
     # -- plumbing
     def last_error(self) -> str:
@@ -219,6 +222,8 @@ class ColqContext:
 
     def close(self) -> None:
         if self.handle:
+            for q in list(self._queries):
+                q.close()
             self.lib.colq_destroy(self.handle)
             self.handle = C.c_void_p()
 

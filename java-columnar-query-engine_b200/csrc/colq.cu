@@ -161,6 +161,7 @@ struct colq_ctx {
     cudaStream_t stream = nullptr;
     std::vector<Table> tables;
     std::map<std::string, int> registry;
+    std::vector<colq_query*> queries;  // live queries; destroyed with the context
     std::string err;
     // communicator
     NcclApi nccl;
@@ -1196,6 +1197,7 @@ colq_status colq_destroy(colq_ctx* ctx) {
     if (!ctx) return COLQ_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    while (!ctx->queries.empty()) colq_query_destroy(ctx->queries.back());  // a context owns its queries
     destroy_peerbox(ctx);
     if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
     ctx->tables.clear();
@@ -1451,12 +1453,15 @@ colq_status colq_query_create(colq_ctx* ctx, const char* table_name, colq_query*
     q->ctx = ctx;
     q->table_name = table_name;
     q->nodes.emplace_back();  // rootNode (DS/Query.java:22-25)
+    ctx->queries.push_back(q);
     *out_query = q;
     return COLQ_OK;
 }
 
 colq_status colq_query_destroy(colq_query* q) {
     if (!q) return COLQ_OK;
+    auto& live = q->ctx->queries;
+    live.erase(std::remove(live.begin(), live.end(), q), live.end());
     cudaSetDevice(q->ctx->device);
     cudaStreamSynchronize(q->ctx->stream);
     if (q->graph_exec) cudaGraphExecDestroy(q->graph_exec);
