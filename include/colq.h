@@ -17,7 +17,8 @@
  *   - colq_last_error(ctx) returns the message of the last non-OK status on that context (the text a
  *     QueryResult.Failure carries, DS/QueryResult.java:7).
  *   - host buffers are BORROWED for the duration of the call; the library copies them to HBM and owns
- *     the device memory until colq_destroy.
+ *     the device memory until colq_destroy.  Exception: the `*_host` variants keep borrowing pinned buffers
+ *     (see "Host-resident columns").
  *   - bitmasks use the java.util.BitSet word layout: row i <-> words[i >> 6] & (1L << (i & 63)),
  *     little-endian uint64, so BitSet.valueOf(LongBuffer) wraps the output directly.
  *   - one context per process and GPU; calls on one context must not overlap (the Java shim holds a lock).
@@ -84,7 +85,14 @@ typedef enum colq_option {
        peers' HBM over NVLink (CUDA-IPC mailboxes); 0: NCCL all-gathers */
     COLQ_OPT_PEER_EXCHANGE = 3,
     /* 1 (default): one cooperative compaction launch; 0: popcount / scan / write as three launches */
-    COLQ_OPT_FUSED_COMPACT = 4
+    COLQ_OPT_FUSED_COMPACT = 4,
+    /* 1 (default): the root node's lazy FK chains are walked by the fused compaction kernel for the rows that
+       survived the root's predicates (the row scan stays a pure coalesced stream); 0: inside the row scan.
+       Needs COLQ_OPT_LAZY_FK and COLQ_OPT_FUSED_COMPACT. */
+    COLQ_OPT_DEFER_CHAINS = 5,
+    /* 1 (default): the first scan that streams a host-resident column (colq_*_host) over PCIe also leaves a copy in
+       HBM, which later queries use; 0: keep streaming from pinned host memory every time */
+    COLQ_OPT_PROMOTE = 6
 } colq_option;
 
 typedef struct colq_ctx colq_ctx;       /* one DataSystem instance  (E/DataSystemSerialIndices.java:14-22) */
@@ -95,7 +103,7 @@ typedef struct colq_timing {
     double gpu_ms;          /* CUDA-event time of the whole kernel(+collective) pipeline of the last execute */
     int32_t kernel_launches;/* kernels of this library launched by the last execute */
     int32_t collectives;    /* NCCL calls issued by the last execute */
-    int64_t h2d_bytes;      /* bytes copied host->device by the last execute (query constants) */
+    int64_t h2d_bytes;      /* bytes the last execute streamed host->device: host-resident columns it scanned in full */
     int64_t d2h_bytes;      /* bytes copied device->host by the last execute (count, bitmask, indices) */
 } colq_timing;
 
@@ -118,6 +126,10 @@ const char *colq_last_error(const colq_ctx *ctx);
 colq_status colq_set_stream(colq_ctx *ctx, void *cuda_stream);
 colq_status colq_get_stream(colq_ctx *ctx, void **out_cuda_stream);
 colq_status colq_synchronize(colq_ctx *ctx);
+/* Freed device buffers (dropped tables, query scratch) are parked in a per-device cache and re-used instead of going
+   through cudaFree / cudaMalloc (milliseconds each, device-synchronising). colq_trim returns them to the driver;
+   the last colq_destroy on a device does it implicitly. Cache limit: COLQ_CACHE_GB (default 24). */
+colq_status colq_trim(colq_ctx *ctx);
 
 /* ---- multi-GPU: one process per GPU, host bootstraps the communicator ---------------- */
 
@@ -151,6 +163,33 @@ colq_status colq_col_str_device(colq_ctx *ctx, colq_table table, int ordinal, co
                                 int64_t n, int64_t n_bytes);
 
 /*
+ * Host-resident columns: the off-heap MemorySegment the Java shim fills IS the column (north_star: "off-heap
+ * MemorySegment column buffers").  Like DataSystemSerialIndices.register (E/DataSystemSerialIndices.java:27-29,
+ * which only keeps a reference) nothing is copied at registration: the buffer is BORROWED until colq_table_destroy
+ * / colq_destroy and the kernels read it in place over PCIe (pinned, device-mapped memory).  A query therefore moves
+ * only the bytes it touches -- the columns it scans, plus single sectors of the foreign-key columns it walks lazily --
+ * and the first scan that streams a whole column also leaves a copy in HBM (COLQ_OPT_PROMOTE), so the next query on
+ * it runs at HBM speed.
+ *   - buffers must be pinned: allocate them with colq_host_alloc (Java: MemorySegment.ofAddress(p).reinterpret(n))
+ *     or pin an Arena allocation with colq_host_register; 16-byte aligned;
+ *   - `*_capacity` is the usable size of the buffer in bytes: int / association columns need n*4 rounded up to 16,
+ *     string offsets (n+1)*4 rounded up to 16, string bytes n_bytes rounded up to 16 plus 32 (the TMA path reads
+ *     whole 16-byte lines);
+ *   - to-one targets of colq_associate_fk_host are range-checked on the rows a query walks, not at registration: a
+ *     target outside the associated table makes colq_execute / colq_fetch return COLQ_THROW_NULL (the reference's
+ *     NPE at associateTo, M/InMemoryTable.java:70-71).
+ */
+colq_status colq_host_alloc(colq_ctx *ctx, int64_t bytes, void **out_ptr);
+colq_status colq_host_free(colq_ctx *ctx, void *ptr);
+colq_status colq_host_register(colq_ctx *ctx, void *ptr, int64_t bytes);
+colq_status colq_host_unregister(colq_ctx *ctx, void *ptr);
+colq_status colq_col_i32_host(colq_ctx *ctx, colq_table table, int ordinal, const int32_t *values_pinned,
+                              int64_t capacity_bytes, int64_t n);
+colq_status colq_col_str_host(colq_ctx *ctx, colq_table table, int ordinal, const uint32_t *offsets_pinned,
+                              int64_t offsets_capacity, const uint8_t *bytes_pinned, int64_t bytes_capacity, int64_t n,
+                              int64_t n_bytes);
+
+/*
  * x.associateTo(y, associations) (M/InMemoryTable.java:44-90): creates the forward AssociationColumn on x at
  * x_ordinal AND its reverse (transposed) column on y at y_ordinal, cross-linked (:83-85).  Only the forward data
  * is stored; hops through the reverse column are executed as a push through the forward data, which is the same
@@ -166,6 +205,9 @@ colq_status colq_associate_csr(colq_ctx *ctx, colq_table x, int x_ordinal, colq_
                                const int64_t *offsets, const int32_t *targets, int64_t n, int64_t nnz);
 colq_status colq_associate_fk_device(colq_ctx *ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal,
                                      const void *fk_device, int64_t n);
+/* host-resident variant of colq_associate_fk (see "Host-resident columns" above) */
+colq_status colq_associate_fk_host(colq_ctx *ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal,
+                                   const int32_t *fk_pinned, int64_t capacity_bytes, int64_t n);
 
 /* Release a table's device memory and its registrations (the reference leaves this to the garbage collector).
    Association columns of other tables that pointed at it become unset. The handle stays reserved. */

@@ -17,7 +17,7 @@ OK, FAILURE, THROW_INDEX_OOB, THROW_NULL, THROW_ILLEGAL_STATE, THROW_ILLEGAL_ARG
 # colq_placement
 REPLICATED, SHARDED = 0, 1
 # colq_option
-OPT_LAZY_FK, OPT_PROFILE, OPT_GRAPH, OPT_PEER_EXCHANGE, OPT_FUSED_COMPACT = 0, 1, 2, 3, 4
+OPT_LAZY_FK, OPT_PROFILE, OPT_GRAPH, OPT_PEER_EXCHANGE, OPT_FUSED_COMPACT, OPT_DEFER_CHAINS, OPT_PROMOTE = 0, 1, 2, 3, 4, 5, 6
 
 
 class Timing(C.Structure):
@@ -41,6 +41,7 @@ SIGNATURES = {
     "colq_set_stream": (_int, [_p, _p]),
     "colq_get_stream": (_int, [_p, C.POINTER(_p)]),
     "colq_synchronize": (_int, [_p]),
+    "colq_trim": (_int, [_p]),
     "colq_comm_unique_id": (_int, [_p, _p]),
     "colq_comm_init": (_int, [_p, _p, _int, _int]),
     "colq_comm_info": (_int, [_p, C.POINTER(_int), C.POINTER(_int)]),
@@ -51,6 +52,13 @@ SIGNATURES = {
     "colq_col_bool": (_int, [_p, _i32, _int, _p, _i64]),
     "colq_col_i32_device": (_int, [_p, _i32, _int, _p, _i64]),
     "colq_col_str_device": (_int, [_p, _i32, _int, _p, _i64, _p, _i64, _i64, _i64]),
+    "colq_host_alloc": (_int, [_p, _i64, C.POINTER(_p)]),
+    "colq_host_free": (_int, [_p, _p]),
+    "colq_host_register": (_int, [_p, _p, _i64]),
+    "colq_host_unregister": (_int, [_p, _p]),
+    "colq_col_i32_host": (_int, [_p, _i32, _int, _p, _i64, _i64]),
+    "colq_col_str_host": (_int, [_p, _i32, _int, _p, _i64, _p, _i64, _i64, _i64]),
+    "colq_associate_fk_host": (_int, [_p, _i32, _int, _i32, _int, _p, _i64, _i64]),
     "colq_associate_fk": (_int, [_p, _i32, _int, _i32, _int, _p, _i64]),
     "colq_associate_csr": (_int, [_p, _i32, _int, _i32, _int, _p, _p, _i64, _i64]),
     "colq_associate_fk_device": (_int, [_p, _i32, _int, _i32, _int, _p, _i64]),

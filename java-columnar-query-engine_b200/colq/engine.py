@@ -124,6 +124,8 @@ class ColqContext:
                                 "(libcolq has no CPU fallback)")
         self.device = device
         self._keepalive: List[object] = []
+        self._host_buffers: Dict[int, int] = {}      # address of a host_alloc array -> pointer to free
+        self._host_views: Dict[int, np.ndarray] = {}  # address of a host_column view -> its padded raw buffer
         self._queries = weakref.WeakSet()   # colq_destroy frees a context's queries: close them first
 
     # -- plumbing
@@ -184,6 +186,62 @@ class ColqContext:
         self._check(self.lib.colq_col_str_device(self.handle, table, ordinal, C.c_void_p(off_ptr), off_cap,
                                                  C.c_void_p(bytes_ptr), bytes_cap, n, n_bytes))
 
+    # -- pinned host memory and host-resident columns (include/colq.h "Host-resident columns")
+    def host_alloc(self, nbytes: int) -> np.ndarray:
+        """A pinned, device-mapped off-heap buffer as a uint8 array (the Java shim wraps the same pointer in a
+        MemorySegment).  Freed by ``host_free`` or when the context closes."""
+        p = C.c_void_p()
+        self._check(self.lib.colq_host_alloc(self.handle, int(nbytes), C.byref(p)))
+        n = max(int(nbytes), 16)
+        a = np.ctypeslib.as_array((C.c_uint8 * n).from_address(p.value))
+        self._host_buffers[a.ctypes.data] = p.value
+        return a
+
+    def host_free(self, buf: np.ndarray) -> None:
+        p = self._host_buffers.pop(buf.ctypes.data)
+        self._check(self.lib.colq_host_free(self.handle, C.c_void_p(p)))
+
+    def host_register(self, buf: np.ndarray) -> None:
+        self._check(self.lib.colq_host_register(self.handle, C.c_void_p(buf.ctypes.data), buf.nbytes))
+
+    def host_unregister(self, buf: np.ndarray) -> None:
+        self._check(self.lib.colq_host_unregister(self.handle, C.c_void_p(buf.ctypes.data)))
+
+    def host_column(self, values: np.ndarray, dtype, pad_bytes: int = 64) -> np.ndarray:
+        """Copy ``values`` into a fresh pinned buffer padded for whole-line reads; returns the typed view (length n)."""
+        v = np.ascontiguousarray(values, dtype=dtype)
+        raw = self.host_alloc((v.nbytes + 15) // 16 * 16 + pad_bytes)
+        raw[: v.nbytes] = v.view(np.uint8).reshape(-1)
+        raw[v.nbytes:] = 0
+        out = raw[: v.nbytes].view(dtype)
+        self._host_views[out.ctypes.data] = raw
+        return out
+
+    def _capacity(self, a: np.ndarray) -> int:
+        raw = self._host_views.get(a.ctypes.data)
+        return int(raw.nbytes) if raw is not None else int(a.nbytes)
+
+    def col_i32_host(self, table: int, ordinal: int, values: np.ndarray, capacity_bytes: Optional[int] = None, n: Optional[int] = None) -> None:
+        """``values`` must live in pinned memory (``host_column`` / ``host_alloc`` / a pinned torch tensor)."""
+        n = values.shape[0] if n is None else n
+        cap = self._capacity(values) if capacity_bytes is None else capacity_bytes
+        self._keepalive.append(values)
+        self._check(self.lib.colq_col_i32_host(self.handle, table, ordinal, _ptr(values), cap, n))
+
+    def col_str_host(self, table: int, ordinal: int, offsets: np.ndarray, data: np.ndarray, n: int, n_bytes: int,
+                     offsets_capacity: Optional[int] = None, bytes_capacity: Optional[int] = None) -> None:
+        oc = self._capacity(offsets) if offsets_capacity is None else offsets_capacity
+        bc = self._capacity(data) if bytes_capacity is None else bytes_capacity
+        self._keepalive.append((offsets, data))
+        self._check(self.lib.colq_col_str_host(self.handle, table, ordinal, _ptr(offsets), oc, _ptr(data), bc, n, n_bytes))
+
+    def associate_fk_host(self, x: int, x_ordinal: int, y: int, y_ordinal: int, fk: np.ndarray,
+                          capacity_bytes: Optional[int] = None, n: Optional[int] = None) -> None:
+        n = fk.shape[0] if n is None else n
+        cap = self._capacity(fk) if capacity_bytes is None else capacity_bytes
+        self._keepalive.append(fk)
+        self._check(self.lib.colq_associate_fk_host(self.handle, x, x_ordinal, y, y_ordinal, _ptr(fk), cap, n))
+
     def associate_fk(self, x: int, x_ordinal: int, y: int, y_ordinal: int, fk: np.ndarray) -> None:
         f = np.ascontiguousarray(fk, dtype=np.int32)
         self._check(self.lib.colq_associate_fk(self.handle, x, x_ordinal, y, y_ordinal, _ptr(f), f.shape[0]))
@@ -224,6 +282,11 @@ class ColqContext:
         if self.handle:
             for q in list(self._queries):
                 q.close()
+            self._keepalive.clear()
+            self._host_views.clear()
+            for p in list(self._host_buffers.values()):
+                self.lib.colq_host_free(self.handle, C.c_void_p(p))
+            self._host_buffers.clear()
             self.lib.colq_destroy(self.handle)
             self.handle = C.c_void_p()
 
@@ -238,7 +301,13 @@ class DataSystemColq(DataSystem):
     """The reference-facing engine: same two methods as ``DataSystemSerialIndices``."""
 
     def __init__(self, device: int = 0, lazy_fk: bool = True, context: Optional[ColqContext] = None,
-                 options: Optional[Dict[int, int]] = None):
+                 options: Optional[Dict[int, int]] = None, residency: str = "device"):
+        """``residency``: "device" copies every column to HBM at the first ``execute`` (default); "host" keeps int,
+        string and to-one association columns in pinned off-heap buffers that the kernels stream in place over PCIe
+        (only what a query touches moves; fully scanned columns are promoted to HBM by that first scan)."""
+        if residency not in ("device", "host"):
+            raise ValueError(residency)
+        self.residency = residency
         self.ctx = context or ColqContext(device)
         self.lazy_fk = lazy_fk
         self.options = dict(options or {})   # colq_option -> value, applied to every query
@@ -284,10 +353,19 @@ class DataSystemColq(DataSystem):
             cols = t.columns()
             for ordinal in range(self._uploaded[tid], len(cols)):
                 c = cols[ordinal]
+                host = self.residency == "host" and t.size() > 0
                 if isinstance(c, IntegerColumn):
-                    self.ctx.col_i32(h, ordinal, c.ints())
+                    if host:
+                        self.ctx.col_i32_host(h, ordinal, self.ctx.host_column(c.ints(), np.int32))
+                    else:
+                        self.ctx.col_i32(h, ordinal, c.ints())
                 elif isinstance(c, StringColumn):
-                    self.ctx.col_str(h, ordinal, c.offsets, c.data)
+                    if host:
+                        off = self.ctx.host_column(c.offsets, np.uint32)
+                        dat = self.ctx.host_column(c.data, np.uint8)
+                        self.ctx.col_str_host(h, ordinal, off, dat, t.size(), int(c.data.shape[0]))
+                    else:
+                        self.ctx.col_str(h, ordinal, c.offsets, c.data)
                 elif isinstance(c, BooleanColumn):
                     self.ctx.col_bool(h, ordinal, c.bools())
         for tid, t in seen.items():
@@ -300,7 +378,9 @@ class DataSystemColq(DataSystem):
                     rev = c.reverse_associated_column()
                     y_ordinal = next(i for i, yc in enumerate(y.columns()) if yc is rev)
                     fk = c.fk()
-                    if fk is not None:
+                    if fk is not None and self.residency == "host" and t.size() > 0:
+                        self.ctx.associate_fk_host(h, ordinal, self._handles[id(y)], y_ordinal, self.ctx.host_column(fk, np.int32))
+                    elif fk is not None:
                         self.ctx.associate_fk(h, ordinal, self._handles[id(y)], y_ordinal, fk)
                     else:
                         _kind, offsets, targets = c.csr()

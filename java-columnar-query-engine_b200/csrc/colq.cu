@@ -25,6 +25,7 @@
 #include <deque>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -38,6 +39,48 @@ using namespace colq;
 // =====================================================================================================
 
 namespace {
+
+// Freed device buffers are parked here and handed out again (best fit, at most 25 % larger than asked): cudaMalloc /
+// cudaFree of multi-GB column buffers cost milliseconds to tens of milliseconds and synchronise the device, which
+// would dominate a cold query over host-resident tables (DESIGN.md "e2e").  All work of a context is enqueued on one
+// stream, so a block that is re-issued is only touched by work ordered after its previous user.
+struct DeviceCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks;
+    size_t cached_bytes = 0;
+    size_t limit_bytes = (size_t)(getenv("COLQ_CACHE_GB") ? atof(getenv("COLQ_CACHE_GB")) : 24.0) * ((size_t)1 << 30);
+    int live_contexts = 0;
+
+    void* take(size_t bytes, size_t* block_bytes) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = free_blocks.lower_bound(bytes);
+        if (it == free_blocks.end() || it->first > bytes + bytes / 4 + 4096) return nullptr;
+        void* p = it->second;
+        *block_bytes = it->first;
+        cached_bytes -= it->first;
+        free_blocks.erase(it);
+        return p;
+    }
+    bool park(void* p, size_t bytes) {
+        std::lock_guard<std::mutex> g(mu);
+        if (bytes < (1 << 16) || cached_bytes + bytes > limit_bytes) return false;
+        free_blocks.emplace(bytes, p);
+        cached_bytes += bytes;
+        return true;
+    }
+    void trim() {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& kv : free_blocks) cudaFree(kv.second);
+        free_blocks.clear();
+        cached_bytes = 0;
+    }
+};
+DeviceCache& device_cache() {
+    static DeviceCache caches[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return caches[dev & 63];
+}
 
 struct DevBuf {
     void* ptr = nullptr;
@@ -57,7 +100,7 @@ struct DevBuf {
     }
     ~DevBuf() { release(); }
     void release() {
-        if (owned && ptr) cudaFree(ptr);
+        if (owned && ptr && !device_cache().park(ptr, bytes)) cudaFree(ptr);
         ptr = nullptr; bytes = 0; owned = false;
     }
 };
@@ -71,6 +114,7 @@ struct Column {
     DevBuf offsets;   // string offsets (u32, n+1) | CSR offsets (i64, n+1)
     DevBuf targets;   // CSR targets
     int64_t n_bytes = 0;         // string payload bytes
+    int64_t nnz = 0;             // CSR edges
     int64_t bytes_capacity = 0;  // usable allocation of `data` for strings (multiple of 16)
     int64_t max_tile_bytes = 0;  // largest payload of a 1024-row scan tile (sizes the TMA ring slot)
     // association columns (M/InMemoryColumn.java:85-138)
@@ -78,6 +122,12 @@ struct Column {
     bool is_fk = false;    // forward data is a dense to-one array (else CSR)
     int peer_table = -1;   // associatedEntity
     int peer_ordinal = -1; // reverseAssociatedColumn
+    // host-resident columns (colq_*_host): `data` / `offsets` point at pinned host memory that the kernels read in
+    // place over PCIe.  The first scan that streams the whole column also fills `promoted*` (HBM copies), which then
+    // replace the host pointers: later queries run at HBM speed.  Sparsely walked columns (lazy FK chains) stay put.
+    bool host_resident = false;
+    bool fk_validated = true;  // false: to-one targets are range-checked on the rows a query walks, not at ingest
+    DevBuf promoted, promoted_offsets;
 };
 
 struct Table {
@@ -181,7 +231,7 @@ struct colq_ctx {
         int64_t slot_cap = 0;
         size_t slot_bytes = 0;
     } peer;
-    int compact_grid = 0;  // co-resident grid of compact_fused_kernel
+    int compact_grid[CF_MAX_GATHER + 1] = {};  // co-resident grid of compact_fused_kernel<NG>
     std::map<std::pair<int, size_t>, int> str_occupancy;  // (kernel mode, dynamic smem bytes) -> resident CTAs per SM
 };
 
@@ -189,7 +239,11 @@ struct colq_query {
     colq_ctx* ctx = nullptr;
     std::string table_name;
     std::vector<QNode> nodes;
-    int opt_lazy = 1, opt_profile = 0, opt_graph = 1, opt_peer = 1, opt_fused_compact = 1;
+    int opt_lazy = 1, opt_profile = 0, opt_graph = 1, opt_peer = 1, opt_fused_compact = 1, opt_defer = 1, opt_promote = 1;
+    std::vector<GatherD> deferred;  // root-node FK chains resolved by the compaction kernel instead of the row scan
+    std::vector<Column*> pending_promotions;  // host-resident columns whose HBM copy this execution fills
+    bool lazy_oob = false;  // the plan walks a to-one column that was not range-checked at ingest
+    int64_t promoted_bytes = 0;
     DevBuf barrier_buf;  // {arrival count, generation} of the cooperative compaction kernel
     // execution state
     Pool pool;
@@ -262,9 +316,19 @@ inline int64_t bitmap_words(int64_t n_rows) { return (n_rows + 31) / 32; }
 
 colq_status dev_alloc(colq_ctx* ctx, DevBuf& b, size_t bytes) {
     b.release();
-    void* p = nullptr;
-    CU(ctx, cudaMalloc(&p, std::max<size_t>(bytes, 16)));
-    b.ptr = p; b.bytes = std::max<size_t>(bytes, 16); b.owned = true;
+    bytes = std::max<size_t>(bytes, 16);
+    DeviceCache& cache = device_cache();
+    size_t got = 0;
+    void* p = cache.take(bytes, &got);
+    if (!p) {
+        got = bytes;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {  // out of memory: give the parked blocks back and retry once
+            cudaGetLastError();
+            cache.trim();
+            CU(ctx, cudaMalloc(&p, bytes));
+        }
+    }
+    b.ptr = p; b.bytes = got; b.owned = true;
     return COLQ_OK;
 }
 
@@ -403,6 +467,37 @@ struct Planner {
 
     bool sharded(const Table& t) const { return ctx->n_ranks > 1 && t.placement == COLQ_SHARDED; }
 
+    u32* oob_flag() const { return (u32*)q->idx_buf.ptr + RESULT_FLAGS_WORD; }
+
+    // a to-one column about to be walked by a kernel: unvalidated (host-resident) ones report bad targets lazily
+    u32* oob_for(const Column& fk_col) {
+        if (fk_col.fk_validated) return nullptr;
+        q->lazy_oob = true;
+        return oob_flag();
+    }
+
+    // first-touch promotion of a host-resident column that the next launch reads in full: allocate the HBM copy the
+    // kernel fills.  Out of device memory is not an error -- the column simply keeps being streamed over PCIe.
+    bool want_promotion(const Column& col_c, size_t data_bytes, size_t offsets_bytes) {
+        Column& col = const_cast<Column&>(col_c);
+        if (!col.host_resident || !q->opt_promote) return false;
+        if (!col.promoted.ptr) {
+            DevBuf d, o;
+            if (dev_alloc(ctx, d, data_bytes) != COLQ_OK || (offsets_bytes && dev_alloc(ctx, o, offsets_bytes) != COLQ_OK)) {
+                cudaGetLastError();
+                return false;
+            }
+            // the kernels write whole 16-byte lines of real data; zero the padding behind them once
+            cudaMemsetAsync((char*)d.ptr + (data_bytes - 64), 0, 64, ctx->stream);
+            if (offsets_bytes) cudaMemsetAsync((char*)o.ptr + (offsets_bytes - 32), 0, 32, ctx->stream);
+            col.promoted = std::move(d);
+            col.promoted_offsets = std::move(o);
+        }
+        q->pending_promotions.push_back(&col);
+        q->promoted_bytes += (int64_t)(data_bytes + offsets_bytes);
+        return true;
+    }
+
     bool lazy_eligible(int xi) const {
         const XNode& x = q->xnodes[xi];
         if (!q->opt_lazy || !x.preds.empty() || x.children.size() != 1) return false;
@@ -436,12 +531,14 @@ struct Planner {
                     g.fk[0] = (const int32_t*)col.data.ptr;
                     g.n[0] = CT.n_rows;
                     g.depth = 1;
+                    g.oob = oob_for(col);
                     int cj = ci;
                     while (g.depth < GATHER_MAX_DEPTH && lazy_eligible(cj)) {
                         XNode& c = q->xnodes[cj];
                         const Column& ccol = ctx->tables[c.table].cols[c.children[0].first];
                         g.fk[g.depth] = (const int32_t*)ccol.data.ptr;
                         g.n[g.depth] = ctx->tables[ccol.peer_table].n_rows;
+                        if (u32* f = oob_for(ccol)) g.oob = f;
                         g.depth++;
                         c.fused = true;
                         cj = c.children[0].second;
@@ -529,6 +626,11 @@ struct Planner {
             P.cap = (int)round_up(cap, 16);
             P.stages = std::max(2, std::min(stages_env, (int)ST_MAX_STAGES));
             P.n_tiles = (n + ST_ROWS - 1) / ST_ROWS;
+            if (col.host_resident) q->timing.h2d_bytes += (n + 1) * 4 + col.n_bytes;  // streamed over PCIe by this launch
+            if (P.n_tiles > 0 && want_promotion(col, (size_t)round_up(col.n_bytes, 16) + 64, (size_t)round_up((n + 1) * 4, 16) + 32)) {
+                P.promote_bytes = (uint8_t*)col.promoted.ptr;
+                P.promote_offsets = (u32*)col.promoted_offsets.ptr;
+            }
             P.in_bits = cur;
             u32* ob;
             ST(out_buf(&ob));
@@ -546,6 +648,14 @@ struct Planner {
         for (const Crit* c : xr.preds)
             if (!c->is_str) ints.push_back(c);
         size_t pi = 0, gi = 0;
+        // The root's criteria-free to-one chains need not stall the streaming scan: when a predicate (or an earlier
+        // mask) already thins the rows out, hand the chains to the fused compaction, which walks them for the
+        // surviving bits only, spread over the whole grid (COLQ_OPT_DEFER_CHAINS).
+        if (xi == 0 && !consume.push && q->opt_defer && q->opt_lazy && q->opt_fused_compact && !gathers.empty() &&
+            gathers.size() <= (size_t)CF_MAX_GATHER && (!ints.empty() || cur != nullptr)) {
+            q->deferred = gathers;
+            gi = gathers.size();
+        }
         while (pi < ints.size() || gi < gathers.size()) {
             Op o{};
             o.kind = K_SCAN_ROWS; o.node = xi; o.name = "scan_rows";
@@ -564,6 +674,8 @@ struct Planner {
                 } else {
                     d.lo = c->lo;
                     d.span = (u32)((int64_t)c->hi - (int64_t)c->lo);
+                    if (col.host_resident) q->timing.h2d_bytes += n * 4;
+                    if (n > 0 && want_promotion(col, (size_t)round_up(n * 4 + 16, 16) + 64, 0)) d.promote = (int32_t*)col.promoted.ptr;
                 }
                 bytes += n * 4;
             }
@@ -596,7 +708,7 @@ struct Planner {
             ST(out_buf(&ob));
             P.out_bits = ob;
             o.acct_rows = n;
-            o.acct_bytes = (n + 1) * 8 + (int64_t)(ci.col->targets.bytes) + bitmap_words(n) * 4;
+            o.acct_bytes = (n + 1) * 8 + ci.col->nnz * 4 + bitmap_words(n) * 4;
             q->ops.push_back(o);
             cur = ob;
         }
@@ -613,7 +725,7 @@ struct Planner {
                 last->rows.out_bits = nullptr;
                 xr.bits = nullptr; xr.all_ones = false; xr.fused = true;
             } else if (last && consume.fwd->is_fk) {
-                PushD pd{(const int32_t*)consume.fwd->data.ptr, consume.reach, consume.n_parent};
+                PushD pd{(const int32_t*)consume.fwd->data.ptr, consume.reach, consume.n_parent, oob_for(*consume.fwd)};
                 if (last->kind == K_SCAN_ROWS) { last->rows.push = pd; last->rows.out_bits = nullptr; }
                 else if (last->kind == K_SCAN_STR) { last->str.push = pd; last->str.out_bits = nullptr; }
                 else { last->csr.push = pd; last->csr.out_bits = nullptr; }
@@ -634,8 +746,9 @@ struct Planner {
                 }
                 P.reach = consume.reach;
                 P.n_parent = consume.n_parent;
+                P.oob = consume.fwd->is_fk ? oob_for(*consume.fwd) : nullptr;
                 o.acct_rows = n;
-                o.acct_bytes = bitmap_words(n) * 4 + (consume.fwd->is_fk ? n * 4 : (int64_t)consume.fwd->targets.bytes);
+                o.acct_bytes = bitmap_words(n) * 4 + (consume.fwd->is_fk ? n * 4 : consume.fwd->nnz * 4);
                 q->ops.push_back(o);
                 xr.bits = cur;
                 xr.all_ones = (cur == nullptr);
@@ -676,6 +789,14 @@ void launch_scan_rows(const Op& o, cudaStream_t s) {
     }
 }
 
+inline const void* compact_fused_fn(int ng) {
+    switch (ng) {
+        case 0: return (const void*)compact_fused_kernel<0>;
+        case 1: return (const void*)compact_fused_kernel<1>;
+        default: return (const void*)compact_fused_kernel<2>;
+    }
+}
+
 inline int grid_for(int64_t work_items, int threads, int sm_count, int per_sm) {
     int64_t g = (work_items + threads - 1) / threads;
     return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)sm_count * per_sm));
@@ -700,28 +821,31 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
             const int nl = o.str.needle_len, op = o.str.op;
             const bool fixed = (op == OP_EQ || op == OP_NE || op == OP_STARTS_WITH || op == OP_ENDS_WITH) && nl >= 1 && nl <= 16;
             const int mode = fixed ? -((nl + 3) / 4) - (op == OP_EQ ? 0 : 4) : op;
+            const bool promote = o.str.promote_bytes != nullptr;
             void (*kern)(const ScanStrParams) = nullptr;
+#define COLQ_STR_KERNEL(M) (promote ? scan_str_kernel<M, true> : scan_str_kernel<M, false>)
             switch (mode) {
-                case -1: kern = scan_str_kernel<-1>; break;
-                case -2: kern = scan_str_kernel<-2>; break;
-                case -3: kern = scan_str_kernel<-3>; break;
-                case -4: kern = scan_str_kernel<-4>; break;
-                case -5: kern = scan_str_kernel<-5>; break;
-                case -6: kern = scan_str_kernel<-6>; break;
-                case -7: kern = scan_str_kernel<-7>; break;
-                case -8: kern = scan_str_kernel<-8>; break;
-                case OP_EQ: kern = scan_str_kernel<OP_EQ>; break;
-                case OP_CONTAINS: kern = scan_str_kernel<OP_CONTAINS>; break;
-                case OP_CMP_GT: kern = scan_str_kernel<OP_CMP_GT>; break;
-                case OP_CMP_LT: kern = scan_str_kernel<OP_CMP_LT>; break;
-                case OP_CMP_GE: kern = scan_str_kernel<OP_CMP_GE>; break;
-                case OP_CMP_LE: kern = scan_str_kernel<OP_CMP_LE>; break;
-                case OP_NE: kern = scan_str_kernel<OP_NE>; break;
-                case OP_STARTS_WITH: kern = scan_str_kernel<OP_STARTS_WITH>; break;
-                default: kern = scan_str_kernel<OP_ENDS_WITH>; break;
+                case -1: kern = COLQ_STR_KERNEL(-1); break;
+                case -2: kern = COLQ_STR_KERNEL(-2); break;
+                case -3: kern = COLQ_STR_KERNEL(-3); break;
+                case -4: kern = COLQ_STR_KERNEL(-4); break;
+                case -5: kern = COLQ_STR_KERNEL(-5); break;
+                case -6: kern = COLQ_STR_KERNEL(-6); break;
+                case -7: kern = COLQ_STR_KERNEL(-7); break;
+                case -8: kern = COLQ_STR_KERNEL(-8); break;
+                case OP_EQ: kern = COLQ_STR_KERNEL(OP_EQ); break;
+                case OP_CONTAINS: kern = COLQ_STR_KERNEL(OP_CONTAINS); break;
+                case OP_CMP_GT: kern = COLQ_STR_KERNEL(OP_CMP_GT); break;
+                case OP_CMP_LT: kern = COLQ_STR_KERNEL(OP_CMP_LT); break;
+                case OP_CMP_GE: kern = COLQ_STR_KERNEL(OP_CMP_GE); break;
+                case OP_CMP_LE: kern = COLQ_STR_KERNEL(OP_CMP_LE); break;
+                case OP_NE: kern = COLQ_STR_KERNEL(OP_NE); break;
+                case OP_STARTS_WITH: kern = COLQ_STR_KERNEL(OP_STARTS_WITH); break;
+                default: kern = COLQ_STR_KERNEL(OP_ENDS_WITH); break;
             }
+#undef COLQ_STR_KERNEL
             if (o.grid == 0) {
-                const std::pair<int, size_t> key(mode, o.smem);
+                const std::pair<int, size_t> key(promote ? mode + 100 : mode, o.smem);
                 auto it = ctx->str_occupancy.find(key);
                 if (it == ctx->str_occupancy.end()) {
                     CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -779,7 +903,7 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
             break;
         case K_COMPACT_FUSED: {
             void* args[] = {(void*)&o.cfused};
-            CU(ctx, cudaLaunchCooperativeKernel((const void*)compact_fused_kernel, dim3(o.grid), dim3(CP_THREADS), args, 0, s));
+            CU(ctx, cudaLaunchCooperativeKernel(compact_fused_fn(o.ng), dim3(o.grid), dim3(CP_THREADS), args, 0, s));
             q->timing.kernel_launches++;
             break;
         }
@@ -809,7 +933,10 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
 
 colq_status ensure_idx_capacity(colq_query* q, int64_t want) {
     const size_t need = (size_t)(want + GATHER_HEADER_WORDS) * 4;
-    if (q->idx_buf.bytes < need) ST(dev_alloc(q->ctx, q->idx_buf, need));
+    if (q->idx_buf.bytes < need) {
+        ST(dev_alloc(q->ctx, q->idx_buf, need));
+        CU(q->ctx, cudaMemsetAsync(q->idx_buf.ptr, 0, GATHER_HEADER_WORDS * 4, q->ctx->stream));
+    }
     q->d_total = (u64*)q->idx_buf.ptr;
     q->d_idx = (int32_t*)q->idx_buf.ptr + GATHER_HEADER_WORDS;
     q->idx_capacity = (int64_t)(q->idx_buf.bytes / 4) - GATHER_HEADER_WORDS;
@@ -824,12 +951,21 @@ colq_status run_pipeline(colq_query* q) {
     q->pool.reset();
     q->ops.clear();
     q->timing = colq_timing{};
+    q->deferred.clear();
+    q->pending_promotions.clear();
+    q->lazy_oob = false;
+    q->promoted_bytes = 0;
+    // the result block first: the planner hands its flags word to kernels that range-check lazily
+    const Table& RT = ctx->tables[q->root_table];
+    const int64_t n = RT.n_rows;
+    q->gathered = ctx->n_ranks > 1 && RT.placement == COLQ_SHARDED;
+    const bool peer_gather = q->gathered && ctx->peer.ok && q->opt_peer;
+    if (q->want_idx_capacity <= 0) q->want_idx_capacity = (q->gathered && !peer_gather) ? (1 << 16) : (1 << 20);
+    ST(ensure_idx_capacity(q, q->want_idx_capacity));
     Planner pl{q, ctx};
     NodeBits root;
     ST(pl.eval(0, Consume{}, &root));
 
-    const Table& RT = ctx->tables[q->root_table];
-    const int64_t n = RT.n_rows;
     if (root.all_ones) {  // matchingBits.set(0, size) (E/ExecutionContext.java:83-87)
         u32* b;
         ST(pl.alloc_bitmap(n, &b));
@@ -848,16 +984,13 @@ colq_status run_pipeline(colq_query* q) {
     void *bc, *bo;
     ST(pool_alloc(q, (size_t)n_blocks * 4, &bc));
     ST(pool_alloc(q, (size_t)n_blocks * 8, &bo));
-    q->gathered = ctx->n_ranks > 1 && RT.placement == COLQ_SHARDED;
-    const bool peer_gather = q->gathered && ctx->peer.ok && q->opt_peer;
-    if (q->want_idx_capacity <= 0) q->want_idx_capacity = (q->gathered && !peer_gather) ? (1 << 16) : (1 << 20);
-    ST(ensure_idx_capacity(q, q->want_idx_capacity));
     if (q->opt_fused_compact) {
         // one cooperative launch: per-tile popcount, grid barrier, ordered write
-        if (ctx->compact_grid == 0) {
+        const int ng = (int)q->deferred.size();
+        if (ctx->compact_grid[ng] == 0) {
             int occ = 0;
-            CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, compact_fused_kernel, CP_THREADS, 0));
-            ctx->compact_grid = ctx->sm_count * std::max(1, std::min(occ, 8));
+            CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, compact_fused_fn(ng), CP_THREADS, 0));
+            ctx->compact_grid[ng] = ctx->sm_count * std::max(1, std::min(occ, 8));
         }
         if (!q->barrier_buf.ptr) {
             ST(dev_alloc(ctx, q->barrier_buf, 64));
@@ -870,7 +1003,11 @@ colq_status run_pipeline(colq_query* q) {
         P.bits = root.bits; P.n_words = n_words; P.n_tiles = n_tiles; P.tile_counts = (u32*)bc;
         P.barrier = (u32*)q->barrier_buf.ptr; P.total = q->d_total; P.out_idx = q->d_idx; P.capacity = q->idx_capacity;
         P.row_base = RT.row_base;  // global row index = shard-local index + the shard's base
-        f.grid = (int)std::min<int64_t>(n_tiles, ctx->compact_grid);
+        P.n_rows = n;
+        f.ng = ng;
+        for (int g = 0; g < ng; ++g) P.gather[g] = q->deferred[g];
+        if (ng) f.name = "compact_fused+chains";
+        f.grid = (int)std::min<int64_t>(n_tiles, ctx->compact_grid[ng]);
         q->ops.push_back(f);
     } else {
         Op p{};
@@ -931,12 +1068,25 @@ colq_status run_pipeline(colq_query* q) {
         }
     }
     CU(ctx, cudaEventRecord(q->ev_start, s));
+    if (q->lazy_oob) CU(ctx, cudaMemsetAsync((u32*)q->idx_buf.ptr + RESULT_FLAGS_WORD, 0, 4, s));
     if (prof) CU(ctx, cudaEventRecord(q->stage_ev[0], s));
     for (size_t i = 0; i < q->ops.size(); ++i) {
         ST(launch_op(q, q->ops[i], s));
         if (prof) CU(ctx, cudaEventRecord(q->stage_ev[i + 1], s));
     }
     CU(ctx, cudaEventRecord(q->ev_stop, s));
+    // first-touch promotion: the scans enqueued above fill the HBM copies; everything enqueued later on this stream
+    // (the next query's plan included) reads those instead of the pinned host memory
+    for (Column* c : q->pending_promotions) {
+        if (!c->host_resident || !c->promoted.ptr) continue;
+        c->data = std::move(c->promoted);
+        if (c->kind == COL_STR) {
+            c->offsets = std::move(c->promoted_offsets);
+            c->bytes_capacity = (int64_t)(c->data.bytes & ~(size_t)15);
+        }
+        c->host_resident = false;
+    }
+    q->pending_promotions.clear();
     q->executed = true;
     return COLQ_OK;
 }
@@ -949,13 +1099,16 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const Table& RT = ctx->tables[q->root_table];
-    u64 local = 0;
+    u64 header[2] = {0, 0};  // [count | flags, pad]
     u64 ginfo[4] = {0, 0, 0, 0};
     const bool gather = q->gathered;
-    CU(ctx, cudaMemcpyAsync(&local, q->d_total, 8, cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaMemcpyAsync(header, q->d_total, 16, cudaMemcpyDeviceToHost, s));
     if (gather) CU(ctx, cudaMemcpyAsync(ginfo, q->ginfo_buf.ptr, 32, cudaMemcpyDeviceToHost, s));
     CU(ctx, cudaStreamSynchronize(s));
-    q->timing.d2h_bytes += gather ? 40 : 8;
+    q->timing.d2h_bytes += gather ? 48 : 16;
+    const u64 local = header[0];
+    if (q->lazy_oob && (header[1] & 1u))  // M/InMemoryTable.java:70-71 would have thrown at associateTo
+        return fail(ctx, COLQ_THROW_NULL, "association target outside the associated table (found while walking a host-resident to-one column)");
     float ms = 0;
     CU(ctx, cudaEventElapsedTime(&ms, q->ev_start, q->ev_stop));
     q->timing.gpu_ms = ms;
@@ -1189,6 +1342,11 @@ colq_status colq_create(int device, colq_ctx** out_ctx) {
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return COLQ_ERR_DEVICE;
     ctx->stream = ctx->own_stream;
+    {
+        DeviceCache& cache = device_cache();
+        std::lock_guard<std::mutex> g(cache.mu);
+        cache.live_contexts++;
+    }
     *out_ctx = ctx.release();
     return COLQ_OK;
 }
@@ -1203,6 +1361,21 @@ colq_status colq_destroy(colq_ctx* ctx) {
     ctx->tables.clear();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
+    DeviceCache& cache = device_cache();
+    bool last;
+    {
+        std::lock_guard<std::mutex> g(cache.mu);
+        last = --cache.live_contexts == 0;
+    }
+    if (last) cache.trim();  // the last context of this device returns every parked block to the driver
+    return COLQ_OK;
+}
+
+colq_status colq_trim(colq_ctx* ctx) {
+    if (!ctx) return COLQ_THROW_NULL;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    device_cache().trim();
     return COLQ_OK;
 }
 
@@ -1210,6 +1383,9 @@ const char* colq_last_error(const colq_ctx* ctx) { return ctx ? ctx->err.c_str()
 
 colq_status colq_set_stream(colq_ctx* ctx, void* cuda_stream) {
     if (!ctx) return COLQ_THROW_NULL;
+    // buffers are recycled in stream order (DeviceCache): drain the old stream before work moves to another one
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return COLQ_OK;
 }
@@ -1359,6 +1535,109 @@ colq_status colq_col_str_device(colq_ctx* ctx, colq_table table, int ordinal, co
     return finish_str(ctx, c, n, n_bytes);
 }
 
+// ---- pinned host memory and host-resident columns -----------------------------------------------------
+
+colq_status colq_host_alloc(colq_ctx* ctx, int64_t bytes, void** out_ptr) {
+    if (!ctx || !out_ptr) return COLQ_THROW_NULL;
+    *out_ptr = nullptr;
+    if (bytes < 0) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "negative size");
+    CU(ctx, cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    CU(ctx, cudaHostAlloc(&p, (size_t)std::max<int64_t>(bytes, 16), cudaHostAllocMapped | cudaHostAllocPortable));
+    *out_ptr = p;
+    return COLQ_OK;
+}
+
+colq_status colq_host_free(colq_ctx* ctx, void* ptr) {
+    if (!ctx) return COLQ_THROW_NULL;
+    if (!ptr) return COLQ_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaFreeHost(ptr));
+    return COLQ_OK;
+}
+
+colq_status colq_host_register(colq_ctx* ctx, void* ptr, int64_t bytes) {
+    if (!ctx || !ptr) return COLQ_THROW_NULL;
+    if (bytes <= 0) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "non-positive size");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    return COLQ_OK;
+}
+
+colq_status colq_host_unregister(colq_ctx* ctx, void* ptr) {
+    if (!ctx || !ptr) return COLQ_THROW_NULL;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaHostUnregister(ptr));
+    return COLQ_OK;
+}
+
+// the device-side alias of a pinned host buffer (identical to the host address under UVA for cudaHostAlloc memory)
+static colq_status pinned_alias(colq_ctx* ctx, const void* host, const char* what, const void** out) {
+    cudaPointerAttributes at{};
+    cudaError_t e = cudaPointerGetAttributes(&at, host);
+    if (e != cudaSuccess || at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) {
+        cudaGetLastError();
+        return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "%s is not pinned host memory (allocate it with colq_host_alloc or pin it with colq_host_register)", what);
+    }
+    if ((uintptr_t)at.devicePointer & 15) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "%s must be 16-byte aligned", what);
+    *out = at.devicePointer;
+    return COLQ_OK;
+}
+
+colq_status colq_col_i32_host(colq_ctx* ctx, colq_table table, int ordinal, const int32_t* values_pinned, int64_t capacity_bytes, int64_t n) {
+    if (!ctx || !values_pinned) return COLQ_THROW_NULL;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (capacity_bytes < round_up(n * 4, 16)) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "host column buffer must be padded to a multiple of 16 bytes (need %lld, have %lld)", (long long)round_up(n * 4, 16), (long long)capacity_bytes);
+    const void* alias;
+    ST(pinned_alias(ctx, values_pinned, "the int column buffer", &alias));
+    Column* c;
+    ST(slot_for(ctx, table, ordinal, n, &c));
+    c->data.ptr = const_cast<void*>(alias); c->data.bytes = (size_t)capacity_bytes; c->data.owned = false;
+    c->kind = COL_I32; c->n = n; c->host_resident = true;
+    return COLQ_OK;
+}
+
+colq_status colq_col_str_host(colq_ctx* ctx, colq_table table, int ordinal, const uint32_t* offsets_pinned, int64_t offsets_capacity,
+                              const uint8_t* bytes_pinned, int64_t bytes_capacity, int64_t n, int64_t n_bytes) {
+    if (!ctx || !offsets_pinned || !bytes_pinned) return COLQ_THROW_NULL;
+    if (n_bytes < 0 || n_bytes > (int64_t)0xfffffff0ll) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "string payload of %lld bytes exceeds the uint32 offset range", (long long)n_bytes);
+    if (offsets_pinned[0] != 0 || (int64_t)offsets_pinned[n] != n_bytes) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "offsets must start at 0 and end at n_bytes");
+    const int64_t need_off = round_up((n + 1) * 4, 16), need_bytes = round_up(n_bytes, 16) + ST_SLACK;
+    if (offsets_capacity < need_off || bytes_capacity < need_bytes)
+        return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "host string buffers are too tight for whole-line reads: offsets need %lld bytes (have %lld), bytes need %lld (have %lld)",
+                    (long long)need_off, (long long)offsets_capacity, (long long)need_bytes, (long long)bytes_capacity);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const void *oa, *ba;
+    ST(pinned_alias(ctx, offsets_pinned, "the string offsets buffer", &oa));
+    ST(pinned_alias(ctx, bytes_pinned, "the string bytes buffer", &ba));
+    Column* c;
+    ST(slot_for(ctx, table, ordinal, n, &c));
+    c->offsets.ptr = const_cast<void*>(oa); c->offsets.bytes = (size_t)offsets_capacity; c->offsets.owned = false;
+    c->data.ptr = const_cast<void*>(ba); c->data.bytes = (size_t)bytes_capacity; c->data.owned = false;
+    c->bytes_capacity = bytes_capacity & ~(int64_t)15;
+    c->host_resident = true;
+    // the ring slot size needs the largest tile payload: one offset per 1024 rows, read over PCIe by a tiny kernel
+    return finish_str(ctx, c, n, n_bytes);
+}
+
+colq_status colq_associate_fk_host(colq_ctx* ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal, const int32_t* fk_pinned,
+                                   int64_t capacity_bytes, int64_t n) {
+    if (!ctx || !fk_pinned) return COLQ_THROW_NULL;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (capacity_bytes < round_up(n * 4, 16)) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "host column buffer must be padded to a multiple of 16 bytes");
+    const void* alias;
+    ST(pinned_alias(ctx, fk_pinned, "the association buffer", &alias));
+    Column* f;
+    ST(link_assoc(ctx, x, x_ordinal, y, y_ordinal, true, &f));
+    if (n != f->n) { unlink_assoc(ctx, x, x_ordinal, y, y_ordinal); return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "association height %lld != table rows", (long long)n); }
+    f->data.ptr = const_cast<void*>(alias); f->data.bytes = (size_t)capacity_bytes; f->data.owned = false;
+    f->host_resident = true;
+    f->fk_validated = false;  // checked on the rows a query walks (kernels flag a bad target; colq_execute reports it)
+    return COLQ_OK;
+}
+
 colq_status colq_col_bool(colq_ctx* ctx, colq_table table, int ordinal, const uint8_t* values, int64_t n) {
     if (!ctx || (!values && n > 0)) return COLQ_THROW_NULL;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1410,6 +1689,7 @@ colq_status colq_associate_csr(colq_ctx* ctx, colq_table x, int x_ordinal, colq_
     Column* f;
     ST(link_assoc(ctx, x, x_ordinal, y, y_ordinal, false, &f));
     if (n != f->n) { unlink_assoc(ctx, x, x_ordinal, y, y_ordinal); return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "association height %lld != table rows", (long long)n); }
+    f->nnz = nnz;
     colq_status st = upload(ctx, f->offsets, offsets, (size_t)(n + 1) * 8, (size_t)(n + 1) * 8 + 16);
     if (st == COLQ_OK) st = upload(ctx, f->targets, targets, (size_t)nnz * 4, (size_t)nnz * 4 + 16);
     if (st != COLQ_OK) unlink_assoc(ctx, x, x_ordinal, y, y_ordinal);
@@ -1517,6 +1797,8 @@ colq_status colq_query_set_option(colq_query* q, colq_option option, int value) 
         case COLQ_OPT_GRAPH: q->opt_graph = value; break;
         case COLQ_OPT_PEER_EXCHANGE: q->opt_peer = value; break;
         case COLQ_OPT_FUSED_COMPACT: q->opt_fused_compact = value; break;
+        case COLQ_OPT_DEFER_CHAINS: q->opt_defer = value; break;
+        case COLQ_OPT_PROMOTE: q->opt_promote = value; break;
         default: return fail(q->ctx, COLQ_THROW_ILLEGAL_ARG, "unknown option %d", (int)option);
     }
     return COLQ_OK;

@@ -94,6 +94,8 @@ struct PushD {
     const int32_t* fk;  // forward to-one column on the CHILD table (child row -> parent row, -1 = None); null = no push
     u32* reach;         // parent-sized bitmask, zero-initialised
     int64_t n_parent;
+    u32* oob;           // nullable: set to 1 when a walked target is outside the parent table (host-resident columns
+                        // are range-checked lazily, on the rows a query walks, instead of at ingest)
 };
 
 __device__ __forceinline__ void push_init(const PushD& ps, u32* s_reach) {
@@ -103,7 +105,10 @@ __device__ __forceinline__ void push_init(const PushD& ps, u32* s_reach) {
 }
 __device__ __forceinline__ void push_row(const PushD& ps, u32* s_reach, int64_t row) {
     int32_t t = ps.fk[row];
-    if (t < 0 || t >= ps.n_parent) return;  // None, or (never via associateTo) out of range: vanishes at the AND
+    if (t < 0 || t >= ps.n_parent) {  // None, or (never via associateTo) out of range: vanishes at the AND
+        if (t != -1 && ps.oob != nullptr) *ps.oob = 1u;
+        return;
+    }
     u32 m = 1u << (t & 31);
     if (ps.n_parent <= PUSH_SMEM_BITS) {
         if (!(s_reach[t >> 5] & m)) atomicOr(&s_reach[t >> 5], m);
@@ -148,6 +153,8 @@ struct IntPredD {
     const int32_t* col;
     int32_t lo;
     u32 span;  // row passes iff (u32)(v - lo) <= span, i.e. lo <= v <= lo + span (closed interval, no overflow)
+    int32_t* promote;  // nullable: `col` is pinned HOST memory streamed over PCIe; every value read is also stored
+                       // here so that the column is HBM-resident for the next query (first-touch promotion)
 };
 
 // A chain of to-one hops r0 -fk[0]-> r1 -fk[1]-> ... ending in a bitmask test.
@@ -156,6 +163,7 @@ struct GatherD {
     int64_t n[GATHER_MAX_DEPTH];  // n[d] = rows of the table that fk[d]'s values index into
     int depth;
     const u32* bits;  // final test; null = every row of the last table matches
+    u32* oob;         // nullable: see PushD::oob
 };
 
 struct ScanRowsParams {
@@ -170,7 +178,10 @@ struct ScanRowsParams {
 __device__ __forceinline__ bool gather_eval(const GatherD& g, int64_t r, int level) {
     for (int d = level; d < g.depth; ++d) {
         int32_t t = g.fk[d][r];
-        if (t < 0 || t >= g.n[d]) return false;  // Association.None, or a target that vanishes at the AND
+        if (t < 0 || t >= g.n[d]) {  // Association.None, or a target that vanishes at the AND
+            if (t != -1 && g.oob != nullptr) *g.oob = 1u;
+            return false;
+        }
         r = t;
     }
     return g.bits == nullptr ? true : bit_test(g.bits, r);
@@ -211,6 +222,14 @@ __global__ void __launch_bounds__(SR_THREADS) scan_rows_kernel(const ScanRowsPar
             for (int p = 0; p < NP; ++p)
 #pragma unroll
                 for (int j = 0; j < SR_V; ++j) v[p][j] = ldg_stream_v4(P.pred[p].col + wbase + j * 128 + lane * 4);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                if (P.pred[p].promote != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < SR_V; ++j)
+                        *reinterpret_cast<int4*>(P.pred[p].promote + wbase + j * 128 + lane * 4) = v[p][j];
+                }
+            }
             if (EAGER) {
 #pragma unroll
                 for (int g = 0; g < NG; ++g)
@@ -237,9 +256,10 @@ __global__ void __launch_bounds__(SR_THREADS) scan_rows_kernel(const ScanRowsPar
                     bool ok = r < P.n;
 #pragma unroll
                     for (int p = 0; p < NP; ++p) {
-                        if (ok) {
+                        if (r < P.n) {  // (every row is read even when an earlier predicate failed: promotion copies it)
                             int32_t x = P.pred[p].col[r];
-                            ok = (u32)(x - P.pred[p].lo) <= P.pred[p].span;
+                            if (P.pred[p].promote != nullptr) P.pred[p].promote[r] = x;
+                            ok = ok && (u32)(x - P.pred[p].lo) <= P.pred[p].span;
                         }
                     }
                     if (EAGER) {
@@ -278,7 +298,9 @@ __global__ void __launch_bounds__(SR_THREADS) scan_rows_kernel(const ScanRowsPar
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         if (m & (1u << e)) {
-                            bool ok = f[e] >= 0 && f[e] < P.gather[g].n[0] && gather_eval(P.gather[g], f[e], 1);
+                            bool ok = f[e] >= 0 && f[e] < P.gather[g].n[0];
+                            if (!ok && f[e] != -1 && P.gather[g].oob != nullptr) *P.gather[g].oob = 1u;
+                            ok = ok && gather_eval(P.gather[g], f[e], 1);
                             if (!ok) m &= ~(1u << e);
                         }
                     }
@@ -383,11 +405,17 @@ struct ScanStrParams {
     const u32* in_bits;
     u32* out_bits;
     PushD push;
+    // nullable pair: `offsets` / `bytes` are pinned HOST memory streamed over PCIe; every staged tile is also written
+    // to these HBM copies so that the column is resident for the next query (first-touch promotion)
+    u32* promote_offsets;
+    uint8_t* promote_bytes;
 };
 
 struct StrTileMeta {
     u32 a0;    // 16-byte-aligned global byte offset the staged slice starts at (offsets are uint32)
     u32 fast;  // 1: bytes were staged in shared memory, 0: read them from global memory
+    u32 sz;    // bytes of the 16-byte-aligned slice [a0, a0 + sz) covering the tile's strings
+    u32 pad;
 };
 
 // ---- word loaders: the same row tests run over the staged slice (ld.shared) or the column itself (ld.global)
@@ -525,8 +553,9 @@ __device__ __forceinline__ bool fixed_test(const W& hay, u32 pos, int len, const
 
 // MODE >= 0: generic path for operator MODE.  MODE in -1..-4: fixed path, EQ only, NW = -MODE needle words.
 // MODE in -5..-8: fixed path, run-time operator (EQ / NE / STARTS_WITH / ENDS_WITH), NW = -MODE - 4.
-template <int MODE>
-__global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParams P) {
+// PROMOTE: the column is pinned host memory; every tile is also copied into the HBM buffers P.promote_*.
+template <int MODE, bool PROMOTE = false>
+__global__ void __launch_bounds__(ST_THREADS, (MODE == -1 || MODE == -2) ? 4 : 3) scan_str_kernel(const ScanStrParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     // layout: [stage: offsets | bytes(cap + slack)] x STAGES | needle words | full[] | empty[] | metas | reach
     const int stage_bytes = st_stage_bytes(P.cap);
@@ -590,6 +619,7 @@ __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParam
                 const bool fast = sz <= (u64)P.cap && (int64_t)a1 <= P.bytes_capacity;
                 s_meta[s].a0 = (u32)a0;
                 s_meta[s].fast = fast ? 1u : 0u;
+                s_meta[s].sz = (int64_t)a1 <= P.bytes_capacity ? (u32)sz : (u32)(P.bytes_capacity - (int64_t)a0);
                 mbar_arrive_expect_tx(&s_full[s], off_bytes + (fast ? (u32)sz : 0u));
                 tma_bulk_g2s(base, P.offsets + r0, off_bytes, &s_full[s]);
                 if (fast && sz > 0) tma_bulk_g2s(base + ST_OFF_BYTES, P.bytes + a0, (u32)sz, &s_full[s]);
@@ -669,6 +699,28 @@ __global__ void __launch_bounds__(ST_THREADS) scan_str_kernel(const ScanStrParam
                     const int len = (int)(o[j + 1] - o[j]);
                     const bool m = slow_row_test(op, hay, pos, len, s_needle, nlen);
                     nib |= m ? (1u << j) : 0u;
+                }
+            }
+            if (PROMOTE) {
+                // first-touch promotion: the tile just crossed PCIe into shared memory -- leave a copy in HBM
+                const u32 off_lines = (u32)(((nr + 1) * 4 + 15) >> 4);
+                uint4* dst_o = reinterpret_cast<uint4*>(P.promote_offsets + r0);
+                for (u32 i = tid; i < off_lines; i += ST_CONSUMER_THREADS) {
+                    uint4 x;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(so + i * 16));
+                    dst_o[i] = x;
+                }
+                const u32 lines = s_meta[s].sz >> 4;
+                uint4* dst_b = reinterpret_cast<uint4*>(P.promote_bytes + a0);
+                if (fast) {
+                    for (u32 i = tid; i < lines; i += ST_CONSUMER_THREADS) {
+                        uint4 x;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(so + ST_OFF_BYTES + i * 16));
+                        dst_b[i] = x;
+                    }
+                } else {
+                    const uint4* src_b = reinterpret_cast<const uint4*>(P.bytes + a0);
+                    for (u32 i = tid; i < lines; i += ST_CONSUMER_THREADS) dst_b[i] = src_b[i];
                 }
             }
             // all shared-memory reads of this slot are done: hand it back to the producer
@@ -772,6 +824,7 @@ struct PushBitsParams {
     const int32_t* targets;
     u32* reach;
     int64_t n_parent;
+    u32* oob;                // nullable: see PushD::oob
 };
 
 __global__ void __launch_bounds__(256) push_bits_kernel(const PushBitsParams P) {
@@ -783,6 +836,8 @@ __global__ void __launch_bounds__(256) push_bits_kernel(const PushBitsParams P) 
             if (t >= 0 && t < P.n_parent) {
                 u32 m = 1u << (t & 31);
                 if (!(P.reach[t >> 5] & m)) atomicOr(&P.reach[t >> 5], m);
+            } else if (t != -1 && P.oob != nullptr) {
+                *P.oob = 1u;
             }
         } else {
             for (int64_t e = P.offsets[r]; e < P.offsets[r + 1]; ++e) {
@@ -863,7 +918,8 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32* s_warp, u32& blo
 
 __device__ __forceinline__ uint4 load_words4(const u32* bits, int64_t w0, int64_t n_words) {
     // bitmask allocations are padded to whole compaction blocks, so the vector load is always in bounds
-    uint4 v = *reinterpret_cast<const uint4*>(bits + w0);
+    // L2 (.cg) load: compact_fused_kernel<NG > 0> clears bits with atomics between its two passes over a tile
+    uint4 v = __ldcg(reinterpret_cast<const uint4*>(bits + w0));
     if (w0 + 0 >= n_words) v.x = 0;
     if (w0 + 1 >= n_words) v.y = 0;
     if (w0 + 2 >= n_words) v.z = 0;
@@ -933,6 +989,8 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(const u32* bits, in
 // info[2] = true total.
 // ---------------------------------------------------------------------------------------------
 constexpr int GATHER_HEADER_WORDS = 4;
+constexpr int RESULT_FLAGS_WORD = 2;  // result block = [u64 count | u32 flags | u32 pad | indices...]; flags bit 0: a walked
+                                      // to-one target was outside its table (lazy range check of host-resident columns)
 constexpr int MAX_RANKS = 64;
 
 __global__ void __launch_bounds__(256) unpack_gather_kernel(const int32_t* blocks, int n_ranks, int64_t cap, int32_t* out,
@@ -1137,8 +1195,10 @@ __global__ void __launch_bounds__(256) peer_gather_recv_kernel(const PeerGatherP
 constexpr int CF_VEC = 4;                                   // 128-bit loads per thread per tile
 constexpr int CF_WORDS_PER_TILE = CP_THREADS * 4 * CF_VEC;  // 4096 words = 131072 rows
 
+constexpr int CF_MAX_GATHER = 2;
+
 struct CompactFusedParams {
-    const u32* bits;
+    u32* bits;             // root bitmask; phase 1 clears the bits whose deferred FK chain fails (NG > 0)
     int64_t n_words;
     int64_t n_tiles;       // tiles of CF_WORDS_PER_TILE words
     u32* tile_counts;      // [n_tiles]
@@ -1147,6 +1207,8 @@ struct CompactFusedParams {
     int32_t* out_idx;
     int64_t capacity;
     int64_t row_base;
+    int64_t n_rows;
+    GatherD gather[CF_MAX_GATHER];  // deferred to-one chains of the root node (see compact_fused_kernel)
 };
 
 // thread t of a tile owns words [16 t, 16 t + 16): four consecutive 128-bit loads
@@ -1161,16 +1223,89 @@ __device__ __forceinline__ u32 cf_load(const CompactFusedParams& P, int64_t tile
     return c;
 }
 
+// NG > 0: the root node's criteria-free to-one FK chains (ExecutionContext.Node.filterParent, One branch,
+// E/ExecutionContext.java:114, in pull form) were DEFERRED by the planner: the root's row scan ran as a pure
+// coalesced predicate scan, and the chains are walked here, in phase 1, only for the rows whose bit is still set.
+// After a selective predicate that is a fraction of a percent of the rows, spread evenly over every resident
+// thread of the grid (all walks in flight at once) instead of stalling the streaming warps of the scan.
+constexpr int CF_LIST_CAP = 4096;  // survivors of one 131072-row tile that are resolved block-wide (3 % selectivity)
+
+template <int NG>
 __global__ void __launch_bounds__(CP_THREADS) compact_fused_kernel(const CompactFusedParams P) {
     __shared__ u32 s_warp[33];
     __shared__ u64 s_base;
+    __shared__ u32 s_list[NG > 0 ? CF_LIST_CAP : 1];
+    __shared__ u32 s_removed;
     uint4 v[CF_VEC];
     {
-        // phase 1: popcount my tiles
+        // phase 1: (resolve deferred chains,) popcount my tiles
         for (int64_t t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
             u32 c = cf_load(P, t, v);
             u32 total;
-            block_exclusive_scan(c, s_warp, total);
+            const u32 ex = block_exclusive_scan(c, s_warp, total);
+            if (NG > 0 && total != 0) {
+                const u32 lw0 = threadIdx.x * 4 * CF_VEC;  // first word of this thread inside the tile
+                const int64_t tile_w0 = t * CF_WORDS_PER_TILE;
+                if (total <= CF_LIST_CAP) {
+                    // the tile's surviving rows go into one shared list and are walked round-robin by the whole
+                    // block: every chain of the tile is in flight at once, whatever thread found the bit
+                    if (threadIdx.x == 0) s_removed = 0;
+                    u32 pos = ex;
+#pragma unroll
+                    for (int k = 0; k < CF_VEC; ++k) {
+                        const u32 w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            u32 m = w[j];
+                            while (m) {
+                                const int b = __ffs(m) - 1;
+                                m &= m - 1;
+                                s_list[pos++] = ((lw0 + 4 * k + j) << 5) + b;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    u32 removed = 0;
+                    for (u32 i = threadIdx.x; i < total; i += CP_THREADS) {
+                        const u32 lr = s_list[i];
+                        const int64_t row = (tile_w0 << 5) + lr;
+                        bool ok = row < P.n_rows;
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) ok = ok && gather_eval(P.gather[g], row, 0);
+                        if (!ok) {
+                            atomicAnd(&P.bits[tile_w0 + (lr >> 5)], ~(1u << (lr & 31)));
+                            ++removed;
+                        }
+                    }
+                    if (removed) atomicAdd(&s_removed, removed);
+                    __syncthreads();
+                    total -= s_removed;
+                } else {
+                    // dense tile: every thread walks the bits of its own 16 words
+                    c = 0;
+#pragma unroll
+                    for (int k = 0; k < CF_VEC; ++k) {
+                        const u32 w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            u32 m = w[j], keep = w[j];
+                            const int64_t rb = (tile_w0 + lw0 + 4 * k + j) << 5;
+                            while (m) {
+                                const int b = __ffs(m) - 1;
+                                m &= m - 1;
+                                bool ok = rb + b < P.n_rows;
+#pragma unroll
+                                for (int g = 0; g < NG; ++g) ok = ok && gather_eval(P.gather[g], rb + b, 0);
+                                if (!ok) keep &= ~(1u << b);
+                            }
+                            if (keep != w[j]) P.bits[tile_w0 + lw0 + 4 * k + j] = keep;
+                            c += __popc(keep);
+                        }
+                    }
+                    __syncthreads();
+                    block_exclusive_scan(c, s_warp, total);
+                }
+            }
             if (threadIdx.x == 0) P.tile_counts[t] = total;
             __syncthreads();
         }

@@ -17,8 +17,8 @@ def engines():
     from oracle_system import OracleDataSystem
     made = []
 
-    def new_gpu(lazy_fk=True):
-        ds = DataSystemColq(0, lazy_fk=lazy_fk)
+    def new_gpu(lazy_fk=True, **kw):
+        ds = DataSystemColq(0, lazy_fk=lazy_fk, **kw)
         made.append(ds)
         return ds
 
@@ -27,9 +27,19 @@ def engines():
         ds.close()
 
 
-def both(engines, build, queries, lazy_modes=(True, False)):
-    """Build the same tables for the oracle and the GPU engine, run each query on both, compare row sets bit for bit."""
+LAZY, EAGER = dict(lazy_fk=True), dict(lazy_fk=False)
+NO_DEFER = dict(lazy_fk=True, options={5: 0})            # COLQ_OPT_DEFER_CHAINS=0: FK chains inside the row scan
+HOST = dict(lazy_fk=True, residency="host")              # columns stay in pinned host memory, promoted on first scan
+HOST_NO_PROMOTE = dict(lazy_fk=True, residency="host", options={6: 0})   # COLQ_OPT_PROMOTE=0: always streamed
+ALL_VARIANTS = (LAZY, EAGER, NO_DEFER, HOST, HOST_NO_PROMOTE)
+
+
+def both(engines, build, queries, lazy_modes=(True, False), variants=None):
+    """Build the same tables for the oracle and the GPU engine, run each query on both, compare row sets bit for bit.
+    Every query runs twice per engine variant: with host-resident columns the first run streams (and promotes) them,
+    the second reads the promoted HBM copies."""
     new_gpu, new_oracle = engines
+    variants = variants if variants is not None else [dict(lazy_fk=lz) for lz in lazy_modes]
     oracle = new_oracle()
     build(oracle)
     want = []
@@ -37,9 +47,11 @@ def both(engines, build, queries, lazy_modes=(True, False)):
         r = oracle.execute(q())
         assert isinstance(r, QueryResult.Success), getattr(r, "message", None)
         want.append((oracle.last_indices.copy(), oracle.last_words.copy(), oracle.node_cardinalities()))
-    for lazy in lazy_modes:
-        gpu = new_gpu(lazy)
-        build(gpu)
+    for variant, rep_i in [(v, i) for v in variants for i in range(2 if v.get("residency") == "host" else 1)]:
+        lazy = variant.get("lazy_fk", True)
+        if rep_i == 0:
+            gpu = new_gpu(**variant)
+            build(gpu)
         for q, (idx, words, cards) in zip(queries, want):
             r = gpu.execute(q())
             assert isinstance(r, QueryResult.Success), getattr(r, "message", None)
@@ -54,7 +66,8 @@ def both(engines, build, queries, lazy_modes=(True, False)):
                 assert a == -1 or a == b, (gc, cards)   # -1: node fused away, never materialised
             if not lazy:
                 assert gc[0] == cards[0]
-        gpu.close()
+        if rep_i == (1 if variant.get("residency") == "host" else 0):
+            gpu.close()
 
 
 # ------------------------------------------------------------------ the reference's own tests + failure paths
@@ -114,7 +127,7 @@ def test_int_range_scan_sizes(engines, n):
     def q5():
         return Query("t")
 
-    both(engines, build, [q1, q2, q3, q4, q5], lazy_modes=(True,))
+    both(engines, build, [q1, q2, q3, q4, q5], variants=(LAZY, HOST))
 
 
 # ------------------------------------------------------------------ string scans: every operator, ragged lengths
@@ -147,7 +160,7 @@ def test_string_ops(engines, n, max_len):
                 q.root_node.add_criteria(Criteria.StringCriteria(0, StringPredicate(op, nd)))
                 return q
             queries.append(mk)
-    both(engines, build, queries, lazy_modes=(True,))
+    both(engines, build, queries, variants=(LAZY, HOST) if n in (1025, 3000, 70_000) else (LAZY,))
 
 
 def test_two_string_criteria_and_int_on_one_node(engines):
@@ -166,7 +179,7 @@ def test_two_string_criteria_and_int_on_one_node(engines):
         qq.root_node.add_criteria(Criteria.StringCriteria(0, StringPredicate(2, "xz")))
         return qq
 
-    both(engines, build, [q], lazy_modes=(True,))
+    both(engines, build, [q], variants=(LAZY, HOST, HOST_NO_PROMOTE))
 
 
 # ------------------------------------------------------------------ associations: random graphs, forward and reverse hops
@@ -237,7 +250,7 @@ def test_random_association_graphs(engines, seed):
         return q
 
     both(engines, build, [chain_down, chain_down_no_root_pred, chain_up, mid_criteria, two_children, reverse_of_many,
-                          no_criteria_anywhere])
+                          no_criteria_anywhere], variants=ALL_VARIANTS)
 
 
 # ------------------------------------------------------------------ parallel universes
@@ -248,7 +261,87 @@ def test_plymouth_universes_match_oracle(engines, base_geography, U):
     def build(ds):
         G.register_geography(ds, geo)
 
-    both(engines, build, [G.plymouth_query, G.north_south_north_query])
+    both(engines, build, [G.plymouth_query, G.north_south_north_query], variants=ALL_VARIANTS)
+
+
+def test_deferred_chains_are_planned_into_the_compaction(engines, base_geography):
+    """The root's lazy FK chains move from the row scan into the fused compaction kernel (COLQ_OPT_DEFER_CHAINS)."""
+    new_gpu, _ = engines
+    geo = G.build_tables(2, base=base_geography)
+    for opts, want_names in (({}, ["scan_rows<1,0,lazy>", "compact_fused+chains"]), ({5: 0}, ["scan_rows<1,1,lazy>", "compact_fused"])):
+        ds = new_gpu(options=opts)
+        G.register_geography(ds, geo)
+        assert isinstance(ds.execute(G.plymouth_query()), QueryResult.Success)
+        names = [n for n, *_ in ds.last_query.profile()]
+        for w in want_names:
+            assert w in names, (opts, names)
+        ds.close()
+
+
+def test_host_resident_columns_stream_then_promote(base_geography):
+    """colq_*_host: nothing is copied at registration; the first query streams the scanned columns over PCIe (h2d_bytes
+    says how much) and promotes them, the second query moves nothing."""
+    from colq.engine import DataSystemColq
+    from oracle_system import OracleDataSystem
+    U = 7
+    geo = G.build_tables(U, base=base_geography)
+    oracle = OracleDataSystem()
+    G.register_geography(oracle, geo)
+    oracle.execute(G.plymouth_query())
+    ds = DataSystemColq(0, residency="host")
+    G.register_geography(ds, geo)
+    streamed = []
+    for _ in range(3):
+        r = ds.execute(G.plymouth_query())
+        assert isinstance(r, QueryResult.Success)
+        assert np.array_equal(ds.last_query.fetch(want_indices=True).indices, oracle.last_indices)
+        streamed.append(int(ds.last_timing.h2d_bytes))
+    nz, nc = U * G.N_ZIPS, U * G.N_CITIES
+    name_bytes = int(np.asarray(base_geography["city_name_bytes"]).shape[0]) * U
+    assert streamed[0] == 4 * nz + 4 * (nc + 1) + name_bytes     # population + name offsets + name bytes, nothing else
+    assert streamed[1] == 0 and streamed[2] == 0                  # promoted by the first scan
+    ds.close()
+    oracle.close()
+
+
+def test_host_resident_fk_is_range_checked_on_walked_rows():
+    """A to-one target outside the associated table is the reference's NPE at associateTo (M/InMemoryTable.java:70-71).
+    Host-resident association columns are never read in bulk, so the check happens on the rows a query walks."""
+    from colq import _ffi
+    from colq.engine import ColqContext
+    ctx = ColqContext(0)
+    n = 5000
+    vals = ctx.host_column(np.arange(n, dtype=np.int32), np.int32)
+    fk = np.zeros(n, dtype=np.int32)
+    fk[4321] = 99            # parent table has 3 rows
+    fk[17] = -1              # Association.None is fine
+    fkh = ctx.host_column(fk, np.int32)
+    child, parent = ctx.table_create(n), ctx.table_create(3)
+    ctx.col_i32(parent, 0, np.array([1, 2, 3], dtype=np.int32))
+    ctx.col_i32_host(child, 0, vals)
+    ctx.associate_fk_host(child, 1, parent, 1, fkh)
+    ctx.register("child", child)
+    ctx.register("parent", parent)
+    for lo, hi, bad in ((0, 100, False), (4000, 4400, True)):
+        for defer in (1, 0):
+            q = ctx.query("child")
+            q.set_option(_ffi.OPT_DEFER_CHAINS, defer)
+            q.criteria_i32_range(0, 0, lo, hi)
+            q.child(0, 1)
+            if bad:
+                with pytest.raises(TypeError, match="outside the associated table"):
+                    q.execute()
+            else:
+                assert q.execute().count == hi - lo + 1 - 1   # row 17 is None
+            q.close()
+    # reverse direction: parent <- child push walks only the matching child rows
+    q = ctx.query("parent")
+    c = q.child(0, 1)
+    q.criteria_i32_range(c, 0, 4321, 4321)
+    with pytest.raises(TypeError, match="outside the associated table"):
+        q.execute()
+    q.close()
+    ctx.close()
 
 
 def test_three_launch_compaction_path_matches(engines, base_geography):
@@ -268,7 +361,7 @@ def test_three_launch_compaction_path_matches(engines, base_geography):
         got = ds.last_query.fetch(want_indices=True)
         assert np.array_equal(got.indices, oracle.last_indices)
         names = [n for n, *_ in ds.last_query.profile()]
-        assert ("compact_fused" in names) == bool(fused)
+        assert any(n.startswith("compact_fused") for n in names) == bool(fused)
         ds.close()
 
 
