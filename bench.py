@@ -155,6 +155,27 @@ def ncu_traffic(kernel_prefix: str):
     return None
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this rank's process to the CPUs next to its GPU before any pinned host buffer is allocated, so that the
+    buffers the e2e leg streams over PCIe are first-touched on the GPU's own NUMA node (no cross-socket hop)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(path + "/numa_node").read())
+        cpus = set()
+        for part in open(path + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return {"numa_node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as e:  # best effort: a box without sysfs topology just keeps the default placement
+        return {"bound": False, "error": repr(e)}
+
+
 # ------------------------------------------------------------------------------------------------ CPU legs
 def oracle_run(U, n_threads, repeats):
     """Times orc_execute (tables already resident in host memory, like the reference's execute) on U universes."""
@@ -209,6 +230,7 @@ def run_colq(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
@@ -254,9 +276,11 @@ def run_colq(args, rank, local_rank, world):
 
     # ---- value: K steps, resident tables, CUDA events on the launching stream, max over ranks
     sampler = ClockSampler(local_rank)
+    q.set_option(_ffi.OPT_PROFILE, 2)  # one CUDA-event pair per step around the dominant launch, inside the timed region
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
             q.execute_async()
+        q.profile_hot()  # drop the warm-up samples
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler.start()
@@ -267,6 +291,8 @@ def run_colq(args, rank, local_rank, world):
         stream.synchronize()
         clocks = sampler.stop()
         barrier()
+    hot_name, hot_ms, _hot_rows, hot_bytes, hot_samples = q.profile_hot()
+    q.set_option(_ffi.OPT_PROFILE, 0)
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
     res = q.fetch(want_indices=True, index_capacity=31 * U + 16)
@@ -286,13 +312,12 @@ def run_colq(args, rank, local_rank, world):
                 a[1] += 1
     q.set_option(_ffi.OPT_PROFILE, 0)
     stages = {k: {"ms": v[0] / v[1], "rows": v[2], "algorithmic_bytes": v[3]} for k, v in acc.items() if v[1]}
-    dom = max(stages, key=lambda k: stages[k]["ms"])
     peak, peak_src = measured_peak()
-    achieved = stages[dom]["algorithmic_bytes"] / (stages[dom]["ms"] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(dom), "peak_source": peak_src, "ms_per_launch": stages[dom]["ms"],
-                "algorithmic_bytes_per_launch": stages[dom]["algorithmic_bytes"],
-                "share_of_step": stages[dom]["ms"] / sum(s["ms"] for s in stages.values())}
+    achieved = hot_bytes / (hot_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": hot_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(hot_name), "peak_source": peak_src, "ms_per_launch": hot_ms,
+                "algorithmic_bytes_per_launch": hot_bytes, "share_of_step": hot_ms / ms_step,
+                "timed": f"CUDA events around this launch in each of the {hot_samples} timed steps (COLQ_OPT_PROFILE=2), mean"}
 
     # whole-query algorithmic bytes for the HBM GB/s half of BASELINE's metric
     algo_bytes = 4 * geo.n_zip_rows * 2 + 4 * (geo.n_city_rows + 1) + geo.name_bytes + 4 * geo.n_city_rows + 4 * 31 * geo.n_universes
@@ -425,7 +450,7 @@ def run_colq(args, rank, local_rank, world):
             "e2e_resident": {"value": rows / (ms_res * 1e-3), "unit": "rows/s", "ms_per_step": ms_res, "h2d_bytes_per_step": 0,
                              "d2h_bytes_per_step": d2h_res, "what": "colq_execute with resident tables, matched indices read back every step"},
             "small_query_latency": small,
-            "clocks": clocks, "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+            "host_numa": numa, "clocks": clocks, "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "collectives_per_step": collectives_per_step,
         }
         print(json.dumps(line), flush=True)
@@ -499,9 +524,11 @@ def run_single_table(args):
         raise SystemExit(f"GPU count {res.count} != independent expectation {expect}")
     launches = int(res.timing.kernel_launches)
     sampler = ClockSampler(0)
+    q.set_option(_ffi.OPT_PROFILE, 2)
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
             q.execute_async()
+        q.profile_hot()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler.start()
@@ -512,6 +539,7 @@ def run_single_table(args):
         stream.synchronize()
         clocks = sampler.stop()
     ms_step = e0.elapsed_time(e1) / args.steps
+    hot_name, hot_ms, _hot_rows, hot_bytes, hot_samples = q.profile_hot()
     q.set_option(_ffi.OPT_PROFILE, 1)
     acc = {}
     for _ in range(args.profile_steps):
@@ -522,18 +550,18 @@ def run_single_table(args):
                 a[0] += ms
                 a[1] += 1
     stages = {k: {"ms": v[0] / v[1], "algorithmic_bytes": v[3]} for k, v in acc.items() if v[1]}
-    dom = max(stages, key=lambda k: stages[k]["ms"])
     peak, peak_src = measured_peak()
-    achieved = stages[dom]["algorithmic_bytes"] / (stages[dom]["ms"] * 1e-3) / 1e9
+    achieved = hot_bytes / (hot_ms * 1e-3) / 1e9
     line = {
         "metric": metric, "value": n / (ms_step * 1e-3), "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32" if args.workload == "int_scan" else "u8", "data": "synthetic",
         "config": dict(workload, l2_policy="inputs larger than L2 (no flush)", matches=expect),
         "hbm_gbs_query_algorithmic": algo(expect) / (ms_step * 1e-3) / 1e9, "query_algorithmic_bytes": algo(expect),
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "ms_per_launch": stages[dom]["ms"],
-                     "algorithmic_bytes_per_launch": stages[dom]["algorithmic_bytes"]},
+        "roofline": {"bound": "hbm", "kernel": hot_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(hot_name), "peak_source": peak_src, "ms_per_launch": hot_ms,
+                     "algorithmic_bytes_per_launch": hot_bytes, "share_of_step": hot_ms / ms_step,
+                     "timed": f"CUDA events around this launch in each of the {hot_samples} timed steps (COLQ_OPT_PROFILE=2), mean"},
         "stages_ms": {k: round(v["ms"], 5) for k, v in stages.items()},
         "cpu_baseline": None, "e2e": None, "clocks": clocks, "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
     }

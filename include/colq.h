@@ -77,7 +77,9 @@ typedef enum colq_option {
     /* 1 (default): a criteria-free node reached through a to-one foreign key is evaluated lazily, only at
        the rows its parent still needs (fused FK chain gather); 0: always materialise every node's bitmask. */
     COLQ_OPT_LAZY_FK = 0,
-    /* 1: record one CUDA event pair per kernel so colq_profile() can report per-stage times (adds launch gaps) */
+    /* 1: record one CUDA event pair per kernel so colq_profile() can report per-stage times (adds launch gaps);
+       2: one event pair per execution, around the launch with the most algorithmic bytes only, kept for every
+          execution since the last colq_profile_hot() (up to 4096) -- cheap enough to leave on inside a timed region */
     COLQ_OPT_PROFILE = 1,
     /* reserved: CUDA-graph replay of the op list (accepted and ignored in this version) */
     COLQ_OPT_GRAPH = 2,
@@ -251,6 +253,9 @@ colq_status colq_fetch(colq_ctx *ctx, colq_query *query, uint64_t *out_bitmask, 
                        int32_t *out_indices, int64_t indices_capacity, int64_t *out_count, colq_timing *out_timing);
 /* per-kernel stages of the last execute of `query` (times only with COLQ_OPT_PROFILE); returns the stage count */
 colq_status colq_profile(const colq_query *query, colq_stage *out_stages, int capacity, int *out_n_stages);
+/* COLQ_OPT_PROFILE == 2: synchronises, then reports the dominant launch of `query` -- name, rows, algorithmic bytes and
+   the MEAN CUDA-event duration over the *out_samples executions recorded since the previous call -- and resets. */
+colq_status colq_profile_hot(colq_query *query, colq_stage *out_stage, int *out_samples);
 /* cardinality of every execution node's bitmask after the last execute, in the reference's node creation (BFS)
    order; -1 for nodes that were fused away and never materialised. Debug / parity aid. */
 colq_status colq_node_cardinalities(colq_ctx *ctx, const colq_query *query, int64_t *out, int capacity, int *out_n);

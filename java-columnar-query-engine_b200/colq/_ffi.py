@@ -75,6 +75,7 @@ SIGNATURES = {
     "colq_execute_async": (_int, [_p, _p]),
     "colq_fetch": (_int, [_p, _p, _p, _i64, _p, _i64, C.POINTER(_i64), C.POINTER(Timing)]),
     "colq_profile": (_int, [_p, C.POINTER(Stage), _int, C.POINTER(_int)]),
+    "colq_profile_hot": (_int, [_p, C.POINTER(Stage), C.POINTER(_int)]),
     "colq_node_cardinalities": (_int, [_p, _p, C.POINTER(_i64), _int, C.POINTER(_int)]),
 }
 

@@ -92,6 +92,13 @@ class ColqQuery:
         self.ctx._check(self.ctx.lib.colq_profile(self.handle, stages, 64, C.byref(n)))
         return [(stages[i].name.decode(), stages[i].ms, stages[i].rows, stages[i].bytes) for i in range(min(n.value, 64))]
 
+    def profile_hot(self) -> Tuple[str, float, int, int, int]:
+        """(name, mean ms, rows, algorithmic bytes, samples) of the dominant launch since the last call (OPT_PROFILE=2)."""
+        st = _ffi.Stage()
+        n = C.c_int()
+        self.ctx._check(self.ctx.lib.colq_profile_hot(self.handle, C.byref(st), C.byref(n)))
+        return st.name.decode(), st.ms, st.rows, st.bytes, n.value
+
     def node_cardinalities(self) -> List[int]:
         out = (C.c_int64 * 64)()
         n = C.c_int()

@@ -152,7 +152,7 @@ struct QNode {
 };
 
 // one kernel launch (or collective / memset) of a planned query
-enum OpKind { K_SCAN_ROWS, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER, K_COMPACT_FUSED, K_PEER_MASK_OR, K_PEER_GATHER };
+enum OpKind { K_SCAN_ROWS, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER, K_COMPACT_FUSED, K_PEER_MASK_PUBLISH, K_PEER_MASK_COLLECT, K_PEER_GATHER };
 
 struct Op {
     OpKind kind;
@@ -177,6 +177,7 @@ struct Op {
     CompactFusedParams cfused{};
     PeerMaskParams pmask{};
     PeerGatherParams pgather{};
+    int publish_op = -1;  // K_PEER_MASK_COLLECT / a csr_pull with a fused collect: index of the matching publish
     // launch shape for scan_str
     int grid = 0;
     size_t smem = 0;
@@ -241,6 +242,7 @@ struct colq_query {
     std::vector<QNode> nodes;
     int opt_lazy = 1, opt_profile = 0, opt_graph = 1, opt_peer = 1, opt_fused_compact = 1, opt_defer = 1, opt_promote = 1;
     std::vector<GatherD> deferred;  // root-node FK chains resolved by the compaction kernel instead of the row scan
+    int own_begin = -1, own_end = -1;  // root-node scan ops that depend on no child (hoistable behind a mask publish)
     std::vector<Column*> pending_promotions;  // host-resident columns whose HBM copy this execution fills
     bool lazy_oob = false;  // the plan walks a to-one column that was not range-checked at ingest
     int64_t promoted_bytes = 0;
@@ -263,6 +265,11 @@ struct colq_query {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     std::vector<cudaEvent_t> stage_ev;
     std::vector<colq_stage> stages;
+    // COLQ_OPT_PROFILE == 2: one event pair per execution around the launch with the most algorithmic bytes, kept
+    // for every step of a timed region and averaged by colq_profile_hot (bench.py's live roofline figure)
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> hot_ring;
+    size_t hot_used = 0;
+    colq_stage hot_stage{};
     colq_timing timing{};
     bool executed = false;
     // captured CUDA graph of the op sequence
@@ -571,11 +578,14 @@ struct Planner {
                     Op g{};
                     g.node = xi; g.dst = reach; g.n_words = bitmap_words(n);
                     if (ctx->peer.ok && q->opt_peer && g.n_words <= MASK_WORDS_MAX) {
-                        g.kind = K_PEER_MASK_OR; g.name = "peer_mask_or";
+                        g.kind = K_PEER_MASK_PUBLISH; g.name = "peer_mask_publish";
                         PeerMaskParams& P = g.pmask;
                         P.reach = reach; P.n_words = (int)g.n_words; P.n_ranks = ctx->n_ranks; P.rank = ctx->rank;
                         P.peers = ctx->peer.d_peers; P.status = ctx->peer.d_status;
                         g.acct_bytes = g.n_words * 4 * ctx->n_ranks;
+                        q->ops.push_back(g);
+                        g.kind = K_PEER_MASK_COLLECT; g.name = "peer_mask_collect";
+                        g.publish_op = (int)q->ops.size() - 1;
                     } else {
                         g.kind = K_ALLGATHER_OR; g.name = "allgather_or_mask";
                         void* gb;
@@ -603,6 +613,8 @@ struct Planner {
             return COLQ_OK;
         };
 
+        const bool own_independent = (xi == 0 && cur == nullptr && csrs.empty());  // so far no child touched `cur`
+        const size_t own_first = q->ops.size();
         // ---- string criteria: one TMA-staged scan each
         for (const Crit* c : xr.preds) {
             if (!c->is_str) continue;
@@ -691,6 +703,11 @@ struct Planner {
             o.acct_bytes = bytes + bitmap_words(n) * 4;
             q->ops.push_back(o);
             cur = ob;
+        }
+
+        if (own_independent && q->deferred.size() == gathers.size() && q->ops.size() > own_first) {
+            q->own_begin = (int)own_first;
+            q->own_end = (int)q->ops.size();
         }
 
         // ---- forward to-many hops
@@ -862,6 +879,10 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
         }
         case K_CSR_PULL: {
             int grid = (int)((o.csr.n + 255) / 256);
+            if (o.csr.pm.n_words > 0) {
+                o.csr.pm.epoch = q->ops[o.publish_op].pmask.epoch;
+                grid = 1;  // the exchange must be collected even when the parent table is empty
+            }
             if (grid == 0) break;
             csr_pull_kernel<<<grid, 256, 0, s>>>(o.csr);
             q->timing.kernel_launches++;
@@ -907,9 +928,14 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
             q->timing.kernel_launches++;
             break;
         }
-        case K_PEER_MASK_OR:
+        case K_PEER_MASK_PUBLISH:
             o.pmask.epoch = ++ctx->peer.mask_epoch;
-            peer_mask_or_kernel<<<1, 256, 0, s>>>(o.pmask);
+            peer_mask_publish_kernel<<<1, 256, 0, s>>>(o.pmask);
+            q->timing.kernel_launches++;
+            break;
+        case K_PEER_MASK_COLLECT:
+            o.pmask.epoch = q->ops[o.publish_op].pmask.epoch;
+            peer_mask_collect_kernel<<<1, 256, 0, s>>>(o.pmask);
             q->timing.kernel_launches++;
             break;
         case K_PEER_GATHER:
@@ -952,6 +978,7 @@ colq_status run_pipeline(colq_query* q) {
     q->ops.clear();
     q->timing = colq_timing{};
     q->deferred.clear();
+    q->own_begin = q->own_end = -1;
     q->pending_promotions.clear();
     q->lazy_oob = false;
     q->promoted_bytes = 0;
@@ -965,6 +992,35 @@ colq_status run_pipeline(colq_query* q) {
     Planner pl{q, ctx};
     NodeBits root;
     ST(pl.eval(0, Consume{}, &root));
+
+    // ---- peepholes over the op list (multi-GPU exchanges)
+    // (1) overlap: the root's own predicate scans depend on no child, so they run between the first mask PUBLISH and
+    //     its COLLECT -- the NVLink round trip and the wait for the slowest rank hide behind a bandwidth-bound scan
+    if (q->own_begin >= 0) {
+        int pub = -1;
+        for (int i = 0; i < q->own_begin; ++i)
+            if (q->ops[i].kind == K_PEER_MASK_PUBLISH) { pub = i; break; }
+        if (pub >= 0 && pub + 1 < q->own_begin) {
+            const int shift = q->own_end - q->own_begin;
+            std::rotate(q->ops.begin() + pub + 1, q->ops.begin() + q->own_begin, q->ops.begin() + q->own_end);
+            for (Op& o : q->ops)  // ops between pub and own_begin moved right by `shift`; publish itself did not move
+                if (o.publish_op > pub && o.publish_op < q->own_begin) o.publish_op += shift;
+        }
+    }
+    // (2) a COLLECT directly followed by a single-block csr_pull over the collected mask becomes that kernel's prologue
+    for (size_t i = 0; i + 1 < q->ops.size(); ++i) {
+        Op& c = q->ops[i];
+        Op& n = q->ops[i + 1];
+        if (c.kind == K_PEER_MASK_COLLECT && n.kind == K_CSR_PULL && n.csr.n <= 256 && n.csr.child_bits == c.pmask.reach) {
+            n.csr.pm = c.pmask;
+            n.publish_op = c.publish_op;
+            n.name = "peer_mask_collect+csr_pull";
+            n.acct_bytes += c.acct_bytes;
+            q->ops.erase(q->ops.begin() + i);
+            for (Op& o : q->ops)
+                if (o.publish_op > (int)i) o.publish_op -= 1;
+        }
+    }
 
     if (root.all_ones) {  // matchingBits.set(0, size) (E/ExecutionContext.java:83-87)
         u32* b;
@@ -1059,7 +1115,22 @@ colq_status run_pipeline(colq_query* q) {
         CU(ctx, cudaEventCreate(&q->ev_start));
         CU(ctx, cudaEventCreate(&q->ev_stop));
     }
-    const bool prof = q->opt_profile != 0;
+    const bool prof = q->opt_profile == 1;
+    int hot = -1;
+    if (q->opt_profile == 2) {
+        int64_t best = -1;
+        for (size_t i = 0; i < q->ops.size(); ++i)
+            if (q->ops[i].acct_bytes > best && q->ops[i].kind != K_ZERO) { best = q->ops[i].acct_bytes; hot = (int)i; }
+        if (q->hot_used == q->hot_ring.size()) {
+            if (q->hot_ring.size() >= 4096) hot = -1;  // ring full: stop sampling until colq_profile_hot drains it
+            else {
+                cudaEvent_t a, b;
+                CU(ctx, cudaEventCreate(&a));
+                CU(ctx, cudaEventCreate(&b));
+                q->hot_ring.emplace_back(a, b);
+            }
+        }
+    }
     if (prof) {
         while (q->stage_ev.size() < q->ops.size() + 1) {
             cudaEvent_t e;
@@ -1071,8 +1142,19 @@ colq_status run_pipeline(colq_query* q) {
     if (q->lazy_oob) CU(ctx, cudaMemsetAsync((u32*)q->idx_buf.ptr + RESULT_FLAGS_WORD, 0, 4, s));
     if (prof) CU(ctx, cudaEventRecord(q->stage_ev[0], s));
     for (size_t i = 0; i < q->ops.size(); ++i) {
+        if ((int)i == hot) CU(ctx, cudaEventRecord(q->hot_ring[q->hot_used].first, s));
         ST(launch_op(q, q->ops[i], s));
         if (prof) CU(ctx, cudaEventRecord(q->stage_ev[i + 1], s));
+        if ((int)i == hot) {
+            CU(ctx, cudaEventRecord(q->hot_ring[q->hot_used++].second, s));
+            const Op& o = q->ops[i];
+            colq_stage& st = q->hot_stage;
+            snprintf(st.name, sizeof st.name, "%s", o.name);
+            if (o.kind == K_SCAN_ROWS) snprintf(st.name, sizeof st.name, "scan_rows<%d,%d,%s>%s", o.np, o.ng, o.eager ? "eager" : "lazy", o.rows.push.fk ? "+push" : "");
+            if (o.kind == K_SCAN_STR) snprintf(st.name, sizeof st.name, "scan_str<op%d>%s", o.str.op, o.str.push.fk ? "+push" : "");
+            st.rows = o.acct_rows;
+            st.bytes = o.acct_bytes;
+        }
     }
     CU(ctx, cudaEventRecord(q->ev_stop, s));
     // first-touch promotion: the scans enqueued above fill the HBM copies; everything enqueued later on this stream
@@ -1748,6 +1830,7 @@ colq_status colq_query_destroy(colq_query* q) {
     if (q->ev_start) cudaEventDestroy(q->ev_start);
     if (q->ev_stop) cudaEventDestroy(q->ev_stop);
     for (cudaEvent_t e : q->stage_ev) cudaEventDestroy(e);
+    for (auto& pr : q->hot_ring) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     delete q;
     return COLQ_OK;
 }
@@ -1831,6 +1914,24 @@ colq_status colq_profile(const colq_query* q, colq_stage* out_stages, int capaci
     if (!q || !out_n_stages) return COLQ_THROW_NULL;
     *out_n_stages = (int)q->stages.size();
     for (int i = 0; i < capacity && i < (int)q->stages.size(); ++i) out_stages[i] = q->stages[i];
+    return COLQ_OK;
+}
+
+colq_status colq_profile_hot(colq_query* q, colq_stage* out_stage, int* out_samples) {
+    if (!q || !out_stage || !out_samples) return COLQ_THROW_NULL;
+    colq_ctx* ctx = q->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    double sum = 0;
+    for (size_t i = 0; i < q->hot_used; ++i) {
+        float t = 0;
+        CU(ctx, cudaEventElapsedTime(&t, q->hot_ring[i].first, q->hot_ring[i].second));
+        sum += t;
+    }
+    *out_stage = q->hot_stage;
+    out_stage->ms = q->hot_used ? sum / (double)q->hot_used : -1.0;
+    *out_samples = (int)q->hot_used;
+    q->hot_used = 0;
     return COLQ_OK;
 }
 

@@ -764,6 +764,90 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == -1 || MODE == -2) ? 4 : 3
 }
 
 // ---------------------------------------------------------------------------------------------
+// Peer-memory exchange over NVLink (multi-GPU, one process per GPU).
+//
+// Every rank owns a MAILBOX in its HBM that all peers have mapped through CUDA IPC.  A collective is: store my
+// contribution straight into every peer's mailbox slot [parity][my rank] (plain st.global over NVLink), fence, then
+// publish an epoch flag with st.release.sys; the consumer spins on the flags in its OWN memory (ld.acquire.sys) and
+// reads the slots locally.  Slots are double-buffered by epoch parity: a rank can only be one exchange ahead of any
+// peer (it needs that peer's flag to finish the current one), so a slot is never overwritten while it is still read.
+// These replace ncclAllGather on the data path: ~5 us instead of ~25-70 us for the 8-byte state mask.
+// A spin that exceeds PEER_TIMEOUT_NS sets *status and gives up (the host reports COLQ_ERR_DEVICE) -- no hangs.
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_RANKS = 64;
+constexpr int MASK_SLOT_BYTES = 4096;
+constexpr int MASK_WORDS_MAX = (MASK_SLOT_BYTES - 16) / 4;
+constexpr size_t PEER_GATHER_AREA_OFFSET = (size_t)2 * MAX_RANKS * MASK_SLOT_BYTES;
+constexpr int GATHER_SLOT_HEADER = 256;  // [u64 flag][u64 count] + pad, keeps the index payload 256-byte aligned
+constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ull;
+
+__device__ __forceinline__ u64 ld_acquire_sys(const u64* p) {
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(u64* p, u64 v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 global_timer_ns() {
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool peer_wait(const u64* flag, u64 epoch, u32* status) {
+    const u64 t0 = global_timer_ns();
+    while (ld_acquire_sys(flag) != epoch) {
+        if (global_timer_ns() - t0 > PEER_TIMEOUT_NS) {
+            atomicExch(status, 1u);
+            return false;
+        }
+    }
+    return true;
+}
+
+struct PeerMaskParams {
+    u32* reach;            // in: this rank's mask; out: OR over all ranks
+    int n_words;           // <= MASK_WORDS_MAX
+    int n_ranks, rank;
+    uint8_t* const* peers; // device array: mailbox base of every rank (own entry = local pointer)
+    u64 epoch;
+    u32* status;
+};
+
+// OR-allreduce of a small replicated-table mask -- the collective half of a sharded -> replicated filterParent hop --
+// split in two so that independent work can run between the halves (the planner puts the root table's predicate scan
+// there): PUBLISH stores this rank's words into every peer's mailbox and raises the flags; COLLECT waits for all
+// ranks' flags in local memory and ORs the slots.  COLLECT also runs as the prologue of a single-block csr_pull.
+__global__ void __launch_bounds__(256) peer_mask_publish_kernel(const PeerMaskParams P) {
+    const size_t area = (size_t)(P.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
+    for (int r = 0; r < P.n_ranks; ++r) {
+        u32* dst = reinterpret_cast<u32*>(P.peers[r] + area + (size_t)P.rank * MASK_SLOT_BYTES + 16);
+        for (int w = threadIdx.x; w < P.n_words; w += blockDim.x) dst[w] = P.reach[w];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < P.n_ranks)
+        st_release_sys(reinterpret_cast<u64*>(P.peers[threadIdx.x] + area + (size_t)P.rank * MASK_SLOT_BYTES), P.epoch);
+}
+
+// block-wide; ends with a __syncthreads()
+__device__ __forceinline__ void peer_mask_collect(const PeerMaskParams& P) {
+    const size_t area = (size_t)(P.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
+    const uint8_t* mine = P.peers[P.rank] + area;
+    if ((int)threadIdx.x < P.n_ranks)
+        peer_wait(reinterpret_cast<const u64*>(mine + (size_t)threadIdx.x * MASK_SLOT_BYTES), P.epoch, P.status);
+    __syncthreads();
+    for (int w = threadIdx.x; w < P.n_words; w += blockDim.x) {
+        u32 v = 0;
+        for (int r = 0; r < P.n_ranks; ++r) v |= reinterpret_cast<const u32*>(mine + (size_t)r * MASK_SLOT_BYTES + 16)[w];
+        P.reach[w] = v;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) peer_mask_collect_kernel(const PeerMaskParams P) { peer_mask_collect(P); }
+
+// ---------------------------------------------------------------------------------------------
 // K4b  csr_pull: to-many association hop on the forward side
 //
 // Replaces ExecutionContext.Node.filterParent, Association.Many branch (E/ExecutionContext.java:111-113), in pull
@@ -780,10 +864,12 @@ struct CsrPullParams {
     const u32* in_bits;      // nullable
     u32* out_bits;
     PushD push;
+    PeerMaskParams pm;       // pm.n_words > 0 (single-block launches only): collect the child mask exchange first
 };
 
 __global__ void __launch_bounds__(256) csr_pull_kernel(const CsrPullParams P) {
     __shared__ u32 s_reach[PUSH_SMEM_WORDS];
+    if (P.pm.n_words > 0) peer_mask_collect(P.pm);
     const bool do_push = P.push.fk != nullptr;
     if (do_push) {
         push_init(P.push, s_reach);
@@ -991,7 +1077,6 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(const u32* bits, in
 constexpr int GATHER_HEADER_WORDS = 4;
 constexpr int RESULT_FLAGS_WORD = 2;  // result block = [u64 count | u32 flags | u32 pad | indices...]; flags bit 0: a walked
                                       // to-one target was outside its table (lazy range check of host-resident columns)
-constexpr int MAX_RANKS = 64;
 
 __global__ void __launch_bounds__(256) unpack_gather_kernel(const int32_t* blocks, int n_ranks, int64_t cap, int32_t* out,
                                                           u64* info) {
@@ -1021,79 +1106,6 @@ __global__ void __launch_bounds__(256) unpack_gather_kernel(const int32_t* block
         int r = 0;
         while (r + 1 < n_ranks && i >= s_off[r + 1]) ++r;
         out[i] = blocks[r * stride_words + GATHER_HEADER_WORDS + (i - s_off[r])];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Peer-memory exchange over NVLink (multi-GPU, one process per GPU).
-//
-// Every rank owns a MAILBOX in its HBM that all peers have mapped through CUDA IPC.  A collective is: store my
-// contribution straight into every peer's mailbox slot [parity][my rank] (plain st.global over NVLink), fence, then
-// publish an epoch flag with st.release.sys; the consumer spins on the flags in its OWN memory (ld.acquire.sys) and
-// reads the slots locally.  Slots are double-buffered by epoch parity: a rank can only be one exchange ahead of any
-// peer (it needs that peer's flag to finish the current one), so a slot is never overwritten while it is still read.
-// These replace ncclAllGather on the data path: ~5 us instead of ~25-70 us for the 8-byte state mask.
-// A spin that exceeds PEER_TIMEOUT_NS sets *status and gives up (the host reports COLQ_ERR_DEVICE) -- no hangs.
-// ---------------------------------------------------------------------------------------------
-
-constexpr int MASK_SLOT_BYTES = 4096;
-constexpr int MASK_WORDS_MAX = (MASK_SLOT_BYTES - 16) / 4;
-constexpr size_t PEER_GATHER_AREA_OFFSET = (size_t)2 * MAX_RANKS * MASK_SLOT_BYTES;
-constexpr int GATHER_SLOT_HEADER = 256;  // [u64 flag][u64 count] + pad, keeps the index payload 256-byte aligned
-constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ull;
-
-__device__ __forceinline__ u64 ld_acquire_sys(const u64* p) {
-    u64 v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(u64* p, u64 v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ u64 global_timer_ns() {
-    u64 t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ bool peer_wait(const u64* flag, u64 epoch, u32* status) {
-    const u64 t0 = global_timer_ns();
-    while (ld_acquire_sys(flag) != epoch) {
-        if (global_timer_ns() - t0 > PEER_TIMEOUT_NS) {
-            atomicExch(status, 1u);
-            return false;
-        }
-    }
-    return true;
-}
-
-struct PeerMaskParams {
-    u32* reach;            // in: this rank's mask; out: OR over all ranks
-    int n_words;           // <= MASK_WORDS_MAX
-    int n_ranks, rank;
-    uint8_t* const* peers; // device array: mailbox base of every rank (own entry = local pointer)
-    u64 epoch;
-    u32* status;
-};
-
-// OR-allreduce of a small replicated-table mask: the collective half of a sharded -> replicated filterParent hop
-__global__ void __launch_bounds__(256) peer_mask_or_kernel(const PeerMaskParams P) {
-    const size_t area = (size_t)(P.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
-    for (int r = 0; r < P.n_ranks; ++r) {
-        u32* dst = reinterpret_cast<u32*>(P.peers[r] + area + (size_t)P.rank * MASK_SLOT_BYTES + 16);
-        for (int w = threadIdx.x; w < P.n_words; w += blockDim.x) dst[w] = P.reach[w];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < P.n_ranks) {
-        st_release_sys(reinterpret_cast<u64*>(P.peers[threadIdx.x] + area + (size_t)P.rank * MASK_SLOT_BYTES), P.epoch);
-        peer_wait(reinterpret_cast<const u64*>(P.peers[P.rank] + area + (size_t)threadIdx.x * MASK_SLOT_BYTES), P.epoch, P.status);
-    }
-    __syncthreads();
-    const uint8_t* mine = P.peers[P.rank] + area;
-    for (int w = threadIdx.x; w < P.n_words; w += blockDim.x) {
-        u32 v = 0;
-        for (int r = 0; r < P.n_ranks; ++r) v |= reinterpret_cast<const u32*>(mine + (size_t)r * MASK_SLOT_BYTES + 16)[w];
-        P.reach[w] = v;
     }
 }
 
