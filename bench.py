@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-small-queries", action="store_true", help="skip the 1-universe latency measurements (keeps ncu launch lists clean)")
     ap.add_argument("--eager", action="store_true", help="disable the lazy FK chain (materialise every node)")
+    ap.add_argument("--dict-names", action="store_true",
+                    help="SURVEY 8f variant, not the headline: the city-name column is dictionary-encoded (int32 codes + 16.6k distinct "
+                         "names); the name predicate runs over the dictionary and the row scan tests code bits. Implies --no-e2e.")
     ap.add_argument("--workload", default="plymouth", choices=["plymouth", "int_scan", "str_eq"],
                     help="plymouth = BASELINE configs[3] (the headline); int_scan = configs[1] (1B-row int range scan + "
                          "compaction); str_eq = configs[4] (city-name equality, one GPU's 62.5M-row shard). The last two are "
@@ -257,7 +260,9 @@ def run_colq(args, rank, local_rank, world):
 
     U = args.universes
     base = G.load_base()
-    geo = build_geography_on_device(ctx, U, world, rank, base=base, device=dev, sharded=world > 1)
+    geo = build_geography_on_device(ctx, U, world, rank, base=base, device=dev, sharded=world > 1, dict_names=args.dict_names)
+    if args.dict_names:
+        args.no_e2e = True
     q = plymouth_colq_query(ctx, lazy_fk=not args.eager)
 
     # ---- correctness gate before any number: the result must be exactly {u * 29353 + r}
@@ -321,6 +326,8 @@ def run_colq(args, rank, local_rank, world):
 
     # whole-query algorithmic bytes for the HBM GB/s half of BASELINE's metric
     algo_bytes = 4 * geo.n_zip_rows * 2 + 4 * (geo.n_city_rows + 1) + geo.name_bytes + 4 * geo.n_city_rows + 4 * 31 * geo.n_universes
+    if args.dict_names:  # codes (4 B per city row) replace name offsets + bytes
+        algo_bytes = 4 * geo.n_zip_rows * 2 + 4 * geo.n_city_rows * 2 + 4 * 31 * geo.n_universes
     algo_total = algo_bytes
     if world > 1:
         t = torch.tensor([float(algo_bytes)], dtype=torch.float64, device=dev)
@@ -443,7 +450,7 @@ def run_colq(args, rank, local_rank, world):
         line = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic", "config": workload_config(U, world, not args.eager),
+            "data": "synthetic", "config": dict(workload_config(U, world, not args.eager), **({"city_names": "dictionary-encoded"} if args.dict_names else {})),
             "hbm_gbs_query_algorithmic": query_gbs, "query_algorithmic_bytes": algo_total,
             "roofline": roofline, "stages_ms": {k: round(v["ms"], 5) for k, v in stages.items()},
             "cpu_baseline": cpu, "e2e": e2e, "e2e_upload_all_columns": e2e_upload,

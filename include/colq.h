@@ -192,6 +192,24 @@ colq_status colq_col_str_host(colq_ctx *ctx, colq_table table, int ordinal, cons
                               int64_t n_bytes);
 
 /*
+ * Dictionary-encoded StringColumn: row i holds the string dictionary[codes[i]]; the
+ * dictionary is an ordinary offsets + bytes column of n_dict DISTINCT values (host buffers, copied).  Every string
+ * criterion is evaluated once per distinct value -- by the string kernel over the dictionary for the structured
+ * predicates, or by the HOST for an opaque Predicate<String> lambda (colq_query_criteria_str_accept) -- and the row
+ * scan (4 bytes per row instead of offsets + bytes) only tests bit `code` of the resulting n_dict-bit mask.  This is
+ * how the reference's unchanged lambdas (app/.../Runner.java:236,255-259) run without a CPU row scan.
+ * _device adopts an int32 code buffer already in HBM; _host borrows a pinned one (see "Host-resident columns").
+ */
+colq_status colq_col_str_dict(colq_ctx *ctx, colq_table table, int ordinal, const int32_t *codes, int64_t n,
+                              const uint32_t *dict_offsets, const uint8_t *dict_bytes, int64_t n_dict, int64_t n_dict_bytes);
+colq_status colq_col_str_dict_device(colq_ctx *ctx, colq_table table, int ordinal, const void *codes_device, int64_t n,
+                                     const uint32_t *dict_offsets, const uint8_t *dict_bytes, int64_t n_dict,
+                                     int64_t n_dict_bytes);
+colq_status colq_col_str_dict_host(colq_ctx *ctx, colq_table table, int ordinal, const int32_t *codes_pinned,
+                                   int64_t capacity_bytes, int64_t n, const uint32_t *dict_offsets,
+                                   const uint8_t *dict_bytes, int64_t n_dict, int64_t n_dict_bytes);
+
+/*
  * x.associateTo(y, associations) (M/InMemoryTable.java:44-90): creates the forward AssociationColumn on x at
  * x_ordinal AND its reverse (transposed) column on y at y_ordinal, cross-linked (:83-85).  Only the forward data
  * is stored; hops through the reverse column are executed as a push through the forward data, which is the same
@@ -229,6 +247,11 @@ colq_status colq_query_criteria_i32_range(colq_query *query, int node, int ordin
 /* addCriteria(new Criteria.StringCriteria(ordinal, <op needle>)) (DS/Criteria.java:17) */
 colq_status colq_query_criteria_str(colq_query *query, int node, int ordinal, colq_str_op op, const uint8_t *needle,
                                     int32_t needle_len);
+/* addCriteria(new Criteria.StringCriteria(ordinal, <any Predicate<String>>)) over a dictionary-encoded column: the host
+   evaluated the predicate on each of the n_dict dictionary entries; bit d of accept_words (BitSet layout) = result for
+   entry d.  COLQ_FAILURE at execute when the column is not dictionary-encoded. */
+colq_status colq_query_criteria_str_accept(colq_query *query, int node, int ordinal, const uint64_t *accept_words,
+                                           int64_t n_dict);
 colq_status colq_query_set_option(colq_query *query, colq_option option, int value);
 
 /*

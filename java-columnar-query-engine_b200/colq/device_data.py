@@ -42,14 +42,15 @@ def _padded(t: torch.Tensor, pad_elems: int) -> torch.Tensor:
 
 def build_geography_on_device(ctx: ColqContext, n_universes: int, n_ranks: int = 1, rank: int = 0,
                               base: Optional[Dict[str, np.ndarray]] = None, device: Optional[torch.device] = None,
-                              sharded: bool = False) -> DeviceGeography:
-    """Runner.java:89-196 for this rank's universe range, generated in HBM and registered by pointer."""
+                              sharded: bool = False, dict_names: bool = False) -> DeviceGeography:
+    """Runner.java:89-196 for this rank's universe range, generated in HBM and registered by pointer.
+    ``dict_names``: the city-name column is stored dictionary-encoded (int32 codes + the distinct names)."""
     base = base or load_base()
     device = device or torch.device("cuda", ctx.device)
     u0, u1 = universe_range(n_universes, n_ranks, rank)
     U = u1 - u0
     nb = int(base["city_name_bytes"].shape[0])
-    assert U * nb < 2 ** 32 - 64, "city-name bytes exceed the uint32 offset range; use more ranks"
+    assert dict_names or U * nb < 2 ** 32 - 64, "city-name bytes exceed the uint32 offset range; use more ranks"
 
     def dev(a, dtype):
         return torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dtype)
@@ -61,12 +62,18 @@ def build_geography_on_device(ctx: ColqContext, n_universes: int, n_ranks: int =
     zc = dev(base["zip_city"], torch.int64)[None, :] + (u * N_CITIES)[:, None]
     t["zip_city"] = _padded(zc.reshape(-1).to(torch.int32), 16)
     del zc
-    off = dev(base["city_name_offsets"][:-1].astype(np.int64), torch.int64)[None, :] + (u * nb)[:, None]
-    off = torch.cat([off.reshape(-1), torch.tensor([U * nb], device=device, dtype=torch.int64)])
-    # uint32 offsets stored in an int32 tensor (same bits); values >= 2^31 wrap, which is exactly the uint32 encoding
-    t["city_name_offsets"] = _padded(((off + 2 ** 31) % 2 ** 32 - 2 ** 31).to(torch.int32), 16)
-    del off
-    t["city_name_bytes"] = _padded(dev(base["city_name_bytes"], torch.uint8).repeat(U), 64)
+    if dict_names:
+        from .engine import encode_dictionary
+        from .in_memory import StringColumn
+        codes1, d_off, d_bytes, _values = encode_dictionary(StringColumn(offsets=base["city_name_offsets"], data=base["city_name_bytes"]))
+        t["city_name_codes"] = _padded(dev(codes1, torch.int32).repeat(U), 16)
+    else:
+        off = dev(base["city_name_offsets"][:-1].astype(np.int64), torch.int64)[None, :] + (u * nb)[:, None]
+        off = torch.cat([off.reshape(-1), torch.tensor([U * nb], device=device, dtype=torch.int64)])
+        # uint32 offsets stored in an int32 tensor (same bits); values >= 2^31 wrap, which is exactly the uint32 encoding
+        t["city_name_offsets"] = _padded(((off + 2 ** 31) % 2 ** 32 - 2 ** 31).to(torch.int32), 16)
+        del off
+        t["city_name_bytes"] = _padded(dev(base["city_name_bytes"], torch.uint8).repeat(U), 64)
     t["city_state"] = _padded(dev(base["city_state"], torch.int32).repeat(U), 16)
     torch.cuda.synchronize(device)
 
@@ -77,8 +84,11 @@ def build_geography_on_device(ctx: ColqContext, n_universes: int, n_ranks: int =
     zips = ctx.table_create(nz, place, u0 * N_ZIPS)
     ctx.col_str(states, 0, base["state_code_offsets"], base["state_code_bytes"])
     ctx.col_str(states, 1, base["state_name_offsets"], base["state_name_bytes"])
-    tt = t["city_name_offsets"], t["city_name_bytes"]
-    ctx.col_str_device(cities, 0, tt[0].data_ptr(), tt[0].numel() * 4, tt[1].data_ptr(), tt[1].numel(), nc, U * nb, keepalive=tt)
+    if dict_names:
+        ctx.col_str_dict_device(cities, 0, t["city_name_codes"].data_ptr(), nc, d_off, d_bytes, keepalive=t["city_name_codes"])
+    else:
+        tt = t["city_name_offsets"], t["city_name_bytes"]
+        ctx.col_str_device(cities, 0, tt[0].data_ptr(), tt[0].numel() * 4, tt[1].data_ptr(), tt[1].numel(), nc, U * nb, keepalive=tt)
     ctx.associate_fk_device(cities, 1, states, 2, t["city_state"].data_ptr(), nc, keepalive=t["city_state"])
     ctx.col_i32_device(zips, 0, t["zip_code"].data_ptr(), nz, keepalive=t["zip_code"])
     ctx.col_i32_device(zips, 1, t["zip_pop"].data_ptr(), nz, keepalive=t["zip_pop"])

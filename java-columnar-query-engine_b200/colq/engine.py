@@ -15,7 +15,7 @@ from __future__ import annotations
 import ctypes as C
 import weakref
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -53,6 +53,38 @@ class ExecResult:
     timing: _ffi.Timing
 
 
+def encode_dictionary(col: StringColumn):
+    """Dictionary-encode a string column: ``(codes int32[n], dict_offsets uint32[d+1], dict_bytes uint8[], values)``
+    with the d distinct values in first-appearance order (what the Java shim does while it copies ``String[]`` into
+    off-heap segments)."""
+    n = col.height()
+    off, data = col.offsets, col.data
+    raw = data.tobytes()
+    index: Dict[bytes, int] = {}
+    codes = np.empty(n, dtype=np.int32)
+    for i in range(n):
+        b = raw[int(off[i]):int(off[i + 1])]
+        code = index.get(b)
+        if code is None:
+            code = index[b] = len(index)
+        codes[i] = code
+    keys = list(index.keys())
+    d_off = np.zeros(len(keys) + 1, dtype=np.uint32)
+    if keys:
+        np.cumsum([len(k) for k in keys], out=d_off[1:])
+    d_bytes = np.frombuffer(b"".join(keys), dtype=np.uint8).copy() if keys else np.zeros(0, dtype=np.uint8)
+    return codes, d_off, d_bytes, [k.decode("utf-8") for k in keys]
+
+
+def accept_words(flags: Sequence[bool]) -> np.ndarray:
+    """bool per dictionary entry -> java.util.BitSet words (bit d of word d >> 6)."""
+    bits = np.asarray(flags, dtype=np.uint8)
+    packed = np.packbits(bits, bitorder="little")
+    out = np.zeros((bits.shape[0] + 63) // 64 * 8 or 8, dtype=np.uint8)
+    out[: packed.shape[0]] = packed
+    return out.view(np.uint64)
+
+
 class ColqQuery:
     def __init__(self, ctx: "ColqContext", table_name: str):
         self.ctx = ctx
@@ -71,6 +103,10 @@ class ColqQuery:
     def criteria_str(self, node: int, ordinal: int, op: int, needle: bytes) -> None:
         buf = (C.c_uint8 * max(len(needle), 1)).from_buffer_copy(needle or b"\0")
         self.ctx._check(self.ctx.lib.colq_query_criteria_str(self.handle, node, ordinal, op, buf, len(needle)))
+
+    def criteria_str_accept(self, node: int, ordinal: int, words: np.ndarray, n_dict: int) -> None:
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.colq_query_criteria_str_accept(self.handle, node, ordinal, _ptr(w), n_dict))
 
     def set_option(self, option: int, value: int) -> None:
         self.ctx._check(self.ctx.lib.colq_query_set_option(self.handle, option, value))
@@ -178,6 +214,30 @@ class ColqContext:
         o = np.ascontiguousarray(offsets, dtype=np.uint32)
         d = np.ascontiguousarray(data, dtype=np.uint8)
         self._check(self.lib.colq_col_str(self.handle, table, ordinal, _ptr(o), _ptr(d), o.shape[0] - 1, d.shape[0]))
+
+    def col_str_dict(self, table: int, ordinal: int, codes: np.ndarray, dict_offsets: np.ndarray, dict_bytes: np.ndarray) -> None:
+        c = np.ascontiguousarray(codes, dtype=np.int32)
+        o = np.ascontiguousarray(dict_offsets, dtype=np.uint32)
+        d = np.ascontiguousarray(dict_bytes, dtype=np.uint8)
+        self._check(self.lib.colq_col_str_dict(self.handle, table, ordinal, _ptr(c), c.shape[0], _ptr(o), _ptr(d), o.shape[0] - 1, d.shape[0]))
+
+    def col_str_dict_device(self, table: int, ordinal: int, codes_ptr: int, n: int, dict_offsets: np.ndarray, dict_bytes: np.ndarray,
+                            keepalive=None) -> None:
+        o = np.ascontiguousarray(dict_offsets, dtype=np.uint32)
+        d = np.ascontiguousarray(dict_bytes, dtype=np.uint8)
+        self._keepalive.append(keepalive)
+        self._check(self.lib.colq_col_str_dict_device(self.handle, table, ordinal, C.c_void_p(codes_ptr), n, _ptr(o), _ptr(d),
+                                                      o.shape[0] - 1, d.shape[0]))
+
+    def col_str_dict_host(self, table: int, ordinal: int, codes: np.ndarray, dict_offsets: np.ndarray, dict_bytes: np.ndarray,
+                          capacity_bytes: Optional[int] = None, n: Optional[int] = None) -> None:
+        n = codes.shape[0] if n is None else n
+        cap = self._capacity(codes) if capacity_bytes is None else capacity_bytes
+        o = np.ascontiguousarray(dict_offsets, dtype=np.uint32)
+        d = np.ascontiguousarray(dict_bytes, dtype=np.uint8)
+        self._keepalive.append(codes)
+        self._check(self.lib.colq_col_str_dict_host(self.handle, table, ordinal, _ptr(codes), cap, n, _ptr(o), _ptr(d),
+                                                    o.shape[0] - 1, d.shape[0]))
 
     def col_bool(self, table: int, ordinal: int, values: np.ndarray) -> None:
         v = np.ascontiguousarray(values, dtype=np.uint8)
@@ -308,13 +368,17 @@ class DataSystemColq(DataSystem):
     """The reference-facing engine: same two methods as ``DataSystemSerialIndices``."""
 
     def __init__(self, device: int = 0, lazy_fk: bool = True, context: Optional[ColqContext] = None,
-                 options: Optional[Dict[int, int]] = None, residency: str = "device"):
+                 options: Optional[Dict[int, int]] = None, residency: str = "device", dictionary: bool = False):
         """``residency``: "device" copies every column to HBM at the first ``execute`` (default); "host" keeps int,
         string and to-one association columns in pinned off-heap buffers that the kernels stream in place over PCIe
         (only what a query touches moves; fully scanned columns are promoted to HBM by that first scan)."""
         if residency not in ("device", "host"):
             raise ValueError(residency)
         self.residency = residency
+        # dictionary=True: string columns are stored dictionary-encoded; every string criterion -- structured or an
+        # opaque lambda like the reference's -- is evaluated per DISTINCT value and the GPU row scan tests code bits
+        self.dictionary = dictionary
+        self._dict_values: Dict[Tuple[int, int], List[str]] = {}   # (id(table), ordinal) -> distinct values
         self.ctx = context or ColqContext(device)
         self.lazy_fk = lazy_fk
         self.options = dict(options or {})   # colq_option -> value, applied to every query
@@ -366,6 +430,13 @@ class DataSystemColq(DataSystem):
                         self.ctx.col_i32_host(h, ordinal, self.ctx.host_column(c.ints(), np.int32))
                     else:
                         self.ctx.col_i32(h, ordinal, c.ints())
+                elif isinstance(c, StringColumn) and self.dictionary:
+                    codes, d_off, d_bytes, values = encode_dictionary(c)
+                    self._dict_values[(tid, ordinal)] = values
+                    if host:
+                        self.ctx.col_str_dict_host(h, ordinal, self.ctx.host_column(codes, np.int32), d_off, d_bytes)
+                    else:
+                        self.ctx.col_str_dict(h, ordinal, codes, d_off, d_bytes)
                 elif isinstance(c, StringColumn):
                     if host:
                         off = self.ctx.host_column(c.offsets, np.uint32)
@@ -406,9 +477,9 @@ class DataSystemColq(DataSystem):
         cq.set_option(_ffi.OPT_LAZY_FK, 1 if self.lazy_fk else 0)
         for opt, val in self.options.items():
             cq.set_option(opt, val)
-        stack = [(query.root_node, 0)]
+        stack = [(query.root_node, 0, self._tables[query.table_name])]
         while stack:
-            node, nid = stack.pop()
+            node, nid, node_table = stack.pop()
             for crit in node.get_criteria():
                 if isinstance(crit, Criteria.IntCriteria):
                     p = crit.integer_predicate
@@ -419,15 +490,26 @@ class DataSystemColq(DataSystem):
                     cq.criteria_i32_range(nid, crit.ordinal, p.lo, p.hi)
                 elif isinstance(crit, Criteria.StringCriteria):
                     p = crit.string_predicate
+                    values = self._dict_values.get((id(node_table), crit.ordinal)) if node_table is not None else None
+                    if not isinstance(p, StringPredicate) and values is not None and callable(p):
+                        # the reference's opaque Predicate<String> (DS/Criteria.java:17): run it once per distinct value
+                        cq.criteria_str_accept(nid, crit.ordinal, accept_words([bool(p(v)) for v in values]), len(values))
+                        continue
                     if not isinstance(p, StringPredicate):
                         cq.close()
                         return None, ("The criterion on ordinal %d is an opaque Predicate<String> lambda; the GPU engine only runs "
-                                      "structured predicates (colq.data_system.str_equals & co.) and has no CPU fallback." % crit.ordinal)
+                                      "structured predicates (colq.data_system.str_equals & co.) over plain string columns and has no CPU "
+                                      "fallback; construct DataSystemColq(dictionary=True) to run opaque string predicates per distinct value." % crit.ordinal)
                     cq.criteria_str(nid, crit.ordinal, p.op, p.needle)
                 else:
                     raise TypeError(f"not a Criteria: {crit!r}")
             for ordinal, child in node.get_children_by_ordinal().items():
-                stack.append((child, cq.child(nid, ordinal)))
+                child_table = None
+                if node_table is not None and 0 <= ordinal < len(node_table.columns()):
+                    col = node_table.columns()[ordinal]
+                    if isinstance(col, AssociationColumn):
+                        child_table = col.associated_entity
+                stack.append((child, cq.child(nid, ordinal), child_table))
         return cq, None
 
     def execute(self, query: Query):

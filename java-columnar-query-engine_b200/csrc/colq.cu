@@ -125,6 +125,9 @@ struct Column {
     // host-resident columns (colq_*_host): `data` / `offsets` point at pinned host memory that the kernels read in
     // place over PCIe.  The first scan that streams the whole column also fills `promoted*` (HBM copies), which then
     // replace the host pointers: later queries run at HBM speed.  Sparsely walked columns (lazy FK chains) stay put.
+    // dictionary-encoded string column (colq_col_str_dict): `data` holds int32 codes, the n_dict DISTINCT values live
+    // in an ordinary (offsets, bytes) string column of their own.  A predicate is evaluated once per distinct value.
+    std::unique_ptr<Column> dict;
     bool host_resident = false;
     bool fk_validated = true;  // false: to-one targets are range-checked on the rows a query walks, not at ingest
     DevBuf promoted, promoted_offsets;
@@ -144,6 +147,10 @@ struct Crit {
     int op = 0;
     std::vector<uint8_t> needle;
     DevBuf needle_dev;
+    // an opaque Predicate<String> over a dictionary-encoded column: the host evaluated it per dictionary entry
+    bool is_accept = false;
+    int64_t accept_n = 0;
+    DevBuf accept_dev;
 };
 
 struct QNode {
@@ -152,13 +159,14 @@ struct QNode {
 };
 
 // one kernel launch (or collective / memset) of a planned query
-enum OpKind { K_SCAN_ROWS, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER, K_COMPACT_FUSED, K_PEER_MASK_PUBLISH, K_PEER_MASK_COLLECT, K_PEER_GATHER };
+enum OpKind { K_SCAN_ROWS, K_SCAN_CODES, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER, K_COMPACT_FUSED, K_PEER_MASK_PUBLISH, K_PEER_MASK_COLLECT, K_PEER_GATHER };
 
 struct Op {
     OpKind kind;
     int node = -1;
     int np = 0, ng = 0;
     bool eager = false;
+    ScanCodesParams codes{};
     bool never = false;  // an empty int interval: the launch degenerates to clearing the mask
     ScanRowsParams rows{};
     ScanStrParams str{};
@@ -410,6 +418,10 @@ colq_status verify(colq_query* q) {
                 case COL_STR:
                     if (!c.is_str)
                         return fail(ctx, COLQ_FAILURE, "The column is a string column but the criterion is not a string predicate.");
+                    if (c.is_accept && !col.dict)
+                        return fail(ctx, COLQ_FAILURE, "An opaque string predicate can only run over a dictionary-encoded column (colq_col_str_dict): it is evaluated per distinct value on the host; there is no CPU fallback for the row scan.");
+                    if (c.is_accept && c.accept_n != col.dict->n)
+                        return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "accept set has %lld entries but the column's dictionary has %lld", (long long)c.accept_n, (long long)col.dict->n);
                     break;
                 case COL_I32:
                     if (c.is_str)
@@ -616,13 +628,11 @@ struct Planner {
         const bool own_independent = (xi == 0 && cur == nullptr && csrs.empty());  // so far no child touched `cur`
         const size_t own_first = q->ops.size();
         // ---- string criteria: one TMA-staged scan each
-        for (const Crit* c : xr.preds) {
-            if (!c->is_str) continue;
-            const Column& col = T.cols[c->ordinal];
+        auto make_scan_str = [&](const Column& col, int64_t rows, const Crit* c, const u32* in_bits, u32* out_bits) -> Op {
             Op o{};
             o.kind = K_SCAN_STR; o.node = xi; o.name = "scan_str";
             ScanStrParams& P = o.str;
-            P.n = n;
+            P.n = rows;
             P.offsets = (const u32*)col.offsets.ptr;
             P.bytes = (const uint8_t*)col.data.ptr;
             P.bytes_capacity = col.bytes_capacity;
@@ -637,20 +647,63 @@ struct Planner {
             int64_t cap = std::min<int64_t>(std::max<int64_t>(col.max_tile_bytes + 48, 2048), 40960);
             P.cap = (int)round_up(cap, 16);
             P.stages = std::max(2, std::min(stages_env, (int)ST_MAX_STAGES));
-            P.n_tiles = (n + ST_ROWS - 1) / ST_ROWS;
-            if (col.host_resident) q->timing.h2d_bytes += (n + 1) * 4 + col.n_bytes;  // streamed over PCIe by this launch
-            if (P.n_tiles > 0 && want_promotion(col, (size_t)round_up(col.n_bytes, 16) + 64, (size_t)round_up((n + 1) * 4, 16) + 32)) {
+            P.n_tiles = (rows + ST_ROWS - 1) / ST_ROWS;
+            if (col.host_resident) q->timing.h2d_bytes += (rows + 1) * 4 + col.n_bytes;  // streamed over PCIe by this launch
+            if (P.n_tiles > 0 && want_promotion(col, (size_t)round_up(col.n_bytes, 16) + 64, (size_t)round_up((rows + 1) * 4, 16) + 32)) {
                 P.promote_bytes = (uint8_t*)col.promoted.ptr;
                 P.promote_offsets = (u32*)col.promoted_offsets.ptr;
             }
-            P.in_bits = cur;
-            u32* ob;
-            ST(out_buf(&ob));
-            P.out_bits = ob;
+            P.in_bits = in_bits;
+            P.out_bits = out_bits;
             o.smem = (size_t)P.stages * st_stage_bytes(P.cap) + st_needle_region(P.needle_len) + 2 * ST_MAX_STAGES * 8 +
                      ST_MAX_STAGES * sizeof(StrTileMeta) + PUSH_SMEM_WORDS * 4;
+            o.acct_rows = rows;
+            o.acct_bytes = (rows + 1) * 4 + col.n_bytes + bitmap_words(rows) * 4;
+            return o;
+        };
+        for (const Crit* c : xr.preds) {
+            if (!c->is_str) continue;
+            const Column& col = T.cols[c->ordinal];
+            u32* ob;
+            ST(out_buf(&ob));
+            if (!col.dict) {
+                q->ops.push_back(make_scan_str(col, n, c, cur, ob));
+                cur = ob;
+                continue;
+            }
+            // dictionary-encoded column: evaluate the predicate once per DISTINCT value, then test bit `code` per row
+            const Column& D = *col.dict;
+            const u32* accept = (const u32*)c->accept_dev.ptr;  // opaque predicate: the host evaluated it per entry
+            if (!c->is_accept) {
+                u32* dbits;
+                ST(alloc_bitmap(D.n, &dbits));
+                Op ds = make_scan_str(D, D.n, c, nullptr, dbits);
+                ds.name = "scan_str_dictionary";
+                if (D.n == 0) {  // nothing to scan; the mask must still be defined
+                    Op z{};
+                    z.kind = K_ZERO; z.node = xi; z.dst = dbits; z.n_alloc_words = bitmap_alloc_words(0); z.name = "memset_dict_mask";
+                    q->ops.push_back(z);
+                } else q->ops.push_back(ds);
+                accept = dbits;
+            }
+            Op o{};
+            o.kind = K_SCAN_CODES; o.node = xi; o.name = "scan_codes";
+            ScanCodesParams& P = o.codes;
+            P.n = n;
+            P.codes = (const int32_t*)col.data.ptr;
+            P.accept = accept;
+            P.n_dict = (u32)D.n;
+            const int64_t mask_words = (bitmap_words(D.n) + 3) & ~(int64_t)3;
+            P.mask_words = mask_words <= SC_SMEM_MASK_WORDS ? (int)mask_words : 0;
+            P.in_bits = cur;
+            P.out_bits = ob;
+            if (D.n == 0) o.never = true;
+            else {
+                if (col.host_resident) q->timing.h2d_bytes += n * 4;
+                if (n > 0 && want_promotion(col, (size_t)round_up(n * 4 + 16, 16) + 64, 0)) P.promote = (int32_t*)col.promoted.ptr;
+            }
             o.acct_rows = n;
-            o.acct_bytes = (n + 1) * 4 + col.n_bytes + bitmap_words(n) * 4;
+            o.acct_bytes = n * 4 + bitmap_words(n) * 4;
             q->ops.push_back(o);
             cur = ob;
         }
@@ -735,15 +788,17 @@ struct Planner {
             Op* last = nullptr;
             if (q->ops.size() > first_op) {
                 Op& l = q->ops.back();
-                if (l.node == xi && (l.kind == K_SCAN_ROWS || l.kind == K_SCAN_STR || l.kind == K_CSR_PULL)) last = &l;
+                if (l.node == xi && (l.kind == K_SCAN_ROWS || l.kind == K_SCAN_CODES || l.kind == K_SCAN_STR || l.kind == K_CSR_PULL)) last = &l;
             }
             if (last && last->never) {
                 // no row of this node matches: nothing to push, and nobody else reads the mask
                 last->rows.out_bits = nullptr;
+                last->codes.out_bits = nullptr;
                 xr.bits = nullptr; xr.all_ones = false; xr.fused = true;
             } else if (last && consume.fwd->is_fk) {
                 PushD pd{(const int32_t*)consume.fwd->data.ptr, consume.reach, consume.n_parent, oob_for(*consume.fwd)};
                 if (last->kind == K_SCAN_ROWS) { last->rows.push = pd; last->rows.out_bits = nullptr; }
+                else if (last->kind == K_SCAN_CODES) { last->codes.push = pd; last->codes.out_bits = nullptr; }
                 else if (last->kind == K_SCAN_STR) { last->str.push = pd; last->str.out_bits = nullptr; }
                 else { last->csr.push = pd; last->csr.out_bits = nullptr; }
                 // out_bits dropped: nobody else reads this node's mask (debug cardinality reports -1)
@@ -806,6 +861,13 @@ void launch_scan_rows(const Op& o, cudaStream_t s) {
     }
 }
 
+void stage_name(const Op& o, char* out, size_t cap) {
+    if (o.kind == K_SCAN_CODES) snprintf(out, cap, "scan_codes%s", o.codes.push.fk ? "+push" : "");
+    else if (o.kind == K_SCAN_ROWS) snprintf(out, cap, "scan_rows<%d,%d,%s>%s", o.np, o.ng, o.eager ? "eager" : "lazy", o.rows.push.fk ? "+push" : "");
+    else if (o.kind == K_SCAN_STR) snprintf(out, cap, "%s<op%d>%s", o.name, o.str.op, o.str.push.fk ? "+push" : "");
+    else snprintf(out, cap, "%s", o.name);
+}
+
 inline const void* compact_fused_fn(int ng) {
     switch (ng) {
         case 0: return (const void*)compact_fused_kernel<0>;
@@ -832,6 +894,19 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
                 q->timing.kernel_launches++;
             }
             break;
+        case K_SCAN_CODES: {
+            if (o.never) {  // an empty dictionary: no row matches
+                if (o.codes.out_bits) CU(ctx, cudaMemsetAsync(o.codes.out_bits, 0, (size_t)bitmap_alloc_words(o.codes.n) * 4, s));
+                break;
+            }
+            const int grid = (int)((o.codes.n + SC_BLOCK_ROWS - 1) / SC_BLOCK_ROWS);
+            if (grid == 0) break;
+            const size_t smem = (size_t)(PUSH_SMEM_WORDS + o.codes.mask_words) * 4;
+            if (o.codes.mask_words > 0) scan_codes_kernel<true><<<grid, SR_THREADS, smem, s>>>(o.codes);
+            else scan_codes_kernel<false><<<grid, SR_THREADS, smem, s>>>(o.codes);
+            q->timing.kernel_launches++;
+            break;
+        }
         case K_SCAN_STR: {
             if (o.str.n_tiles == 0) break;
             // fixed family: EQ / NE / STARTS_WITH / ENDS_WITH with a needle of 1..16 bytes; generic family otherwise
@@ -1149,9 +1224,7 @@ colq_status run_pipeline(colq_query* q) {
             CU(ctx, cudaEventRecord(q->hot_ring[q->hot_used++].second, s));
             const Op& o = q->ops[i];
             colq_stage& st = q->hot_stage;
-            snprintf(st.name, sizeof st.name, "%s", o.name);
-            if (o.kind == K_SCAN_ROWS) snprintf(st.name, sizeof st.name, "scan_rows<%d,%d,%s>%s", o.np, o.ng, o.eager ? "eager" : "lazy", o.rows.push.fk ? "+push" : "");
-            if (o.kind == K_SCAN_STR) snprintf(st.name, sizeof st.name, "scan_str<op%d>%s", o.str.op, o.str.push.fk ? "+push" : "");
+            stage_name(o, st.name, sizeof st.name);
             st.rows = o.acct_rows;
             st.bytes = o.acct_bytes;
         }
@@ -1250,9 +1323,7 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
         const Op& o = q->ops[i];
         if (o.kind == K_ZERO) continue;
         colq_stage st{};
-        snprintf(st.name, sizeof st.name, "%s", o.name);
-        if (o.kind == K_SCAN_ROWS) snprintf(st.name, sizeof st.name, "scan_rows<%d,%d,%s>%s", o.np, o.ng, o.eager ? "eager" : "lazy", o.rows.push.fk ? "+push" : "");
-        if (o.kind == K_SCAN_STR) snprintf(st.name, sizeof st.name, "scan_str<op%d>%s", o.str.op, o.str.push.fk ? "+push" : "");
+        stage_name(o, st.name, sizeof st.name);
         st.rows = o.acct_rows;
         st.bytes = o.acct_bytes;
         st.ms = -1.0;
@@ -1573,6 +1644,15 @@ static colq_status finish_str(colq_ctx* ctx, Column* c, int64_t n, int64_t n_byt
     return COLQ_OK;
 }
 
+// upload an (offsets, bytes) pair into `c` with the padding the TMA path needs
+static colq_status fill_str(colq_ctx* ctx, Column* c, const uint32_t* offsets, const uint8_t* bytes, int64_t n, int64_t n_bytes) {
+    ST(upload(ctx, c->offsets, offsets, (size_t)(n + 1) * 4, (size_t)round_up((n + 1) * 4, 16) + 16));
+    size_t cap = (size_t)round_up(n_bytes, 16) + ST_SLACK;
+    ST(upload(ctx, c->data, bytes, (size_t)n_bytes, cap));
+    c->bytes_capacity = (int64_t)cap;
+    return finish_str(ctx, c, n, n_bytes);
+}
+
 colq_status colq_col_str(colq_ctx* ctx, colq_table table, int ordinal, const uint32_t* offsets, const uint8_t* bytes, int64_t n,
                          int64_t n_bytes) {
     if (!ctx || !offsets || (!bytes && n_bytes > 0)) return COLQ_THROW_NULL;
@@ -1581,11 +1661,88 @@ colq_status colq_col_str(colq_ctx* ctx, colq_table table, int ordinal, const uin
     CU(ctx, cudaSetDevice(ctx->device));
     Column* c;
     ST(slot_for(ctx, table, ordinal, n, &c));
-    ST(upload(ctx, c->offsets, offsets, (size_t)(n + 1) * 4, (size_t)round_up((n + 1) * 4, 16) + 16));
-    size_t cap = (size_t)round_up(n_bytes, 16) + ST_SLACK;
-    ST(upload(ctx, c->data, bytes, (size_t)n_bytes, cap));
-    c->bytes_capacity = (int64_t)cap;
-    return finish_str(ctx, c, n, n_bytes);
+    return fill_str(ctx, c, offsets, bytes, n, n_bytes);
+}
+
+// ---- dictionary-encoded string columns ---------------------------------------------------------------
+
+static colq_status pinned_alias(colq_ctx* ctx, const void* host, const char* what, const void** out);
+
+static colq_status check_dict_args(colq_ctx* ctx, const uint32_t* dict_offsets, const uint8_t* dict_bytes, int64_t n_dict, int64_t n_dict_bytes) {
+    if (!dict_offsets || (!dict_bytes && n_dict_bytes > 0)) return COLQ_THROW_NULL;
+    if (n_dict < 0 || n_dict > INT32_MAX) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "dictionary size %lld outside [0, 2^31)", (long long)n_dict);
+    if (n_dict_bytes < 0 || n_dict_bytes > (int64_t)0xfffffff0ll) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "dictionary payload exceeds the uint32 offset range");
+    if (dict_offsets[0] != 0 || (int64_t)dict_offsets[n_dict] != n_dict_bytes) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "dictionary offsets must start at 0 and end at n_dict_bytes");
+    return COLQ_OK;
+}
+
+// codes are in HBM (or pinned host memory) at c->data; attach the dictionary and validate the code range
+static colq_status finish_dict(colq_ctx* ctx, Column* c, int64_t n, const uint32_t* dict_offsets, const uint8_t* dict_bytes, int64_t n_dict,
+                               int64_t n_dict_bytes, bool check_codes) {
+    std::unique_ptr<Column> d(new Column());
+    ST(fill_str(ctx, d.get(), dict_offsets, dict_bytes, n_dict, n_dict_bytes));
+    if (check_codes && n > 0) {
+        DevBuf mm;
+        ST(dev_alloc(ctx, mm, 8));
+        int32_t init[2] = {INT32_MAX, INT32_MIN};
+        CU(ctx, cudaMemcpyAsync(mm.ptr, init, 8, cudaMemcpyHostToDevice, ctx->stream));
+        fk_minmax_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>((const int32_t*)c->data.ptr, n, (int32_t*)mm.ptr, (int32_t*)mm.ptr + 1);
+        CU(ctx, cudaGetLastError());
+        int32_t got[2];
+        CU(ctx, cudaMemcpyAsync(got, mm.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (got[0] < 0 || got[1] >= n_dict)
+            return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "dictionary code outside [0, %lld) (min %d, max %d)", (long long)n_dict, got[0], got[1]);
+    }
+    c->kind = COL_STR; c->n = n; c->n_bytes = 0;
+    c->dict = std::move(d);
+    return COLQ_OK;
+}
+
+colq_status colq_col_str_dict(colq_ctx* ctx, colq_table table, int ordinal, const int32_t* codes, int64_t n, const uint32_t* dict_offsets,
+                              const uint8_t* dict_bytes, int64_t n_dict, int64_t n_dict_bytes) {
+    if (!ctx || (!codes && n > 0)) return COLQ_THROW_NULL;
+    ST(check_dict_args(ctx, dict_offsets, dict_bytes, n_dict, n_dict_bytes));
+    CU(ctx, cudaSetDevice(ctx->device));
+    Column* c;
+    ST(slot_for(ctx, table, ordinal, n, &c));
+    ST(upload(ctx, c->data, codes, (size_t)n * 4, (size_t)round_up(n * 4 + 16, 16)));
+    colq_status st = finish_dict(ctx, c, n, dict_offsets, dict_bytes, n_dict, n_dict_bytes, true);
+    if (st != COLQ_OK) *c = Column();
+    return st;
+}
+
+colq_status colq_col_str_dict_device(colq_ctx* ctx, colq_table table, int ordinal, const void* codes_device, int64_t n,
+                                     const uint32_t* dict_offsets, const uint8_t* dict_bytes, int64_t n_dict, int64_t n_dict_bytes) {
+    if (!ctx || (!codes_device && n > 0)) return COLQ_THROW_NULL;
+    if ((uintptr_t)codes_device & 15) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "device column must be 16-byte aligned");
+    ST(check_dict_args(ctx, dict_offsets, dict_bytes, n_dict, n_dict_bytes));
+    CU(ctx, cudaSetDevice(ctx->device));
+    Column* c;
+    ST(slot_for(ctx, table, ordinal, n, &c));
+    c->data.ptr = const_cast<void*>(codes_device); c->data.bytes = (size_t)n * 4; c->data.owned = false;
+    colq_status st = finish_dict(ctx, c, n, dict_offsets, dict_bytes, n_dict, n_dict_bytes, true);
+    if (st != COLQ_OK) *c = Column();
+    return st;
+}
+
+colq_status colq_col_str_dict_host(colq_ctx* ctx, colq_table table, int ordinal, const int32_t* codes_pinned, int64_t capacity_bytes,
+                                   int64_t n, const uint32_t* dict_offsets, const uint8_t* dict_bytes, int64_t n_dict, int64_t n_dict_bytes) {
+    if (!ctx || !codes_pinned) return COLQ_THROW_NULL;
+    ST(check_dict_args(ctx, dict_offsets, dict_bytes, n_dict, n_dict_bytes));
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (capacity_bytes < round_up(n * 4, 16)) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "host column buffer must be padded to a multiple of 16 bytes");
+    const void* alias;
+    ST(pinned_alias(ctx, codes_pinned, "the dictionary-code buffer", &alias));
+    Column* c;
+    ST(slot_for(ctx, table, ordinal, n, &c));
+    c->data.ptr = const_cast<void*>(alias); c->data.bytes = (size_t)capacity_bytes; c->data.owned = false;
+    // codes stay in host memory and are not read at registration: the row scan treats a code outside the dictionary
+    // as "no match" (it fails the [0, n_dict) range test before the mask lookup)
+    colq_status st = finish_dict(ctx, c, n, dict_offsets, dict_bytes, n_dict, n_dict_bytes, false);
+    if (st != COLQ_OK) *c = Column();
+    else c->host_resident = true;
+    return st;
 }
 
 colq_status colq_col_str_device(colq_ctx* ctx, colq_table table, int ordinal, const void* offsets_device, int64_t offsets_capacity,
@@ -1868,6 +2025,20 @@ colq_status colq_query_criteria_str(colq_query* q, int node, int ordinal, colq_s
     c.ordinal = ordinal; c.is_str = true; c.op = (int)op;
     c.needle.assign(needle, needle + len);
     ST(upload(ctx, c.needle_dev, needle, (size_t)len, (size_t)round_up(len + 16, 16)));
+    q->nodes[node].crit.push_back(std::move(c));
+    return COLQ_OK;
+}
+
+colq_status colq_query_criteria_str_accept(colq_query* q, int node, int ordinal, const uint64_t* accept_words, int64_t n_dict) {
+    if (!q || (!accept_words && n_dict > 0)) return COLQ_THROW_NULL;
+    colq_ctx* ctx = q->ctx;
+    if (node < 0 || (size_t)node >= q->nodes.size()) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "unknown query node %d", node);
+    if (n_dict < 0) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "negative dictionary size");
+    CU(ctx, cudaSetDevice(ctx->device));
+    Crit c;
+    c.ordinal = ordinal; c.is_str = true; c.is_accept = true; c.accept_n = n_dict;
+    const size_t words = (size_t)((n_dict + 63) / 64);
+    ST(upload(ctx, c.accept_dev, accept_words, words * 8, (size_t)bitmap_alloc_words(n_dict) * 4));
     q->nodes[node].crit.push_back(std::move(c));
     return COLQ_OK;
 }

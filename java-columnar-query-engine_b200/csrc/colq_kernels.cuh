@@ -354,6 +354,126 @@ __global__ void __launch_bounds__(SR_THREADS) scan_rows_kernel(const ScanRowsPar
 }
 
 // ---------------------------------------------------------------------------------------------
+// K2'  scan_codes: string predicate over a DICTIONARY-ENCODED column -> bitmask
+//
+// Replaces ExecutionContext.Node.filterSelf (E/ExecutionContext.java:79-94) over StringColumn.where
+// (M/InMemoryColumn.java:71-74) when the column is stored as int32 dictionary codes.  The predicate was evaluated
+// once per DISTINCT value -- by scan_str over the dictionary, or on the host for an opaque lambda -- into an
+// n_dict-bit accept mask; the row scan streams 4 bytes per row and tests bit `code`.  The mask is staged in shared
+// memory (random 4-byte gathers: ~3 bank-conflict cycles per warp instead of up to 16 L1 wavefronts); dictionaries
+// beyond SC_SMEM_MASK_WORDS * 32 entries are looked up through L1/L2.  Same row mapping as scan_rows, SC_ITER
+// consecutive 4096-row tiles per CTA so that the mask copy is amortised.
+// ---------------------------------------------------------------------------------------------
+
+constexpr int SC_ITER = 8;
+constexpr int SC_BLOCK_ROWS = SR_BLOCK_ROWS * SC_ITER;  // 32768
+constexpr int SC_SMEM_MASK_WORDS = 8192;                // 32 KB: dictionaries of up to 262144 entries
+
+struct ScanCodesParams {
+    int64_t n;
+    const int32_t* codes;
+    int32_t* promote;     // nullable: first-touch promotion of host-resident codes (see IntPredD::promote)
+    const u32* accept;    // n_dict-bit mask, allocation padded to whole 16-byte lines
+    u32 n_dict;
+    int mask_words;       // words staged in shared memory (0: look the mask up in global memory)
+    const u32* in_bits;
+    u32* out_bits;
+    PushD push;
+};
+
+template <bool SMEM>
+__global__ void __launch_bounds__(SR_THREADS) scan_codes_kernel(const ScanCodesParams P) {
+    extern __shared__ __align__(16) u32 s_dyn[];  // [PUSH_SMEM_WORDS reach | mask_words accept]
+    u32* s_reach = s_dyn;
+    u32* s_accept = s_dyn + PUSH_SMEM_WORDS;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const bool do_push = P.push.fk != nullptr;
+    if (do_push) push_init(P.push, s_reach);
+    if (SMEM) {
+        for (int i = threadIdx.x; i < P.mask_words; i += SR_THREADS) s_accept[i] = __ldg(P.accept + i);
+    }
+    if (do_push || SMEM) __syncthreads();
+    const u32 span = P.n_dict - 1u;
+    auto test = [&](int32_t c) -> bool {
+        if ((u32)c > span) return false;  // a code outside the dictionary matches nothing
+        const u32 w = SMEM ? s_accept[(u32)c >> 5] : __ldg(P.accept + ((u32)c >> 5));
+        return (w >> ((u32)c & 31)) & 1u;
+    };
+
+#pragma unroll 1
+    for (int it = 0; it < SC_ITER; ++it) {
+        const int64_t wbase = ((int64_t)blockIdx.x * SC_ITER + it) * SR_BLOCK_ROWS + (int64_t)warp * SR_WARP_ROWS;
+        if (wbase >= P.n) break;
+        u32 nib[SR_V];
+        if (wbase + SR_WARP_ROWS <= P.n) {
+            int4 v[SR_V];
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) v[j] = ldg_stream_v4(P.codes + wbase + j * 128 + lane * 4);
+            if (P.promote != nullptr) {
+#pragma unroll
+                for (int j = 0; j < SR_V; ++j) *reinterpret_cast<int4*>(P.promote + wbase + j * 128 + lane * 4) = v[j];
+            }
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j)
+                nib[j] = (test(v[j].x) ? 1u : 0u) | (test(v[j].y) ? 2u : 0u) | (test(v[j].z) ? 4u : 0u) | (test(v[j].w) ? 8u : 0u);
+        } else {
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) {
+                u32 m = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int64_t r = wbase + j * 128 + lane * 4 + e;
+                    if (r < P.n) {
+                        const int32_t c = P.codes[r];
+                        if (P.promote != nullptr) P.promote[r] = c;
+                        m |= test(c) ? (1u << e) : 0u;
+                    }
+                }
+                nib[j] = m;
+            }
+        }
+        if (P.in_bits != nullptr) {
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) {
+                u32 w = P.in_bits[((wbase + j * 128) >> 5) + (lane >> 3)];
+                nib[j] &= (w >> ((lane & 7) * 4)) & 0xFu;
+            }
+        }
+        if (do_push) {
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) {
+                u32 m = nib[j];
+                while (m) {
+                    int e = __ffs(m) - 1;
+                    m &= m - 1;
+                    push_row(P.push, s_reach, wbase + j * 128 + lane * 4 + e);
+                }
+            }
+        }
+        if (P.out_bits != nullptr) {
+            u32 y[SR_V];
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) {
+                u32 x = nib[j] << ((lane & 7) * 4);
+                x |= __shfl_xor_sync(FULL_MASK, x, 1);
+                x |= __shfl_xor_sync(FULL_MASK, x, 2);
+                x |= __shfl_xor_sync(FULL_MASK, x, 4);
+                y[j] = __shfl_sync(FULL_MASK, x, (lane & 3) * 8);
+            }
+            u32 out = y[0];
+#pragma unroll
+            for (int j = 1; j < SR_V; ++j) out = ((lane >> 2) == j) ? y[j] : out;
+            if (lane < 4 * SR_V) P.out_bits[(wbase >> 5) + lane] = out;
+        }
+    }
+    if (do_push) {
+        __syncthreads();
+        push_flush(P.push, s_reach);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2  scan_str: string predicate over an (offsets, bytes) column -> bitmask, TMA-staged, warp-specialised
 //
 // Replaces ExecutionContext.Node.filterSelf (E/ExecutionContext.java:79-94) over StringColumn.where

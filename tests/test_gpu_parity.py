@@ -31,7 +31,9 @@ LAZY, EAGER = dict(lazy_fk=True), dict(lazy_fk=False)
 NO_DEFER = dict(lazy_fk=True, options={5: 0})            # COLQ_OPT_DEFER_CHAINS=0: FK chains inside the row scan
 HOST = dict(lazy_fk=True, residency="host")              # columns stay in pinned host memory, promoted on first scan
 HOST_NO_PROMOTE = dict(lazy_fk=True, residency="host", options={6: 0})   # COLQ_OPT_PROMOTE=0: always streamed
-ALL_VARIANTS = (LAZY, EAGER, NO_DEFER, HOST, HOST_NO_PROMOTE)
+DICT = dict(lazy_fk=True, dictionary=True)               # string columns dictionary-encoded: code lookup row scans
+DICT_HOST = dict(lazy_fk=True, dictionary=True, residency="host")
+ALL_VARIANTS = (LAZY, EAGER, NO_DEFER, HOST, HOST_NO_PROMOTE, DICT, DICT_HOST)
 
 
 def both(engines, build, queries, lazy_modes=(True, False), variants=None):
@@ -76,6 +78,14 @@ def both(engines, build, queries, lazy_modes=(True, False), variants=None):
 def test_tck(engines, case, lazy):
     new_gpu, _ = engines
     case(lambda: new_gpu(lazy))
+
+
+@pytest.mark.parametrize("variant", [HOST, DICT, DICT_HOST], ids=["host", "dict", "dict_host"])
+@pytest.mark.parametrize("case", tck.REFERENCE_TESTS + tck.FAILURE_TESTS + tck.EXTRA_TESTS, ids=lambda f: f.__name__)
+def test_tck_other_physical_layouts(engines, case, variant):
+    """The reference's QueryTest + failure cases again, with host-resident and dictionary-encoded columns."""
+    new_gpu, _ = engines
+    case(lambda: new_gpu(**variant))
 
 
 def test_headline_queries_one_universe(engines, expected, base_geography):
@@ -160,7 +170,7 @@ def test_string_ops(engines, n, max_len):
                 q.root_node.add_criteria(Criteria.StringCriteria(0, StringPredicate(op, nd)))
                 return q
             queries.append(mk)
-    both(engines, build, queries, variants=(LAZY, HOST) if n in (1025, 3000, 70_000) else (LAZY,))
+    both(engines, build, queries, variants=(LAZY, HOST, DICT, DICT_HOST) if n in (1025, 3000, 70_000) else (LAZY, DICT))
 
 
 def test_two_string_criteria_and_int_on_one_node(engines):
@@ -179,7 +189,7 @@ def test_two_string_criteria_and_int_on_one_node(engines):
         qq.root_node.add_criteria(Criteria.StringCriteria(0, StringPredicate(2, "xz")))
         return qq
 
-    both(engines, build, [q], variants=(LAZY, HOST, HOST_NO_PROMOTE))
+    both(engines, build, [q], variants=(LAZY, HOST, HOST_NO_PROMOTE, DICT, DICT_HOST))
 
 
 # ------------------------------------------------------------------ associations: random graphs, forward and reverse hops
@@ -391,3 +401,112 @@ def test_plymouth_full_size_properties(base_geography, expected):
     del geo
     ctx.close()
     torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------ opaque lambdas over dictionary-encoded columns
+def test_reference_lambdas_run_unchanged_over_dictionary_columns(engines, base_geography, expected):
+    """The reference's criteria are opaque lambdas (DS/Criteria.java:17; app/.../Runner.java:236,255-259).  With
+    dictionary-encoded string columns the engine evaluates them once per DISTINCT value on the host and the GPU row scan
+    tests code bits: the Runner's own lambdas give the oracle's answers (the oracle runs the structured twins)."""
+    new_gpu, new_oracle = engines
+    geo = G.build_tables(3, base=base_geography)
+    oracle = new_oracle()
+    G.register_geography(oracle, geo)
+    oracle.execute(G.plymouth_query())
+    want_ply = oracle.last_indices.copy()
+    oracle.execute(G.north_south_north_query())
+    want_nsn = oracle.last_indices.copy()
+
+    def plymouth_lambda():   # Runner.java:230-236 with "PLYMOUTH"::equals as a plain callable
+        q = Query("zips")
+        q.root_node.add_criteria(Criteria.IntCriteria(1, int_range(10_000, 10_099)))
+        q.root_node.create_child(2).create_child(1).create_child(3).create_child(2).add_criteria(
+            Criteria.StringCriteria(0, lambda s: s == "PLYMOUTH"))
+        return q
+
+    def nsn_lambda():        # Runner.java:254-259 with s -> s.contains(..)
+        q = Query("states")
+        q.root_node.add_criteria(Criteria.StringCriteria(1, lambda s: "North" in s))
+        n = q.root_node.create_child(3)
+        n.add_criteria(Criteria.StringCriteria(1, lambda s: "South" in s))
+        n.create_child(3).add_criteria(Criteria.StringCriteria(1, lambda s: "North" in s))
+        return q
+
+    for variant in (DICT, DICT_HOST):
+        ds = new_gpu(**variant)
+        G.register_geography(ds, geo)
+        for make, want in ((plymouth_lambda, want_ply), (nsn_lambda, want_nsn)):
+            r = ds.execute(make())
+            assert isinstance(r, QueryResult.Success), getattr(r, "message", None)
+            assert np.array_equal(ds.last_query.fetch(want_indices=True).indices, want)
+        names = [n for n, *_ in ds.last_query.profile()]
+        assert any(n.startswith("scan_codes") for n in names) and not any(n.startswith("scan_str") for n in names), names
+        # an arbitrary predicate no structured operator covers
+        q = Query("cities")
+        q.root_node.add_criteria(Criteria.StringCriteria(0, lambda s: len(s) == 7 and s[::-1] < s))
+        r = ds.execute(q)
+        assert isinstance(r, QueryResult.Success)
+        names_col = geo.cities.columns()[0]
+        want = np.array([i for i in range(names_col.height()) if (lambda s: len(s) == 7 and s[::-1] < s)(names_col.get(i))], dtype=np.int32)
+        assert np.array_equal(ds.last_query.fetch(want_indices=True).indices, want)
+        ds.close()
+    # without a dictionary an opaque lambda is still a Failure, never a CPU row scan
+    ds = new_gpu()
+    G.register_geography(ds, geo)
+    r = ds.execute(plymouth_lambda())
+    assert isinstance(r, QueryResult.Failure) and "no CPU" in r.message
+    ds.close()
+
+
+def test_dictionary_abi_errors():
+    from colq import _ffi
+    from colq.engine import ColqContext, ColqError, accept_words
+    ctx = ColqContext(0)
+    t = ctx.table_create(4)
+    d_off = np.array([0, 1, 3], dtype=np.uint32)
+    d_bytes = np.frombuffer(b"abb", dtype=np.uint8)
+    with pytest.raises(ValueError, match="dictionary code outside"):
+        ctx.col_str_dict(t, 0, np.array([0, 1, 2, 0], dtype=np.int32), d_off, d_bytes)
+    ctx.col_str_dict(t, 0, np.array([0, 1, 1, 0], dtype=np.int32), d_off, d_bytes)
+    ctx.col_str(t, 1, np.array([0, 1, 2, 3, 4], dtype=np.uint32), np.frombuffer(b"wxyz", dtype=np.uint8))
+    ctx.register("t", t)
+    q = ctx.query("t")
+    q.criteria_str_accept(0, 0, accept_words([False, True]), 2)
+    r = q.execute()
+    assert r.count == 2 and list(r.indices) == [1, 2]
+    q.close()
+    q = ctx.query("t")
+    q.criteria_str(0, 0, 0, b"a")          # structured EQ over the dictionary
+    r = q.execute()
+    assert list(r.indices) == [0, 3]
+    q.close()
+    q = ctx.query("t")
+    q.criteria_str_accept(0, 0, accept_words([True, True, True]), 3)   # wrong dictionary size
+    with pytest.raises(ValueError, match="accept set has 3 entries"):
+        q.execute()
+    q.close()
+    q = ctx.query("t")
+    q.criteria_str_accept(0, 1, accept_words([True] * 4), 4)           # plain string column: Failure, no CPU scan
+    with pytest.raises(ColqError) as e:
+        q.execute()
+    assert e.value.status == _ffi.FAILURE and "dictionary-encoded" in str(e.value)
+    q.close()
+    ctx.close()
+
+
+def test_large_dictionary_is_looked_up_in_global_memory(engines):
+    """More than 262144 distinct values: the accept mask no longer fits the shared-memory staging of scan_codes."""
+    n = 300_000
+    col = StringColumn([f"k{i:06d}" if i % 7 else "dup" for i in range(n)])
+
+    def build(ds):
+        ds.register("s", InMemoryTable.of_columns(col))
+
+    def mk(op, nd):
+        def q():
+            qq = Query("s")
+            qq.root_node.add_criteria(Criteria.StringCriteria(0, StringPredicate(op, nd)))
+            return qq
+        return q
+
+    both(engines, build, [mk(0, "dup"), mk(1, "9999"), mk(2, "k150000"), mk(7, "k29")], variants=(DICT, DICT_HOST))

@@ -73,3 +73,19 @@ def test_universe_replication_shapes(base_geography):
     shard = G.build_tables(10, n_ranks=4, rank=2, base=base_geography)
     assert shard.n_universes == 2 and shard.zip_row_base == 6 * G.N_ZIPS
     assert int(shard.zips.columns()[2].fk().max()) < shard.cities.size()   # keys are shard-local
+
+
+def test_dictionary_encoding_host_logic():
+    """engine.encode_dictionary / accept_words: what the shim does before any GPU call."""
+    from colq.engine import accept_words, encode_dictionary
+    from colq.in_memory import StringColumn
+    col = StringColumn(["b", "a", "", "b", "é", "a", "b"])
+    codes, d_off, d_bytes, values = encode_dictionary(col)
+    assert values == ["b", "a", "", "é"]                       # first-appearance order
+    assert codes.tolist() == [0, 1, 2, 0, 3, 1, 0]
+    assert d_off.tolist() == [0, 1, 2, 2, 4] and bytes(d_bytes) == "baé".encode()
+    empty = encode_dictionary(StringColumn([]))
+    assert empty[0].shape == (0,) and empty[1].tolist() == [0] and empty[3] == []
+    w = accept_words([True, False, True] + [False] * 61 + [True])
+    assert w.dtype == np.uint64 and w.tolist() == [5, 1]
+    assert accept_words([]).tolist() == [0]
