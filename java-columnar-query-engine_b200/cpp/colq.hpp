@@ -8,6 +8,8 @@
 #pragma once
 
 #include <cstdint>
+#include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -152,8 +154,11 @@ inline StringOp strCompareGt(std::string v) { return {COLQ_STR_CMP_GT, std::move
 inline StringOp strCompareLt(std::string v) { return {COLQ_STR_CMP_LT, std::move(v)}; }
 
 // ---- DS/Criteria.java:10-20, DS/Query.java:17-54, DS/QueryResult.java:3-9
+// an opaque Predicate<String> like the reference's own lambdas (app/.../Runner.java:236,255-259): runs only over
+// dictionary-encoded columns (Options::dictionary), evaluated once per DISTINCT value on the host
+using StringLambda = std::function<bool(const std::string&)>;
 struct IntCriteria { int ordinal; IntRange integerPredicate; };
-struct StringCriteria { int ordinal; StringOp stringPredicate; };
+struct StringCriteria { int ordinal; std::variant<StringOp, StringLambda> stringPredicate; };
 using Criteria = std::variant<IntCriteria, StringCriteria>;
 
 class Query {
@@ -177,14 +182,25 @@ struct Success { std::shared_ptr<InMemoryTable> resultSet; };
 struct Failure { std::string message; };
 using QueryResult = std::variant<Success, Failure>;
 
+// physical layout of the registered tables on the engine side (include/colq.h "Host-resident columns" and
+// "Dictionary-encoded StringColumn"); results are identical in every combination
+enum class Residency { Device, Host };
+struct Options {
+    Residency residency = Residency::Device;  // Host: columns stay in pinned off-heap buffers, streamed over PCIe, promoted on first scan
+    bool dictionary = false;                  // string columns as int32 codes + distinct values; enables StringLambda criteria
+};
+
 // ---- E/DataSystemSerialIndices.java:14-102 over libcolq.so
 class DataSystemColq {
 public:
-    explicit DataSystemColq(int device = 0) {
+    explicit DataSystemColq(int device = 0, Options options = {}) : options_(options) {
         if (colq_create(device, &ctx_) != COLQ_OK)
             throw std::runtime_error("colq_create failed: no usable sm_100 GPU (libcolq has no CPU fallback)");
     }
-    ~DataSystemColq() { colq_destroy(ctx_); }
+    ~DataSystemColq() {
+        for (void* p : hostBuffers_) colq_host_free(ctx_, p);
+        colq_destroy(ctx_);
+    }
     DataSystemColq(const DataSystemColq&) = delete;
 
     void registerTable(const std::string& name, std::shared_ptr<InMemoryTable> table) { tables_[name] = std::move(table); }
@@ -198,7 +214,7 @@ public:
         colq_query* q = nullptr;
         check(colq_query_create(ctx_, query.tableName.c_str(), &q));
         struct Guard { colq_query* q; ~Guard() { colq_query_destroy(q); } } guard{q};
-        translate(q, query.rootNode, 0);
+        if (std::string why = translate(q, query.rootNode, 0, &table); !why.empty()) return Failure{why};
         BitSet bits;
         bits.words.assign((size_t)((table.size() + 63) / 64), 0);
         int64_t count = 0;
@@ -217,22 +233,50 @@ private:
             default: throw std::runtime_error(std::string("libcolq status ") + std::to_string((int)st) + ": " + colq_last_error(ctx_));
         }
     }
-    void translate(colq_query* q, const Query::Node& node, int id) {
+    // returns a Failure message for an opaque predicate the engine cannot run, else ""
+    std::string translate(colq_query* q, const Query::Node& node, int id, InMemoryTable* table) {
         for (const Criteria& c : node.criteria) {
-            if (auto* ic = std::get_if<IntCriteria>(&c))
+            if (auto* ic = std::get_if<IntCriteria>(&c)) {
                 check(colq_query_criteria_i32_range(q, id, ic->ordinal, ic->integerPredicate.lo, ic->integerPredicate.hi));
-            else {
-                const auto& sc = std::get<StringCriteria>(c);
-                check(colq_query_criteria_str(q, id, sc.ordinal, sc.stringPredicate.op,
-                                              reinterpret_cast<const uint8_t*>(sc.stringPredicate.value.data()),
-                                              (int32_t)sc.stringPredicate.value.size()));
+                continue;
             }
+            const auto& sc = std::get<StringCriteria>(c);
+            if (auto* op = std::get_if<StringOp>(&sc.stringPredicate)) {
+                check(colq_query_criteria_str(q, id, sc.ordinal, op->op, reinterpret_cast<const uint8_t*>(op->value.data()),
+                                              (int32_t)op->value.size()));
+                continue;
+            }
+            auto dv = table ? dictValues_.find({table, sc.ordinal}) : dictValues_.end();
+            if (dv == dictValues_.end())
+                return "The criterion on ordinal " + std::to_string(sc.ordinal) + " is an opaque string predicate; the GPU engine runs those only over "
+                       "dictionary-encoded columns (Options::dictionary) and has no CPU fallback.";
+            const auto& fn = std::get<StringLambda>(sc.stringPredicate);
+            std::vector<uint64_t> words(dv->second.size() / 64 + 1, 0);
+            for (size_t d = 0; d < dv->second.size(); ++d)
+                if (fn(dv->second[d])) words[d >> 6] |= uint64_t(1) << (d & 63);
+            check(colq_query_criteria_str_accept(q, id, sc.ordinal, words.data(), (int64_t)dv->second.size()));
         }
         for (const auto& [ordinal, child] : node.children) {
             int cid = 0;
             check(colq_query_child(q, id, ordinal, &cid));
-            translate(q, *child, cid);
+            InMemoryTable* childTable = nullptr;
+            if (table && ordinal >= 0 && ordinal < table->width())
+                if (auto* a = std::get_if<AssociationColumn>(&table->columns[(size_t)ordinal])) childTable = a->associatedEntity;
+            if (std::string why = translate(q, *child, cid, childTable); !why.empty()) return why;
         }
+        return {};
+    }
+    // a pinned, device-mapped copy of `n` elements, padded for whole-line reads (freed with the data system)
+    template <class T>
+    T* hostCopy(const T* src, size_t n, int64_t* capacityBytes) {
+        const size_t bytes = (n * sizeof(T) + 15) / 16 * 16 + 64;
+        void* p = nullptr;
+        check(colq_host_alloc(ctx_, (int64_t)bytes, &p));
+        hostBuffers_.push_back(p);
+        std::memset(p, 0, bytes);
+        if (n) std::memcpy(p, src, n * sizeof(T));
+        *capacityBytes = (int64_t)bytes;
+        return static_cast<T*>(p);
     }
     void syncTables() {
         std::vector<InMemoryTable*> todo, seen;
@@ -252,12 +296,40 @@ private:
         }
         for (auto* t : seen) for (int o = uploaded_[t]; o < t->width(); ++o) {
             const colq_table h = handles_[t];
-            if (auto* c = std::get_if<IntegerColumn>(&t->columns[(size_t)o])) check(colq_col_i32(ctx_, h, o, c->ints.data(), (int64_t)c->ints.size()));
-            else if (auto* s = std::get_if<StringColumn>(&t->columns[(size_t)o])) {
+            const bool host = options_.residency == Residency::Host && t->size() > 0;
+            int64_t cap = 0, cap2 = 0;
+            if (auto* c = std::get_if<IntegerColumn>(&t->columns[(size_t)o])) {
+                if (host) check(colq_col_i32_host(ctx_, h, o, hostCopy(c->ints.data(), c->ints.size(), &cap), cap, (int64_t)c->ints.size()));
+                else check(colq_col_i32(ctx_, h, o, c->ints.data(), (int64_t)c->ints.size()));
+            } else if (auto* s = std::get_if<StringColumn>(&t->columns[(size_t)o])) {
+                const int64_t n = (int64_t)s->strings.size();
+                if (options_.dictionary) {
+                    // dictionary-encode: distinct values in first-appearance order
+                    std::map<std::string, int32_t> index;
+                    std::vector<std::string>& values = dictValues_[{t, o}];
+                    std::vector<int32_t> codes;
+                    for (const std::string& v : s->strings) {
+                        auto [it, fresh] = index.emplace(v, (int32_t)values.size());
+                        if (fresh) values.push_back(v);
+                        codes.push_back(it->second);
+                    }
+                    std::vector<uint32_t> off(values.size() + 1, 0);
+                    std::string bytes;
+                    for (size_t i = 0; i < values.size(); ++i) { bytes += values[i]; off[i + 1] = (uint32_t)bytes.size(); }
+                    const auto* db = reinterpret_cast<const uint8_t*>(bytes.data());
+                    if (host) check(colq_col_str_dict_host(ctx_, h, o, hostCopy(codes.data(), codes.size(), &cap), cap, n, off.data(), db, (int64_t)values.size(), (int64_t)bytes.size()));
+                    else check(colq_col_str_dict(ctx_, h, o, codes.data(), n, off.data(), db, (int64_t)values.size(), (int64_t)bytes.size()));
+                    continue;
+                }
                 std::vector<uint32_t> off(s->strings.size() + 1, 0);
                 std::string bytes;
                 for (size_t i = 0; i < s->strings.size(); ++i) { bytes += s->strings[i]; off[i + 1] = (uint32_t)bytes.size(); }
-                check(colq_col_str(ctx_, h, o, off.data(), reinterpret_cast<const uint8_t*>(bytes.data()), (int64_t)s->strings.size(), (int64_t)bytes.size()));
+                const auto* sb = reinterpret_cast<const uint8_t*>(bytes.data());
+                if (host) {
+                    uint32_t* ho = hostCopy(off.data(), off.size(), &cap);
+                    uint8_t* hb = hostCopy(sb, bytes.size(), &cap2);
+                    check(colq_col_str_host(ctx_, h, o, ho, cap, hb, cap2, n, (int64_t)bytes.size()));
+                } else check(colq_col_str(ctx_, h, o, off.data(), sb, n, (int64_t)bytes.size()));
             } else if (auto* b = std::get_if<BooleanColumn>(&t->columns[(size_t)o])) check(colq_col_bool(ctx_, h, o, b->bools.data(), (int64_t)b->bools.size()));
         }
         for (auto* t : seen) for (int o = uploaded_[t]; o < t->width(); ++o) {
@@ -269,7 +341,10 @@ private:
             if (toOne) {
                 std::vector<int32_t> fk;
                 for (auto& as : a->associations) fk.push_back(std::holds_alternative<One>(as) ? std::get<One>(as).idx : -1);
-                check(colq_associate_fk(ctx_, hx, o, hy, a->reverseOrdinal, fk.data(), (int64_t)fk.size()));
+                int64_t cap = 0;
+                if (options_.residency == Residency::Host && !fk.empty())
+                    check(colq_associate_fk_host(ctx_, hx, o, hy, a->reverseOrdinal, hostCopy(fk.data(), fk.size(), &cap), cap, (int64_t)fk.size()));
+                else check(colq_associate_fk(ctx_, hx, o, hy, a->reverseOrdinal, fk.data(), (int64_t)fk.size()));
             } else {
                 std::vector<int64_t> off{0};
                 std::vector<int32_t> tgt;
@@ -289,6 +364,9 @@ private:
     }
 
     colq_ctx* ctx_ = nullptr;
+    Options options_;
+    std::vector<void*> hostBuffers_;
+    std::map<std::pair<InMemoryTable*, int>, std::vector<std::string>> dictValues_;
     std::map<std::string, std::shared_ptr<InMemoryTable>> tables_;
     std::map<InMemoryTable*, colq_table> handles_;
     std::map<InMemoryTable*, int> uploaded_;

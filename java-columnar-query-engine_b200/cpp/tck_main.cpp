@@ -9,6 +9,7 @@
 using namespace colq;
 
 static int failures = 0;
+static Options g_options;  // every case runs once per physical layout (device / host-resident x plain / dictionary)
 #define EXPECT(cond)                                                          \
     do {                                                                      \
         if (!(cond)) { std::printf("  FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); ++failures; } \
@@ -20,7 +21,7 @@ static std::shared_ptr<InMemoryTable> success(const QueryResult& r) {
 }
 
 static void intQuery_oneColumnTable() {  // QueryTest.java:37-73
-    DataSystemColq ds;
+    DataSystemColq ds(0, g_options);
     ds.registerTable("ints", InMemoryTable::ofColumns({ofInts({-1, 0, 1, 2, 3})}));
     Query query("ints");
     query.rootNode.addCriteria(IntCriteria{0, intGreaterThan(0)});
@@ -31,7 +32,7 @@ static void intQuery_oneColumnTable() {  // QueryTest.java:37-73
 }
 
 static void intQuery_twoColumnTable() {  // QueryTest.java:78-108
-    DataSystemColq ds;
+    DataSystemColq ds(0, g_options);
     ds.registerTable("cities", InMemoryTable::ofColumns({ofStrings({"Minneapolis", "Rochester", "Duluth"}), ofInts({425336, 121395, 86697})}));
     Query query("cities");
     query.rootNode.addCriteria(IntCriteria{1, intBetweenExclusive(100000, 150000)});
@@ -42,7 +43,7 @@ static void intQuery_twoColumnTable() {  // QueryTest.java:78-108
 }
 
 static void multiCriteria_rootEntity() {  // QueryTest.java:113-144
-    DataSystemColq ds;
+    DataSystemColq ds(0, g_options);
     ds.registerTable("strings", InMemoryTable::ofColumns({ofStrings({"a", "a", "b", "c", "c", "d"})}));
     Query query("strings");
     query.rootNode.addCriteria(StringCriteria{0, strCompareGt("a")}).addCriteria(StringCriteria{0, strCompareLt("d")});
@@ -52,7 +53,7 @@ static void multiCriteria_rootEntity() {  // QueryTest.java:113-144
 }
 
 static void queryOnAssociationProperty() {  // QueryTest.java:150-229
-    DataSystemColq ds;
+    DataSystemColq ds(0, g_options);
     auto cities = InMemoryTable::ofColumns({ofStrings({"Minneapolis", "Pierre", "Duluth"})});
     ds.registerTable("cities", cities);
     auto states = InMemoryTable::ofColumns({ofStrings({"Minnesota", "South Dakota"})});
@@ -76,7 +77,7 @@ static void queryOnAssociationProperty() {  // QueryTest.java:150-229
 }
 
 static void multiCriteria_includingIntermediateEntity() {  // QueryTest.java:231-343
-    DataSystemColq ds;
+    DataSystemColq ds(0, g_options);
     auto sections = InMemoryTable::ofColumns({
         ofStrings({"maple trees", "lilacs", "", "", "", "", "Boston ferns", "rose bush", "cedar trees"}),
         ofStrings({"trees", "shrubs", "", "", "", "", "ferns", "shrubs", "trees"})});
@@ -94,7 +95,7 @@ static void multiCriteria_includingIntermediateEntity() {  // QueryTest.java:231
 }
 
 static void failures_followTheVerifier() {  // E/Verifier.java:62-104, E/DataSystemSerialIndices.java:54-57
-    DataSystemColq ds;
+    DataSystemColq ds(0, g_options);
     ds.registerTable("t", InMemoryTable::ofColumns({ofStrings({"a"}), ofInts({1})}));
     auto r = ds.execute(Query("nope"));
     EXPECT(std::get<Failure>(r).message == "The query targets the table 'nope' but that table is not registered");
@@ -112,6 +113,27 @@ static void failures_followTheVerifier() {  // E/Verifier.java:62-104, E/DataSys
     EXPECT(threw);
 }
 
+// The reference's criteria are opaque lambdas (QueryTest.java:169,194; Runner.java:236,255-259).  Over dictionary-encoded
+// columns they run unchanged (evaluated per distinct value on the host); over plain columns they are a Failure.
+static void opaqueLambdas_onlyOverDictionaryColumns() {
+    DataSystemColq ds(0, g_options);
+    auto cities = InMemoryTable::ofColumns({ofStrings({"Minneapolis", "Pierre", "Duluth", "Pierre"})});
+    ds.registerTable("cities", cities);
+    auto states = InMemoryTable::ofColumns({ofStrings({"Minnesota", "South Dakota"})});
+    ds.registerTable("states", states);
+    cities->associateTo(*states, {toOne(0), toOne(1), toOne(0), toOne(1)});
+    Query query("cities");
+    query.rootNode.addCriteria(StringCriteria{0, StringLambda([](const std::string& s) { return s.size() == 6; })})
+        .createChild(1).addCriteria(StringCriteria{0, StringLambda([](const std::string& s) { return s.find("South") != std::string::npos; })});
+    const QueryResult r = ds.execute(query);
+    if (g_options.dictionary) {
+        const auto tp = success(r);
+        EXPECT((std::get<StringColumn>(tp->columns[0]).strings == std::vector<std::string>{"Pierre", "Pierre"}));
+    } else {
+        EXPECT(std::holds_alternative<Failure>(r) && std::get<Failure>(r).message.find("no CPU fallback") != std::string::npos);
+    }
+}
+
 int main() {
     const std::pair<const char*, std::function<void()>> cases[] = {
         {"intQuery_oneColumnTable", intQuery_oneColumnTable},
@@ -120,10 +142,18 @@ int main() {
         {"queryOnAssociationProperty", queryOnAssociationProperty},
         {"multiCriteria_includingIntermediateEntity", multiCriteria_includingIntermediateEntity},
         {"failures_followTheVerifier", failures_followTheVerifier},
+        {"opaqueLambdas_onlyOverDictionaryColumns", opaqueLambdas_onlyOverDictionaryColumns},
     };
-    for (auto& c : cases) {
-        std::printf("[ RUN ] %s\n", c.first);
-        try { c.second(); } catch (const std::exception& e) { std::printf("  EXCEPTION %s\n", e.what()); ++failures; }
+    const std::pair<const char*, Options> layouts[] = {
+        {"device", Options{Residency::Device, false}}, {"host-resident", Options{Residency::Host, false}},
+        {"device+dictionary", Options{Residency::Device, true}}, {"host-resident+dictionary", Options{Residency::Host, true}},
+    };
+    for (auto& l : layouts) {
+        g_options = l.second;
+        for (auto& c : cases) {
+            std::printf("[ RUN ] %s (%s)\n", c.first, l.first);
+            try { c.second(); } catch (const std::exception& e) { std::printf("  EXCEPTION %s\n", e.what()); ++failures; }
+        }
     }
     std::printf("%s (%d failure(s))\n", failures ? "FAILED" : "PASSED", failures);
     return failures ? 1 : 0;

@@ -45,6 +45,16 @@ final class ColqLibrary {
     static final MethodHandle colq_query_child = h("colq_query_child", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS);
     static final MethodHandle colq_query_criteria_i32_range = h("colq_query_criteria_i32_range", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT);
     static final MethodHandle colq_query_criteria_str = h("colq_query_criteria_str", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT);
+    // host-resident columns: pinned, device-mapped off-heap buffers the kernels read in place (include/colq.h)
+    static final MethodHandle colq_host_alloc = h("colq_host_alloc", JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS);
+    static final MethodHandle colq_host_free = h("colq_host_free", JAVA_INT, ADDRESS, ADDRESS);
+    static final MethodHandle colq_col_i32_host = h("colq_col_i32_host", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG);
+    static final MethodHandle colq_col_str_host = h("colq_col_str_host", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG, JAVA_LONG, JAVA_LONG);
+    static final MethodHandle colq_associate_fk_host = h("colq_associate_fk_host", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG);
+    // dictionary-encoded string columns and opaque Predicate<String> criteria evaluated per distinct value
+    static final MethodHandle colq_col_str_dict = h("colq_col_str_dict", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG);
+    static final MethodHandle colq_col_str_dict_host = h("colq_col_str_dict_host", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG);
+    static final MethodHandle colq_query_criteria_str_accept = h("colq_query_criteria_str_accept", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG);
     static final MethodHandle colq_execute = h("colq_execute", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS);
 
     private ColqLibrary() {}

@@ -49,11 +49,30 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
     private final Arena arena = Arena.ofShared();
     private final MemorySegment ctx;
 
+    /**
+     * Physical layout on the engine side; results are identical in every combination.
+     * hostResident: int / string / to-one association columns live in pinned off-heap segments (colq_host_alloc) that the
+     * kernels read in place over PCIe -- nothing is copied at registration, a query moves only what it touches, and the
+     * first full scan of a column leaves a copy in HBM.  dictionary: string columns are stored as int32 codes + distinct
+     * values, and ANY Predicate&lt;String&gt; -- including the app's unchanged lambdas (Runner.java:236,255-259) -- is
+     * evaluated once per distinct value here and applied on the GPU as a code lookup.
+     */
+    public record Layout(boolean hostResident, boolean dictionary) {}
+
+    private final Layout layout;
+    private final java.util.ArrayList<MemorySegment> hostBuffers = new java.util.ArrayList<>();
+    private final IdentityHashMap<Table, Map<Integer, String[]>> dictionaryValues = new IdentityHashMap<>();
+
     public DataSystemColq() {
-        this(0);
+        this(0, new Layout(false, false));
     }
 
     public DataSystemColq(int device) {
+        this(device, new Layout(false, false));
+    }
+
+    public DataSystemColq(int device, Layout layout) {
+        this.layout = layout;
         try (Arena a = Arena.ofConfined()) {
             MemorySegment out = a.allocate(ADDRESS);
             int st = (int) colq_create.invokeExact(device, out);
@@ -84,7 +103,7 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
             check((int) colq_query_create.invokeExact(ctx, call.allocateFrom(query.tableName), qOut));
             MemorySegment q = qOut.get(ADDRESS, 0);
             try {
-                String opaque = translate(call, q, query);
+                String opaque = translate(call, q, query, table);
                 if (opaque != null) return new QueryResult.Failure(opaque);
                 long words = (table.size() + 63L) / 64L;
                 MemorySegment mask = call.allocate(JAVA_LONG, Math.max(words, 1));
@@ -106,10 +125,10 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
     }
 
     // ------------------------------------------------------------------------------------------ Query -> colq_query
-    private String translate(Arena call, MemorySegment q, Query query) throws Throwable {
-        record Pending(Query.Node node, int id) {}
+    private String translate(Arena call, MemorySegment q, Query query, Table root) throws Throwable {
+        record Pending(Query.Node node, int id, Table table) {}
         var stack = new ArrayDeque<Pending>();
-        stack.push(new Pending(query.rootNode, 0));
+        stack.push(new Pending(query.rootNode, 0, root));
         while (!stack.isEmpty()) {
             Pending p = stack.pop();
             for (Criteria c : p.node().getCriteria()) {
@@ -120,6 +139,16 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
                         check((int) colq_query_criteria_i32_range.invokeExact(q, p.id(), ordinal, lo, hi));
                     }
                     case Criteria.StringCriteria(int ordinal, var pred) -> {
+                        String[] distinct = p.table() == null ? null : dictionaryValues.getOrDefault(p.table(), Map.of()).get(ordinal);
+                        if (!(pred instanceof Predicates.StringOp) && distinct != null) {
+                            // an opaque Predicate<String>: run it once per DISTINCT value, ship the accept set
+                            long words = distinct.length / 64 + 1;
+                            MemorySegment accept = call.allocate(JAVA_LONG, words);
+                            for (int d = 0; d < distinct.length; d++)
+                                if (pred.test(distinct[d])) accept.setAtIndex(JAVA_LONG, d >> 6, accept.getAtIndex(JAVA_LONG, d >> 6) | (1L << (d & 63)));
+                            check((int) colq_query_criteria_str_accept.invokeExact(q, p.id(), ordinal, accept, (long) distinct.length));
+                            continue;
+                        }
                         if (!(pred instanceof Predicates.StringOp op))
                             return "The criterion on ordinal %d is an opaque Predicate<String> lambda; the GPU engine only runs structured predicates (dgroomes.data_system_b200.Predicates) and has no CPU fallback.".formatted(ordinal);
                         byte[] needle = op.needle();
@@ -132,7 +161,10 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
             for (Map.Entry<Integer, Query.Node> e : p.node().getChildrenByOrdinal().entrySet()) {
                 MemorySegment out = call.allocate(JAVA_INT);
                 check((int) colq_query_child.invokeExact(q, p.id(), (int) e.getKey(), out));
-                stack.push(new Pending(e.getValue(), out.get(JAVA_INT, 0)));
+                Table child = null;
+                if (p.table() != null && e.getKey() >= 0 && e.getKey() < p.table().columns().size()
+                        && p.table().columns().get(e.getKey()) instanceof AssociationColumn ac) child = ac.associatedEntity();
+                stack.push(new Pending(e.getValue(), out.get(JAVA_INT, 0), child));
             }
         }
         return null;
@@ -162,17 +194,57 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
             for (int ordinal = uploadedColumns.get(t); ordinal < cols.size(); ordinal++) {
                 switch (cols.get(ordinal)) {
                     case InMemoryColumn.IntegerColumn(int[] ints) -> {
-                        MemorySegment seg = call.allocate(JAVA_INT, Math.max(ints.length, 1));
-                        MemorySegment.copy(ints, 0, seg, JAVA_INT, 0, ints.length);
-                        check((int) colq_col_i32.invokeExact(ctx, h, ordinal, seg, (long) ints.length));
+                        if (layout.hostResident() && ints.length > 0) {
+                            MemorySegment seg = pinned(4L * ints.length);
+                            MemorySegment.copy(ints, 0, seg, JAVA_INT, 0, ints.length);
+                            check((int) colq_col_i32_host.invokeExact(ctx, h, ordinal, seg, seg.byteSize(), (long) ints.length));
+                        } else {
+                            MemorySegment seg = call.allocate(JAVA_INT, Math.max(ints.length, 1));
+                            MemorySegment.copy(ints, 0, seg, JAVA_INT, 0, ints.length);
+                            check((int) colq_col_i32.invokeExact(ctx, h, ordinal, seg, (long) ints.length));
+                        }
+                    }
+                    case InMemoryColumn.StringColumn(String[] strings) when layout.dictionary() -> {
+                        // dictionary-encode while copying off-heap: distinct values in first-appearance order
+                        var index = new HashMap<String, Integer>();
+                        var distinct = new java.util.ArrayList<String>();
+                        int[] codes = new int[strings.length];
+                        for (int i = 0; i < strings.length; i++) {
+                            Integer code = index.get(strings[i]);
+                            if (code == null) { code = distinct.size(); index.put(strings[i], code); distinct.add(strings[i]); }
+                            codes[i] = code;
+                        }
+                        dictionaryValues.computeIfAbsent(t, k -> new HashMap<>()).put(ordinal, distinct.toArray(String[]::new));
+                        byte[][] enc = new byte[distinct.size()][];
+                        long total = 0;
+                        for (int i = 0; i < enc.length; i++) { enc[i] = distinct.get(i).getBytes(StandardCharsets.UTF_8); total += enc[i].length; }
+                        MemorySegment off = call.allocate(JAVA_INT, enc.length + 1L);
+                        MemorySegment bytes = call.allocate(Math.max(total, 1));
+                        long pos = 0;
+                        for (int i = 0; i < enc.length; i++) {
+                            off.setAtIndex(JAVA_INT, i, (int) pos);
+                            MemorySegment.copy(enc[i], 0, bytes, JAVA_BYTE, pos, enc[i].length);
+                            pos += enc[i].length;
+                        }
+                        off.setAtIndex(JAVA_INT, enc.length, (int) pos);
+                        if (layout.hostResident() && codes.length > 0) {
+                            MemorySegment seg = pinned(4L * codes.length);
+                            MemorySegment.copy(codes, 0, seg, JAVA_INT, 0, codes.length);
+                            check((int) colq_col_str_dict_host.invokeExact(ctx, h, ordinal, seg, seg.byteSize(), (long) codes.length, off, bytes, (long) enc.length, total));
+                        } else {
+                            MemorySegment seg = call.allocate(JAVA_INT, Math.max(codes.length, 1));
+                            MemorySegment.copy(codes, 0, seg, JAVA_INT, 0, codes.length);
+                            check((int) colq_col_str_dict.invokeExact(ctx, h, ordinal, seg, (long) codes.length, off, bytes, (long) enc.length, total));
+                        }
                     }
                     case InMemoryColumn.StringColumn(String[] strings) -> {
                         // offsets + UTF-8 bytes: byte equality == String.equals, byte substring == String.contains
                         byte[][] enc = new byte[strings.length][];
                         long total = 0;
                         for (int i = 0; i < strings.length; i++) { enc[i] = strings[i].getBytes(StandardCharsets.UTF_8); total += enc[i].length; }
-                        MemorySegment off = call.allocate(JAVA_INT, strings.length + 1L);
-                        MemorySegment bytes = call.allocate(Math.max(total, 1));
+                        boolean host = layout.hostResident() && strings.length > 0;
+                        MemorySegment off = host ? pinned(4L * (strings.length + 1L)) : call.allocate(JAVA_INT, strings.length + 1L);
+                        MemorySegment bytes = host ? pinned(total) : call.allocate(Math.max(total, 1));
                         long pos = 0;
                         for (int i = 0; i < strings.length; i++) {
                             off.setAtIndex(JAVA_INT, i, (int) pos);
@@ -180,7 +252,8 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
                             pos += enc[i].length;
                         }
                         off.setAtIndex(JAVA_INT, strings.length, (int) pos);
-                        check((int) colq_col_str.invokeExact(ctx, h, ordinal, off, bytes, (long) strings.length, total));
+                        if (host) check((int) colq_col_str_host.invokeExact(ctx, h, ordinal, off, off.byteSize(), bytes, bytes.byteSize(), (long) strings.length, total));
+                        else check((int) colq_col_str.invokeExact(ctx, h, ordinal, off, bytes, (long) strings.length, total));
                     }
                     case InMemoryColumn.BooleanColumn(boolean[] bools) -> {
                         MemorySegment seg = call.allocate(Math.max(bools.length, 1));
@@ -224,9 +297,11 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
             else if (a instanceof Association.One) nnz++;
         }
         if (toOne) {
-            MemorySegment fk = call.allocate(JAVA_INT, Math.max(assoc.length, 1));
+            boolean host = layout.hostResident() && assoc.length > 0;
+            MemorySegment fk = host ? pinned(4L * assoc.length) : call.allocate(JAVA_INT, Math.max(assoc.length, 1));
             for (int i = 0; i < assoc.length; i++) fk.setAtIndex(JAVA_INT, i, assoc[i] instanceof Association.One(int idx) ? idx : -1);
-            check((int) colq_associate_fk.invokeExact(ctx, x, xOrdinal, y, yOrdinal, fk, (long) assoc.length));
+            if (host) check((int) colq_associate_fk_host.invokeExact(ctx, x, xOrdinal, y, yOrdinal, fk, fk.byteSize(), (long) assoc.length));
+            else check((int) colq_associate_fk.invokeExact(ctx, x, xOrdinal, y, yOrdinal, fk, (long) assoc.length));
         } else {
             MemorySegment off = call.allocate(JAVA_LONG, assoc.length + 1L);
             MemorySegment tgt = call.allocate(JAVA_INT, Math.max(nnz, 1));
@@ -241,6 +316,19 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
             }
             off.setAtIndex(JAVA_LONG, assoc.length, pos);
             check((int) colq_associate_csr.invokeExact(ctx, x, xOrdinal, y, yOrdinal, off, tgt, (long) assoc.length, nnz));
+        }
+    }
+
+    /** A pinned, device-mapped off-heap segment of at least {@code bytes} bytes, padded for whole-line reads. */
+    private MemorySegment pinned(long bytes) throws Throwable {
+        long padded = (bytes + 15) / 16 * 16 + 64;
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment out = a.allocate(ADDRESS);
+            check((int) colq_host_alloc.invokeExact(ctx, padded, out));
+            MemorySegment seg = out.get(ADDRESS, 0).reinterpret(padded);
+            seg.fill((byte) 0);
+            hostBuffers.add(seg);
+            return seg;
         }
     }
 
@@ -268,6 +356,8 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
     @Override
     public synchronized void close() {
         try {
+            for (MemorySegment seg : hostBuffers) { int ignored = (int) colq_host_free.invokeExact(ctx, seg); }
+            hostBuffers.clear();
             int ignored = (int) colq_destroy.invokeExact(ctx);
         } catch (Throwable t) {
             throw new IllegalStateException(t);
