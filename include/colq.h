@@ -274,6 +274,30 @@ colq_status colq_execute(colq_ctx *ctx, colq_query *query, uint64_t *out_bitmask
 colq_status colq_execute_async(colq_ctx *ctx, colq_query *query);
 colq_status colq_fetch(colq_ctx *ctx, colq_query *query, uint64_t *out_bitmask, int64_t bitmask_capacity_words,
                        int32_t *out_indices, int64_t indices_capacity, int64_t *out_count, colq_timing *out_timing);
+/*
+ * Result materialisation -- the value half of Table.subset(BitSet) (M/InMemoryTable.java:106-159).  The reference
+ * re-scans every column for the set bits; here the ascending index list of the last colq_execute / colq_fetch is
+ * already in HBM, so one column of the result is a device-side gather (O(matches)) copied to the host in compact form.
+ * Rows are this rank's matching rows of the query's ROOT table (colq_result_count), ascending.
+ *   _i32  : IntegerColumn values, or the targets of a stored to-one AssociationColumn (-1 = None; indices are NOT
+ *           re-mapped, exactly like the reference :143-154)
+ *   _bool : BooleanColumn values (0 / 1)
+ *   _str  : StringColumn (plain or dictionary-encoded) as count+1 uint32 offsets + UTF-8 bytes
+ *   _csr  : a stored to-many AssociationColumn as count+1 int64 offsets + int32 targets (un-remapped)
+ * The reverse side of an association has no stored data (it is the transpose of its peer): COLQ_FAILURE; the host
+ * subsets its own copy.  Too small a buffer: COLQ_ERR_CAPACITY with the out-counts set, so the caller can size and
+ * call again (passing NULL buffers is the size query).
+ */
+colq_status colq_result_count(colq_ctx *ctx, colq_query *query, int64_t *out_rows);
+colq_status colq_result_i32(colq_ctx *ctx, colq_query *query, int ordinal, int32_t *out_values, int64_t capacity,
+                            int64_t *out_count);
+colq_status colq_result_bool(colq_ctx *ctx, colq_query *query, int ordinal, uint8_t *out_values, int64_t capacity,
+                             int64_t *out_count);
+colq_status colq_result_str(colq_ctx *ctx, colq_query *query, int ordinal, uint32_t *out_offsets, int64_t offsets_capacity,
+                            uint8_t *out_bytes, int64_t bytes_capacity, int64_t *out_count, int64_t *out_n_bytes);
+colq_status colq_result_csr(colq_ctx *ctx, colq_query *query, int ordinal, int64_t *out_offsets, int64_t offsets_capacity,
+                            int32_t *out_targets, int64_t targets_capacity, int64_t *out_count, int64_t *out_nnz);
+
 /* per-kernel stages of the last execute of `query` (times only with COLQ_OPT_PROFILE); returns the stage count */
 colq_status colq_profile(const colq_query *query, colq_stage *out_stages, int capacity, int *out_n_stages);
 /* COLQ_OPT_PROFILE == 2: synchronises, then reports the dominant launch of `query` -- name, rows, algorithmic bytes and

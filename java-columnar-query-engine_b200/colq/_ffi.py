@@ -79,6 +79,11 @@ SIGNATURES = {
     "colq_execute_async": (_int, [_p, _p]),
     "colq_fetch": (_int, [_p, _p, _p, _i64, _p, _i64, C.POINTER(_i64), C.POINTER(Timing)]),
     "colq_profile": (_int, [_p, C.POINTER(Stage), _int, C.POINTER(_int)]),
+    "colq_result_count": (_int, [_p, _p, C.POINTER(_i64)]),
+    "colq_result_i32": (_int, [_p, _p, _int, _p, _i64, C.POINTER(_i64)]),
+    "colq_result_bool": (_int, [_p, _p, _int, _p, _i64, C.POINTER(_i64)]),
+    "colq_result_str": (_int, [_p, _p, _int, _p, _i64, _p, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
+    "colq_result_csr": (_int, [_p, _p, _int, _p, _i64, _p, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "colq_profile_hot": (_int, [_p, C.POINTER(Stage), C.POINTER(_int)]),
     "colq_node_cardinalities": (_int, [_p, _p, C.POINTER(_i64), _int, C.POINTER(_int)]),
 }

@@ -128,6 +128,43 @@ class ColqQuery:
         self.ctx._check(self.ctx.lib.colq_profile(self.handle, stages, 64, C.byref(n)))
         return [(stages[i].name.decode(), stages[i].ms, stages[i].rows, stages[i].bytes) for i in range(min(n.value, 64))]
 
+    # -- result materialisation on the device (the value half of Table.subset, include/colq.h)
+    def result_count(self) -> int:
+        n = C.c_int64()
+        self.ctx._check(self.ctx.lib.colq_result_count(self.ctx.handle, self.handle, C.byref(n)))
+        return n.value
+
+    def _result_fixed(self, fn, ordinal: int, dtype) -> np.ndarray:
+        n = self.result_count()
+        out = np.empty(max(n, 1), dtype=dtype)
+        got = C.c_int64()
+        self.ctx._check(fn(self.ctx.handle, self.handle, ordinal, _ptr(out), n, C.byref(got)))
+        return out[: got.value]
+
+    def result_i32(self, ordinal: int) -> np.ndarray:
+        return self._result_fixed(self.ctx.lib.colq_result_i32, ordinal, np.int32)
+
+    def result_bool(self, ordinal: int) -> np.ndarray:
+        return self._result_fixed(self.ctx.lib.colq_result_bool, ordinal, np.uint8)
+
+    def _result_var(self, fn, ordinal: int, off_dtype, elem_dtype) -> Tuple[np.ndarray, np.ndarray]:
+        n, total = C.c_int64(), C.c_int64()
+        st = fn(self.ctx.handle, self.handle, ordinal, None, 0, None, 0, C.byref(n), C.byref(total))   # size query
+        if st not in (_ffi.OK, _ffi.ERR_CAPACITY):
+            self.ctx._check(st)
+        off = np.zeros(n.value + 1, dtype=off_dtype)
+        data = np.empty(max(total.value, 1), dtype=elem_dtype)
+        self.ctx._check(fn(self.ctx.handle, self.handle, ordinal, _ptr(off), n.value + 1, _ptr(data), total.value, C.byref(n), C.byref(total)))
+        return off, data[: total.value]
+
+    def result_str(self, ordinal: int) -> Tuple[np.ndarray, np.ndarray]:
+        """(offsets uint32[count+1], UTF-8 bytes) of a string column at the matching rows."""
+        return self._result_var(self.ctx.lib.colq_result_str, ordinal, np.uint32, np.uint8)
+
+    def result_csr(self, ordinal: int) -> Tuple[np.ndarray, np.ndarray]:
+        """(offsets int64[count+1], targets int32) of a stored to-many association column at the matching rows."""
+        return self._result_var(self.ctx.lib.colq_result_csr, ordinal, np.int64, np.int32)
+
     def profile_hot(self) -> Tuple[str, float, int, int, int]:
         """(name, mean ms, rows, algorithmic bytes, samples) of the dominant launch since the last call (OPT_PROFILE=2)."""
         st = _ffi.Stage()
@@ -368,7 +405,8 @@ class DataSystemColq(DataSystem):
     """The reference-facing engine: same two methods as ``DataSystemSerialIndices``."""
 
     def __init__(self, device: int = 0, lazy_fk: bool = True, context: Optional[ColqContext] = None,
-                 options: Optional[Dict[int, int]] = None, residency: str = "device", dictionary: bool = False):
+                 options: Optional[Dict[int, int]] = None, residency: str = "device", dictionary: bool = False,
+                 materialize: str = "host"):
         """``residency``: "device" copies every column to HBM at the first ``execute`` (default); "host" keeps int,
         string and to-one association columns in pinned off-heap buffers that the kernels stream in place over PCIe
         (only what a query touches moves; fully scanned columns are promoted to HBM by that first scan)."""
@@ -378,6 +416,11 @@ class DataSystemColq(DataSystem):
         # dictionary=True: string columns are stored dictionary-encoded; every string criterion -- structured or an
         # opaque lambda like the reference's -- is evaluated per DISTINCT value and the GPU row scan tests code bits
         self.dictionary = dictionary
+        # materialize="device": the result Table's int / string / stored association columns are gathered on the GPU
+        # (colq_result_*) instead of the registered table's host-side subset
+        if materialize not in ("host", "device"):
+            raise ValueError(materialize)
+        self.materialize = materialize
         self._dict_values: Dict[Tuple[int, int], List[str]] = {}   # (id(table), ordinal) -> distinct values
         self.ctx = context or ColqContext(device)
         self.lazy_fk = lazy_fk
@@ -537,8 +580,28 @@ class DataSystemColq(DataSystem):
         placement, base = self._placement.get(id(table), (_ffi.REPLICATED, 0))
         local = res.indices - base if placement == _ffi.SHARDED else res.indices
         matching_rows = BitSet.from_indices(local, table.size())
+        if self.materialize == "device" and placement != _ffi.SHARDED:
+            return QueryResult.Success(self._materialize_on_device(table, cq, local))
         # table.subset(executionContext.matchingRows()) (:100): the registered table builds the result itself
         return QueryResult.Success(table.subset(matching_rows))
+
+    def _materialize_on_device(self, table: Table, cq: ColqQuery, rows: np.ndarray) -> Table:
+        """M/InMemoryTable.java:106-159 with the per-column row copies done by the GPU (colq_result_*); columns the
+        engine holds no data for (the reverse side of an association) are subset by the host table's own column."""
+        from .in_memory import InMemoryTable
+        out = []
+        idx = rows.astype(np.int64)
+        for ordinal, c in enumerate(table.columns()):
+            if isinstance(c, IntegerColumn):
+                out.append(IntegerColumn(cq.result_i32(ordinal)))
+            elif isinstance(c, StringColumn):
+                off, data = cq.result_str(ordinal)
+                out.append(StringColumn(offsets=off, data=data))
+            elif isinstance(c, BooleanColumn):
+                out.append(BooleanColumn(cq.result_bool(ordinal).astype(bool)))
+            else:
+                out.append(c.take(idx))   # association columns keep their host form (indices un-remapped, no reverse link)
+        return InMemoryTable(out)
 
     def close(self) -> None:
         if self.last_query is not None:

@@ -299,8 +299,10 @@ private:
             const bool host = options_.residency == Residency::Host && t->size() > 0;
             int64_t cap = 0, cap2 = 0;
             if (auto* c = std::get_if<IntegerColumn>(&t->columns[(size_t)o])) {
-                if (host) check(colq_col_i32_host(ctx_, h, o, hostCopy(c->ints.data(), c->ints.size(), &cap), cap, (int64_t)c->ints.size()));
-                else check(colq_col_i32(ctx_, h, o, c->ints.data(), (int64_t)c->ints.size()));
+                if (host) {
+                    const int32_t* pinned = hostCopy(c->ints.data(), c->ints.size(), &cap);  // (sets cap: keep it a separate statement)
+                    check(colq_col_i32_host(ctx_, h, o, pinned, cap, (int64_t)c->ints.size()));
+                } else check(colq_col_i32(ctx_, h, o, c->ints.data(), (int64_t)c->ints.size()));
             } else if (auto* s = std::get_if<StringColumn>(&t->columns[(size_t)o])) {
                 const int64_t n = (int64_t)s->strings.size();
                 if (options_.dictionary) {
@@ -317,8 +319,10 @@ private:
                     std::string bytes;
                     for (size_t i = 0; i < values.size(); ++i) { bytes += values[i]; off[i + 1] = (uint32_t)bytes.size(); }
                     const auto* db = reinterpret_cast<const uint8_t*>(bytes.data());
-                    if (host) check(colq_col_str_dict_host(ctx_, h, o, hostCopy(codes.data(), codes.size(), &cap), cap, n, off.data(), db, (int64_t)values.size(), (int64_t)bytes.size()));
-                    else check(colq_col_str_dict(ctx_, h, o, codes.data(), n, off.data(), db, (int64_t)values.size(), (int64_t)bytes.size()));
+                    if (host) {
+                        const int32_t* pinned = hostCopy(codes.data(), codes.size(), &cap);
+                        check(colq_col_str_dict_host(ctx_, h, o, pinned, cap, n, off.data(), db, (int64_t)values.size(), (int64_t)bytes.size()));
+                    } else check(colq_col_str_dict(ctx_, h, o, codes.data(), n, off.data(), db, (int64_t)values.size(), (int64_t)bytes.size()));
                     continue;
                 }
                 std::vector<uint32_t> off(s->strings.size() + 1, 0);
@@ -342,9 +346,10 @@ private:
                 std::vector<int32_t> fk;
                 for (auto& as : a->associations) fk.push_back(std::holds_alternative<One>(as) ? std::get<One>(as).idx : -1);
                 int64_t cap = 0;
-                if (options_.residency == Residency::Host && !fk.empty())
-                    check(colq_associate_fk_host(ctx_, hx, o, hy, a->reverseOrdinal, hostCopy(fk.data(), fk.size(), &cap), cap, (int64_t)fk.size()));
-                else check(colq_associate_fk(ctx_, hx, o, hy, a->reverseOrdinal, fk.data(), (int64_t)fk.size()));
+                if (options_.residency == Residency::Host && !fk.empty()) {
+                    const int32_t* pinned = hostCopy(fk.data(), fk.size(), &cap);
+                    check(colq_associate_fk_host(ctx_, hx, o, hy, a->reverseOrdinal, pinned, cap, (int64_t)fk.size()));
+                } else check(colq_associate_fk(ctx_, hx, o, hy, a->reverseOrdinal, fk.data(), (int64_t)fk.size()));
             } else {
                 std::vector<int64_t> off{0};
                 std::vector<int32_t> tgt;

@@ -280,6 +280,8 @@ struct colq_query {
     colq_stage hot_stage{};
     colq_timing timing{};
     bool executed = false;
+    int64_t local_count = -1;     // this rank's matching rows after the last fetch (-1: not fetched yet)
+    DevBuf mat_a, mat_b;          // scratch of the result-materialisation gathers
     // captured CUDA graph of the op sequence
     cudaGraphExec_t graph_exec = nullptr;
     std::vector<Op> graph_ops;
@@ -1052,6 +1054,7 @@ colq_status run_pipeline(colq_query* q) {
     q->pool.reset();
     q->ops.clear();
     q->timing = colq_timing{};
+    q->local_count = -1;
     q->deferred.clear();
     q->own_begin = q->own_end = -1;
     q->pending_promotions.clear();
@@ -1298,6 +1301,7 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
         return fetch_results(q, out_bitmask, bitmask_cap, out_idx, idx_cap, out_count, out_timing);
     }
 
+    q->local_count = (int64_t)local;
     if (out_count) *out_count = count;
     colq_status rc = COLQ_OK;
     if (out_bitmask) {
@@ -2086,6 +2090,124 @@ colq_status colq_profile(const colq_query* q, colq_stage* out_stages, int capaci
     *out_n_stages = (int)q->stages.size();
     for (int i = 0; i < capacity && i < (int)q->stages.size(); ++i) out_stages[i] = q->stages[i];
     return COLQ_OK;
+}
+
+}  // extern "C"
+
+// ---- result materialisation (K5) --------------------------------------------------------------------
+
+namespace {
+
+colq_status result_prologue(colq_ctx* ctx, colq_query* q, int ordinal, const Table** T, const Column** col) {
+    if (q->ctx != ctx) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "query belongs to another context");
+    if (q->local_count < 0) return fail(ctx, COLQ_THROW_ILLEGAL_STATE, "no fetched result: call colq_execute or colq_fetch first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    *T = &ctx->tables[q->root_table];
+    if (ordinal < 0 || (size_t)ordinal >= (*T)->cols.size()) return fail(ctx, COLQ_THROW_INDEX_OOB, "Index %d out of bounds for length %d", ordinal, (int)(*T)->cols.size());
+    *col = &(*T)->cols[ordinal];
+    if ((*col)->kind == COL_UNSET) return fail(ctx, COLQ_THROW_ILLEGAL_STATE, "column %d was never set", ordinal);
+    return COLQ_OK;
+}
+
+template <typename T>
+colq_status result_fixed(colq_ctx* ctx, colq_query* q, const Table& tb, const void* src, T* out, int64_t capacity, int64_t* out_count) {
+    const int64_t n = q->local_count;
+    if (out_count) *out_count = n;
+    if (n == 0) return COLQ_OK;
+    if (!out || capacity < n) return fail(ctx, COLQ_ERR_CAPACITY, "result capacity %lld < %lld rows", (long long)capacity, (long long)n);
+    if (q->mat_a.bytes < (size_t)n * sizeof(T)) ST(dev_alloc(ctx, q->mat_a, (size_t)n * sizeof(T)));
+    cudaStream_t s = ctx->stream;
+    gather_values_kernel<T><<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, s>>>((const T*)src, q->d_idx, tb.row_base, n, (T*)q->mat_a.ptr);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(out, q->mat_a.ptr, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    return COLQ_OK;
+}
+
+// lengths -> offsets -> payload copy; OutOffT is the host offset type (uint32 strings, int64 CSR)
+template <typename OffT, typename ElemT, typename OutOffT>
+colq_status result_var(colq_ctx* ctx, colq_query* q, const Table& tb, const OffT* src_off, const int32_t* codes, const ElemT* src,
+                       OutOffT* out_off, int64_t off_capacity, ElemT* out, int64_t capacity, int64_t* out_count, int64_t* out_total,
+                       uint64_t max_total) {
+    const int64_t n = q->local_count;
+    if (out_count) *out_count = n;
+    cudaStream_t s = ctx->stream;
+    if (q->mat_a.bytes < (size_t)(n + 1) * 8) ST(dev_alloc(ctx, q->mat_a, (size_t)(n + 1) * 8));
+    GatherVarParams<OffT> P{src_off, codes, q->d_idx, tb.row_base, n, (u64*)q->mat_a.ptr};
+    gather_var_lens_kernel<OffT><<<grid_for(std::max<int64_t>(n, 1), 256, ctx->sm_count, 8), 256, 0, s>>>(P);
+    if (n > 0) scan_u64_inplace_kernel<<<1, 1024, 0, s>>>(P.out_off, n);
+    CU(ctx, cudaGetLastError());
+    u64 total = 0;
+    CU(ctx, cudaMemcpyAsync(&total, P.out_off + n, 8, cudaMemcpyDeviceToHost, s));
+    CU(ctx, cudaStreamSynchronize(s));
+    if (out_total) *out_total = (int64_t)total;
+    if (total > max_total) return fail(ctx, COLQ_ERR_CAPACITY, "result payload of %llu elements exceeds the offset range of this column type", (unsigned long long)total);
+    if (!out_off || off_capacity < n + 1 || (total > 0 && (!out || capacity < (int64_t)total)))
+        return fail(ctx, COLQ_ERR_CAPACITY, "result capacity too small: need %lld offsets and %llu payload elements", (long long)(n + 1), (unsigned long long)total);
+    std::vector<u64> host_off((size_t)n + 1);
+    CU(ctx, cudaMemcpyAsync(host_off.data(), P.out_off, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (total > 0) {
+        if (q->mat_b.bytes < (size_t)total * sizeof(ElemT)) ST(dev_alloc(ctx, q->mat_b, (size_t)total * sizeof(ElemT)));
+        gather_var_copy_kernel<OffT, ElemT><<<grid_for((n + 31) / 32 * 32, 256, ctx->sm_count, 8), 256, 0, s>>>(P, src, (ElemT*)q->mat_b.ptr);
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaMemcpyAsync(out, q->mat_b.ptr, (size_t)total * sizeof(ElemT), cudaMemcpyDeviceToHost, s));
+    }
+    CU(ctx, cudaStreamSynchronize(s));
+    for (int64_t i = 0; i <= n; ++i) out_off[i] = (OutOffT)host_off[(size_t)i];
+    return COLQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+colq_status colq_result_count(colq_ctx* ctx, colq_query* q, int64_t* out_rows) {
+    if (!ctx || !q || !out_rows) return COLQ_THROW_NULL;
+    if (q->local_count < 0) return fail(ctx, COLQ_THROW_ILLEGAL_STATE, "no fetched result: call colq_execute or colq_fetch first");
+    *out_rows = q->local_count;
+    return COLQ_OK;
+}
+
+colq_status colq_result_i32(colq_ctx* ctx, colq_query* q, int ordinal, int32_t* out_values, int64_t capacity, int64_t* out_count) {
+    if (!ctx || !q) return COLQ_THROW_NULL;
+    const Table* T; const Column* c;
+    ST(result_prologue(ctx, q, ordinal, &T, &c));
+    const bool to_one = c->kind == COL_ASSOC && c->forward && c->is_fk;
+    if (c->kind != COL_I32 && !to_one)
+        return fail(ctx, COLQ_FAILURE, "column %d is neither an integer column nor a stored to-one association column", ordinal);
+    return result_fixed<int32_t>(ctx, q, *T, c->data.ptr, out_values, capacity, out_count);
+}
+
+colq_status colq_result_bool(colq_ctx* ctx, colq_query* q, int ordinal, uint8_t* out_values, int64_t capacity, int64_t* out_count) {
+    if (!ctx || !q) return COLQ_THROW_NULL;
+    const Table* T; const Column* c;
+    ST(result_prologue(ctx, q, ordinal, &T, &c));
+    if (c->kind != COL_BOOL) return fail(ctx, COLQ_FAILURE, "column %d is not a boolean column", ordinal);
+    return result_fixed<uint8_t>(ctx, q, *T, c->data.ptr, out_values, capacity, out_count);
+}
+
+colq_status colq_result_str(colq_ctx* ctx, colq_query* q, int ordinal, uint32_t* out_offsets, int64_t offsets_capacity, uint8_t* out_bytes,
+                            int64_t bytes_capacity, int64_t* out_count, int64_t* out_n_bytes) {
+    if (!ctx || !q) return COLQ_THROW_NULL;
+    const Table* T; const Column* c;
+    ST(result_prologue(ctx, q, ordinal, &T, &c));
+    if (c->kind != COL_STR) return fail(ctx, COLQ_FAILURE, "column %d is not a string column", ordinal);
+    const Column* payload = c->dict ? c->dict.get() : c;
+    return result_var<u32, uint8_t, uint32_t>(ctx, q, *T, (const u32*)payload->offsets.ptr, c->dict ? (const int32_t*)c->data.ptr : nullptr,
+                                              (const uint8_t*)payload->data.ptr, out_offsets, offsets_capacity, out_bytes, bytes_capacity,
+                                              out_count, out_n_bytes, 0xfffffff0ull);
+}
+
+colq_status colq_result_csr(colq_ctx* ctx, colq_query* q, int ordinal, int64_t* out_offsets, int64_t offsets_capacity, int32_t* out_targets,
+                            int64_t targets_capacity, int64_t* out_count, int64_t* out_nnz) {
+    if (!ctx || !q) return COLQ_THROW_NULL;
+    const Table* T; const Column* c;
+    ST(result_prologue(ctx, q, ordinal, &T, &c));
+    if (!(c->kind == COL_ASSOC && c->forward && !c->is_fk))
+        return fail(ctx, COLQ_FAILURE, "column %d is not a stored to-many association column", ordinal);
+    return result_var<int64_t, int32_t, int64_t>(ctx, q, *T, (const int64_t*)c->offsets.ptr, nullptr, (const int32_t*)c->targets.ptr,
+                                                 out_offsets, offsets_capacity, out_targets, targets_capacity, out_count, out_nnz,
+                                                 ~0ull >> 1);
 }
 
 colq_status colq_profile_hot(colq_query* q, colq_stage* out_stage, int* out_samples) {

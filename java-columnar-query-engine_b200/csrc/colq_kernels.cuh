@@ -361,13 +361,16 @@ __global__ void __launch_bounds__(SR_THREADS) scan_rows_kernel(const ScanRowsPar
 // once per DISTINCT value -- by scan_str over the dictionary, or on the host for an opaque lambda -- into an
 // n_dict-bit accept mask; the row scan streams 4 bytes per row and tests bit `code`.  The mask is staged in shared
 // memory (random 4-byte gathers: ~3 bank-conflict cycles per warp instead of up to 16 L1 wavefronts); dictionaries
-// beyond SC_SMEM_MASK_WORDS * 32 entries are looked up through L1/L2.  Same row mapping as scan_rows, SC_ITER
-// consecutive 4096-row tiles per CTA so that the mask copy is amortised.
+// beyond SC_SMEM_MASK_WORDS * 32 entries are looked up through L1/L2.  When the staged mask has at most SC_FEW bits
+// set -- an equality predicate accepts exactly ONE dictionary entry -- the CTA extracts those codes once and the row
+// test is a handful of register compares with no shared-memory traffic at all.  Same row mapping as scan_rows,
+// SC_ITER consecutive 4096-row tiles per CTA so that the mask copy is amortised.
 // ---------------------------------------------------------------------------------------------
 
 constexpr int SC_ITER = 8;
 constexpr int SC_BLOCK_ROWS = SR_BLOCK_ROWS * SC_ITER;  // 32768
 constexpr int SC_SMEM_MASK_WORDS = 8192;                // 32 KB: dictionaries of up to 262144 entries
+constexpr int SC_FEW = 4;                               // accepted codes that are tested by register compares
 
 struct ScanCodesParams {
     int64_t n;
@@ -393,9 +396,36 @@ __global__ void __launch_bounds__(SR_THREADS) scan_codes_kernel(const ScanCodesP
     if (SMEM) {
         for (int i = threadIdx.x; i < P.mask_words; i += SR_THREADS) s_accept[i] = __ldg(P.accept + i);
     }
-    if (do_push || SMEM) __syncthreads();
+    __shared__ u32 s_few[SC_FEW];
+    __shared__ u32 s_nfew;
+    if (threadIdx.x == 0) s_nfew = 0;
+    __syncthreads();
+    if (SMEM) {
+        // how many dictionary entries does the predicate accept?  (bits past n_dict are zero by construction)
+        for (int i = threadIdx.x; i < P.mask_words; i += SR_THREADS) {
+            u32 w = s_accept[i];
+            while (w) {
+                const int b = __ffs(w) - 1;
+                w &= w - 1;
+                const u32 slot = atomicAdd(&s_nfew, 1u);
+                if (slot < SC_FEW) s_few[slot] = ((u32)i << 5) + b;
+            }
+        }
+        __syncthreads();
+    }
+    const u32 n_few = SMEM ? s_nfew : SC_FEW + 1;
+    const bool few = n_few <= SC_FEW;
+    u32 k[SC_FEW];
+#pragma unroll
+    for (int i = 0; i < SC_FEW; ++i) k[i] = (few && i < (int)n_few) ? s_few[i] : 0xffffffffu;  // codes are >= 0: never equal
     const u32 span = P.n_dict - 1u;
     auto test = [&](int32_t c) -> bool {
+        if (few) {
+            bool m = false;
+#pragma unroll
+            for (int i = 0; i < SC_FEW; ++i) m = m || ((u32)c == k[i]);
+            return m;
+        }
         if ((u32)c > span) return false;  // a code outside the dictionary matches nothing
         const u32 w = SMEM ? s_accept[(u32)c >> 5] : __ldg(P.accept + ((u32)c >> 5));
         return (w >> ((u32)c & 31)) & 1u;
@@ -1496,6 +1526,111 @@ __global__ void __launch_bounds__(CP_THREADS) compact_fused_kernel(const Compact
     }
     // the block that owns the last tile knows the grand total
     if ((P.n_tiles - 1) % gridDim.x == blockIdx.x && threadIdx.x == 0) *P.total = running + P.tile_counts[P.n_tiles - 1];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5  result materialisation: the value half of Table.subset(BitSet) (M/InMemoryTable.java:106-159)
+//
+// The reference re-scans every column for the set bits (hot loop 3: `for i in [0, size): if bits.get(i) copy`).  Here
+// the compacted ascending index list already exists in HBM, so a column of the result is a gather: O(matches), not
+// O(rows).  Int / boolean / to-one association columns (indices un-remapped, :143-154) are plain gathers; string
+// columns (plain or dictionary-encoded) take lengths -> exclusive scan -> byte copy; to-many association columns the
+// same over (offsets, targets).
+// ---------------------------------------------------------------------------------------------
+
+template <typename T>
+__global__ void __launch_bounds__(256) gather_values_kernel(const T* col, const int32_t* idx, int64_t row_base, int64_t n, T* out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = col[(int64_t)idx[i] - row_base];
+}
+
+// variable-length columns: element e of the source spans src_off[e] .. src_off[e + 1] (OffT = u32 for strings, int64
+// for CSR associations); `codes` (nullable) maps a row to its dictionary entry
+template <typename OffT>
+struct GatherVarParams {
+    const OffT* src_off;
+    const int32_t* codes;
+    const int32_t* idx;
+    int64_t row_base;
+    int64_t n;
+    u64* out_off;  // n + 1 entries: lengths first, then (after scan_u64_inplace_kernel) exclusive offsets
+};
+
+template <typename OffT>
+__global__ void __launch_bounds__(256) gather_var_lens_kernel(const GatherVarParams<OffT> P) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+        int64_t e = (int64_t)P.idx[i] - P.row_base;
+        if (P.codes != nullptr) e = P.codes[e];
+        P.out_off[i + 1] = (u64)(P.src_off[e + 1] - P.src_off[e]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.out_off[0] = 0;
+}
+
+// single block: a[1..n] becomes its inclusive prefix sum (a[0] = 0 stays), i.e. a[i] = start of element i
+__global__ void __launch_bounds__(1024) scan_u64_inplace_kernel(u64* a, int64_t n) {
+    __shared__ u64 s_warp[33];
+    __shared__ u64 s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base = 1; base <= n; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        u64 v = i <= n ? a[i] : 0, incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            u64 t = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            u64 w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                u64 t = __shfl_up_sync(FULL_MASK, wi, d);
+                if (lane >= d) wi += t;
+            }
+            s_warp[lane] = wi - w;
+            if (lane == 31) s_warp[32] = wi;
+        }
+        __syncthreads();
+        const u64 carry = s_carry;
+        if (i <= n) a[i] = carry + s_warp[warp] + incl;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + s_warp[32];
+        __syncthreads();
+    }
+}
+
+// copy the payloads: ELEM = 1 (string bytes) or 4 (CSR targets).  One lane per result row for short rows; rows
+// longer than 64 elements are copied by the whole warp.
+template <typename OffT, typename ElemT>
+__global__ void __launch_bounds__(256) gather_var_copy_kernel(const GatherVarParams<OffT> P, const ElemT* src, ElemT* out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t n_groups = (P.n + 31) >> 5;
+    for (int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < n_groups; g += warp_stride) {
+        const int64_t i = g * 32 + lane;
+        u64 s0 = 0, d0 = 0, len = 0;
+        if (i < P.n) {
+            int64_t e = (int64_t)P.idx[i] - P.row_base;
+            if (P.codes != nullptr) e = P.codes[e];
+            s0 = (u64)P.src_off[e];
+            len = (u64)P.src_off[e + 1] - s0;
+            d0 = P.out_off[i];
+        }
+        const bool is_long = len > 64;
+        if (!is_long)
+            for (u64 b = 0; b < len; ++b) out[d0 + b] = src[s0 + b];
+        u32 longs = __ballot_sync(FULL_MASK, is_long);
+        while (longs) {
+            const int l = __ffs(longs) - 1;
+            longs &= longs - 1;
+            const u64 ls = __shfl_sync(FULL_MASK, s0, l), ld = __shfl_sync(FULL_MASK, d0, l), ll = __shfl_sync(FULL_MASK, len, l);
+            for (u64 b = lane; b < ll; b += 32) out[ld + b] = src[ls + b];
+        }
+    }
 }
 
 // popcount of a whole bitmask into one u64 (node cardinalities; not on the timed path)

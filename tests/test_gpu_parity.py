@@ -510,3 +510,108 @@ def test_large_dictionary_is_looked_up_in_global_memory(engines):
         return q
 
     both(engines, build, [mk(0, "dup"), mk(1, "9999"), mk(2, "k150000"), mk(7, "k29")], variants=(DICT, DICT_HOST))
+
+
+# ------------------------------------------------------------------ result materialisation on the device
+def _same_tables(a, b):
+    from colq.in_memory import AssociationColumn, BooleanColumn
+    assert a.width() == b.width() and a.size() == b.size()
+    for ca, cb in zip(a.columns(), b.columns()):
+        assert type(ca) is type(cb)
+        if isinstance(ca, IntegerColumn):
+            assert np.array_equal(ca.ints(), cb.ints())
+        elif isinstance(ca, StringColumn):
+            assert np.array_equal(ca.offsets, cb.offsets) and np.array_equal(ca.data, cb.data)
+        elif isinstance(ca, BooleanColumn):
+            assert np.array_equal(ca.bools(), cb.bools())
+        else:
+            ka, oa, ta = ca.csr()
+            kb, ob, tb = cb.csr()
+            assert np.array_equal(ka, kb) and np.array_equal(oa, ob) and np.array_equal(ta, tb)
+
+
+@pytest.mark.parametrize("variant", [dict(), dict(residency="host"), dict(dictionary=True), dict(dictionary=True, residency="host")],
+                         ids=["device", "host", "dict", "dict_host"])
+def test_result_table_gathered_on_device_equals_host_subset(engines, variant):
+    """Table.subset (M/InMemoryTable.java:106-159): the result table whose columns were gathered by the GPU
+    (colq_result_*) equals the one the registered table builds on the host, column by column, for every column kind."""
+    from colq.in_memory import BooleanColumn
+    new_gpu, _ = engines
+    rng = np.random.default_rng(11)
+    n, m = 30_011, 257
+    strings = random_strings(rng, n, 9, np.array(list("abcé ")))
+    strings[5] = "x" * 3000                                     # a long row: copied by the whole warp
+    vals = rng.integers(-1000, 1000, size=n, dtype=np.int32)
+    flags = rng.integers(0, 2, size=n).astype(bool)
+    fk = rng.integers(-1, m, size=n, dtype=np.int32)
+    deg = rng.integers(0, 4, size=n)
+    off = np.zeros(n + 1, dtype=np.int64); np.cumsum(deg, out=off[1:])
+    tgt = rng.integers(0, m, size=int(off[-1]), dtype=np.int32)
+
+    def build(ds):
+        A = InMemoryTable.of_columns(IntegerColumn(vals), StringColumn(strings), BooleanColumn(flags))
+        B = InMemoryTable.of_columns(IntegerColumn(np.arange(m, dtype=np.int32)))
+        A.associate_to(B, fk=fk)                 # A.3 to-one (with Nones), B.1 reverse
+        A.associate_to(B, csr=(off, tgt))        # A.4 to-many, B.2 reverse
+        ds.register("A", A); ds.register("B", B)
+        return A, B
+
+    def queries():
+        q1 = Query("A"); q1.root_node.add_criteria(Criteria.IntCriteria(0, int_range(-50, 120)))
+        q2 = Query("A"); q2.root_node.add_criteria(Criteria.StringCriteria(1, StringPredicate(1, "ab")))
+        q3 = Query("A"); q3.root_node.add_criteria(Criteria.IntCriteria(0, int_range(5000, 6000)))     # empty result
+        q4 = Query("A")                                                                                 # every row
+        q5 = Query("B"); q5.root_node.create_child(1).add_criteria(Criteria.IntCriteria(0, int_range(0, 3)))  # root with reverse columns
+        return [q1, q2, q3, q4, q5]
+
+    host, dev = new_gpu(**variant), new_gpu(materialize="device", **variant)
+    build(host); build(dev)
+    for qh, qd in zip(queries(), queries()):
+        rh, rd = host.execute(qh), dev.execute(qd)
+        assert isinstance(rh, QueryResult.Success) and isinstance(rd, QueryResult.Success)
+        _same_tables(rh.result_set, rd.result_set)
+    host.close(); dev.close()
+
+
+def test_result_abi_sizes_and_errors():
+    from colq import _ffi
+    from colq.engine import ColqContext, ColqError
+    import ctypes as C
+    ctx = ColqContext(0)
+    t = ctx.table_create(6)
+    u = ctx.table_create(2)
+    ctx.col_i32(t, 0, np.array([5, 6, 7, 8, 9, 10], dtype=np.int32))
+    ctx.col_str(t, 1, np.array([0, 1, 3, 3, 6, 7, 9], dtype=np.uint32), np.frombuffer(b"abbcccdee", dtype=np.uint8))
+    ctx.col_i32(u, 0, np.array([1, 2], dtype=np.int32))
+    ctx.associate_csr(t, 2, u, 1, np.array([0, 2, 2, 3, 3, 4, 5], dtype=np.int64), np.array([0, 1, 1, 0, 1], dtype=np.int32))
+    ctx.register("t", t)
+    q = ctx.query("t")
+    with pytest.raises(ColqError, match="no fetched result"):
+        q.result_i32(0)
+    q.criteria_i32_range(0, 0, 6, 9)
+    assert q.execute().count == 4
+    assert q.result_count() == 4
+    assert q.result_i32(0).tolist() == [6, 7, 8, 9]
+    off, data = q.result_str(1)
+    assert off.tolist() == [0, 2, 2, 5, 6] and bytes(data) == b"bbcccd"
+    off, tg = q.result_csr(2)
+    assert off.tolist() == [0, 0, 1, 1, 2] and tg.tolist() == [1, 0]
+    out = np.empty(2, dtype=np.int32)
+    got = C.c_int64()
+    st = ctx.lib.colq_result_i32(ctx.handle, q.handle, 0, out.ctypes.data_as(C.c_void_p), 2, C.byref(got))
+    assert st == _ffi.ERR_CAPACITY and got.value == 4
+    with pytest.raises(ColqError, match="not a string column"):
+        q.result_str(0)
+    with pytest.raises(IndexError):
+        q.result_i32(7)
+    q.close()
+    q = ctx.query("t")          # root u: column 1 is the reverse side, no stored data
+    q.close()
+    q = ctx.query("u") if False else None
+    ctx.register("u", u)
+    q = ctx.query("u")
+    q.execute()
+    with pytest.raises(ColqError, match="not a stored to-many"):
+        q.result_csr(1)
+    q.close()
+    ctx.close()
