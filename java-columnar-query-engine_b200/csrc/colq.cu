@@ -185,6 +185,7 @@ struct Op {
     CompactFusedParams cfused{};
     PeerMaskParams pmask{};
     PeerGatherParams pgather{};
+    bool gather = false;  // K_COMPACT_FUSED: the peer-memory final gather is fused into this launch
     int publish_op = -1;  // K_PEER_MASK_COLLECT / a csr_pull with a fused collect: index of the matching publish
     // launch shape for scan_str
     int grid = 0;
@@ -240,7 +241,7 @@ struct colq_ctx {
         int64_t slot_cap = 0;
         size_t slot_bytes = 0;
     } peer;
-    int compact_grid[CF_MAX_GATHER + 1] = {};  // co-resident grid of compact_fused_kernel<NG>
+    int compact_grid[2 * (CF_MAX_GATHER + 1)] = {};  // co-resident grid of compact_fused_kernel<NG, GATHER>
     std::map<std::pair<int, size_t>, int> str_occupancy;  // (kernel mode, dynamic smem bytes) -> resident CTAs per SM
 };
 
@@ -269,6 +270,8 @@ struct colq_query {
     int64_t want_idx_capacity = 0;  // 0 = pick a default at first execute
     // multi-GPU final gather: all ranks' result blocks, then their valid prefixes concatenated in rank order
     bool gathered = false;
+    bool gather_is_peer = false;   // the final gather of the last plan runs over peer memory (fused or two launches)
+    int64_t gather_block_cap = 0;  // indices one rank can contribute to it
     DevBuf gather_buf, gout_buf, ginfo_buf;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     std::vector<cudaEvent_t> stage_ev;
@@ -870,11 +873,14 @@ void stage_name(const Op& o, char* out, size_t cap) {
     else snprintf(out, cap, "%s", o.name);
 }
 
-inline const void* compact_fused_fn(int ng) {
-    switch (ng) {
-        case 0: return (const void*)compact_fused_kernel<0>;
-        case 1: return (const void*)compact_fused_kernel<1>;
-        default: return (const void*)compact_fused_kernel<2>;
+inline const void* compact_fused_fn(int ng, bool gather = false) {
+    switch (ng * 2 + (gather ? 1 : 0)) {
+        case 0: return (const void*)compact_fused_kernel<0, false>;
+        case 1: return (const void*)compact_fused_kernel<0, true>;
+        case 2: return (const void*)compact_fused_kernel<1, false>;
+        case 3: return (const void*)compact_fused_kernel<1, true>;
+        case 4: return (const void*)compact_fused_kernel<2, false>;
+        default: return (const void*)compact_fused_kernel<2, true>;
     }
 }
 
@@ -901,8 +907,9 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
                 if (o.codes.out_bits) CU(ctx, cudaMemsetAsync(o.codes.out_bits, 0, (size_t)bitmap_alloc_words(o.codes.n) * 4, s));
                 break;
             }
-            const int grid = (int)((o.codes.n + SC_BLOCK_ROWS - 1) / SC_BLOCK_ROWS);
-            if (grid == 0) break;
+            const int64_t tiles = (o.codes.n + SR_BLOCK_ROWS - 1) / SR_BLOCK_ROWS;
+            if (tiles == 0) break;
+            const int grid = (int)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * SC_CTAS_PER_SM);
             const size_t smem = (size_t)(PUSH_SMEM_WORDS + o.codes.mask_words) * 4;
             if (o.codes.mask_words > 0) scan_codes_kernel<true><<<grid, SR_THREADS, smem, s>>>(o.codes);
             else scan_codes_kernel<false><<<grid, SR_THREADS, smem, s>>>(o.codes);
@@ -1000,8 +1007,9 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
             q->timing.kernel_launches++;
             break;
         case K_COMPACT_FUSED: {
+            if (o.gather) o.cfused.pg.epoch = ++ctx->peer.gather_epoch;
             void* args[] = {(void*)&o.cfused};
-            CU(ctx, cudaLaunchCooperativeKernel(compact_fused_fn(o.ng), dim3(o.grid), dim3(CP_THREADS), args, 0, s));
+            CU(ctx, cudaLaunchCooperativeKernel(compact_fused_fn(o.ng, o.gather), dim3(o.grid), dim3(CP_THREADS), args, 0, s));
             q->timing.kernel_launches++;
             break;
         }
@@ -1118,13 +1126,17 @@ colq_status run_pipeline(colq_query* q) {
     void *bc, *bo;
     ST(pool_alloc(q, (size_t)n_blocks * 4, &bc));
     ST(pool_alloc(q, (size_t)n_blocks * 8, &bo));
+    q->gather_is_peer = peer_gather;
+    q->gather_block_cap = q->idx_capacity;
     if (q->opt_fused_compact) {
         // one cooperative launch: per-tile popcount, grid barrier, ordered write
         const int ng = (int)q->deferred.size();
-        if (ctx->compact_grid[ng] == 0) {
+        const bool fuse_gather = peer_gather;  // the final gather becomes phases 3 and 4 of the compaction launch
+        const int variant = ng * 2 + (fuse_gather ? 1 : 0);
+        if (ctx->compact_grid[variant] == 0) {
             int occ = 0;
-            CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, compact_fused_fn(ng), CP_THREADS, 0));
-            ctx->compact_grid[ng] = ctx->sm_count * std::max(1, std::min(occ, 8));
+            CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, compact_fused_fn(ng, fuse_gather), CP_THREADS, 0));
+            ctx->compact_grid[variant] = ctx->sm_count * std::max(1, std::min(occ, 8));
         }
         if (!q->barrier_buf.ptr) {
             ST(dev_alloc(ctx, q->barrier_buf, 64));
@@ -1140,8 +1152,22 @@ colq_status run_pipeline(colq_query* q) {
         P.n_rows = n;
         f.ng = ng;
         for (int g = 0; g < ng; ++g) P.gather[g] = q->deferred[g];
-        if (ng) f.name = "compact_fused+chains";
-        f.grid = (int)std::min<int64_t>(n_tiles, ctx->compact_grid[ng]);
+        f.name = ng ? (fuse_gather ? "compact_fused+chains+gather" : "compact_fused+chains") : (fuse_gather ? "compact_fused+gather" : "compact_fused");
+        f.grid = (int)std::min<int64_t>(n_tiles, ctx->compact_grid[variant]);
+        if (fuse_gather) {
+            if (!q->ginfo_buf.ptr) ST(dev_alloc(ctx, q->ginfo_buf, 64));
+            const int64_t cap = std::min<int64_t>(q->idx_capacity, ctx->peer.slot_cap);
+            if (q->gout_buf.bytes < (size_t)cap * 4 * ctx->n_ranks) ST(dev_alloc(ctx, q->gout_buf, (size_t)cap * 4 * ctx->n_ranks));
+            PeerGatherParams& G = P.pg;
+            G.count = q->d_total; G.idx = q->d_idx; G.idx_capacity = q->idx_capacity; G.slot_cap = ctx->peer.slot_cap;
+            G.slot_bytes = ctx->peer.slot_bytes; G.n_ranks = ctx->n_ranks; G.rank = ctx->rank; G.peers = ctx->peer.d_peers;
+            G.done = ctx->peer.d_done; G.blocks_per_peer = 0; G.status = ctx->peer.d_status;
+            G.out = (int32_t*)q->gout_buf.ptr; G.info = (u64*)q->ginfo_buf.ptr;
+            f.gather = true;
+            f.capacity = cap;
+            q->gather_is_peer = true;
+            q->gather_block_cap = cap;
+        }
         q->ops.push_back(f);
     } else {
         Op p{};
@@ -1159,13 +1185,14 @@ colq_status run_pipeline(colq_query* q) {
         c.name = "compact"; c.acct_rows = n; c.acct_bytes = n_words * 4;
         q->ops.push_back(c);
     }
-    if (q->gathered) {
+    if (q->gathered && !(peer_gather && q->opt_fused_compact)) {
         // final gather of matched indices, entirely on the device
         if (!q->ginfo_buf.ptr) ST(dev_alloc(ctx, q->ginfo_buf, 64));
         if (peer_gather) {
             // own kernels over NVLink peer memory: every rank stores its indices into every peer's mailbox slot
             const int64_t cap = std::min<int64_t>(q->idx_capacity, ctx->peer.slot_cap);
             if (q->gout_buf.bytes < (size_t)cap * 4 * ctx->n_ranks) ST(dev_alloc(ctx, q->gout_buf, (size_t)cap * 4 * ctx->n_ranks));
+            q->gather_block_cap = cap;
             Op g{};
             g.kind = K_PEER_GATHER; g.node = 0; g.name = "peer_gather_indices"; g.capacity = cap;
             PeerGatherParams& P = g.pgather;
@@ -1280,10 +1307,8 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
     int64_t count = (int64_t)local;
     const int32_t* src_idx = q->d_idx;
     if (gather) {
-        bool peer_gather = false;
-        int64_t block_cap = q->idx_capacity;
-        for (const Op& o : q->ops)
-            if (o.kind == K_PEER_GATHER) { peer_gather = true; block_cap = o.capacity; }
+        const bool peer_gather = q->gather_is_peer;
+        const int64_t block_cap = q->gather_block_cap;
         if ((int64_t)ginfo[1] > block_cap) {
             // some rank found more rows than a result block holds: every rank sees the same gathered counts, so all
             // of them grow the block (or leave the fixed-size mailbox path) and run the query again

@@ -363,12 +363,11 @@ __global__ void __launch_bounds__(SR_THREADS) scan_rows_kernel(const ScanRowsPar
 // memory (random 4-byte gathers: ~3 bank-conflict cycles per warp instead of up to 16 L1 wavefronts); dictionaries
 // beyond SC_SMEM_MASK_WORDS * 32 entries are looked up through L1/L2.  When the staged mask has at most SC_FEW bits
 // set -- an equality predicate accepts exactly ONE dictionary entry -- the CTA extracts those codes once and the row
-// test is a handful of register compares with no shared-memory traffic at all.  Same row mapping as scan_rows,
-// SC_ITER consecutive 4096-row tiles per CTA so that the mask copy is amortised.
+// test is a handful of register compares with no shared-memory traffic at all.  Same row mapping as scan_rows, in a
+// persistent grid (4096-row tiles round-robin) so that the mask staging is paid once per CTA.
 // ---------------------------------------------------------------------------------------------
 
-constexpr int SC_ITER = 8;
-constexpr int SC_BLOCK_ROWS = SR_BLOCK_ROWS * SC_ITER;  // 32768
+constexpr int SC_CTAS_PER_SM = 8;                       // persistent grid: SMs x 8 CTAs of 256 threads
 constexpr int SC_SMEM_MASK_WORDS = 8192;                // 32 KB: dictionaries of up to 262144 entries
 constexpr int SC_FEW = 4;                               // accepted codes that are tested by register compares
 
@@ -431,9 +430,11 @@ __global__ void __launch_bounds__(SR_THREADS) scan_codes_kernel(const ScanCodesP
         return (w >> ((u32)c & 31)) & 1u;
     };
 
+    // persistent CTAs: 4096-row tiles round-robin, so the prologue above is paid once per CTA
+    const int64_t n_tiles = (P.n + SR_BLOCK_ROWS - 1) / SR_BLOCK_ROWS;
 #pragma unroll 1
-    for (int it = 0; it < SC_ITER; ++it) {
-        const int64_t wbase = ((int64_t)blockIdx.x * SC_ITER + it) * SR_BLOCK_ROWS + (int64_t)warp * SR_WARP_ROWS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t wbase = tile * SR_BLOCK_ROWS + (int64_t)warp * SR_WARP_ROWS;
         if (wbase >= P.n) break;
         u32 nib[SR_V];
         if (wbase + SR_WARP_ROWS <= P.n) {
@@ -1371,7 +1372,28 @@ struct CompactFusedParams {
     int64_t row_base;
     int64_t n_rows;
     GatherD gather[CF_MAX_GATHER];  // deferred to-one chains of the root node (see compact_fused_kernel)
+    PeerGatherParams pg;            // GATHER kernels: the multi-GPU final gather runs as phases 3 and 4 of this launch
 };
+
+// sense-reversal grid barrier on {arrival count, generation}; self-resetting.  The grid must be co-resident
+// (cooperative launch).
+__device__ __forceinline__ void grid_barrier(u32* bar) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile u32* gen = bar + 1;
+        const u32 my_gen = *gen;
+        if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+            bar[0] = 0;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (*gen == my_gen) {}
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
 
 // thread t of a tile owns words [16 t, 16 t + 16): four consecutive 128-bit loads
 __device__ __forceinline__ u32 cf_load(const CompactFusedParams& P, int64_t tile, uint4 (&v)[CF_VEC]) {
@@ -1392,7 +1414,10 @@ __device__ __forceinline__ u32 cf_load(const CompactFusedParams& P, int64_t tile
 // thread of the grid (all walks in flight at once) instead of stalling the streaming warps of the scan.
 constexpr int CF_LIST_CAP = 4096;  // survivors of one 131072-row tile that are resolved block-wide (3 % selectivity)
 
-template <int NG>
+// GATHER (multi-GPU, sharded root): after the ordered write the same launch stores this rank's indices into every
+// peer's mailbox slot over NVLink (phase 3: coalesced 128-bit stores, then the epoch flags), waits for all ranks'
+// flags and concatenates the valid prefixes in rank order (phase 4) -- the former peer_gather_send / _recv launches.
+template <int NG, bool GATHER = false>
 __global__ void __launch_bounds__(CP_THREADS) compact_fused_kernel(const CompactFusedParams P) {
     __shared__ u32 s_warp[33];
     __shared__ u64 s_base;
@@ -1471,22 +1496,7 @@ __global__ void __launch_bounds__(CP_THREADS) compact_fused_kernel(const Compact
             if (threadIdx.x == 0) P.tile_counts[t] = total;
             __syncthreads();
         }
-        // grid barrier (sense reversal on a generation word; the grid is co-resident by cooperative launch)
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            volatile u32* gen = P.barrier + 1;
-            const u32 my_gen = *gen;
-            if (atomicAdd(P.barrier, 1u) == gridDim.x - 1) {
-                P.barrier[0] = 0;
-                __threadfence();
-                atomicAdd(P.barrier + 1, 1u);
-            } else {
-                while (*gen == my_gen) {}
-            }
-            __threadfence();
-        }
-        __syncthreads();
+        grid_barrier(P.barrier);
     }
     // phase 2: prefix of each of my tiles = sum of the counts of all earlier tiles (carried forward), then write
     int64_t prev_tile = 0;
@@ -1526,6 +1536,76 @@ __global__ void __launch_bounds__(CP_THREADS) compact_fused_kernel(const Compact
     }
     // the block that owns the last tile knows the grand total
     if ((P.n_tiles - 1) % gridDim.x == blockIdx.x && threadIdx.x == 0) *P.total = running + P.tile_counts[P.n_tiles - 1];
+
+    if (GATHER) {
+        const PeerGatherParams& G = P.pg;
+        grid_barrier(P.barrier);  // every index and the total are in HBM
+        // ---- phase 3: my slice of the index list goes to every rank's mailbox (my own included)
+        const size_t area = PEER_GATHER_AREA_OFFSET + (size_t)(G.epoch & 1) * G.n_ranks * G.slot_bytes;
+        const u64 true_count = *reinterpret_cast<const volatile u64*>(P.total);
+        int64_t n = (int64_t)true_count;
+        if (n > P.capacity) n = P.capacity;
+        if (n > G.slot_cap) n = G.slot_cap;
+        const int64_t n4 = n >> 2;  // whole 128-bit lines; block 0 adds the 0..3 tail elements
+        const int4* src4 = reinterpret_cast<const int4*>(P.out_idx);
+        for (int r = 0; r < G.n_ranks; ++r) {
+            int32_t* dst = reinterpret_cast<int32_t*>(G.peers[r] + area + (size_t)G.rank * G.slot_bytes + GATHER_SLOT_HEADER);
+            int4* dst4 = reinterpret_cast<int4*>(dst);
+            for (int64_t i = (int64_t)blockIdx.x * CP_THREADS + threadIdx.x; i < n4; i += (int64_t)gridDim.x * CP_THREADS) dst4[i] = __ldcg(src4 + i);
+            if (blockIdx.x == 0 && (int64_t)threadIdx.x < n - (n4 << 2)) dst[(n4 << 2) + threadIdx.x] = __ldcg(P.out_idx + (n4 << 2) + threadIdx.x);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const u32 prev = atomicAdd(&G.done[0], 1u);
+            if (prev == gridDim.x - 1) {  // every block's stores are out: publish count + flag everywhere
+                G.done[0] = 0;
+                __threadfence_system();
+                for (int r = 0; r < G.n_ranks; ++r) {
+                    u64* slot = reinterpret_cast<u64*>(G.peers[r] + area + (size_t)G.rank * G.slot_bytes);
+                    slot[1] = true_count;
+                }
+                __threadfence_system();
+                for (int r = 0; r < G.n_ranks; ++r)
+                    st_release_sys(reinterpret_cast<u64*>(G.peers[r] + area + (size_t)G.rank * G.slot_bytes), G.epoch);
+            }
+        }
+        // ---- phase 4: wait for every rank's flag in my own memory, then concatenate in rank order
+        __shared__ int64_t s_off[MAX_RANKS + 1];
+        __shared__ int s_ok;
+        const uint8_t* mine = G.peers[G.rank] + area;
+        if (threadIdx.x == 0) s_ok = 1;
+        __syncthreads();
+        if ((int)threadIdx.x < G.n_ranks) {
+            if (!peer_wait(reinterpret_cast<const u64*>(mine + (size_t)threadIdx.x * G.slot_bytes), G.epoch, G.status)) s_ok = 0;
+        }
+        __syncthreads();
+        if (!s_ok) return;
+        if (threadIdx.x == 0) {
+            int64_t off = 0;
+            u64 maxc = 0, total = 0;
+            for (int r = 0; r < G.n_ranks; ++r) {
+                const u64 c = __ldcg(reinterpret_cast<const u64*>(mine + (size_t)r * G.slot_bytes) + 1);
+                s_off[r] = off;
+                off += (int64_t)(c < (u64)G.slot_cap ? c : (u64)G.slot_cap);
+                maxc = c > maxc ? c : maxc;
+                total += c;
+            }
+            s_off[G.n_ranks] = off;
+            if (blockIdx.x == 0) {
+                G.info[0] = (u64)off;
+                G.info[1] = maxc;
+                G.info[2] = total;
+            }
+        }
+        __syncthreads();
+        const int64_t m = s_off[G.n_ranks];
+        for (int64_t i = (int64_t)blockIdx.x * CP_THREADS + threadIdx.x; i < m; i += (int64_t)gridDim.x * CP_THREADS) {
+            int r = 0;
+            while (r + 1 < G.n_ranks && i >= s_off[r + 1]) ++r;
+            G.out[i] = __ldcg(reinterpret_cast<const int32_t*>(mine + (size_t)r * G.slot_bytes + GATHER_SLOT_HEADER) + (i - s_off[r]));
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -46,9 +46,10 @@ def main():
         oracle.close()
 
         geo = G.build_tables(U, n_ranks=world, rank=rank, rename_plymouth_except_last_rank=perturbed)
-        for peer, lazy, defer in ((1, True, 1), (1, True, 0), (1, False, 1), (0, True, 1), (0, False, 1)):
+        for peer, lazy, defer, fused in ((1, True, 1, 1), (1, True, 0, 1), (1, False, 1, 1), (1, True, 1, 0), (0, True, 1, 1), (0, False, 1, 1)):
             if True:
-                ds = DataSystemColq(context=ctx, lazy_fk=lazy, options={_ffi.OPT_PEER_EXCHANGE: peer, _ffi.OPT_DEFER_CHAINS: defer})
+                ds = DataSystemColq(context=ctx, lazy_fk=lazy, options={_ffi.OPT_PEER_EXCHANGE: peer, _ffi.OPT_DEFER_CHAINS: defer,
+                                                                        _ffi.OPT_FUSED_COMPACT: fused})
                 ds._tables.clear()
                 G.register_geography(ds, geo, sharded=True)
                 ds._sync_tables()
@@ -59,8 +60,12 @@ def main():
                 assert np.array_equal(res.indices, want), (rank, perturbed, peer, lazy)
                 names = [n for n, *_ in cq.profile()]
                 if peer and os.environ.get("COLQ_PEER", "1") != "0":
-                    assert "peer_mask_publish" in names and "peer_mask_collect+csr_pull" in names and "peer_gather_indices" in names, names
-                    if lazy and defer:   # the root's predicate scan sits between the two halves of the mask exchange
+                    assert "peer_mask_publish" in names and "peer_mask_collect+csr_pull" in names, names
+                    if fused:    # the final gather runs inside the compaction launch
+                        assert any(n.startswith("compact_fused") and n.endswith("+gather") for n in names), names
+                    else:
+                        assert "peer_gather_indices" in names, names
+                    if lazy and defer and fused:   # the root's predicate scan sits between the two halves of the mask exchange
                         assert names.index("peer_mask_publish") < names.index("scan_rows<1,0,lazy>") < names.index("peer_mask_collect+csr_pull"), names
                 else:
                     assert "allgather_or_mask" in names and "allgather_indices" in names, names
