@@ -907,9 +907,8 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
                 if (o.codes.out_bits) CU(ctx, cudaMemsetAsync(o.codes.out_bits, 0, (size_t)bitmap_alloc_words(o.codes.n) * 4, s));
                 break;
             }
-            const int64_t tiles = (o.codes.n + SR_BLOCK_ROWS - 1) / SR_BLOCK_ROWS;
-            if (tiles == 0) break;
-            const int grid = (int)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * SC_CTAS_PER_SM);
+            const int grid = (int)((o.codes.n + SC_BLOCK_ROWS - 1) / SC_BLOCK_ROWS);
+            if (grid == 0) break;
             const size_t smem = (size_t)(PUSH_SMEM_WORDS + o.codes.mask_words) * 4;
             if (o.codes.mask_words > 0) scan_codes_kernel<true><<<grid, SR_THREADS, smem, s>>>(o.codes);
             else scan_codes_kernel<false><<<grid, SR_THREADS, smem, s>>>(o.codes);

@@ -363,11 +363,13 @@ __global__ void __launch_bounds__(SR_THREADS) scan_rows_kernel(const ScanRowsPar
 // memory (random 4-byte gathers: ~3 bank-conflict cycles per warp instead of up to 16 L1 wavefronts); dictionaries
 // beyond SC_SMEM_MASK_WORDS * 32 entries are looked up through L1/L2.  When the staged mask has at most SC_FEW bits
 // set -- an equality predicate accepts exactly ONE dictionary entry -- the CTA extracts those codes once and the row
-// test is a handful of register compares with no shared-memory traffic at all.  Same row mapping as scan_rows, in a
-// persistent grid (4096-row tiles round-robin) so that the mask staging is paid once per CTA.
+// test is a handful of register compares with no shared-memory traffic at all (one compare per row for the single
+// accepted code of an equality).  Same row mapping as scan_rows, SC_ITER consecutive 4096-row tiles per CTA so that
+// the mask staging is amortised.
 // ---------------------------------------------------------------------------------------------
 
-constexpr int SC_CTAS_PER_SM = 8;                       // persistent grid: SMs x 8 CTAs of 256 threads
+constexpr int SC_ITER = 8;
+constexpr int SC_BLOCK_ROWS = SR_BLOCK_ROWS * SC_ITER;  // 32768 rows per CTA
 constexpr int SC_SMEM_MASK_WORDS = 8192;                // 32 KB: dictionaries of up to 262144 entries
 constexpr int SC_FEW = 4;                               // accepted codes that are tested by register compares
 
@@ -430,11 +432,11 @@ __global__ void __launch_bounds__(SR_THREADS) scan_codes_kernel(const ScanCodesP
         return (w >> ((u32)c & 31)) & 1u;
     };
 
-    // persistent CTAs: 4096-row tiles round-robin, so the prologue above is paid once per CTA
-    const int64_t n_tiles = (P.n + SR_BLOCK_ROWS - 1) / SR_BLOCK_ROWS;
+    // SC_ITER consecutive 4096-row tiles per CTA amortise the prologue above (measured on B200: better than both one
+    // tile per CTA and a persistent grid)
 #pragma unroll 1
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t wbase = tile * SR_BLOCK_ROWS + (int64_t)warp * SR_WARP_ROWS;
+    for (int it = 0; it < SC_ITER; ++it) {
+        const int64_t wbase = ((int64_t)blockIdx.x * SC_ITER + it) * SR_BLOCK_ROWS + (int64_t)warp * SR_WARP_ROWS;
         if (wbase >= P.n) break;
         u32 nib[SR_V];
         if (wbase + SR_WARP_ROWS <= P.n) {
@@ -445,9 +447,16 @@ __global__ void __launch_bounds__(SR_THREADS) scan_codes_kernel(const ScanCodesP
 #pragma unroll
                 for (int j = 0; j < SR_V; ++j) *reinterpret_cast<int4*>(P.promote + wbase + j * 128 + lane * 4) = v[j];
             }
+            if (n_few <= 1) {  // "X"::equals accepts one dictionary entry: a single compare per row
 #pragma unroll
-            for (int j = 0; j < SR_V; ++j)
-                nib[j] = (test(v[j].x) ? 1u : 0u) | (test(v[j].y) ? 2u : 0u) | (test(v[j].z) ? 4u : 0u) | (test(v[j].w) ? 8u : 0u);
+                for (int j = 0; j < SR_V; ++j)
+                    nib[j] = ((u32)v[j].x == k[0] ? 1u : 0u) | ((u32)v[j].y == k[0] ? 2u : 0u) | ((u32)v[j].z == k[0] ? 4u : 0u) |
+                             ((u32)v[j].w == k[0] ? 8u : 0u);
+            } else {
+#pragma unroll
+                for (int j = 0; j < SR_V; ++j)
+                    nib[j] = (test(v[j].x) ? 1u : 0u) | (test(v[j].y) ? 2u : 0u) | (test(v[j].z) ? 4u : 0u) | (test(v[j].w) ? 8u : 0u);
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < SR_V; ++j) {
