@@ -94,7 +94,10 @@ typedef enum colq_option {
     COLQ_OPT_DEFER_CHAINS = 5,
     /* 1 (default): the first scan that streams a host-resident column (colq_*_host) over PCIe also leaves a copy in
        HBM, which later queries use; 0: keep streaming from pinned host memory every time */
-    COLQ_OPT_PROMOTE = 6
+    COLQ_OPT_PROMOTE = 6,
+    /* 1: the multi-GPU final gather runs as two more phases of the cooperative compaction launch instead of the two
+       peer_gather launches (default 0: measured slower on 2-8 B200s, kept selectable and parity-tested) */
+    COLQ_OPT_FUSED_GATHER = 7
 } colq_option;
 
 typedef struct colq_ctx colq_ctx;       /* one DataSystem instance  (E/DataSystemSerialIndices.java:14-22) */

@@ -249,7 +249,7 @@ struct colq_query {
     colq_ctx* ctx = nullptr;
     std::string table_name;
     std::vector<QNode> nodes;
-    int opt_lazy = 1, opt_profile = 0, opt_graph = 1, opt_peer = 1, opt_fused_compact = 1, opt_defer = 1, opt_promote = 1;
+    int opt_lazy = 1, opt_profile = 0, opt_graph = 1, opt_peer = 1, opt_fused_compact = 1, opt_defer = 1, opt_promote = 1, opt_fused_gather = 0;
     std::vector<GatherD> deferred;  // root-node FK chains resolved by the compaction kernel instead of the row scan
     int own_begin = -1, own_end = -1;  // root-node scan ops that depend on no child (hoistable behind a mask publish)
     std::vector<Column*> pending_promotions;  // host-resident columns whose HBM copy this execution fills
@@ -1130,7 +1130,10 @@ colq_status run_pipeline(colq_query* q) {
     if (q->opt_fused_compact) {
         // one cooperative launch: per-tile popcount, grid barrier, ordered write
         const int ng = (int)q->deferred.size();
-        const bool fuse_gather = peer_gather;  // the final gather becomes phases 3 and 4 of the compaction launch
+        // COLQ_OPT_FUSED_GATHER: the final gather becomes phases 3 and 4 of the compaction launch.  Off by default: on
+        // 2, 4 and 8 B200s the two dedicated launches were faster (0.165 vs 0.178 ms per step at N=8) -- the extra grid
+        // barriers serialise on the slowest block, while separate kernels overlap their tails with the peers' stores.
+        const bool fuse_gather = peer_gather && q->opt_fused_gather;
         const int variant = ng * 2 + (fuse_gather ? 1 : 0);
         if (ctx->compact_grid[variant] == 0) {
             int occ = 0;
@@ -1184,7 +1187,7 @@ colq_status run_pipeline(colq_query* q) {
         c.name = "compact"; c.acct_rows = n; c.acct_bytes = n_words * 4;
         q->ops.push_back(c);
     }
-    if (q->gathered && !(peer_gather && q->opt_fused_compact)) {
+    if (q->gathered && !(peer_gather && q->opt_fused_compact && q->opt_fused_gather)) {
         // final gather of matched indices, entirely on the device
         if (!q->ginfo_buf.ptr) ST(dev_alloc(ctx, q->ginfo_buf, 64));
         if (peer_gather) {
@@ -2081,6 +2084,7 @@ colq_status colq_query_set_option(colq_query* q, colq_option option, int value) 
         case COLQ_OPT_FUSED_COMPACT: q->opt_fused_compact = value; break;
         case COLQ_OPT_DEFER_CHAINS: q->opt_defer = value; break;
         case COLQ_OPT_PROMOTE: q->opt_promote = value; break;
+        case COLQ_OPT_FUSED_GATHER: q->opt_fused_gather = value; break;
         default: return fail(q->ctx, COLQ_THROW_ILLEGAL_ARG, "unknown option %d", (int)option);
     }
     return COLQ_OK;
