@@ -86,16 +86,18 @@ typedef enum colq_option {
     /* 1 (default): multi-GPU exchanges (state-mask OR, final index gather) run as own kernels that store into the
        peers' HBM over NVLink (CUDA-IPC mailboxes); 0: NCCL all-gathers */
     COLQ_OPT_PEER_EXCHANGE = 3,
-    /* 1 (default): one cooperative compaction launch; 0: popcount / scan / write as three launches */
+    /* 1 (default): one cooperative two-phase compaction launch (popcount, grid barrier, ordered write);
+       2: single-pass compaction with decoupled look-back (one ordinary launch, the mask is read once; measured slower
+       on B200); 0: popcount / scan / write as three launches */
     COLQ_OPT_FUSED_COMPACT = 4,
     /* 1 (default): the root node's lazy FK chains are walked by the fused compaction kernel for the rows that
        survived the root's predicates (the row scan stays a pure coalesced stream); 0: inside the row scan.
-       Needs COLQ_OPT_LAZY_FK and COLQ_OPT_FUSED_COMPACT. */
+       Needs COLQ_OPT_LAZY_FK and COLQ_OPT_FUSED_COMPACT >= 1. */
     COLQ_OPT_DEFER_CHAINS = 5,
     /* 1 (default): the first scan that streams a host-resident column (colq_*_host) over PCIe also leaves a copy in
        HBM, which later queries use; 0: keep streaming from pinned host memory every time */
     COLQ_OPT_PROMOTE = 6,
-    /* 1: the multi-GPU final gather runs as two more phases of the cooperative compaction launch instead of the two
+    /* 1: the multi-GPU final gather runs as two more phases of the COOPERATIVE compaction launch instead of the two
        peer_gather launches (default 0: measured slower on 2-8 B200s, kept selectable and parity-tested) */
     COLQ_OPT_FUSED_GATHER = 7
 } colq_option;

@@ -159,7 +159,7 @@ struct QNode {
 };
 
 // one kernel launch (or collective / memset) of a planned query
-enum OpKind { K_SCAN_ROWS, K_SCAN_CODES, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER, K_COMPACT_FUSED, K_PEER_MASK_PUBLISH, K_PEER_MASK_COLLECT, K_PEER_GATHER };
+enum OpKind { K_SCAN_ROWS, K_SCAN_CODES, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER, K_COMPACT_FUSED, K_COMPACT_LOOKBACK, K_PEER_MASK_PUBLISH, K_PEER_MASK_COLLECT, K_PEER_GATHER };
 
 struct Op {
     OpKind kind;
@@ -183,6 +183,7 @@ struct Op {
     int32_t* out_idx = nullptr;
     int64_t capacity = 0, row_base = 0, n_blocks = 0;
     CompactFusedParams cfused{};
+    CompactLookbackParams clook{};
     PeerMaskParams pmask{};
     PeerGatherParams pgather{};
     bool gather = false;  // K_COMPACT_FUSED: the peer-memory final gather is fused into this launch
@@ -256,6 +257,9 @@ struct colq_query {
     bool lazy_oob = false;  // the plan walks a to-one column that was not range-checked at ingest
     int64_t promoted_bytes = 0;
     DevBuf barrier_buf;  // {arrival count, generation} of the cooperative compaction kernel
+    DevBuf lookback_buf;  // [2 counters | pad | tile states] of the single-pass compaction kernel (zeroed once)
+    int64_t lookback_tiles = 0;
+    u32 lookback_epoch = 0;
     // execution state
     Pool pool;
     std::vector<XNode> xnodes;
@@ -1005,6 +1009,20 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
             compact_kernel<<<(int)o.n_blocks, CP_THREADS, 0, s>>>(o.src, o.n_words, o.block_offsets, o.out_idx, o.capacity, o.row_base);
             q->timing.kernel_launches++;
             break;
+        case K_COMPACT_LOOKBACK: {
+            if (++q->lookback_epoch >= (1u << 30)) {  // epoch wrap: start over on cleared states
+                CU(ctx, cudaMemsetAsync(q->lookback_buf.ptr, 0, q->lookback_buf.bytes, s));
+                q->lookback_epoch = 1;
+            }
+            o.clook.epoch = q->lookback_epoch;
+            switch (o.ng) {
+                case 0: compact_lookback_kernel<0><<<o.grid, CP_THREADS, 0, s>>>(o.clook); break;
+                case 1: compact_lookback_kernel<1><<<o.grid, CP_THREADS, 0, s>>>(o.clook); break;
+                default: compact_lookback_kernel<2><<<o.grid, CP_THREADS, 0, s>>>(o.clook); break;
+            }
+            q->timing.kernel_launches++;
+            break;
+        }
         case K_COMPACT_FUSED: {
             if (o.gather) o.cfused.pg.epoch = ++ctx->peer.gather_epoch;
             void* args[] = {(void*)&o.cfused};
@@ -1127,7 +1145,30 @@ colq_status run_pipeline(colq_query* q) {
     ST(pool_alloc(q, (size_t)n_blocks * 8, &bo));
     q->gather_is_peer = peer_gather;
     q->gather_block_cap = q->idx_capacity;
-    if (q->opt_fused_compact) {
+    const bool coop_gather = peer_gather && q->opt_fused_gather && q->opt_fused_compact;  // needs the cooperative kernel
+    if (q->opt_fused_compact >= 2 && !coop_gather) {
+        // single pass with decoupled look-back: one CTA per tile, ordinary launch
+        const int ng = (int)q->deferred.size();
+        const int64_t n_tiles = std::max<int64_t>(1, (n_words + CF_WORDS_PER_TILE - 1) / CF_WORDS_PER_TILE);
+        if (q->lookback_tiles < n_tiles) {
+            ST(dev_alloc(ctx, q->lookback_buf, 64 + (size_t)n_tiles * 8));
+            CU(ctx, cudaMemsetAsync(q->lookback_buf.ptr, 0, q->lookback_buf.bytes, ctx->stream));
+            q->lookback_tiles = n_tiles;
+            q->lookback_epoch = 0;
+        }
+        Op f{};
+        f.kind = K_COMPACT_LOOKBACK; f.node = 0; f.acct_rows = n; f.acct_bytes = n_words * 4;
+        f.name = ng ? "compact_lookback+chains" : "compact_lookback";
+        f.ng = ng;
+        CompactLookbackParams& P = f.clook;
+        P.bits = root.bits; P.n_words = n_words; P.n_tiles = n_tiles;
+        P.counters = (u32*)q->lookback_buf.ptr; P.tile_state = (u64*)((char*)q->lookback_buf.ptr + 64);
+        P.total = q->d_total; P.out_idx = q->d_idx; P.capacity = q->idx_capacity;
+        P.row_base = RT.row_base; P.n_rows = n;
+        for (int g = 0; g < ng; ++g) P.gather[g] = q->deferred[g];
+        f.grid = (int)n_tiles;
+        q->ops.push_back(f);
+    } else if (q->opt_fused_compact) {
         // one cooperative launch: per-tile popcount, grid barrier, ordered write
         const int ng = (int)q->deferred.size();
         // COLQ_OPT_FUSED_GATHER: the final gather becomes phases 3 and 4 of the compaction launch.  Off by default: on
@@ -1187,7 +1228,7 @@ colq_status run_pipeline(colq_query* q) {
         c.name = "compact"; c.acct_rows = n; c.acct_bytes = n_words * 4;
         q->ops.push_back(c);
     }
-    if (q->gathered && !(peer_gather && q->opt_fused_compact && q->opt_fused_gather)) {
+    if (q->gathered && !coop_gather) {
         // final gather of matched indices, entirely on the device
         if (!q->ginfo_buf.ptr) ST(dev_alloc(ctx, q->ginfo_buf, 64));
         if (peer_gather) {
@@ -2000,6 +2041,7 @@ colq_status colq_table_width(const colq_ctx* ctx, colq_table table, int* out_col
 colq_status colq_query_create(colq_ctx* ctx, const char* table_name, colq_query** out_query) {
     if (!ctx || !table_name || !out_query) return COLQ_THROW_NULL;
     colq_query* q = new colq_query();
+    if (const char* e = getenv("COLQ_COMPACT")) q->opt_fused_compact = atoi(e);  // experiment knob: default compaction kernel
     q->ctx = ctx;
     q->table_name = table_name;
     q->nodes.emplace_back();  // rootNode (DS/Query.java:22-25)

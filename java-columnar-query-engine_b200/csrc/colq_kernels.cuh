@@ -1722,6 +1722,198 @@ __global__ void __launch_bounds__(256) gather_var_copy_kernel(const GatherVarPar
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3''  single-PASS compaction with decoupled look-back (COLQ_OPT_FUSED_COMPACT=2).  One CTA per 131072-row tile, tile ids handed out
+// by an atomic counter in CTA start order, so a CTA only ever waits for tiles whose CTAs are already running.  Each CTA:
+// loads its 16 KB of mask once, (NG > 0) resolves the root's deferred FK chains block-wide exactly like
+// compact_fused_kernel, publishes its count, finds its output offset by looking back over its predecessors' published
+// {aggregate | inclusive prefix} words (32 at a time, one warp), and writes its indices from registers.  Against the
+// cooperative two-phase kernel: no grid barrier, no second read of the mask, an ordinary (non-cooperative) launch.
+// Tile states carry a per-launch epoch, so nothing has to be cleared between launches.
+// MEASURED SLOWER than the cooperative kernel on B200 (r01: 74 vs 62 us at 293.5 M rows with chains, 125 vs 94 us at
+// 1 B rows; tile sizes of 64 K / 128 K / 256 K rows tried): with one 16 KB tile per CTA the launch is bound by CTA
+// lifetime x waves, not by bandwidth.  Kept selectable and parity-tested; not the default.
+// ---------------------------------------------------------------------------------------------
+
+struct CompactLookbackParams {
+    u32* bits;
+    int64_t n_words;
+    int64_t n_tiles;    // == gridDim.x
+    u64* tile_state;    // [n_tiles]: epoch << 34 | flag << 32 | value; flag 1 = tile count, 2 = inclusive prefix
+    u32* counters;      // [0] next tile id, [1] finished CTAs; both return to zero at the end of the launch
+    u32 epoch;          // 1 .. 2^30 - 1, different from the previous launch on the same tile_state
+    u64* total;
+    int32_t* out_idx;
+    int64_t capacity;
+    int64_t row_base;
+    int64_t n_rows;
+    GatherD gather[CF_MAX_GATHER];
+};
+
+__device__ __forceinline__ u64 ld_volatile_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(u64* p, u64 v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <int NG>
+__global__ void __launch_bounds__(CP_THREADS) compact_lookback_kernel(const CompactLookbackParams P) {
+    __shared__ u32 s_warp[33];
+    __shared__ u32 s_list[NG > 0 ? CF_LIST_CAP : 1];
+    __shared__ u32 s_tile;
+    __shared__ u64 s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(&P.counters[0], 1u);
+    __syncthreads();
+    const int64_t t = s_tile;
+    const int64_t tile_w0 = t * CF_WORDS_PER_TILE;
+    const u32 lw0 = threadIdx.x * 4 * CF_VEC;  // first word of this thread inside the tile
+
+    uint4 v[CF_VEC];
+    u32 c = 0;
+#pragma unroll
+    for (int k = 0; k < CF_VEC; ++k) {
+        v[k] = load_words4(P.bits, tile_w0 + lw0 + 4 * k, P.n_words);
+        c += __popc(v[k].x) + __popc(v[k].y) + __popc(v[k].z) + __popc(v[k].w);
+    }
+
+    if (NG > 0) {
+        u32 total;
+        const u32 ex = block_exclusive_scan(c, s_warp, total);
+        if (total != 0) {
+            const bool listed = total <= CF_LIST_CAP;
+            if (listed) {
+                // every surviving row of the tile into one shared list, walked round-robin by the whole CTA
+                u32 pos = ex;
+#pragma unroll
+                for (int k = 0; k < CF_VEC; ++k) {
+                    const u32 w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        u32 m = w[j];
+                        while (m) {
+                            const int b = __ffs(m) - 1;
+                            m &= m - 1;
+                            s_list[pos++] = ((lw0 + 4 * k + j) << 5) + b;
+                        }
+                    }
+                }
+                __syncthreads();
+                for (u32 i = threadIdx.x; i < total; i += CP_THREADS) {
+                    const u32 lr = s_list[i];
+                    const int64_t row = (tile_w0 << 5) + lr;
+                    bool ok = row < P.n_rows;
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) ok = ok && gather_eval(P.gather[g], row, 0);
+                    if (!ok) s_list[i] = lr | 0x80000000u;
+                }
+                __syncthreads();
+            }
+            // back to the owner of each word: drop the failed bits (list verdicts, or walk the chains here when the
+            // tile is too dense for the list), and write changed words back -- the root mask is part of the result
+            u32 pos = ex;
+            c = 0;
+#pragma unroll
+            for (int k = 0; k < CF_VEC; ++k) {
+                u32 w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    u32 m = w[j], keep = w[j];
+                    const int64_t rb = (tile_w0 + lw0 + 4 * k + j) << 5;
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        bool ok;
+                        if (listed) ok = !(s_list[pos++] & 0x80000000u);
+                        else {
+                            ok = rb + b < P.n_rows;
+#pragma unroll
+                            for (int g = 0; g < NG; ++g) ok = ok && gather_eval(P.gather[g], rb + b, 0);
+                        }
+                        if (!ok) keep &= ~(1u << b);
+                    }
+                    if (keep != w[j]) P.bits[tile_w0 + lw0 + 4 * k + j] = keep;
+                    w[j] = keep;
+                    c += __popc(keep);
+                }
+                v[k] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        __syncthreads();  // s_warp is reused by the next scan
+    }
+
+    u32 tile_total;
+    const u32 ex = block_exclusive_scan(c, s_warp, tile_total);
+
+    // ---- decoupled look-back (warp 0)
+    if (warp == 0) {
+        const u64 tag = (u64)P.epoch << 34;
+        if (lane == 0) {
+            __threadfence();
+            st_volatile_u64(P.tile_state + t, tag | ((u64)(t == 0 ? 2 : 1) << 32) | tile_total);
+        }
+        u64 base = 0;
+        if (t > 0) {
+            int64_t hi = t - 1;  // newest predecessor of the current window
+            while (true) {
+                const int64_t idx = hi - lane;
+                u64 st;
+                bool valid;
+                do {
+                    st = idx >= 0 ? ld_volatile_u64(P.tile_state + idx) : (tag | (2ull << 32));  // before tile 0: prefix 0
+                    valid = (st >> 34) == (u64)P.epoch && ((st >> 32) & 3u) != 0;
+                } while (!__all_sync(FULL_MASK, valid));
+                const u32 flag = (u32)(st >> 32) & 3u, val = (u32)st;
+                const u32 has_prefix = __ballot_sync(FULL_MASK, flag == 2);
+                const int first = has_prefix ? __ffs(has_prefix) - 1 : 31;  // nearest tile that knows its inclusive prefix
+                u32 contrib = lane <= first ? val : 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(FULL_MASK, contrib, d);
+                base += contrib;
+                if (has_prefix) break;
+                hi -= 32;
+            }
+            if (lane == 0) {
+                __threadfence();
+                st_volatile_u64(P.tile_state + t, tag | (2ull << 32) | (u64)(u32)(base + tile_total));
+            }
+        }
+        if (lane == 0) s_base = base;
+    }
+    __syncthreads();
+
+    // ---- ordered write from registers
+    if (c != 0) {
+        int64_t pos = (int64_t)s_base + ex;
+#pragma unroll
+        for (int k = 0; k < CF_VEC; ++k) {
+            const u32 w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                u32 m = w[j];
+                const int64_t rb = P.row_base + ((tile_w0 + lw0 + 4 * k + j) << 5);
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (pos < P.capacity) P.out_idx[pos] = (int32_t)(rb + b);
+                    ++pos;
+                }
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (t == P.n_tiles - 1) *P.total = s_base + tile_total;
+        const u32 prev = atomicAdd(&P.counters[1], 1u);
+        if (prev == gridDim.x - 1) {  // every CTA has taken its tile id long ago: rearm the counters
+            P.counters[0] = 0;
+            P.counters[1] = 0;
+        }
+    }
+}
+
 // popcount of a whole bitmask into one u64 (node cardinalities; not on the timed path)
 __global__ void __launch_bounds__(256) popc_total_kernel(const u32* bits, int64_t n_words, u64* out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;

@@ -47,8 +47,8 @@ def main():
 
         geo = G.build_tables(U, n_ranks=world, rank=rank, rename_plymouth_except_last_rank=perturbed)
         # (peer exchange, lazy FK, deferred chains, fused compaction, gather fused into the compaction)
-        for peer, lazy, defer, fused, fgather in ((1, True, 1, 1, 0), (1, True, 1, 1, 1), (1, True, 0, 1, 1), (1, False, 1, 1, 0),
-                                                 (1, True, 1, 0, 0), (0, True, 1, 1, 0), (0, False, 1, 1, 0)):
+        for peer, lazy, defer, fused, fgather in ((1, True, 1, 1, 0), (1, True, 1, 2, 0), (1, True, 1, 1, 1), (1, True, 0, 1, 1), (1, False, 1, 1, 0),
+                                                 (1, True, 1, 0, 0), (0, True, 1, 1, 0), (0, False, 1, 2, 0)):
             if True:
                 ds = DataSystemColq(context=ctx, lazy_fk=lazy, options={_ffi.OPT_PEER_EXCHANGE: peer, _ffi.OPT_DEFER_CHAINS: defer,
                                                                         _ffi.OPT_FUSED_COMPACT: fused, _ffi.OPT_FUSED_GATHER: fgather})
@@ -63,7 +63,7 @@ def main():
                 names = [n for n, *_ in cq.profile()]
                 if peer and os.environ.get("COLQ_PEER", "1") != "0":
                     assert "peer_mask_publish" in names and "peer_mask_collect+csr_pull" in names, names
-                    if fused and fgather:    # the final gather runs inside the compaction launch
+                    if fused == 1 and fgather:    # the final gather runs inside the cooperative compaction launch
                         assert any(n.startswith("compact_fused") and n.endswith("+gather") for n in names), names
                     else:
                         assert "peer_gather_indices" in names, names

@@ -33,7 +33,8 @@ HOST = dict(lazy_fk=True, residency="host")              # columns stay in pinne
 HOST_NO_PROMOTE = dict(lazy_fk=True, residency="host", options={6: 0})   # COLQ_OPT_PROMOTE=0: always streamed
 DICT = dict(lazy_fk=True, dictionary=True)               # string columns dictionary-encoded: code lookup row scans
 DICT_HOST = dict(lazy_fk=True, dictionary=True, residency="host")
-ALL_VARIANTS = (LAZY, EAGER, NO_DEFER, HOST, HOST_NO_PROMOTE, DICT, DICT_HOST)
+LOOKBACK = dict(lazy_fk=True, options={4: 2})            # COLQ_OPT_FUSED_COMPACT=2: single-pass look-back compaction
+ALL_VARIANTS = (LAZY, EAGER, NO_DEFER, HOST, HOST_NO_PROMOTE, DICT, DICT_HOST, LOOKBACK)
 
 
 def both(engines, build, queries, lazy_modes=(True, False), variants=None):
@@ -278,7 +279,8 @@ def test_deferred_chains_are_planned_into_the_compaction(engines, base_geography
     """The root's lazy FK chains move from the row scan into the fused compaction kernel (COLQ_OPT_DEFER_CHAINS)."""
     new_gpu, _ = engines
     geo = G.build_tables(2, base=base_geography)
-    for opts, want_names in (({}, ["scan_rows<1,0,lazy>", "compact_fused+chains"]), ({5: 0}, ["scan_rows<1,1,lazy>", "compact_fused"])):
+    for opts, want_names in (({}, ["scan_rows<1,0,lazy>", "compact_fused+chains"]), ({4: 2}, ["scan_rows<1,0,lazy>", "compact_lookback+chains"]),
+                             ({5: 0}, ["scan_rows<1,1,lazy>", "compact_fused"])):
         ds = new_gpu(options=opts)
         G.register_geography(ds, geo)
         assert isinstance(ds.execute(G.plymouth_query()), QueryResult.Success)
@@ -355,7 +357,8 @@ def test_host_resident_fk_is_range_checked_on_walked_rows():
 
 
 def test_three_launch_compaction_path_matches(engines, base_geography):
-    """COLQ_OPT_FUSED_COMPACT=0 keeps the popcount / scan / write launches; both paths must agree with the oracle."""
+    """COLQ_OPT_FUSED_COMPACT: 0 = popcount / scan / write launches, 1 = cooperative two-phase kernel (default),
+    2 = single-pass look-back kernel; all three must agree with the oracle."""
     from colq import _ffi
     from colq.engine import DataSystemColq
     _, new_oracle = engines
@@ -363,7 +366,7 @@ def test_three_launch_compaction_path_matches(engines, base_geography):
     oracle = new_oracle()
     G.register_geography(oracle, geo)
     oracle.execute(G.plymouth_query())
-    for fused in (0, 1):
+    for fused in (0, 1, 2):
         ds = DataSystemColq(0, options={_ffi.OPT_FUSED_COMPACT: fused})
         G.register_geography(ds, geo)
         r = ds.execute(G.plymouth_query())
@@ -371,7 +374,8 @@ def test_three_launch_compaction_path_matches(engines, base_geography):
         got = ds.last_query.fetch(want_indices=True)
         assert np.array_equal(got.indices, oracle.last_indices)
         names = [n for n, *_ in ds.last_query.profile()]
-        assert any(n.startswith("compact_fused") for n in names) == bool(fused)
+        assert any(n.startswith("compact_fused") for n in names) == (fused == 1)
+        assert any(n.startswith("compact_lookback") for n in names) == (fused == 2)
         ds.close()
 
 
