@@ -205,6 +205,12 @@ colq_status colq_col_str_host(colq_ctx *ctx, colq_table table, int ordinal, cons
  * how the reference's unchanged lambdas (app/.../Runner.java:236,255-259) run without a CPU row scan.
  * _device adopts an int32 code buffer already in HBM; _host borrows a pinned one (see "Host-resident columns").
  */
+/* the same for an IntegerColumn: int32 codes + the n_dict distinct int32 values; a closed-interval criterion is evaluated
+   over the distinct values, an opaque IntPredicate lambda by the host (colq_query_criteria_i32_accept) */
+colq_status colq_col_i32_dict(colq_ctx *ctx, colq_table table, int ordinal, const int32_t *codes, int64_t n,
+                              const int32_t *dict_values, int64_t n_dict);
+colq_status colq_col_i32_dict_host(colq_ctx *ctx, colq_table table, int ordinal, const int32_t *codes_pinned,
+                                   int64_t capacity_bytes, int64_t n, const int32_t *dict_values, int64_t n_dict);
 colq_status colq_col_str_dict(colq_ctx *ctx, colq_table table, int ordinal, const int32_t *codes, int64_t n,
                               const uint32_t *dict_offsets, const uint8_t *dict_bytes, int64_t n_dict, int64_t n_dict_bytes);
 colq_status colq_col_str_dict_device(colq_ctx *ctx, colq_table table, int ordinal, const void *codes_device, int64_t n,
@@ -256,6 +262,9 @@ colq_status colq_query_criteria_str(colq_query *query, int node, int ordinal, co
    evaluated the predicate on each of the n_dict dictionary entries; bit d of accept_words (BitSet layout) = result for
    entry d.  COLQ_FAILURE at execute when the column is not dictionary-encoded. */
 colq_status colq_query_criteria_str_accept(colq_query *query, int node, int ordinal, const uint64_t *accept_words,
+                                           int64_t n_dict);
+/* addCriteria(new Criteria.IntCriteria(ordinal, <any IntPredicate>)) over a dictionary-encoded int column (DS/Criteria.java:19) */
+colq_status colq_query_criteria_i32_accept(colq_query *query, int node, int ordinal, const uint64_t *accept_words,
                                            int64_t n_dict);
 colq_status colq_query_set_option(colq_query *query, colq_option option, int value);
 

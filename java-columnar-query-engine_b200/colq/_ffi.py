@@ -59,6 +59,8 @@ SIGNATURES = {
     "colq_col_i32_host": (_int, [_p, _i32, _int, _p, _i64, _i64]),
     "colq_col_str_host": (_int, [_p, _i32, _int, _p, _i64, _p, _i64, _i64, _i64]),
     "colq_associate_fk_host": (_int, [_p, _i32, _int, _i32, _int, _p, _i64, _i64]),
+    "colq_col_i32_dict": (_int, [_p, _i32, _int, _p, _i64, _p, _i64]),
+    "colq_col_i32_dict_host": (_int, [_p, _i32, _int, _p, _i64, _i64, _p, _i64]),
     "colq_col_str_dict": (_int, [_p, _i32, _int, _p, _i64, _p, _p, _i64, _i64]),
     "colq_col_str_dict_device": (_int, [_p, _i32, _int, _p, _i64, _p, _p, _i64, _i64]),
     "colq_col_str_dict_host": (_int, [_p, _i32, _int, _p, _i64, _i64, _p, _p, _i64, _i64]),
@@ -74,6 +76,7 @@ SIGNATURES = {
     "colq_query_criteria_i32_range": (_int, [_p, _int, _int, _i32, _i32]),
     "colq_query_criteria_str": (_int, [_p, _int, _int, _int, _p, _i32]),
     "colq_query_criteria_str_accept": (_int, [_p, _int, _int, _p, _i64]),
+    "colq_query_criteria_i32_accept": (_int, [_p, _int, _int, _p, _i64]),
     "colq_query_set_option": (_int, [_p, _int, _int]),
     "colq_execute": (_int, [_p, _p, _p, _i64, _p, _i64, C.POINTER(_i64), C.POINTER(Timing)]),
     "colq_execute_async": (_int, [_p, _p]),

@@ -108,6 +108,10 @@ class ColqQuery:
         w = np.ascontiguousarray(words, dtype=np.uint64)
         self.ctx._check(self.ctx.lib.colq_query_criteria_str_accept(self.handle, node, ordinal, _ptr(w), n_dict))
 
+    def criteria_i32_accept(self, node: int, ordinal: int, words: np.ndarray, n_dict: int) -> None:
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.colq_query_criteria_i32_accept(self.handle, node, ordinal, _ptr(w), n_dict))
+
     def set_option(self, option: int, value: int) -> None:
         self.ctx._check(self.ctx.lib.colq_query_set_option(self.handle, option, value))
 
@@ -251,6 +255,19 @@ class ColqContext:
         o = np.ascontiguousarray(offsets, dtype=np.uint32)
         d = np.ascontiguousarray(data, dtype=np.uint8)
         self._check(self.lib.colq_col_str(self.handle, table, ordinal, _ptr(o), _ptr(d), o.shape[0] - 1, d.shape[0]))
+
+    def col_i32_dict(self, table: int, ordinal: int, codes: np.ndarray, dict_values: np.ndarray) -> None:
+        c = np.ascontiguousarray(codes, dtype=np.int32)
+        d = np.ascontiguousarray(dict_values, dtype=np.int32)
+        self._check(self.lib.colq_col_i32_dict(self.handle, table, ordinal, _ptr(c), c.shape[0], _ptr(d), d.shape[0]))
+
+    def col_i32_dict_host(self, table: int, ordinal: int, codes: np.ndarray, dict_values: np.ndarray,
+                          capacity_bytes: Optional[int] = None, n: Optional[int] = None) -> None:
+        n = codes.shape[0] if n is None else n
+        cap = self._capacity(codes) if capacity_bytes is None else capacity_bytes
+        d = np.ascontiguousarray(dict_values, dtype=np.int32)
+        self._keepalive.append(codes)
+        self._check(self.lib.colq_col_i32_dict_host(self.handle, table, ordinal, _ptr(codes), cap, n, _ptr(d), d.shape[0]))
 
     def col_str_dict(self, table: int, ordinal: int, codes: np.ndarray, dict_offsets: np.ndarray, dict_bytes: np.ndarray) -> None:
         c = np.ascontiguousarray(codes, dtype=np.int32)
@@ -414,7 +431,10 @@ class DataSystemColq(DataSystem):
             raise ValueError(residency)
         self.residency = residency
         # dictionary=True: string columns are stored dictionary-encoded; every string criterion -- structured or an
-        # opaque lambda like the reference's -- is evaluated per DISTINCT value and the GPU row scan tests code bits
+        # opaque lambda like the reference's -- is evaluated per DISTINCT value and the GPU row scan tests code bits.
+        # dictionary="all": integer columns too, so opaque IntPredicate lambdas run as well (worth it when values repeat)
+        if dictionary not in (False, True, "all"):
+            raise ValueError(dictionary)
         self.dictionary = dictionary
         # materialize="device": the result Table's int / string / stored association columns are gathered on the GPU
         # (colq_result_*) instead of the registered table's host-side subset
@@ -468,7 +488,14 @@ class DataSystemColq(DataSystem):
             for ordinal in range(self._uploaded[tid], len(cols)):
                 c = cols[ordinal]
                 host = self.residency == "host" and t.size() > 0
-                if isinstance(c, IntegerColumn):
+                if isinstance(c, IntegerColumn) and self.dictionary == "all":
+                    values, codes = np.unique(c.ints(), return_inverse=True)
+                    self._dict_values[(tid, ordinal)] = [int(v) for v in values]
+                    if host:
+                        self.ctx.col_i32_dict_host(h, ordinal, self.ctx.host_column(codes.astype(np.int32), np.int32), values)
+                    else:
+                        self.ctx.col_i32_dict(h, ordinal, codes.astype(np.int32), values)
+                elif isinstance(c, IntegerColumn):
                     if host:
                         self.ctx.col_i32_host(h, ordinal, self.ctx.host_column(c.ints(), np.int32))
                     else:
@@ -526,6 +553,11 @@ class DataSystemColq(DataSystem):
             for crit in node.get_criteria():
                 if isinstance(crit, Criteria.IntCriteria):
                     p = crit.integer_predicate
+                    values = self._dict_values.get((id(node_table), crit.ordinal)) if node_table is not None else None
+                    if not isinstance(p, IntPredicate) and values is not None and callable(p):
+                        # the reference's opaque IntPredicate (DS/Criteria.java:19): run it once per distinct value
+                        cq.criteria_i32_accept(nid, crit.ordinal, accept_words([bool(p(v)) for v in values]), len(values))
+                        continue
                     if not isinstance(p, IntPredicate):
                         cq.close()
                         return None, ("The criterion on ordinal %d is an opaque IntPredicate lambda; the GPU engine only runs "

@@ -186,6 +186,7 @@ struct Op {
     CompactLookbackParams clook{};
     PeerMaskParams pmask{};
     PeerGatherParams pgather{};
+    bool dict_scan = false;  // K_SCAN_ROWS over the distinct values of a dictionary-encoded int column
     bool gather = false;  // K_COMPACT_FUSED: the peer-memory final gather is fused into this launch
     int publish_op = -1;  // K_PEER_MASK_COLLECT / a csr_pull with a fused collect: index of the matching publish
     // launch shape for scan_str
@@ -435,6 +436,10 @@ colq_status verify(colq_query* q) {
                 case COL_I32:
                     if (c.is_str)
                         return fail(ctx, COLQ_FAILURE, "The column is an integer column but the criterion is not an integer predicate.");
+                    if (c.is_accept && !col.dict)
+                        return fail(ctx, COLQ_FAILURE, "An opaque integer predicate can only run over a dictionary-encoded column (colq_col_i32_dict): it is evaluated per distinct value on the host; there is no CPU fallback for the row scan.");
+                    if (c.is_accept && c.accept_n != col.dict->n)
+                        return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "accept set has %lld entries but the column's dictionary has %lld", (long long)c.accept_n, (long long)col.dict->n);
                     break;
                 case COL_BOOL:
                     return fail(ctx, COLQ_FAILURE, "Boolean columns are not supported yet.");
@@ -671,8 +676,8 @@ struct Planner {
             return o;
         };
         for (const Crit* c : xr.preds) {
-            if (!c->is_str) continue;
             const Column& col = T.cols[c->ordinal];
+            if (!c->is_str && !col.dict) continue;  // plain int columns: fused row scans below
             u32* ob;
             ST(out_buf(&ob));
             if (!col.dict) {
@@ -686,13 +691,26 @@ struct Planner {
             if (!c->is_accept) {
                 u32* dbits;
                 ST(alloc_bitmap(D.n, &dbits));
-                Op ds = make_scan_str(D, D.n, c, nullptr, dbits);
-                ds.name = "scan_str_dictionary";
-                if (D.n == 0) {  // nothing to scan; the mask must still be defined
+                if (D.n == 0 || (!c->is_str && c->lo > c->hi)) {  // nothing can match; the mask must still be defined
                     Op z{};
-                    z.kind = K_ZERO; z.node = xi; z.dst = dbits; z.n_alloc_words = bitmap_alloc_words(0); z.name = "memset_dict_mask";
+                    z.kind = K_ZERO; z.node = xi; z.dst = dbits; z.n_alloc_words = bitmap_alloc_words(D.n); z.name = "memset_dict_mask";
                     q->ops.push_back(z);
-                } else q->ops.push_back(ds);
+                } else if (c->is_str) {
+                    Op ds = make_scan_str(D, D.n, c, nullptr, dbits);
+                    ds.name = "scan_str_dictionary";
+                    q->ops.push_back(ds);
+                } else {  // the closed interval over the DISTINCT values
+                    Op ds{};
+                    ds.kind = K_SCAN_ROWS; ds.node = xi; ds.name = "scan_rows"; ds.np = 1;
+                    ds.rows.n = D.n;
+                    ds.rows.out_bits = dbits;
+                    ds.rows.pred[0].col = (const int32_t*)D.data.ptr;
+                    ds.rows.pred[0].lo = c->lo;
+                    ds.rows.pred[0].span = (u32)((int64_t)c->hi - (int64_t)c->lo);
+                    ds.dict_scan = true;
+                    ds.acct_rows = D.n; ds.acct_bytes = D.n * 4 + bitmap_words(D.n) * 4;
+                    q->ops.push_back(ds);
+                }
                 accept = dbits;
             }
             Op o{};
@@ -720,7 +738,7 @@ struct Planner {
         // ---- int criteria + forward to-one hops: fused row scans, at most 2 predicates and 2 chains per launch
         std::vector<const Crit*> ints;
         for (const Crit* c : xr.preds)
-            if (!c->is_str) ints.push_back(c);
+            if (!c->is_str && !T.cols[c->ordinal].dict) ints.push_back(c);
         size_t pi = 0, gi = 0;
         // The root's criteria-free to-one chains need not stall the streaming scan: when a predicate (or an earlier
         // mask) already thins the rows out, hand the chains to the fused compaction, which walks them for the
@@ -872,6 +890,7 @@ void launch_scan_rows(const Op& o, cudaStream_t s) {
 
 void stage_name(const Op& o, char* out, size_t cap) {
     if (o.kind == K_SCAN_CODES) snprintf(out, cap, "scan_codes%s", o.codes.push.fk ? "+push" : "");
+    else if (o.kind == K_SCAN_ROWS && o.dict_scan) snprintf(out, cap, "scan_rows_dictionary");
     else if (o.kind == K_SCAN_ROWS) snprintf(out, cap, "scan_rows<%d,%d,%s>%s", o.np, o.ng, o.eager ? "eager" : "lazy", o.rows.push.fk ? "+push" : "");
     else if (o.kind == K_SCAN_STR) snprintf(out, cap, "%s<op%d>%s", o.name, o.str.op, o.str.push.fk ? "+push" : "");
     else snprintf(out, cap, "%s", o.name);
@@ -1798,6 +1817,58 @@ colq_status colq_col_str_dict_device(colq_ctx* ctx, colq_table table, int ordina
     return st;
 }
 
+// IntegerColumn stored dictionary-encoded: codes + the DISTINCT int32 values
+static colq_status finish_dict_i32(colq_ctx* ctx, Column* c, int64_t n, const int32_t* dict_values, int64_t n_dict, bool check_codes) {
+    if (n_dict < 0 || n_dict > INT32_MAX) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "dictionary size %lld outside [0, 2^31)", (long long)n_dict);
+    std::unique_ptr<Column> d(new Column());
+    ST(upload(ctx, d->data, dict_values, (size_t)n_dict * 4, (size_t)round_up(n_dict * 4 + 16, 16)));
+    d->kind = COL_I32; d->n = n_dict;
+    if (check_codes && n > 0) {
+        DevBuf mm;
+        ST(dev_alloc(ctx, mm, 8));
+        int32_t init[2] = {INT32_MAX, INT32_MIN};
+        CU(ctx, cudaMemcpyAsync(mm.ptr, init, 8, cudaMemcpyHostToDevice, ctx->stream));
+        fk_minmax_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>((const int32_t*)c->data.ptr, n, (int32_t*)mm.ptr, (int32_t*)mm.ptr + 1);
+        CU(ctx, cudaGetLastError());
+        int32_t got[2];
+        CU(ctx, cudaMemcpyAsync(got, mm.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (got[0] < 0 || got[1] >= n_dict)
+            return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "dictionary code outside [0, %lld) (min %d, max %d)", (long long)n_dict, got[0], got[1]);
+    }
+    c->kind = COL_I32; c->n = n;
+    c->dict = std::move(d);
+    return COLQ_OK;
+}
+
+colq_status colq_col_i32_dict(colq_ctx* ctx, colq_table table, int ordinal, const int32_t* codes, int64_t n, const int32_t* dict_values,
+                              int64_t n_dict) {
+    if (!ctx || (!codes && n > 0) || (!dict_values && n_dict > 0)) return COLQ_THROW_NULL;
+    CU(ctx, cudaSetDevice(ctx->device));
+    Column* c;
+    ST(slot_for(ctx, table, ordinal, n, &c));
+    ST(upload(ctx, c->data, codes, (size_t)n * 4, (size_t)round_up(n * 4 + 16, 16)));
+    colq_status st = finish_dict_i32(ctx, c, n, dict_values, n_dict, true);
+    if (st != COLQ_OK) *c = Column();
+    return st;
+}
+
+colq_status colq_col_i32_dict_host(colq_ctx* ctx, colq_table table, int ordinal, const int32_t* codes_pinned, int64_t capacity_bytes,
+                                   int64_t n, const int32_t* dict_values, int64_t n_dict) {
+    if (!ctx || !codes_pinned || (!dict_values && n_dict > 0)) return COLQ_THROW_NULL;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (capacity_bytes < round_up(n * 4, 16)) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "host column buffer must be padded to a multiple of 16 bytes");
+    const void* alias;
+    ST(pinned_alias(ctx, codes_pinned, "the dictionary-code buffer", &alias));
+    Column* c;
+    ST(slot_for(ctx, table, ordinal, n, &c));
+    c->data.ptr = const_cast<void*>(alias); c->data.bytes = (size_t)capacity_bytes; c->data.owned = false;
+    colq_status st = finish_dict_i32(ctx, c, n, dict_values, n_dict, false);
+    if (st != COLQ_OK) *c = Column();
+    else c->host_resident = true;
+    return st;
+}
+
 colq_status colq_col_str_dict_host(colq_ctx* ctx, colq_table table, int ordinal, const int32_t* codes_pinned, int64_t capacity_bytes,
                                    int64_t n, const uint32_t* dict_offsets, const uint8_t* dict_bytes, int64_t n_dict, int64_t n_dict_bytes) {
     if (!ctx || !codes_pinned) return COLQ_THROW_NULL;
@@ -2116,6 +2187,12 @@ colq_status colq_query_criteria_str_accept(colq_query* q, int node, int ordinal,
     return COLQ_OK;
 }
 
+colq_status colq_query_criteria_i32_accept(colq_query* q, int node, int ordinal, const uint64_t* accept_words, int64_t n_dict) {
+    colq_status st = colq_query_criteria_str_accept(q, node, ordinal, accept_words, n_dict);
+    if (st == COLQ_OK) q->nodes[node].crit.back().is_str = false;
+    return st;
+}
+
 colq_status colq_query_set_option(colq_query* q, colq_option option, int value) {
     if (!q) return COLQ_THROW_NULL;
     switch (option) {
@@ -2245,6 +2322,19 @@ colq_status colq_result_i32(colq_ctx* ctx, colq_query* q, int ordinal, int32_t* 
     const bool to_one = c->kind == COL_ASSOC && c->forward && c->is_fk;
     if (c->kind != COL_I32 && !to_one)
         return fail(ctx, COLQ_FAILURE, "column %d is neither an integer column nor a stored to-one association column", ordinal);
+    if (c->kind == COL_I32 && c->dict) {  // decode: codes at the matching rows -> distinct values
+        const int64_t n = q->local_count;
+        if (out_count) *out_count = n;
+        if (n == 0) return COLQ_OK;
+        if (!out_values || capacity < n) return fail(ctx, COLQ_ERR_CAPACITY, "result capacity %lld < %lld rows", (long long)capacity, (long long)n);
+        if (q->mat_a.bytes < (size_t)n * 4) ST(dev_alloc(ctx, q->mat_a, (size_t)n * 4));
+        gather_decode_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>((const int32_t*)c->data.ptr, (const int32_t*)c->dict->data.ptr,
+                                                                                          q->d_idx, T->row_base, n, (int32_t*)q->mat_a.ptr);
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaMemcpyAsync(out_values, q->mat_a.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return COLQ_OK;
+    }
     return result_fixed<int32_t>(ctx, q, *T, c->data.ptr, out_values, capacity, out_count);
 }
 

@@ -1633,6 +1633,13 @@ __global__ void __launch_bounds__(256) gather_values_kernel(const T* col, const 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = col[(int64_t)idx[i] - row_base];
 }
 
+// dictionary-encoded int column: row -> code -> distinct value
+__global__ void __launch_bounds__(256) gather_decode_kernel(const int32_t* codes, const int32_t* dict, const int32_t* idx, int64_t row_base,
+                                                           int64_t n, int32_t* out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = dict[codes[(int64_t)idx[i] - row_base]];
+}
+
 // variable-length columns: element e of the source spans src_off[e] .. src_off[e + 1] (OffT = u32 for strings, int64
 // for CSR associations); `codes` (nullable) maps a row to its dictionary entry
 template <typename OffT>

@@ -34,7 +34,9 @@ HOST_NO_PROMOTE = dict(lazy_fk=True, residency="host", options={6: 0})   # COLQ_
 DICT = dict(lazy_fk=True, dictionary=True)               # string columns dictionary-encoded: code lookup row scans
 DICT_HOST = dict(lazy_fk=True, dictionary=True, residency="host")
 LOOKBACK = dict(lazy_fk=True, options={4: 2})            # COLQ_OPT_FUSED_COMPACT=2: single-pass look-back compaction
-ALL_VARIANTS = (LAZY, EAGER, NO_DEFER, HOST, HOST_NO_PROMOTE, DICT, DICT_HOST, LOOKBACK)
+DICT_ALL = dict(lazy_fk=True, dictionary="all")          # integer columns dictionary-encoded too
+DICT_ALL_HOST = dict(lazy_fk=True, dictionary="all", residency="host")
+ALL_VARIANTS = (LAZY, EAGER, NO_DEFER, HOST, HOST_NO_PROMOTE, DICT, DICT_HOST, LOOKBACK, DICT_ALL, DICT_ALL_HOST)
 
 
 def both(engines, build, queries, lazy_modes=(True, False), variants=None):
@@ -81,7 +83,7 @@ def test_tck(engines, case, lazy):
     case(lambda: new_gpu(lazy))
 
 
-@pytest.mark.parametrize("variant", [HOST, DICT, DICT_HOST], ids=["host", "dict", "dict_host"])
+@pytest.mark.parametrize("variant", [HOST, DICT, DICT_HOST, DICT_ALL, DICT_ALL_HOST], ids=["host", "dict", "dict_host", "dict_all", "dict_all_host"])
 @pytest.mark.parametrize("case", tck.REFERENCE_TESTS + tck.FAILURE_TESTS + tck.EXTRA_TESTS, ids=lambda f: f.__name__)
 def test_tck_other_physical_layouts(engines, case, variant):
     """The reference's QueryTest + failure cases again, with host-resident and dictionary-encoded columns."""
@@ -138,7 +140,7 @@ def test_int_range_scan_sizes(engines, n):
     def q5():
         return Query("t")
 
-    both(engines, build, [q1, q2, q3, q4, q5], variants=(LAZY, HOST))
+    both(engines, build, [q1, q2, q3, q4, q5], variants=(LAZY, HOST, DICT_ALL) if n < 100_000 else (LAZY, HOST, DICT_ALL, DICT_ALL_HOST))
 
 
 # ------------------------------------------------------------------ string scans: every operator, ragged lengths
@@ -435,6 +437,26 @@ def test_reference_lambdas_run_unchanged_over_dictionary_columns(engines, base_g
         n.add_criteria(Criteria.StringCriteria(1, lambda s: "South" in s))
         n.create_child(3).add_criteria(Criteria.StringCriteria(1, lambda s: "North" in s))
         return q
+
+    def plymouth_all_lambdas():   # Runner.java:230-236 verbatim: i -> i >= 10_000 && i < 10_100 and "PLYMOUTH"::equals
+        q = Query("zips")
+        q.root_node.add_criteria(Criteria.IntCriteria(1, lambda i: i >= 10_000 and i < 10_100))
+        q.root_node.create_child(2).create_child(1).create_child(3).create_child(2).add_criteria(
+            Criteria.StringCriteria(0, lambda s: s == "PLYMOUTH"))
+        return q
+
+    for variant in (DICT_ALL, DICT_ALL_HOST):   # every lambda of the app runs unchanged
+        ds = new_gpu(**variant)
+        G.register_geography(ds, geo)
+        r = ds.execute(plymouth_all_lambdas())
+        assert isinstance(r, QueryResult.Success), getattr(r, "message", None)
+        assert np.array_equal(ds.last_query.fetch(want_indices=True).indices, want_ply)
+        ds.close()
+    ds = new_gpu(**DICT)                        # strings only: the opaque IntPredicate is still a Failure
+    G.register_geography(ds, geo)
+    r = ds.execute(plymouth_all_lambdas())
+    assert isinstance(r, QueryResult.Failure) and "opaque IntPredicate" in r.message
+    ds.close()
 
     for variant in (DICT, DICT_HOST):
         ds = new_gpu(**variant)
