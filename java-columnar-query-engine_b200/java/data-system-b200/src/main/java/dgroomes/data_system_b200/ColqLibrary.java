@@ -54,6 +54,9 @@ final class ColqLibrary {
     // dictionary-encoded string columns and opaque Predicate<String> criteria evaluated per distinct value
     static final MethodHandle colq_col_str_dict = h("colq_col_str_dict", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG);
     static final MethodHandle colq_col_str_dict_host = h("colq_col_str_dict_host", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS, JAVA_LONG, JAVA_LONG);
+    static final MethodHandle colq_col_i32_dict = h("colq_col_i32_dict", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG);
+    static final MethodHandle colq_col_i32_dict_host = h("colq_col_i32_dict_host", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS, JAVA_LONG);
+    static final MethodHandle colq_query_criteria_i32_accept = h("colq_query_criteria_i32_accept", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG);
     static final MethodHandle colq_query_criteria_str_accept = h("colq_query_criteria_str_accept", JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG);
     static final MethodHandle colq_execute = h("colq_execute", JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS);
 

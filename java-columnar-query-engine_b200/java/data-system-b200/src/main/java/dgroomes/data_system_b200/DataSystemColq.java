@@ -57,11 +57,15 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
      * values, and ANY Predicate&lt;String&gt; -- including the app's unchanged lambdas (Runner.java:236,255-259) -- is
      * evaluated once per distinct value here and applied on the GPU as a code lookup.
      */
-    public record Layout(boolean hostResident, boolean dictionary) {}
+    public record Layout(boolean hostResident, boolean dictionary) {
+        /** Everything the unchanged app needs: pinned off-heap columns, string AND integer columns dictionary-encoded. */
+        public static Layout forUnchangedLambdas() { return new Layout(true, true); }
+    }
 
     private final Layout layout;
     private final java.util.ArrayList<MemorySegment> hostBuffers = new java.util.ArrayList<>();
     private final IdentityHashMap<Table, Map<Integer, String[]>> dictionaryValues = new IdentityHashMap<>();
+    private final IdentityHashMap<Table, Map<Integer, int[]>> intDictionaryValues = new IdentityHashMap<>();
 
     public DataSystemColq() {
         this(0, new Layout(false, false));
@@ -134,6 +138,15 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
             for (Criteria c : p.node().getCriteria()) {
                 switch (c) {
                     case Criteria.IntCriteria(int ordinal, var pred) -> {
+                        int[] distinctInts = p.table() == null ? null : intDictionaryValues.getOrDefault(p.table(), Map.of()).get(ordinal);
+                        if (!(pred instanceof Predicates.IntRange) && distinctInts != null) {
+                            // an opaque IntPredicate (Runner.java:231): run it once per DISTINCT value, ship the accept set
+                            MemorySegment accept = call.allocate(JAVA_LONG, distinctInts.length / 64 + 1);
+                            for (int d = 0; d < distinctInts.length; d++)
+                                if (pred.test(distinctInts[d])) accept.setAtIndex(JAVA_LONG, d >> 6, accept.getAtIndex(JAVA_LONG, d >> 6) | (1L << (d & 63)));
+                            check((int) colq_query_criteria_i32_accept.invokeExact(q, p.id(), ordinal, accept, (long) distinctInts.length));
+                            continue;
+                        }
                         if (!(pred instanceof Predicates.IntRange(int lo, int hi)))
                             return "The criterion on ordinal %d is an opaque IntPredicate lambda; the GPU engine only runs structured predicates (dgroomes.data_system_b200.Predicates) and has no CPU fallback.".formatted(ordinal);
                         check((int) colq_query_criteria_i32_range.invokeExact(q, p.id(), ordinal, lo, hi));
@@ -193,6 +206,23 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
             List<? extends Column> cols = t.columns();
             for (int ordinal = uploadedColumns.get(t); ordinal < cols.size(); ordinal++) {
                 switch (cols.get(ordinal)) {
+                    case InMemoryColumn.IntegerColumn(int[] ints) when layout.dictionary() -> {
+                        int[] distinct = java.util.Arrays.stream(ints).distinct().sorted().toArray();
+                        int[] codes = new int[ints.length];
+                        for (int i = 0; i < ints.length; i++) codes[i] = java.util.Arrays.binarySearch(distinct, ints[i]);
+                        intDictionaryValues.computeIfAbsent(t, k -> new HashMap<>()).put(ordinal, distinct);
+                        MemorySegment dict = call.allocate(JAVA_INT, Math.max(distinct.length, 1));
+                        MemorySegment.copy(distinct, 0, dict, JAVA_INT, 0, distinct.length);
+                        if (layout.hostResident() && codes.length > 0) {
+                            MemorySegment seg = pinned(4L * codes.length);
+                            MemorySegment.copy(codes, 0, seg, JAVA_INT, 0, codes.length);
+                            check((int) colq_col_i32_dict_host.invokeExact(ctx, h, ordinal, seg, seg.byteSize(), (long) codes.length, dict, (long) distinct.length));
+                        } else {
+                            MemorySegment seg = call.allocate(JAVA_INT, Math.max(codes.length, 1));
+                            MemorySegment.copy(codes, 0, seg, JAVA_INT, 0, codes.length);
+                            check((int) colq_col_i32_dict.invokeExact(ctx, h, ordinal, seg, (long) codes.length, dict, (long) distinct.length));
+                        }
+                    }
                     case InMemoryColumn.IntegerColumn(int[] ints) -> {
                         if (layout.hostResident() && ints.length > 0) {
                             MemorySegment seg = pinned(4L * ints.length);
