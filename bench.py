@@ -375,7 +375,7 @@ def run_colq(args, rank, local_rank, world):
 
         def e2e_step(upload: bool):
             """upload=False (the product's host path): the big columns stay in the pinned host buffers and are
-            registered in place (colq_*_host); the query's kernels stream what they touch over PCIe.
+            registered in place (colq_*_host); the query moves only what it touches over PCIe.
             upload=True: every column is copied to HBM first (colq_col_* / colq_associate_fk), then the query runs."""
             states = ctx.table_create(51, _ffi.REPLICATED, 0)
             cities = ctx.table_create(nc, place, geo.u0 * N_CITIES)
@@ -426,11 +426,11 @@ def run_colq(args, rank, local_rank, world):
                "h2d_bytes_per_step": int(r3.timing.h2d_bytes) + small_h2d,
                "d2h_bytes_per_step": int(r3.timing.d2h_bytes), "ms_per_step": ms_e2e, "steps": args.e2e_steps,
                "what": "per step, per rank: colq_table_create, the big columns registered IN PLACE in pinned host memory "
-                       "(colq_col_*_host / colq_associate_fk_host: no bulk copy), colq_execute -- its kernels stream the "
-                       "scanned columns (ZIP population, city-name offsets + bytes) over PCIe and read single sectors of the "
-                       "lazily walked FK columns -- matched indices read back, colq_table_destroy. h2d_bytes_per_step counts "
-                       "the fully streamed columns only; the never-touched ZIP-code column and the sparsely walked FK columns "
-                       "(3.4 GB) do not cross PCIe"}
+                       "(colq_col_*_host / colq_associate_fk_host: nothing copied at registration), colq_execute -- the columns "
+                       "the query scans in full (ZIP population, city-name offsets + bytes) are brought to HBM by the copy engine "
+                       "ahead of their kernels, the lazily walked FK columns are read in place, single sectors over PCIe -- "
+                       "matched indices read back, colq_table_destroy. h2d_bytes_per_step counts the fully scanned columns; the "
+                       "never-touched ZIP-code column and all but ~0.5 M sectors of the FK columns (3.4 GB) do not cross PCIe"}
         ms_up, r4 = time_e2e(upload=True)
         e2e_upload = {"value": rows / (ms_up * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": int(h2d),
                       "d2h_bytes_per_step": int(r4.timing.d2h_bytes), "ms_per_step": ms_up, "steps": args.e2e_steps,

@@ -94,8 +94,12 @@ typedef enum colq_option {
        survived the root's predicates (the row scan stays a pure coalesced stream); 0: inside the row scan.
        Needs COLQ_OPT_LAZY_FK and COLQ_OPT_FUSED_COMPACT >= 1. */
     COLQ_OPT_DEFER_CHAINS = 5,
-    /* 1 (default): the first scan that streams a host-resident column (colq_*_host) over PCIe also leaves a copy in
-       HBM, which later queries use; 0: keep streaming from pinned host memory every time */
+    /* what happens when a launch is about to read a host-resident column (colq_*_host) IN FULL:
+       2 (default): the copy engine brings that column to HBM first (cudaMemcpyAsync on the query's stream), the
+          launch and all later queries read the HBM copy;
+       1: the scan kernel reads the pinned host memory in place and writes the HBM copy as a side effect;
+       0: always read in place, never keep a copy (tables larger than HBM).
+       Sparsely walked columns (lazy FK chains) are read in place in every mode. */
     COLQ_OPT_PROMOTE = 6,
     /* 1: the multi-GPU final gather runs as two more phases of the COOPERATIVE compaction launch instead of the two
        peer_gather launches (default 0: measured slower on 2-8 B200s, kept selectable and parity-tested) */

@@ -29,14 +29,15 @@ def engines():
 
 LAZY, EAGER = dict(lazy_fk=True), dict(lazy_fk=False)
 NO_DEFER = dict(lazy_fk=True, options={5: 0})            # COLQ_OPT_DEFER_CHAINS=0: FK chains inside the row scan
-HOST = dict(lazy_fk=True, residency="host")              # columns stay in pinned host memory, promoted on first scan
-HOST_NO_PROMOTE = dict(lazy_fk=True, residency="host", options={6: 0})   # COLQ_OPT_PROMOTE=0: always streamed
+HOST = dict(lazy_fk=True, residency="host")              # columns stay in pinned host memory; DMA upload at the first full scan
+HOST_NO_PROMOTE = dict(lazy_fk=True, residency="host", options={6: 0})   # COLQ_OPT_PROMOTE=0: always read in place
+HOST_KERNEL_PROMOTE = dict(lazy_fk=True, residency="host", options={6: 1})   # =1: the scan kernel writes the HBM copy
 DICT = dict(lazy_fk=True, dictionary=True)               # string columns dictionary-encoded: code lookup row scans
 DICT_HOST = dict(lazy_fk=True, dictionary=True, residency="host")
 LOOKBACK = dict(lazy_fk=True, options={4: 2})            # COLQ_OPT_FUSED_COMPACT=2: single-pass look-back compaction
 DICT_ALL = dict(lazy_fk=True, dictionary="all")          # integer columns dictionary-encoded too
 DICT_ALL_HOST = dict(lazy_fk=True, dictionary="all", residency="host")
-ALL_VARIANTS = (LAZY, EAGER, NO_DEFER, HOST, HOST_NO_PROMOTE, DICT, DICT_HOST, LOOKBACK, DICT_ALL, DICT_ALL_HOST)
+ALL_VARIANTS = (LAZY, EAGER, NO_DEFER, HOST, HOST_NO_PROMOTE, HOST_KERNEL_PROMOTE, DICT, DICT_HOST, LOOKBACK, DICT_ALL, DICT_ALL_HOST)
 
 
 def both(engines, build, queries, lazy_modes=(True, False), variants=None):
@@ -173,7 +174,7 @@ def test_string_ops(engines, n, max_len):
                 q.root_node.add_criteria(Criteria.StringCriteria(0, StringPredicate(op, nd)))
                 return q
             queries.append(mk)
-    both(engines, build, queries, variants=(LAZY, HOST, DICT, DICT_HOST) if n in (1025, 3000, 70_000) else (LAZY, DICT))
+    both(engines, build, queries, variants=(LAZY, HOST, HOST_KERNEL_PROMOTE, DICT, DICT_HOST) if n in (1025, 3000, 70_000) else (LAZY, DICT))
 
 
 def test_two_string_criteria_and_int_on_one_node(engines):
@@ -192,7 +193,7 @@ def test_two_string_criteria_and_int_on_one_node(engines):
         qq.root_node.add_criteria(Criteria.StringCriteria(0, StringPredicate(2, "xz")))
         return qq
 
-    both(engines, build, [q], variants=(LAZY, HOST, HOST_NO_PROMOTE, DICT, DICT_HOST))
+    both(engines, build, [q], variants=(LAZY, HOST, HOST_NO_PROMOTE, HOST_KERNEL_PROMOTE, DICT, DICT_HOST))
 
 
 # ------------------------------------------------------------------ associations: random graphs, forward and reverse hops
@@ -293,8 +294,8 @@ def test_deferred_chains_are_planned_into_the_compaction(engines, base_geography
 
 
 def test_host_resident_columns_stream_then_promote(base_geography):
-    """colq_*_host: nothing is copied at registration; the first query streams the scanned columns over PCIe (h2d_bytes
-    says how much) and promotes them, the second query moves nothing."""
+    """colq_*_host: nothing is copied at registration; the first query moves exactly the columns it scans in full over
+    PCIe (h2d_bytes says how much) and leaves them in HBM, the second query moves nothing -- in both promotion modes."""
     from colq.engine import DataSystemColq
     from oracle_system import OracleDataSystem
     U = 7
@@ -302,19 +303,21 @@ def test_host_resident_columns_stream_then_promote(base_geography):
     oracle = OracleDataSystem()
     G.register_geography(oracle, geo)
     oracle.execute(G.plymouth_query())
-    ds = DataSystemColq(0, residency="host")
-    G.register_geography(ds, geo)
-    streamed = []
-    for _ in range(3):
-        r = ds.execute(G.plymouth_query())
-        assert isinstance(r, QueryResult.Success)
-        assert np.array_equal(ds.last_query.fetch(want_indices=True).indices, oracle.last_indices)
-        streamed.append(int(ds.last_timing.h2d_bytes))
     nz, nc = U * G.N_ZIPS, U * G.N_CITIES
     name_bytes = int(np.asarray(base_geography["city_name_bytes"]).shape[0]) * U
-    assert streamed[0] == 4 * nz + 4 * (nc + 1) + name_bytes     # population + name offsets + name bytes, nothing else
-    assert streamed[1] == 0 and streamed[2] == 0                  # promoted by the first scan
-    ds.close()
+    for promote in (2, 1, 0):
+        ds = DataSystemColq(0, residency="host", options={6: promote})
+        G.register_geography(ds, geo)
+        streamed = []
+        for _ in range(3):
+            r = ds.execute(G.plymouth_query())
+            assert isinstance(r, QueryResult.Success)
+            assert np.array_equal(ds.last_query.fetch(want_indices=True).indices, oracle.last_indices)
+            streamed.append(int(ds.last_timing.h2d_bytes))
+        touched = 4 * nz + 4 * (nc + 1) + name_bytes     # population + name offsets + name bytes, nothing else
+        assert streamed[0] == touched
+        assert streamed[1:] == ([0, 0] if promote else [touched, touched])
+        ds.close()
     oracle.close()
 
 
