@@ -410,7 +410,8 @@ def run_colq(args, rank, local_rank, world):
             return r
 
         def time_e2e(upload: bool):
-            r3 = e2e_step(upload)  # warm-up (also first-touch of the pinned pages)
+            for _ in range(2):  # warm-up: first touch of the pinned pages, and the device-buffer cache reaches its fixed point
+                r3 = e2e_step(upload)
             assert r3.count == 31 * U and np.array_equal(r3.indices.astype(np.int64), want)
             barrier()
             t0 = time.perf_counter()
