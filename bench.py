@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-small-queries", action="store_true", help="skip the 1-universe latency measurements (keeps ncu launch lists clean)")
     ap.add_argument("--eager", action="store_true", help="disable the lazy FK chain (materialise every node)")
+    ap.add_argument("--weak", action="store_true",
+                    help="weak-scaling variant (not the driver's line): --universes per GPU instead of in total, i.e. every rank "
+                         "holds the N=1 workload; reported with scaling=weak")
     ap.add_argument("--dict-names", action="store_true",
                     help="SURVEY 8f variant, not the headline: the city-name column is dictionary-encoded (int32 codes + 16.6k distinct "
                          "names); the name predicate runs over the dictionary and the row scan tests code bits. Implies --no-e2e.")
@@ -258,7 +261,7 @@ def run_colq(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    U = args.universes
+    U = args.universes * (world if args.weak else 1)
     base = G.load_base()
     geo = build_geography_on_device(ctx, U, world, rank, base=base, device=dev, sharded=world > 1, dict_names=args.dict_names)
     if args.dict_names:
@@ -455,7 +458,7 @@ def run_colq(args, rank, local_rank, world):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "config": dict(workload_config(U, world, not args.eager), **({"city_names": "dictionary-encoded"} if args.dict_names else {})),
             "hbm_gbs_query_algorithmic": query_gbs, "query_algorithmic_bytes": algo_total,
             "roofline": roofline, "stages_ms": {k: round(v["ms"], 5) for k, v in stages.items()},

@@ -1734,6 +1734,10 @@ colq_status colq_table_create(colq_ctx* ctx, int64_t n_rows, colq_placement plac
     if (!ctx || !out) return COLQ_THROW_NULL;
     if (n_rows < 0 || n_rows > INT32_MAX) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "row count %lld outside [0, 2^31)", (long long)n_rows);
     if (placement != COLQ_REPLICATED && placement != COLQ_SHARDED) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "bad placement %d", (int)placement);
+    // result rows are int32 (a Java int / BitSet index): the GLOBAL index of a sharded table's last row must fit too
+    if (global_row_base < 0 || global_row_base + n_rows > (int64_t)INT32_MAX)
+        return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "global rows [%lld, %lld) exceed the int32 row-index range of the result", (long long)global_row_base,
+                    (long long)(global_row_base + n_rows));
     Table t;
     t.n_rows = n_rows; t.placement = placement; t.row_base = global_row_base;
     ctx->tables.push_back(std::move(t));

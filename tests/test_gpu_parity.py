@@ -644,3 +644,14 @@ def test_result_abi_sizes_and_errors():
         q.result_csr(1)
     q.close()
     ctx.close()
+
+
+def test_global_row_indices_must_fit_int32():
+    """Result rows are int32 (Java int): a shard whose global row range crosses 2^31 is refused at table creation."""
+    from colq import _ffi
+    from colq.engine import ColqContext
+    ctx = ColqContext(0)
+    ctx.table_create(1000, _ffi.SHARDED, 2 ** 31 - 1 - 1000)
+    with pytest.raises(ValueError, match="int32 row-index range"):
+        ctx.table_create(1000, _ffi.SHARDED, 2 ** 31 - 1000)
+    ctx.close()
