@@ -6,10 +6,14 @@
 // but evaluates the node tree bottom-up in ONE post-order pass (the reference's repeated leaf-to-root walks reach
 // the same fixed point because every step is a monotone AND), and fuses work across nodes:
 //   * a hop through a forward to-one column is PULLED (parent row tests its child's bit) inside the parent's scan,
-//   * chains of criteria-free to-one hops are walked lazily only for rows that survived the parent's predicates,
+//   * chains of criteria-free to-one hops are walked lazily only for rows that survived the parent's predicates -- for
+//     the root node inside the compaction kernel, so that the root's row scan stays a pure coalesced stream,
 //   * a hop through a reverse column is PUSHED by the epilogue of the child's own scan kernel,
 //   * in a multi-GPU communicator a push from a sharded child into a replicated parent is followed by the only
-//     data-path collective: an all-gather of the (tiny) parent mask that the next kernel ORs together.
+//     data-path exchange besides the final gather: an OR of the (tiny) parent mask over NVLink peer memory, split
+//     into publish / collect halves with the root's independent predicate scan scheduled between them.
+// Columns may live in HBM or stay in pinned host memory (colq_*_host; moved on first touch only), and string / int
+// columns may be dictionary-encoded (predicates evaluated per distinct value, rows tested by code lookup).
 // There is no CPU fallback anywhere in this file.
 //
 // E = data-system-serial-indices-arrays/src/main/java/dgroomes/data_system_serial_indices_arrays
