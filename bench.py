@@ -499,18 +499,43 @@ def small_query_latency(base):
     return out
 
 
-def run_single_table(args):
-    """int_scan / str_eq: one column, one predicate, one GPU (BASELINE configs[1] and configs[4])."""
+def run_single_table(args, rank=0, local_rank=0, world=1):
+    """int_scan / str_eq: one column, one predicate (BASELINE configs[1] and configs[4]).  str_eq also runs sharded by
+    row range over N ranks (configs[4] as written: 500 M rows across 8 B200) with the final index gather."""
     import torch
+    import torch.distributed as dist
     from colq import _ffi
     from colq import geography as G
     from colq.device_data import build_int_scan_on_device, build_name_scan_on_device
     from colq.engine import ColqContext
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
-    ctx = ColqContext(0)
+    ctx = ColqContext(local_rank)
     ctx.set_stream(stream.cuda_stream)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), world, rank)
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        return int(round(t.item()))
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     base = G.load_base()
     if args.workload == "int_scan":
         n = args.rows or 1_000_000_000
@@ -524,28 +549,35 @@ def run_single_table(args):
         metric = "int_range_scan_rows_per_sec"
         algo = lambda m: 4 * n + 4 * m  # noqa: E731  
     else:
-        n = args.rows or 62_500_000
-        _t, off32, data, idx, total = build_name_scan_on_device(ctx, n, base=base)
+        n = args.rows or (62_500_000 if world == 1 else 500_000_000)   # total rows; each rank holds a contiguous range
+        lo, hi = n * rank // world, n * (rank + 1) // world
+        _t, off32, data, idx, total = build_name_scan_on_device(ctx, hi - lo, base=base, start=lo,
+                                                                placement=_ffi.SHARDED if world > 1 else _ffi.REPLICATED)
         q = ctx.query("names")
         q.criteria_str(0, 0, 0, b"PLYMOUTH")
         names = [bytes(base["city_name_bytes"][base["city_name_offsets"][i]:base["city_name_offsets"][i + 1]]) for i in range(G.N_CITIES)]
         ply = torch.tensor([i for i, s_ in enumerate(names) if s_ == b"PLYMOUTH"], device=dev, dtype=torch.int32)
-        expect = int(torch.isin(idx, ply).sum().item())
-        workload = {"workload": "city_name_equality_scan", "source": "BASELINE.json configs[4] (one GPU's shard of 500M rows)",
-                    "rows": n, "name_bytes": total, "generator": "cityNames[splitmix64(42, i) mod 25701]"}
+        expect = allsum(int(torch.isin(idx, ply).sum().item()))
+        total = allsum(total)
+        workload = {"workload": "city_name_equality_scan",
+                    "source": "BASELINE.json configs[4]" + (" (one GPU's shard of 500M rows)" if world == 1 and n == 62_500_000 else ""),
+                    "rows": n, "name_bytes": total, "generator": "cityNames[splitmix64(42, i) mod 25701]",
+                    "sharding": f"contiguous row ranges over {world} rank(s), final index gather over NVLink peer memory" if world > 1 else "none"}
         metric = "string_equality_scan_rows_per_sec"
         algo = lambda m: 4 * (n + 1) + total + n // 8  # noqa: E731  
     res = q.execute(want_indices=True, index_capacity=max(expect, 1) + 16)
-    if res.count != expect:
-        raise SystemExit(f"GPU count {res.count} != independent expectation {expect}")
+    if res.count != expect or (res.indices.shape[0] > 1 and not np.all(np.diff(res.indices.astype(np.int64)) > 0)):
+        raise SystemExit(f"GPU count {res.count} != independent expectation {expect} (or indices not ascending)")
     launches = int(res.timing.kernel_launches)
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(local_rank)
     q.set_option(_ffi.OPT_PROFILE, 2)
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
             q.execute_async()
         q.profile_hot()
         torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler.start()
         e0.record(stream)
@@ -554,7 +586,7 @@ def run_single_table(args):
         e1.record(stream)
         stream.synchronize()
         clocks = sampler.stop()
-    ms_step = e0.elapsed_time(e1) / args.steps
+    ms_step = allmax(e0.elapsed_time(e1)) / args.steps
     hot_name, hot_ms, _hot_rows, hot_bytes, hot_samples = q.profile_hot()
     q.set_option(_ffi.OPT_PROFILE, 1)
     acc = {}
@@ -569,8 +601,8 @@ def run_single_table(args):
     peak, peak_src = measured_peak()
     achieved = hot_bytes / (hot_ms * 1e-3) / 1e9
     line = {
-        "metric": metric, "value": n / (ms_step * 1e-3), "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": metric, "value": n / (ms_step * 1e-3), "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "int32" if args.workload == "int_scan" else "u8", "data": "synthetic",
         "config": dict(workload, l2_policy="inputs larger than L2 (no flush)", matches=expect),
         "hbm_gbs_query_algorithmic": algo(expect) / (ms_step * 1e-3) / 1e9, "query_algorithmic_bytes": algo(expect),
@@ -581,8 +613,11 @@ def run_single_table(args):
         "stages_ms": {k: round(v["ms"], 5) for k, v in stages.items()},
         "cpu_baseline": None, "e2e": None, "clocks": clocks, "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
     }
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -594,9 +629,9 @@ def main():
         run_reference(args, rank, world)
         return
     if args.workload != "plymouth":
-        if world != 1:
-            raise SystemExit("--workload int_scan / str_eq are single-GPU kernel benchmarks")
-        run_single_table(args)
+        if world != 1 and args.workload != "str_eq":
+            raise SystemExit("--workload int_scan is a single-GPU kernel benchmark")
+        run_single_table(args, rank, local_rank, world)
         return
     if world != args.gpus:
         if args.gpus == 1 and world == 1:

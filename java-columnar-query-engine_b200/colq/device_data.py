@@ -164,9 +164,11 @@ def build_int_scan_on_device(ctx: ColqContext, n_rows: int, base=None, seed: int
     return t, col
 
 
-def build_name_scan_on_device(ctx: ColqContext, n_rows: int, base=None, seed: int = 42, chunk: int = 1 << 23):
+def build_name_scan_on_device(ctx: ColqContext, n_rows: int, base=None, seed: int = 42, chunk: int = 1 << 23,
+                              start: int = 0, placement: int = _ffi.REPLICATED):
     """BASELINE config 5: ``name[i] = cityNames[splitmix64(42, i) mod 25701]`` as offsets + bytes, registered as
-    "names".  Returns (table, offsets tensor, bytes tensor, idx tensor of the drawn base rows)."""
+    "names".  ``start`` / ``placement``: this rank's shard = global rows [start, start + n_rows) with shard-relative
+    offsets.  Returns (table, offsets tensor, bytes tensor, idx tensor of the drawn base rows, payload bytes)."""
     base = base or load_base()
     device = torch.device("cuda", ctx.device)
     boff = torch.from_numpy(base["city_name_offsets"].astype(np.int64)).to(device)
@@ -176,7 +178,7 @@ def build_name_scan_on_device(ctx: ColqContext, n_rows: int, base=None, seed: in
     off = torch.zeros(n_rows + 1 + 16, dtype=torch.int64, device=device)
     for s in range(0, n_rows, 1 << 26):
         c = min(1 << 26, n_rows - s)
-        idx[s:s + c] = splitmix64_mod_device(seed, s, c, N_CITIES, device).to(torch.int32)
+        idx[s:s + c] = splitmix64_mod_device(seed, start + s, c, N_CITIES, device).to(torch.int32)
     for s in range(0, n_rows, 1 << 26):
         c = min(1 << 26, n_rows - s)
         off[s + 1:s + c + 1] = torch.cumsum(blen[idx[s:s + c].long()], 0) + off[s]
@@ -195,7 +197,7 @@ def build_name_scan_on_device(ctx: ColqContext, n_rows: int, base=None, seed: in
     off32 = ((off + 2 ** 31) % 2 ** 32 - 2 ** 31).to(torch.int32)  # uint32 bit pattern in an int32 tensor
     del off
     torch.cuda.synchronize(device)
-    t = ctx.table_create(n_rows, _ffi.REPLICATED, 0)
+    t = ctx.table_create(n_rows, placement, start if placement == _ffi.SHARDED else 0)
     ctx.col_str_device(t, 0, off32.data_ptr(), off32.numel() * 4, data.data_ptr(), data.numel(), n_rows, total, keepalive=(off32, data))
     ctx.register("names", t)
     return t, off32, data, idx, total
