@@ -345,6 +345,9 @@ inline int64_t bitmap_alloc_words(int64_t n_rows) { return round_up(std::max<int
 inline int64_t bitmap_words(int64_t n_rows) { return (n_rows + 31) / 32; }
 
 colq_status dev_alloc(colq_ctx* ctx, DevBuf& b, size_t bytes) {
+    // re-growing a live buffer: work already enqueued on this context's stream may still use the old block, and the
+    // cache could hand it to ANOTHER context (another stream) right away -- drain first (rare: first executions only)
+    if (b.owned && b.ptr) CU(ctx, cudaStreamSynchronize(ctx->stream));
     b.release();
     bytes = std::max<size_t>(bytes, 16);
     DeviceCache& cache = device_cache();
