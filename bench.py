@@ -418,30 +418,35 @@ def run_colq(args, rank, local_rank, world):
             assert r3.count == 31 * U and np.array_equal(r3.indices.astype(np.int64), want)
             barrier()
             t0 = time.perf_counter()
+            per_step = []
             with torch.cuda.stream(stream):
                 e0.record(stream)
                 for _ in range(args.e2e_steps):
+                    t1 = time.perf_counter()
                     r3 = e2e_step(upload)
+                    per_step.append((time.perf_counter() - t1) * 1e3)
                 e1.record(stream)
                 stream.synchronize()
             wall_ms = (time.perf_counter() - t0) * 1e3 / args.e2e_steps
             ms = max_over_ranks(max(e0.elapsed_time(e1) / args.e2e_steps, wall_ms))
             assert r3.count == 31 * U and np.array_equal(r3.indices.astype(np.int64), want)
-            return ms, r3
+            return ms, r3, [round(x, 2) for x in per_step]
 
-        ms_e2e, r3 = time_e2e(upload=False)
+        ms_e2e, r3, steps_ms = time_e2e(upload=False)
         e2e = {"value": rows / (ms_e2e * 1e-3), "unit": "rows/s",
                "h2d_bytes_per_step": int(r3.timing.h2d_bytes) + small_h2d,
                "d2h_bytes_per_step": int(r3.timing.d2h_bytes), "ms_per_step": ms_e2e, "steps": args.e2e_steps,
+               "ms_each_step_rank0": steps_ms,
                "what": "per step, per rank: colq_table_create, the big columns registered IN PLACE in pinned host memory "
                        "(colq_col_*_host / colq_associate_fk_host: nothing copied at registration), colq_execute -- the columns "
                        "the query scans in full (ZIP population, city-name offsets + bytes) are brought to HBM by the copy engine "
                        "ahead of their kernels, the lazily walked FK columns are read in place, single sectors over PCIe -- "
                        "matched indices read back, colq_table_destroy. h2d_bytes_per_step counts the fully scanned columns; the "
                        "never-touched ZIP-code column and all but ~0.5 M sectors of the FK columns (3.4 GB) do not cross PCIe"}
-        ms_up, r4 = time_e2e(upload=True)
+        ms_up, r4, steps_up = time_e2e(upload=True)
         e2e_upload = {"value": rows / (ms_up * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": int(h2d),
                       "d2h_bytes_per_step": int(r4.timing.d2h_bytes), "ms_per_step": ms_up, "steps": args.e2e_steps,
+                      "ms_each_step_rank0": steps_up,
                       "what": "same, but every column is first copied to HBM (colq_col_* / colq_associate_fk), touched or not"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the serial port, like the serial reference engine

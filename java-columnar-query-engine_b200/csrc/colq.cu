@@ -67,7 +67,7 @@ struct DeviceCache {
     }
     bool park(void* p, size_t bytes) {
         std::lock_guard<std::mutex> g(mu);
-        if (bytes < (1 << 16) || cached_bytes + bytes > limit_bytes) return false;
+        if (cached_bytes + bytes > limit_bytes) return false;
         free_blocks.emplace(bytes, p);
         cached_bytes += bytes;
         return true;
@@ -247,6 +247,9 @@ struct colq_ctx {
         int64_t slot_cap = 0;
         size_t slot_bytes = 0;
     } peer;
+    // pinned [header | first FETCH_SPEC indices] staging of colq_fetch: small results come back with ONE sync.  Owned by
+    // the context, allocated once: cudaHostAlloc / cudaFreeHost per query cost up to hundreds of ms on some hosts
+    void* h_stage = nullptr;
     int compact_grid[2 * (CF_MAX_GATHER + 1)] = {};  // co-resident grid of compact_fused_kernel<NG, GATHER>
     std::map<std::pair<int, size_t>, int> str_occupancy;  // (kernel mode, dynamic smem bytes) -> resident CTAs per SM
 };
@@ -294,7 +297,6 @@ struct colq_query {
     bool executed = false;
     int64_t local_count = -1;     // this rank's matching rows after the last fetch (-1: not fetched yet)
     DevBuf mat_a, mat_b;          // scratch of the result-materialisation gathers
-    void* h_stage = nullptr;      // pinned [header | first FETCH_SPEC indices]: small results come back with ONE sync
     // captured CUDA graph of the op sequence
     cudaGraphExec_t graph_exec = nullptr;
     std::vector<Op> graph_ops;
@@ -1395,11 +1397,11 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
     // the first FETCH_SPEC indices are contiguous in the result block, so one copy and one synchronisation fetch both
     constexpr int64_t FETCH_SPEC = 2048;
     const int64_t n_spec = (!gather && out_idx) ? std::min<int64_t>(FETCH_SPEC, q->idx_capacity) : 0;
-    if (n_spec > 0 && !q->h_stage) CU(ctx, cudaHostAlloc(&q->h_stage, 16 + FETCH_SPEC * 4, cudaHostAllocDefault));
+    if (n_spec > 0 && !ctx->h_stage) CU(ctx, cudaHostAlloc(&ctx->h_stage, 16 + FETCH_SPEC * 4, cudaHostAllocDefault));
     if (n_spec > 0) {
-        CU(ctx, cudaMemcpyAsync(q->h_stage, q->d_total, 16 + (size_t)n_spec * 4, cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaMemcpyAsync(ctx->h_stage, q->d_total, 16 + (size_t)n_spec * 4, cudaMemcpyDeviceToHost, s));
         CU(ctx, cudaStreamSynchronize(s));
-        memcpy(header, q->h_stage, 16);
+        memcpy(header, ctx->h_stage, 16);
     } else {
         CU(ctx, cudaMemcpyAsync(header, q->d_total, 16, cudaMemcpyDeviceToHost, s));
         if (gather) CU(ctx, cudaMemcpyAsync(ginfo, q->ginfo_buf.ptr, 32, cudaMemcpyDeviceToHost, s));
@@ -1456,7 +1458,7 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
     if (out_idx) {
         if (idx_cap < count) rc = fail(ctx, COLQ_ERR_CAPACITY, "index capacity %lld < %lld matches", (long long)idx_cap, (long long)count);
         else if (count > 0 && count <= n_spec) {
-            memcpy(out_idx, (const char*)q->h_stage + 16, (size_t)count * 4);  // already here
+            memcpy(out_idx, (const char*)ctx->h_stage + 16, (size_t)count * 4);  // already here
             q->timing.d2h_bytes += count * 4;
         } else if (count > 0) {
             CU(ctx, cudaMemcpyAsync(out_idx, src_idx, (size_t)count * 4, cudaMemcpyDeviceToHost, s));
@@ -1661,6 +1663,7 @@ colq_status colq_destroy(colq_ctx* ctx) {
     destroy_peerbox(ctx);
     if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
     ctx->tables.clear();
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     DeviceCache& cache = device_cache();
@@ -2190,7 +2193,6 @@ colq_status colq_query_destroy(colq_query* q) {
     cudaSetDevice(q->ctx->device);
     cudaStreamSynchronize(q->ctx->stream);
     if (q->graph_exec) cudaGraphExecDestroy(q->graph_exec);
-    if (q->h_stage) cudaFreeHost(q->h_stage);
     if (q->ev_start) cudaEventDestroy(q->ev_start);
     if (q->ev_stop) cudaEventDestroy(q->ev_stop);
     for (cudaEvent_t e : q->stage_ev) cudaEventDestroy(e);
