@@ -89,3 +89,29 @@ def test_dictionary_encoding_host_logic():
     w = accept_words([True, False, True] + [False] * 61 + [True])
     assert w.dtype == np.uint64 and w.tolist() == [5, 1]
     assert accept_words([]).tolist() == [0]
+
+
+def test_bench_reference_arm_contract(tmp_path):
+    """`bench.py --impl reference` (the driver's CPU arm) prints ONE JSON line with the contract's keys, from rank 0
+    only, and never touches a GPU."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    cmd = [sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--cpu-universes", "20"]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "plymouth_query_zip_rows_per_sec" and d["unit"] == "rows/s"
+    assert d["higher_is_better"] is True and d["steps"] == 2 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"] == "plymouth_adjacency_query_10k_universes"
+    # under torchrun the other ranks print nothing and exit 0
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
+    assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
