@@ -52,7 +52,7 @@ struct DeviceCache {
     std::mutex mu;
     std::multimap<size_t, void*> free_blocks;
     size_t cached_bytes = 0;
-    size_t limit_bytes = (size_t)(getenv("COLQ_CACHE_GB") ? atof(getenv("COLQ_CACHE_GB")) : 24.0) * ((size_t)1 << 30);
+    size_t limit_bytes = (size_t)((getenv("COLQ_CACHE_GB") ? atof(getenv("COLQ_CACHE_GB")) : 24.0) * (double)((size_t)1 << 30));
     int live_contexts = 0;
 
     void* take(size_t bytes, size_t* block_bytes) {
