@@ -103,7 +103,10 @@ typedef enum colq_option {
     COLQ_OPT_PROMOTE = 6,
     /* 1: the multi-GPU final gather runs as two more phases of the COOPERATIVE compaction launch instead of the two
        peer_gather launches (default 0: measured slower on 2-8 B200s, kept selectable and parity-tested) */
-    COLQ_OPT_FUSED_GATHER = 7
+    COLQ_OPT_FUSED_GATHER = 7,
+    /* 1 (default): the multi-GPU mask PUBLISH is done by the last CTA of the scan kernel that produced the mask instead
+       of a separate one-block launch */
+    COLQ_OPT_TAIL_PUBLISH = 8
 } colq_option;
 
 typedef struct colq_ctx colq_ctx;       /* one DataSystem instance  (E/DataSystemSerialIndices.java:14-22) */

@@ -190,6 +190,7 @@ struct Op {
     CompactLookbackParams clook{};
     PeerMaskParams pmask{};
     PeerGatherParams pgather{};
+    bool tail_publish = false;  // K_SCAN_STR / K_SCAN_CODES: the last CTA publishes the pushed mask to the peers
     bool dict_scan = false;  // K_SCAN_ROWS over the distinct values of a dictionary-encoded int column
     bool gather = false;  // K_COMPACT_FUSED: the peer-memory final gather is fused into this launch
     int publish_op = -1;  // K_PEER_MASK_COLLECT / a csr_pull with a fused collect: index of the matching publish
@@ -258,7 +259,7 @@ struct colq_query {
     colq_ctx* ctx = nullptr;
     std::string table_name;
     std::vector<QNode> nodes;
-    int opt_lazy = 1, opt_profile = 0, opt_graph = 1, opt_peer = 1, opt_fused_compact = 1, opt_defer = 1, opt_promote = 2, opt_fused_gather = 0;
+    int opt_lazy = 1, opt_profile = 0, opt_graph = 1, opt_peer = 1, opt_fused_compact = 1, opt_defer = 1, opt_promote = 2, opt_fused_gather = 0, opt_tail_publish = 1;
     std::vector<GatherD> deferred;  // root-node FK chains resolved by the compaction kernel instead of the row scan
     int own_begin = -1, own_end = -1;  // root-node scan ops that depend on no child (hoistable behind a mask publish)
     std::vector<Column*> pending_promotions;  // host-resident columns whose HBM copy this execution fills
@@ -844,6 +845,7 @@ struct Planner {
             P.targets = (const int32_t*)ci.col->targets.ptr;
             P.child_bits = ci.child.all_ones ? nullptr : ci.child.bits;
             P.n_child = ci.n_child;
+            P.nnz = ci.col->nnz;
             P.in_bits = cur;
             u32* ob;
             ST(out_buf(&ob));
@@ -933,10 +935,10 @@ void launch_scan_rows(const Op& o, cudaStream_t s) {
 }
 
 void stage_name(const Op& o, char* out, size_t cap) {
-    if (o.kind == K_SCAN_CODES) snprintf(out, cap, "scan_codes%s", o.codes.push.fk ? "+push" : "");
+    if (o.kind == K_SCAN_CODES) snprintf(out, cap, "scan_codes%s%s", o.codes.push.fk ? "+push" : "", o.tail_publish ? "+publish" : "");
     else if (o.kind == K_SCAN_ROWS && o.dict_scan) snprintf(out, cap, "scan_rows_dictionary");
     else if (o.kind == K_SCAN_ROWS) snprintf(out, cap, "scan_rows<%d,%d,%s>%s", o.np, o.ng, o.eager ? "eager" : "lazy", o.rows.push.fk ? "+push" : "");
-    else if (o.kind == K_SCAN_STR) snprintf(out, cap, "%s<op%d>%s", o.name, o.str.op, o.str.push.fk ? "+push" : "");
+    else if (o.kind == K_SCAN_STR) snprintf(out, cap, "%s<op%d>%s%s", o.name, o.str.op, o.str.push.fk ? "+push" : "", o.tail_publish ? "+publish" : "");
     else snprintf(out, cap, "%s", o.name);
 }
 
@@ -976,6 +978,7 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
             }
             const int grid = (int)((o.codes.n + SC_BLOCK_ROWS - 1) / SC_BLOCK_ROWS);
             if (grid == 0) break;
+            if (o.tail_publish) o.pmask.epoch = o.codes.pub.epoch = ++ctx->peer.mask_epoch;
             const size_t smem = (size_t)(PUSH_SMEM_WORDS + o.codes.mask_words) * 4;
             if (o.codes.mask_words > 0) scan_codes_kernel<true><<<grid, SR_THREADS, smem, s>>>(o.codes);
             else scan_codes_kernel<false><<<grid, SR_THREADS, smem, s>>>(o.codes);
@@ -1023,6 +1026,7 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
                 }
                 o.grid = (int)std::min<int64_t>(o.str.n_tiles, (int64_t)ctx->sm_count * it->second);
             }
+            if (o.tail_publish) o.pmask.epoch = o.str.pub.epoch = ++ctx->peer.mask_epoch;
             kern<<<o.grid, ST_THREADS, o.smem, s>>>(o.str);
             q->timing.kernel_launches++;
             break;
@@ -1185,6 +1189,27 @@ colq_status run_pipeline(colq_query* q) {
             q->ops.erase(q->ops.begin() + i);
             for (Op& o : q->ops)
                 if (o.publish_op > (int)i) o.publish_op -= 1;
+        }
+    }
+    // (3) a PUBLISH directly behind the scan whose push epilogue produced that mask is done by the scan's last CTA
+    for (size_t i = 0; q->opt_tail_publish && i + 1 < q->ops.size(); ++i) {
+        Op& sc = q->ops[i];
+        Op& pb = q->ops[i + 1];
+        if (pb.kind != K_PEER_MASK_PUBLISH) continue;
+        PeerMaskParams* slot = nullptr;
+        if (sc.kind == K_SCAN_STR && sc.str.push.fk && sc.str.push.reach == pb.pmask.reach && sc.str.n_tiles > 0) {
+            slot = &sc.str.pub; sc.str.pub_done = ctx->peer.d_done + MAX_RANKS + 8;
+        } else if (sc.kind == K_SCAN_CODES && !sc.never && sc.codes.push.fk && sc.codes.push.reach == pb.pmask.reach && sc.codes.n > 0) {
+            slot = &sc.codes.pub; sc.codes.pub_done = ctx->peer.d_done + MAX_RANKS + 8;
+        }
+        if (!slot) continue;
+        *slot = pb.pmask;
+        sc.tail_publish = true;
+        sc.acct_bytes += pb.acct_bytes;
+        q->ops.erase(q->ops.begin() + i + 1);
+        for (Op& o : q->ops) {
+            if (o.publish_op == (int)i + 1) o.publish_op = (int)i;
+            else if (o.publish_op > (int)i + 1) o.publish_op -= 1;
         }
     }
 
@@ -2269,6 +2294,7 @@ colq_status colq_query_set_option(colq_query* q, colq_option option, int value) 
         case COLQ_OPT_DEFER_CHAINS: q->opt_defer = value; break;
         case COLQ_OPT_PROMOTE: q->opt_promote = value; break;
         case COLQ_OPT_FUSED_GATHER: q->opt_fused_gather = value; break;
+        case COLQ_OPT_TAIL_PUBLISH: q->opt_tail_publish = value; break;
         default: return fail(q->ctx, COLQ_THROW_ILLEGAL_ARG, "unknown option %d", (int)option);
     }
     return COLQ_OK;

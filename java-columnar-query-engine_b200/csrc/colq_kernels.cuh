@@ -354,6 +354,113 @@ __global__ void __launch_bounds__(SR_THREADS) scan_rows_kernel(const ScanRowsPar
 }
 
 // ---------------------------------------------------------------------------------------------
+// Peer-memory exchange over NVLink (multi-GPU, one process per GPU).
+//
+// Every rank owns a MAILBOX in its HBM that all peers have mapped through CUDA IPC.  A collective is: store my
+// contribution straight into every peer's mailbox slot [parity][my rank] (plain st.global over NVLink), fence, then
+// publish an epoch flag with st.release.sys; the consumer spins on the flags in its OWN memory (ld.acquire.sys) and
+// reads the slots locally.  Slots are double-buffered by epoch parity: a rank can only be one exchange ahead of any
+// peer (it needs that peer's flag to finish the current one), so a slot is never overwritten while it is still read.
+// These replace ncclAllGather on the data path: ~5 us instead of ~25-70 us for the 8-byte state mask.
+// A spin that exceeds PEER_TIMEOUT_NS sets *status and gives up (the host reports COLQ_ERR_DEVICE) -- no hangs.
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_RANKS = 64;
+constexpr int MASK_SLOT_BYTES = 4096;
+constexpr int MASK_WORDS_MAX = (MASK_SLOT_BYTES - 16) / 4;
+constexpr size_t PEER_GATHER_AREA_OFFSET = (size_t)2 * MAX_RANKS * MASK_SLOT_BYTES;
+constexpr int GATHER_SLOT_HEADER = 256;  // [u64 flag][u64 count] + pad, keeps the index payload 256-byte aligned
+constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ull;
+
+__device__ __forceinline__ u64 ld_acquire_sys(const u64* p) {
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(u64* p, u64 v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 global_timer_ns() {
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool peer_wait(const u64* flag, u64 epoch, u32* status) {
+    const u64 t0 = global_timer_ns();
+    while (ld_acquire_sys(flag) != epoch) {
+        if (global_timer_ns() - t0 > PEER_TIMEOUT_NS) {
+            atomicExch(status, 1u);
+            return false;
+        }
+    }
+    return true;
+}
+
+struct PeerMaskParams {
+    u32* reach;            // in: this rank's mask; out: OR over all ranks
+    int n_words;           // <= MASK_WORDS_MAX
+    int n_ranks, rank;
+    uint8_t* const* peers; // device array: mailbox base of every rank (own entry = local pointer)
+    u64 epoch;
+    u32* status;
+};
+
+// OR-allreduce of a small replicated-table mask -- the collective half of a sharded -> replicated filterParent hop --
+// split in two so that independent work can run between the halves (the planner puts the root table's predicate scan
+// there): PUBLISH stores this rank's words into every peer's mailbox and raises the flags; COLLECT waits for all
+// ranks' flags in local memory and ORs the slots.  COLLECT also runs as the prologue of a single-block csr_pull.
+__global__ void __launch_bounds__(256) peer_mask_publish_kernel(const PeerMaskParams P) {
+    const size_t area = (size_t)(P.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
+    for (int r = 0; r < P.n_ranks; ++r) {
+        u32* dst = reinterpret_cast<u32*>(P.peers[r] + area + (size_t)P.rank * MASK_SLOT_BYTES + 16);
+        for (int w = threadIdx.x; w < P.n_words; w += blockDim.x) dst[w] = P.reach[w];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < P.n_ranks)
+        st_release_sys(reinterpret_cast<u64*>(P.peers[threadIdx.x] + area + (size_t)P.rank * MASK_SLOT_BYTES), P.epoch);
+}
+
+// PUBLISH from the tail of the kernel that produced the mask (scan_str / scan_codes push epilogue): every CTA has
+// flushed its bits with atomicOr; the LAST CTA to arrive (device-wide counter, re-armed by that CTA) reads the finished
+// mask from L2 and publishes it.  Saves the separate one-block launch.  Call from all threads, after push_flush.
+__device__ __forceinline__ void peer_mask_publish_tail(const PeerMaskParams& P, u32* done) {
+    __shared__ u32 s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(done, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) *done = 0;
+    __threadfence();
+    const size_t area = (size_t)(P.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
+    for (int r = 0; r < P.n_ranks; ++r) {
+        u32* dst = reinterpret_cast<u32*>(P.peers[r] + area + (size_t)P.rank * MASK_SLOT_BYTES + 16);
+        for (int w = threadIdx.x; w < P.n_words; w += blockDim.x) dst[w] = __ldcg(P.reach + w);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < P.n_ranks)
+        st_release_sys(reinterpret_cast<u64*>(P.peers[threadIdx.x] + area + (size_t)P.rank * MASK_SLOT_BYTES), P.epoch);
+}
+
+// block-wide; ends with a __syncthreads()
+__device__ __forceinline__ void peer_mask_collect(const PeerMaskParams& P) {
+    const size_t area = (size_t)(P.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
+    const uint8_t* mine = P.peers[P.rank] + area;
+    if ((int)threadIdx.x < P.n_ranks)
+        peer_wait(reinterpret_cast<const u64*>(mine + (size_t)threadIdx.x * MASK_SLOT_BYTES), P.epoch, P.status);
+    __syncthreads();
+    for (int w = threadIdx.x; w < P.n_words; w += blockDim.x) {
+        u32 v = 0;
+        for (int r = 0; r < P.n_ranks; ++r) v |= reinterpret_cast<const u32*>(mine + (size_t)r * MASK_SLOT_BYTES + 16)[w];
+        P.reach[w] = v;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) peer_mask_collect_kernel(const PeerMaskParams P) { peer_mask_collect(P); }
+
+// ---------------------------------------------------------------------------------------------
 // K2'  scan_codes: string predicate over a DICTIONARY-ENCODED column -> bitmask
 //
 // Replaces ExecutionContext.Node.filterSelf (E/ExecutionContext.java:79-94) over StringColumn.where
@@ -383,6 +490,8 @@ struct ScanCodesParams {
     const u32* in_bits;
     u32* out_bits;
     PushD push;
+    PeerMaskParams pub;   // pub.n_words > 0: the last CTA publishes push.reach to the peers (multi-GPU mask exchange)
+    u32* pub_done;
 };
 
 template <bool SMEM>
@@ -511,6 +620,7 @@ __global__ void __launch_bounds__(SR_THREADS) scan_codes_kernel(const ScanCodesP
         __syncthreads();
         push_flush(P.push, s_reach);
     }
+    if (P.pub.n_words > 0) peer_mask_publish_tail(P.pub, P.pub_done);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -569,6 +679,8 @@ struct ScanStrParams {
     // to these HBM copies so that the column is resident for the next query (first-touch promotion)
     u32* promote_offsets;
     uint8_t* promote_bytes;
+    PeerMaskParams pub;   // pub.n_words > 0: the last CTA publishes push.reach to the peers (multi-GPU mask exchange)
+    u32* pub_done;
 };
 
 struct StrTileMeta {
@@ -921,91 +1033,8 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == -1 || MODE == -2) ? 4 : 3
         __syncthreads();
         push_flush(P.push, s_reach);
     }
+    if (P.pub.n_words > 0) peer_mask_publish_tail(P.pub, P.pub_done);
 }
-
-// ---------------------------------------------------------------------------------------------
-// Peer-memory exchange over NVLink (multi-GPU, one process per GPU).
-//
-// Every rank owns a MAILBOX in its HBM that all peers have mapped through CUDA IPC.  A collective is: store my
-// contribution straight into every peer's mailbox slot [parity][my rank] (plain st.global over NVLink), fence, then
-// publish an epoch flag with st.release.sys; the consumer spins on the flags in its OWN memory (ld.acquire.sys) and
-// reads the slots locally.  Slots are double-buffered by epoch parity: a rank can only be one exchange ahead of any
-// peer (it needs that peer's flag to finish the current one), so a slot is never overwritten while it is still read.
-// These replace ncclAllGather on the data path: ~5 us instead of ~25-70 us for the 8-byte state mask.
-// A spin that exceeds PEER_TIMEOUT_NS sets *status and gives up (the host reports COLQ_ERR_DEVICE) -- no hangs.
-// ---------------------------------------------------------------------------------------------
-constexpr int MAX_RANKS = 64;
-constexpr int MASK_SLOT_BYTES = 4096;
-constexpr int MASK_WORDS_MAX = (MASK_SLOT_BYTES - 16) / 4;
-constexpr size_t PEER_GATHER_AREA_OFFSET = (size_t)2 * MAX_RANKS * MASK_SLOT_BYTES;
-constexpr int GATHER_SLOT_HEADER = 256;  // [u64 flag][u64 count] + pad, keeps the index payload 256-byte aligned
-constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ull;
-
-__device__ __forceinline__ u64 ld_acquire_sys(const u64* p) {
-    u64 v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(u64* p, u64 v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ u64 global_timer_ns() {
-    u64 t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ bool peer_wait(const u64* flag, u64 epoch, u32* status) {
-    const u64 t0 = global_timer_ns();
-    while (ld_acquire_sys(flag) != epoch) {
-        if (global_timer_ns() - t0 > PEER_TIMEOUT_NS) {
-            atomicExch(status, 1u);
-            return false;
-        }
-    }
-    return true;
-}
-
-struct PeerMaskParams {
-    u32* reach;            // in: this rank's mask; out: OR over all ranks
-    int n_words;           // <= MASK_WORDS_MAX
-    int n_ranks, rank;
-    uint8_t* const* peers; // device array: mailbox base of every rank (own entry = local pointer)
-    u64 epoch;
-    u32* status;
-};
-
-// OR-allreduce of a small replicated-table mask -- the collective half of a sharded -> replicated filterParent hop --
-// split in two so that independent work can run between the halves (the planner puts the root table's predicate scan
-// there): PUBLISH stores this rank's words into every peer's mailbox and raises the flags; COLLECT waits for all
-// ranks' flags in local memory and ORs the slots.  COLLECT also runs as the prologue of a single-block csr_pull.
-__global__ void __launch_bounds__(256) peer_mask_publish_kernel(const PeerMaskParams P) {
-    const size_t area = (size_t)(P.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
-    for (int r = 0; r < P.n_ranks; ++r) {
-        u32* dst = reinterpret_cast<u32*>(P.peers[r] + area + (size_t)P.rank * MASK_SLOT_BYTES + 16);
-        for (int w = threadIdx.x; w < P.n_words; w += blockDim.x) dst[w] = P.reach[w];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < P.n_ranks)
-        st_release_sys(reinterpret_cast<u64*>(P.peers[threadIdx.x] + area + (size_t)P.rank * MASK_SLOT_BYTES), P.epoch);
-}
-
-// block-wide; ends with a __syncthreads()
-__device__ __forceinline__ void peer_mask_collect(const PeerMaskParams& P) {
-    const size_t area = (size_t)(P.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
-    const uint8_t* mine = P.peers[P.rank] + area;
-    if ((int)threadIdx.x < P.n_ranks)
-        peer_wait(reinterpret_cast<const u64*>(mine + (size_t)threadIdx.x * MASK_SLOT_BYTES), P.epoch, P.status);
-    __syncthreads();
-    for (int w = threadIdx.x; w < P.n_words; w += blockDim.x) {
-        u32 v = 0;
-        for (int r = 0; r < P.n_ranks; ++r) v |= reinterpret_cast<const u32*>(mine + (size_t)r * MASK_SLOT_BYTES + 16)[w];
-        P.reach[w] = v;
-    }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(256) peer_mask_collect_kernel(const PeerMaskParams P) { peer_mask_collect(P); }
 
 // ---------------------------------------------------------------------------------------------
 // K4b  csr_pull: to-many association hop on the forward side
@@ -1025,21 +1054,42 @@ struct CsrPullParams {
     u32* out_bits;
     PushD push;
     PeerMaskParams pm;       // pm.n_words > 0 (single-block launches only): collect the child mask exchange first
+    int64_t nnz;             // number of edges (targets)
 };
+
+constexpr int CSR_SMEM_EDGES = 2048;  // single-block launches stage up to this many targets (and a <= 4096-row child mask)
 
 __global__ void __launch_bounds__(256) csr_pull_kernel(const CsrPullParams P) {
     __shared__ u32 s_reach[PUSH_SMEM_WORDS];
+    __shared__ int32_t s_tgt[CSR_SMEM_EDGES];
+    __shared__ u32 s_child[PUSH_SMEM_WORDS];
     if (P.pm.n_words > 0) peer_mask_collect(P.pm);
     const bool do_push = P.push.fk != nullptr;
-    if (do_push) {
-        push_init(P.push, s_reach);
-        __syncthreads();
-    }
+    if (do_push) push_init(P.push, s_reach);
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    bool ok = false;
+    // the 51-row state adjacency (219 edges) is one block of pure latency: issue every global load at once -- row bounds,
+    // all targets and the child mask -- instead of a chain of dependent loads per edge
+    const bool staged = gridDim.x == 1 && P.nnz <= CSR_SMEM_EDGES && P.n_child <= PUSH_SMEM_BITS;
+    int64_t e0 = 0, e1 = 0;
     if (r < P.n) {
-        for (int64_t e = P.offsets[r]; e < P.offsets[r + 1] && !ok; ++e) {
+        e0 = P.offsets[r];
+        e1 = P.offsets[r + 1];
+    }
+    if (staged) {
+        for (int i = threadIdx.x; i < (int)P.nnz; i += blockDim.x) s_tgt[i] = P.targets[i];
+        const int cw = (int)((P.n_child + 31) >> 5);
+        for (int i = threadIdx.x; i < cw; i += blockDim.x) s_child[i] = P.child_bits != nullptr ? P.child_bits[i] : 0xffffffffu;
+    }
+    if (do_push || staged) __syncthreads();
+    bool ok = false;
+    if (staged) {
+        for (int64_t e = e0; e < e1 && !ok; ++e) {
+            const int32_t t = s_tgt[e];
+            if (t >= 0 && t < P.n_child) ok = (s_child[t >> 5] >> (t & 31)) & 1u;
+        }
+    } else if (r < P.n) {
+        for (int64_t e = e0; e < e1 && !ok; ++e) {
             int32_t t = P.targets[e];
             if (t >= 0 && t < P.n_child) ok = P.child_bits == nullptr ? true : bit_test(P.child_bits, t);
         }

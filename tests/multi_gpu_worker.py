@@ -47,11 +47,13 @@ def main():
 
         geo = G.build_tables(U, n_ranks=world, rank=rank, rename_plymouth_except_last_rank=perturbed)
         # (peer exchange, lazy FK, deferred chains, fused compaction, gather fused into the compaction)
-        for peer, lazy, defer, fused, fgather in ((1, True, 1, 1, 0), (1, True, 1, 2, 0), (1, True, 1, 1, 1), (1, True, 0, 1, 1), (1, False, 1, 1, 0),
-                                                 (1, True, 1, 0, 0), (0, True, 1, 1, 0), (0, False, 1, 2, 0)):
+        for peer, lazy, defer, fused, fgather, tail in ((1, True, 1, 1, 0, 1), (1, True, 1, 1, 0, 0), (1, True, 1, 2, 0, 1), (1, True, 1, 1, 1, 1),
+                                                       (1, True, 0, 1, 1, 0), (1, False, 1, 1, 0, 1), (1, True, 1, 0, 0, 1), (0, True, 1, 1, 0, 1),
+                                                       (0, False, 1, 2, 0, 1)):
             if True:
                 ds = DataSystemColq(context=ctx, lazy_fk=lazy, options={_ffi.OPT_PEER_EXCHANGE: peer, _ffi.OPT_DEFER_CHAINS: defer,
-                                                                        _ffi.OPT_FUSED_COMPACT: fused, _ffi.OPT_FUSED_GATHER: fgather})
+                                                                        _ffi.OPT_FUSED_COMPACT: fused, _ffi.OPT_FUSED_GATHER: fgather,
+                                                                        _ffi.OPT_TAIL_PUBLISH: tail})
                 ds._tables.clear()
                 G.register_geography(ds, geo, sharded=True)
                 ds._sync_tables()
@@ -62,13 +64,15 @@ def main():
                 assert np.array_equal(res.indices, want), (rank, perturbed, peer, lazy)
                 names = [n for n, *_ in cq.profile()]
                 if peer and os.environ.get("COLQ_PEER", "1") != "0":
-                    assert "peer_mask_publish" in names and "peer_mask_collect+csr_pull" in names, names
+                    pub = [i for i, n in enumerate(names) if n.endswith("publish")]   # own launch, or the scan's last CTA
+                    assert len(pub) == 1 and "peer_mask_collect+csr_pull" in names, names
+                    assert (names[pub[0]] == "peer_mask_publish") == (not tail), names
                     if fused == 1 and fgather:    # the final gather runs inside the cooperative compaction launch
                         assert any(n.startswith("compact_fused") and n.endswith("+gather") for n in names), names
                     else:
                         assert "peer_gather_indices" in names, names
                     if lazy and defer and fused:   # the root's predicate scan sits between the two halves of the mask exchange
-                        assert names.index("peer_mask_publish") < names.index("scan_rows<1,0,lazy>") < names.index("peer_mask_collect+csr_pull"), names
+                        assert pub[0] < names.index("scan_rows<1,0,lazy>") < names.index("peer_mask_collect+csr_pull"), names
                 else:
                     assert "allgather_or_mask" in names and "allgather_indices" in names, names
                 cq.close()
