@@ -31,6 +31,15 @@ import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
+# stdout carries exactly ONE JSON line.  Native libraries print there too (NCCL's "NCCL version ..." banner on rank 0), so
+# file descriptor 1 is pointed at stderr for the whole run and the JSON line is written to the saved, real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 for p in (ROOT / "java-columnar-query-engine_b200", ROOT / "oracle"):
     sys.path.insert(0, str(p))
 
@@ -222,7 +231,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -474,7 +483,7 @@ def run_colq(args, rank, local_rank, world):
             "host_enqueue_us_per_step": host_us, "host_numa": numa, "clocks": clocks, "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "collectives_per_step": collectives_per_step,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -619,7 +628,7 @@ def run_single_table(args, rank=0, local_rank=0, world=1):
         "cpu_baseline": None, "e2e": None, "clocks": clocks, "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
     }
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
