@@ -116,8 +116,10 @@ class ColqQuery:
         self.ctx._check(self.ctx.lib.colq_query_set_option(self.handle, option, value))
 
     def execute(self, want_indices: bool = True, want_bitmask: bool = False, n_rows: int = 0,
-                index_capacity: int = 1 << 20) -> ExecResult:
-        return self.ctx._execute(self, want_indices, want_bitmask, n_rows, index_capacity, fetch_only=False)
+                index_capacity: int = 1 << 20, pinned: bool = False) -> ExecResult:
+        """``pinned``: the indices land in a pinned buffer owned by this query (what the Java shim's off-heap result
+        segment is) and the returned array is a VIEW of it, valid until the next execute / close of the query."""
+        return self.ctx._execute(self, want_indices, want_bitmask, n_rows, index_capacity, fetch_only=False, pinned=pinned)
 
     def execute_async(self) -> None:
         self.ctx._check(self.ctx.lib.colq_execute_async(self.ctx.handle, self.handle))
@@ -381,14 +383,23 @@ class ColqContext:
         return ColqQuery(self, table_name)
 
     def _execute(self, q: ColqQuery, want_indices: bool, want_bitmask: bool, n_rows: int, index_capacity: int,
-                 fetch_only: bool) -> ExecResult:
+                 fetch_only: bool, pinned: bool = False) -> ExecResult:
         fn = self.lib.colq_fetch if fetch_only else self.lib.colq_execute
         count = C.c_int64()
         timing = _ffi.Timing()
         bitmask = np.zeros((n_rows + 63) // 64, dtype=np.uint64) if want_bitmask else None
         cap = max(int(index_capacity), 1)
         while True:
-            idx = np.empty(cap, dtype=np.int32) if want_indices else None
+            if want_indices and pinned:
+                buf = getattr(q, "_pinned_idx", None)
+                if buf is None or buf.shape[0] < cap:
+                    if buf is not None:
+                        self.host_free(q._pinned_raw)
+                    q._pinned_raw = self.host_alloc(cap * 4 + 64)
+                    q._pinned_idx = buf = q._pinned_raw[: cap * 4].view(np.int32)
+                idx = buf
+            else:
+                idx = np.empty(cap, dtype=np.int32) if want_indices else None
             st = fn(self.handle, q.handle, _ptr(bitmask), 0 if bitmask is None else bitmask.shape[0], _ptr(idx),
                     0 if idx is None else cap, C.byref(count), C.byref(timing))
             if st == _ffi.ERR_CAPACITY and want_indices and count.value > cap:
