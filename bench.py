@@ -58,7 +58,10 @@ def parse_args():
     ap.add_argument("--universes", type=int, default=10_000)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--profile-steps", type=int, default=10)
-    ap.add_argument("--cpu-universes", type=int, default=1000, help="bounded sample for the CPU baseline legs")
+    ap.add_argument("--cpu-universes", type=int, default=1000, help="bounded sample for the serial cpu_baseline leg of the GPU arm")
+    ap.add_argument("--reference-universes", type=int, default=0,
+                    help="--impl reference only: run the CPU arm on this many universes instead of the full --universes "
+                         "(a bounded sample for hosts with little RAM: the full 10k-universe tables need ~30 GB)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-small-queries", action="store_true", help="skip the 1-universe latency measurements (keeps ncu launch lists clean)")
@@ -77,14 +80,14 @@ def parse_args():
     return ap.parse_args()
 
 
-def workload_config(U, world, lazy=True):
+def workload_config(U):
+    """The workload alone -- the SAME dict on the GPU arm and on the reference arm (how each arm executes it, sharding and
+    strategy, are top-level keys of the GPU line)."""
     return {
         "workload": "plymouth_adjacency_query_10k_universes" if U == 10_000 else f"plymouth_adjacency_query_{U}_universes",
         "source": "BASELINE.json configs[3]; app/.../Runner.java:230-236",
         "universes": U, "zip_rows": U * N_ZIPS, "city_rows": U * N_CITIES, "state_rows": 51,
-        "sharding": f"universe ranges over {world} rank(s); states replicated",
         "l2_policy": "inputs larger than L2 (no flush)",
-        "strategy": "lazy_fk_chain" if lazy else "materialise_all_nodes",
     }
 
 
@@ -210,24 +213,38 @@ def oracle_run(U, n_threads, repeats):
 
 
 def run_reference(args, rank, world):
-    """The reference arm: the reference engine's own algorithm on the host cores.  The reference is Java and neither
-    this image nor the GPU box has a JVM, so this times the C port of it (oracle/colq_oracle.c) with
-    all host threads on a bounded sample of the same workload."""
+    """The reference arm: the reference engine's own algorithm on the host cores, on the SAME config as the GPU arm (all
+    --universes universes; every step is one full execute of the Plymouth query over resident host tables).  The reference
+    is Java and neither this image nor the GPU box has a JVM, so this times the C port of it
+    (oracle/colq_oracle.c) with all host threads."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    U = args.cpu_universes
+    U = args.reference_universes or args.universes
+    if not args.reference_universes:
+        # the full tables (7.75 GB of columns, the CSR forms and the transposed reverse columns of the literal port) peak
+        # at ~3.4 MB of host RAM per universe; refuse to swap the box to death and fall back to the largest sample that fits
+        try:
+            import psutil
+            fit = int(psutil.virtual_memory().available * 0.8 / 3.4e6)
+            if fit < U:
+                U = max(100, fit)
+        except Exception:
+            pass
     times = oracle_run(U, cores, args.warmup + args.steps)[args.warmup:]
     sec = statistics.mean(times)
     value = U * N_ZIPS / sec
+    sample = (f"all {U} universes ({U * N_ZIPS} ZIP rows) per step" if U == args.universes else
+              f"{U} of {args.universes} universes ({U * N_ZIPS} ZIP rows) per step (--reference-universes)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": dict(workload_config(args.universes, 1), sample_universes=U, sample_zip_rows=U * N_ZIPS),
+        "config": workload_config(args.universes),
+        "same_config_as_gpu_arm": U == args.universes,
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port",
-                         "sample": f"{U} of {args.universes} universes ({U * N_ZIPS} ZIP rows) per step; C port of the serial-indices "
-                                   f"engine with its row loops split over {cores} OpenMP threads; Java engine not timed: no JVM in image"},
+                         "sample": f"{sample}; C port of the serial-indices engine with its row loops split over {cores} OpenMP "
+                                   f"threads (the Java engine itself is single-threaded); Java engine not timed: no JVM in image"},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -272,6 +289,12 @@ def run_colq(args, rank, local_rank, world):
 
     U = args.universes * (world if args.weak else 1)
     base = G.load_base()
+    gate = {"exact": False, "perturbed": None}
+    if world > 1:
+        gate["perturbed"] = perturbed_gate(ctx, rank, world, base)   # raises on any mismatch
+        gate["perturbed_what"] = ("4*N+1 universes, every PLYMOUTH renamed except in the LAST rank's universes (the state mask exists on "
+                                  "one rank only before the OR-exchange); sharded result == unsharded oracle, peer-memory and NCCL "
+                                  "exchanges, raw C ABI and DataSystemColq.execute")
     geo = build_geography_on_device(ctx, U, world, rank, base=base, device=dev, sharded=world > 1, dict_names=args.dict_names)
     if args.dict_names:
         args.no_e2e = True
@@ -288,6 +311,7 @@ def run_colq(args, rank, local_rank, world):
     res = q.execute(want_indices=True, index_capacity=31 * U + 16)
     if res.count != 31 * U or not np.array_equal(res.indices.astype(np.int64), want):
         raise SystemExit(f"rank {rank}: GPU result differs from the oracle-derived expectation (count {res.count} vs {31 * U})")
+    gate["exact"] = True
     launches_per_step = int(res.timing.kernel_launches)
     collectives_per_step = int(res.timing.collectives)
 
@@ -473,7 +497,9 @@ def run_colq(args, rank, local_rank, world):
         line = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic", "config": dict(workload_config(U, world, not args.eager), **({"city_names": "dictionary-encoded"} if args.dict_names else {})),
+            "data": "synthetic", "config": dict(workload_config(U), **({"city_names": "dictionary-encoded"} if args.dict_names else {})),
+            "sharding": f"universe ranges over {world} rank(s); states replicated",
+            "strategy": "lazy_fk_chain" if not args.eager else "materialise_all_nodes", "gate": gate,
             "hbm_gbs_query_algorithmic": query_gbs, "query_algorithmic_bytes": algo_total,
             "roofline": roofline, "stages_ms": {k: round(v["ms"], 5) for k, v in stages.items()},
             "cpu_baseline": cpu, "e2e": e2e, "e2e_upload_all_columns": e2e_upload,
@@ -487,6 +513,50 @@ def run_colq(args, rank, local_rank, world):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def perturbed_gate(ctx, rank, world, base):
+    """Correctness gate of the multi-GPU exchanges, run by every bench invocation at N > 1 before anything is timed.
+    The exact-copy workload cannot catch a broken mask exchange (every rank's local state mask already equals the global
+    one), so this runs the PERTURBED workload of SURVEY.md 8d: PLYMOUTH is renamed in all universes except the last
+    rank's, the sharded engine must still return exactly the unsharded oracle's rows (E/ExecutionContext.java:100-122
+    semantics) -- once over NVLink peer memory, once over NCCL, through the raw C ABI and through the public
+    DataSystemColq.execute."""
+    from colq import _ffi, QueryResult
+    from colq import geography as G
+    from colq.engine import DataSystemColq
+    from oracle_system import OracleDataSystem
+    Ug = 4 * world + 1
+    oracle = OracleDataSystem()
+    G.register_geography(oracle, G.build_tables(Ug, base=base))
+    full = oracle.execute(G.plymouth_query())
+    want = oracle.last_indices.copy()
+    want_codes = np.sort(full.result_set.columns()[0].ints())
+    oracle.close()
+    geo = G.build_tables(Ug, n_ranks=world, rank=rank, base=base, rename_plymouth_except_last_rank=True)
+    lo, hi = geo.zip_row_base, geo.zip_row_base + geo.zips.size()
+    for peer in (1, 0):
+        ds = DataSystemColq(context=ctx, options={_ffi.OPT_PEER_EXCHANGE: peer})
+        G.register_geography(ds, geo, sharded=True)
+        ds._sync_tables()
+        cq, why = ds._translate(G.plymouth_query())
+        assert cq is not None, why
+        res = cq.execute(want_indices=True, index_capacity=64)
+        if res.count != want.shape[0] or not np.array_equal(res.indices, want):
+            raise SystemExit(f"rank {rank}: perturbed multi-GPU gate FAILED (peer={peer}): {res.count} rows vs {want.shape[0]}")
+        cq.close()
+        # the public call: this rank's rows of the result table
+        got = ds.execute(G.plymouth_query())
+        if not isinstance(got, QueryResult.Success):
+            raise SystemExit(f"rank {rank}: perturbed gate, DataSystemColq.execute failed: {got}")
+        mine = want[(want >= lo) & (want < hi)]
+        if got.result_set.size() != mine.shape[0]:
+            raise SystemExit(f"rank {rank}: perturbed gate, DataSystemColq.execute returned {got.result_set.size()} local rows, want {mine.shape[0]}")
+        ds.last_query.close()
+        ds.last_query = None
+        for h in set(ds._handles.values()):
+            ctx.table_destroy(h)
+    return True
 
 
 def small_query_latency(base):

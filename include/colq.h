@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define COLQ_ABI_VERSION 1
+#define COLQ_ABI_VERSION 2
 
 typedef enum colq_status {
     COLQ_OK = 0,
@@ -81,8 +81,8 @@ typedef enum colq_option {
        2: one event pair per execution, around the launch with the most algorithmic bytes only, kept for every
           execution since the last colq_profile_hot() (up to 4096) -- cheap enough to leave on inside a timed region */
     COLQ_OPT_PROFILE = 1,
-    /* reserved: CUDA-graph replay of the op list (accepted and ignored in this version) */
-    COLQ_OPT_GRAPH = 2,
+    /* value 2 is unused (ABI 1 reserved it for CUDA-graph replay, which never existed: a step is now two or three launches,
+       so there is nothing left for a graph to save; colq_query_set_option rejects it) */
     /* 1 (default): multi-GPU exchanges (state-mask OR, final index gather) run as own kernels that store into the
        peers' HBM over NVLink (CUDA-IPC mailboxes); 0: NCCL all-gathers */
     COLQ_OPT_PEER_EXCHANGE = 3,
@@ -101,12 +101,18 @@ typedef enum colq_option {
        0: always read in place, never keep a copy (tables larger than HBM).
        Sparsely walked columns (lazy FK chains) are read in place in every mode. */
     COLQ_OPT_PROMOTE = 6,
-    /* 1: the multi-GPU final gather runs as two more phases of the COOPERATIVE compaction launch instead of the two
-       peer_gather launches (default 0: measured slower on 2-8 B200s, kept selectable and parity-tested) */
+    /* 1 (default): the multi-GPU final gather rides on the kernel that writes the indices (root_fused / compact_fused): every
+       index is also stored into all ranks' mailbox slots over NVLink, the last block publishes the flags; the slots are
+       concatenated when the host fetches the indices.  0: two dedicated peer_gather launches per execution. */
     COLQ_OPT_FUSED_GATHER = 7,
     /* 1 (default): the multi-GPU mask PUBLISH is done by the last CTA of the scan kernel that produced the mask instead
        of a separate one-block launch */
-    COLQ_OPT_TAIL_PUBLISH = 8
+    COLQ_OPT_TAIL_PUBLISH = 8,
+    /* 1 (default): a root node that ends in an int-predicate scan runs as ONE persistent launch -- predicate scan, deferred
+       to-one chains, a tiny to-many hop feeding them (e.g. the 51-row state adjacency, with the multi-GPU mask COLLECT),
+       ordered compaction and the final gather (root_fused_kernel); 0: scan_rows / csr_pull / compact_fused launches.
+       Needs COLQ_OPT_FUSED_COMPACT == 1. */
+    COLQ_OPT_ROOT_FUSED = 9
 } colq_option;
 
 typedef struct colq_ctx colq_ctx;       /* one DataSystem instance  (E/DataSystemSerialIndices.java:14-22) */
@@ -131,6 +137,9 @@ typedef struct colq_stage {
 /* ---- lifecycle ------------------------------------------------------------------------------------ */
 
 int colq_abi_version(void);
+/* identifies the build: "<first 16 hex digits of the SHA-256 over the csrc/ files and this header> <nvcc arch flags>" -- lets a host
+   (and the driver's smoke run) check that the library it loaded was built from the sources next to it */
+const char *colq_build_id(void);
 /* new DataSystemSerialIndices() (E/DataSystemSerialIndices.java:20-22). device = CUDA ordinal. */
 colq_status colq_create(int device, colq_ctx **out_ctx);
 /* also destroys every query still alive on the context */

@@ -17,7 +17,8 @@ OK, FAILURE, THROW_INDEX_OOB, THROW_NULL, THROW_ILLEGAL_STATE, THROW_ILLEGAL_ARG
 # colq_placement
 REPLICATED, SHARDED = 0, 1
 # colq_option
-OPT_LAZY_FK, OPT_PROFILE, OPT_GRAPH, OPT_PEER_EXCHANGE, OPT_FUSED_COMPACT, OPT_DEFER_CHAINS, OPT_PROMOTE, OPT_FUSED_GATHER, OPT_TAIL_PUBLISH = 0, 1, 2, 3, 4, 5, 6, 7, 8
+OPT_LAZY_FK, OPT_PROFILE, OPT_PEER_EXCHANGE, OPT_FUSED_COMPACT, OPT_DEFER_CHAINS, OPT_PROMOTE, OPT_FUSED_GATHER, OPT_TAIL_PUBLISH, OPT_ROOT_FUSED = 0, 1, 3, 4, 5, 6, 7, 8, 9
+ABI_VERSION = 2
 
 
 class Timing(C.Structure):
@@ -35,6 +36,7 @@ _i32, _i64, _int = C.c_int32, C.c_int64, C.c_int
 # every exported symbol of include/colq.h: name -> (restype, argtypes)
 SIGNATURES = {
     "colq_abi_version": (_int, []),
+    "colq_build_id": (C.c_char_p, []),
     "colq_create": (_int, [_int, C.POINTER(_p)]),
     "colq_destroy": (_int, [_p]),
     "colq_last_error": (C.c_char_p, [_p]),

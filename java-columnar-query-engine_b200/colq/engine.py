@@ -201,7 +201,7 @@ class ColqContext:
 
     def __init__(self, device: int = 0):
         self.lib = _ffi.load()
-        if self.lib.colq_abi_version() != 1:
+        if self.lib.colq_abi_version() != _ffi.ABI_VERSION:
             raise RuntimeError("libcolq.so ABI version mismatch")
         self.handle = C.c_void_p()
         st = self.lib.colq_create(device, C.byref(self.handle))
@@ -621,7 +621,13 @@ class DataSystemColq(DataSystem):
             self.last_query.close()
         self.last_query = cq
         placement, base = self._placement.get(id(table), (_ffi.REPLICATED, 0))
-        local = res.indices - base if placement == _ffi.SHARDED else res.indices
+        if placement == _ffi.SHARDED:
+            # with a communicator colq_execute returns ALL ranks' global indices (include/colq.h); the result Table of
+            # this rank is built from its own rows only
+            mine = res.indices[(res.indices >= base) & (res.indices < base + table.size())]
+            local = mine - base
+        else:
+            local = res.indices
         matching_rows = BitSet.from_indices(local, table.size())
         if self.materialize == "device" and placement != _ffi.SHARDED:
             return QueryResult.Success(self._materialize_on_device(table, cq, local))

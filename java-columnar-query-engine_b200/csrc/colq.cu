@@ -163,7 +163,7 @@ struct QNode {
 };
 
 // one kernel launch (or collective / memset) of a planned query
-enum OpKind { K_SCAN_ROWS, K_SCAN_CODES, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER, K_COMPACT_FUSED, K_COMPACT_LOOKBACK, K_PEER_MASK_PUBLISH, K_PEER_MASK_COLLECT, K_PEER_GATHER };
+enum OpKind { K_SCAN_ROWS, K_SCAN_CODES, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER, K_COMPACT_FUSED, K_COMPACT_LOOKBACK, K_ROOT_FUSED, K_PEER_MASK_PUBLISH, K_PEER_MASK_COLLECT, K_PEER_GATHER };
 
 struct Op {
     OpKind kind;
@@ -188,6 +188,7 @@ struct Op {
     int64_t capacity = 0, row_base = 0, n_blocks = 0;
     CompactFusedParams cfused{};
     CompactLookbackParams clook{};
+    RootFusedParams rfused{};
     PeerMaskParams pmask{};
     PeerGatherParams pgather{};
     bool tail_publish = false;  // K_SCAN_STR / K_SCAN_CODES: the last CTA publishes the pushed mask to the peers
@@ -252,6 +253,7 @@ struct colq_ctx {
     // the context, allocated once: cudaHostAlloc / cudaFreeHost per query cost up to hundreds of ms on some hosts
     void* h_stage = nullptr;
     int compact_grid[2 * (CF_MAX_GATHER + 1)] = {};  // co-resident grid of compact_fused_kernel<NG, GATHER>
+    int root_fused_grid[SR_MAX_PRED + 1] = {};       // resident CTAs of root_fused_kernel<NP> on this device
     std::map<std::pair<int, size_t>, int> str_occupancy;  // (kernel mode, dynamic smem bytes) -> resident CTAs per SM
 };
 
@@ -259,13 +261,20 @@ struct colq_query {
     colq_ctx* ctx = nullptr;
     std::string table_name;
     std::vector<QNode> nodes;
-    int opt_lazy = 1, opt_profile = 0, opt_graph = 1, opt_peer = 1, opt_fused_compact = 1, opt_defer = 1, opt_promote = 2, opt_fused_gather = 0, opt_tail_publish = 1;
+    int opt_lazy = 1, opt_profile = 0, opt_peer = 1, opt_fused_compact = 1, opt_defer = 1, opt_promote = 2, opt_fused_gather = 1, opt_tail_publish = 1, opt_root_fused = 1;
     std::vector<GatherD> deferred;  // root-node FK chains resolved by the compaction kernel instead of the row scan
     int own_begin = -1, own_end = -1;  // root-node scan ops that depend on no child (hoistable behind a mask publish)
     std::vector<Column*> pending_promotions;  // host-resident columns whose HBM copy this execution fills
     bool lazy_oob = false;  // the plan walks a to-one column that was not range-checked at ingest
     int64_t promoted_bytes = 0;
     DevBuf barrier_buf;  // {arrival count, generation} of the cooperative compaction kernel
+    DevBuf rf_state_buf;  // root_fused_kernel: [ticket, finished counters | pad to 64 B | one u64 state per CTA]
+    int64_t rf_state_ctas = 0;
+    u32 rf_epoch = 0;
+    // the final gather of the last plan left every rank's indices in the mailbox slots (written by the kernel that
+    // produced them); the concatenation into one list runs when the host fetches the indices
+    bool gather_lazy = false;
+    PeerGatherParams lazy_pg{};
     DevBuf lookback_buf;  // [2 counters | pad | tile states] of the single-pass compaction kernel (zeroed once)
     int64_t lookback_tiles = 0;
     u32 lookback_epoch = 0;
@@ -298,9 +307,6 @@ struct colq_query {
     bool executed = false;
     int64_t local_count = -1;     // this rank's matching rows after the last fetch (-1: not fetched yet)
     DevBuf mat_a, mat_b;          // scratch of the result-materialisation gathers
-    // captured CUDA graph of the op sequence
-    cudaGraphExec_t graph_exec = nullptr;
-    std::vector<Op> graph_ops;
 };
 
 namespace {
@@ -792,6 +798,10 @@ struct Planner {
             q->deferred = gathers;
             gi = gathers.size();
         }
+        // an empty closed interval anywhere in the AND: no row of this node matches, every launch degenerates to clearing
+        // its mask -- and must not stream, upload or promote any column (a promotion would never be filled)
+        bool node_never = false;
+        for (const Crit* c : ints) node_never = node_never || c->lo > c->hi;
         while (pi < ints.size() || gi < gathers.size()) {
             Op o{};
             o.kind = K_SCAN_ROWS; o.node = xi; o.name = "scan_rows";
@@ -803,9 +813,9 @@ struct Planner {
                 const Crit* c = ints[pi++];
                 const Column& col = T.cols[c->ordinal];
                 IntPredD& d = P.pred[o.np++];
-                if (c->lo <= c->hi && n > 0) upload_on_first_scan(col, (size_t)round_up(n * 4 + 16, 16) + 64, (size_t)n * 4, 0, 0);
+                if (!node_never && n > 0) upload_on_first_scan(col, (size_t)round_up(n * 4 + 16, 16) + 64, (size_t)n * 4, 0, 0);
                 d.col = (const int32_t*)col.data.ptr;
-                if (c->lo > c->hi) {  // empty closed interval: no value satisfies it
+                if (node_never) {  // empty closed interval: no value satisfies it
                     o.never = true;
                     d.lo = 0; d.span = 0;
                 } else {
@@ -939,6 +949,9 @@ void stage_name(const Op& o, char* out, size_t cap) {
     else if (o.kind == K_SCAN_ROWS && o.dict_scan) snprintf(out, cap, "scan_rows_dictionary");
     else if (o.kind == K_SCAN_ROWS) snprintf(out, cap, "scan_rows<%d,%d,%s>%s", o.np, o.ng, o.eager ? "eager" : "lazy", o.rows.push.fk ? "+push" : "");
     else if (o.kind == K_SCAN_STR) snprintf(out, cap, "%s<op%d>%s%s", o.name, o.str.op, o.str.push.fk ? "+push" : "", o.tail_publish ? "+publish" : "");
+    else if (o.kind == K_ROOT_FUSED)
+        snprintf(out, cap, "root_fused<%d,%d>%s%s%s", o.np, o.ng, o.rfused.pre.n > 0 ? (o.rfused.pre.pm.n_words > 0 ? "+collect+csr" : "+csr") : "",
+                 o.rfused.pg.n_ranks > 0 ? "+gather" : "", "");
     else snprintf(out, cap, "%s", o.name);
 }
 
@@ -1090,8 +1103,28 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
             q->timing.kernel_launches++;
             break;
         }
+        case K_ROOT_FUSED: {
+            RootFusedParams& P = o.rfused;
+            if (P.pre.pm.n_words > 0) P.pre.pm.epoch = q->ops[o.publish_op].pmask.epoch;
+            if (P.pg.n_ranks > 0) {
+                P.pg.epoch = ++ctx->peer.gather_epoch;
+                q->lazy_pg = P.pg;
+            }
+            if (++q->rf_epoch == 0xffffffffu) {  // epoch wrap: start over on cleared states
+                CU(ctx, cudaMemsetAsync(q->rf_state_buf.ptr, 0, q->rf_state_buf.bytes, s));
+                q->rf_epoch = 1;
+            }
+            P.epoch = q->rf_epoch;
+            if (o.np == 1) root_fused_kernel<1><<<o.grid, RF_THREADS, 0, s>>>(P);
+            else root_fused_kernel<2><<<o.grid, RF_THREADS, 0, s>>>(P);
+            q->timing.kernel_launches++;
+            break;
+        }
         case K_COMPACT_FUSED: {
-            if (o.gather) o.cfused.pg.epoch = ++ctx->peer.gather_epoch;
+            if (o.gather) {
+                o.cfused.pg.epoch = ++ctx->peer.gather_epoch;
+                q->lazy_pg = o.cfused.pg;
+            }
             void* args[] = {(void*)&o.cfused};
             CU(ctx, cudaLaunchCooperativeKernel(compact_fused_fn(o.ng, o.gather), dim3(o.grid), dim3(CP_THREADS), args, 0, s));
             q->timing.kernel_launches++;
@@ -1134,7 +1167,9 @@ colq_status ensure_idx_capacity(colq_query* q, int64_t want) {
     }
     q->d_total = (u64*)q->idx_buf.ptr;
     q->d_idx = (int32_t*)q->idx_buf.ptr + GATHER_HEADER_WORDS;
-    q->idx_capacity = (int64_t)(q->idx_buf.bytes / 4) - GATHER_HEADER_WORDS;
+    // exactly what was asked for, never the slack of a recycled (up to 25 % larger) block: the capacity is an NCCL send
+    // count and the stride of the gathered blocks, so it must be the same number on every rank
+    q->idx_capacity = want;
     return COLQ_OK;
 }
 
@@ -1163,10 +1198,22 @@ colq_status run_pipeline(colq_query* q) {
     NodeBits root;
     ST(pl.eval(0, Consume{}, &root));
 
+    // ---- root fusion (COLQ_OPT_ROOT_FUSED): when the root node ends in a plain predicate scan (its to-one chains, if
+    //      any, deferred), that scan, the chains, the compaction and the final gather become ONE persistent launch
+    //      (root_fused_kernel); a tiny to-many hop that feeds a chain is folded in as well (below)
+    bool fuse_root = false;
+    if (q->opt_root_fused && q->opt_fused_compact == 1 && !q->ops.empty() && !root.all_ones) {
+        const Op& l = q->ops.back();
+        fuse_root = l.kind == K_SCAN_ROWS && l.node == 0 && !l.never && !l.dict_scan && !l.eager && l.ng == 0 && l.np >= 1 &&
+                    l.rows.push.fk == nullptr && l.rows.out_bits != nullptr && l.rows.out_bits == root.bits;
+        for (int p = 0; fuse_root && p < l.np; ++p) fuse_root = l.rows.pred[p].promote == nullptr;
+    }
+
     // ---- peepholes over the op list (multi-GPU exchanges)
     // (1) overlap: the root's own predicate scans depend on no child, so they run between the first mask PUBLISH and
     //     its COLLECT -- the NVLink round trip and the wait for the slowest rank hide behind a bandwidth-bound scan
-    if (q->own_begin >= 0) {
+    //     (a fused root gets the same overlap inside its kernel: the COLLECT sits between its phases A and B)
+    if (q->own_begin >= 0 && !fuse_root) {
         int pub = -1;
         for (int i = 0; i < q->own_begin; ++i)
             if (q->ops[i].kind == K_PEER_MASK_PUBLISH) { pub = i; break; }
@@ -1233,8 +1280,85 @@ colq_status run_pipeline(colq_query* q) {
     ST(pool_alloc(q, (size_t)n_blocks * 8, &bo));
     q->gather_is_peer = peer_gather;
     q->gather_block_cap = q->idx_capacity;
-    const bool coop_gather = peer_gather && q->opt_fused_gather && q->opt_fused_compact;  // needs the cooperative kernel
-    if (q->opt_fused_compact >= 2 && !coop_gather) {
+    q->gather_lazy = false;
+    // peer-memory final gather written by the kernel that produces the indices (gather_store / gather_tail)
+    auto fill_fused_gather = [&](PeerGatherParams& G) -> colq_status {
+        if (!q->ginfo_buf.ptr) ST(dev_alloc(ctx, q->ginfo_buf, 64));
+        const int64_t cap = std::min<int64_t>(q->idx_capacity, ctx->peer.slot_cap);
+        if (q->gout_buf.bytes < (size_t)cap * 4 * ctx->n_ranks) ST(dev_alloc(ctx, q->gout_buf, (size_t)cap * 4 * ctx->n_ranks));
+        G.count = q->d_total; G.idx = q->d_idx; G.idx_capacity = q->idx_capacity; G.slot_cap = cap;
+        G.slot_bytes = ctx->peer.slot_bytes; G.n_ranks = ctx->n_ranks; G.rank = ctx->rank; G.peers = ctx->peer.d_peers;
+        G.done = ctx->peer.d_done; G.blocks_per_peer = 0; G.status = ctx->peer.d_status;
+        G.out = (int32_t*)q->gout_buf.ptr; G.info = (u64*)q->ginfo_buf.ptr;
+        q->gather_is_peer = true;
+        q->gather_block_cap = cap;
+        q->gather_lazy = true;
+        return COLQ_OK;
+    };
+    bool coop_gather = peer_gather && q->opt_fused_gather && q->opt_fused_compact == 1;  // the gather rides on the index writer
+    if (fuse_root) {
+        // ---- the root's scan + chains + (tiny to-many hop) + compaction + gather as one persistent launch
+        Op sc = q->ops.back();
+        q->ops.pop_back();
+        Op f{};
+        f.kind = K_ROOT_FUSED; f.node = 0; f.np = sc.np; f.ng = (int)q->deferred.size();
+        f.acct_rows = n; f.acct_bytes = sc.acct_bytes;
+        RootFusedParams& P = f.rfused;
+        P.n = n;
+        for (int p = 0; p < sc.np; ++p) P.pred[p] = sc.rows.pred[p];
+        P.in_bits = sc.rows.in_bits;
+        P.bits = root.bits;
+        P.n_chunks = (n + SR_WARP_ROWS - 1) / SR_WARP_ROWS;
+        if (ctx->root_fused_grid[sc.np] == 0) {
+            int occ = 0;
+            const void* fn = sc.np == 1 ? (const void*)root_fused_kernel<1> : (const void*)root_fused_kernel<2>;
+            CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, RF_THREADS, 0));
+            ctx->root_fused_grid[sc.np] = ctx->sm_count * std::max(1, occ);
+        }
+        static const int rf_grid_env = getenv("COLQ_RF_GRID") ? atoi(getenv("COLQ_RF_GRID")) : 0;  // experiment knob: CTAs per SM
+        const int64_t max_grid = rf_grid_env > 0 ? (int64_t)ctx->sm_count * rf_grid_env : ctx->root_fused_grid[sc.np];
+        f.grid = (int)std::max<int64_t>(1, std::min<int64_t>((P.n_chunks + RF_WARPS - 1) / RF_WARPS, max_grid));
+        P.chunks_per_warp = std::max<int64_t>(1, (P.n_chunks + (int64_t)f.grid * RF_WARPS - 1) / ((int64_t)f.grid * RF_WARPS));
+        // candidate lists: room for ~3 % of a warp's rows, at least 128; denser CTAs take the dense path
+        P.list_cap = (int)std::max<int64_t>(128, P.chunks_per_warp * (SR_WARP_ROWS / 32));
+        void* lists;
+        ST(pool_alloc(q, (size_t)f.grid * RF_WARPS * P.list_cap * 4, &lists));
+        P.lists = (u32*)lists;
+        if (q->rf_state_ctas < f.grid) {
+            ST(dev_alloc(ctx, q->rf_state_buf, 64 + (size_t)f.grid * 8));
+            CU(ctx, cudaMemsetAsync(q->rf_state_buf.ptr, 0, q->rf_state_buf.bytes, ctx->stream));
+            q->rf_state_ctas = f.grid;
+            q->rf_epoch = 0;
+        }
+        P.counters = (u32*)q->rf_state_buf.ptr;
+        P.cta_state = (u64*)((char*)q->rf_state_buf.ptr + 64);
+        P.ng = f.ng;
+        for (int g = 0; g < f.ng; ++g) P.gather[g] = q->deferred[g];
+        P.total = q->d_total; P.out_idx = q->d_idx; P.capacity = q->idx_capacity; P.row_base = RT.row_base;
+        // fold a tiny to-many hop whose output only feeds a deferred chain: every CTA redoes it in shared memory
+        for (int g = 0; g < f.ng && P.pre.n == 0; ++g) {
+            if (!P.gather[g].bits) continue;
+            for (size_t k = 0; k < q->ops.size(); ++k) {
+                const Op& c = q->ops[k];
+                if (c.kind != K_CSR_PULL || c.csr.out_bits != P.gather[g].bits || c.csr.push.fk != nullptr) continue;
+                if (c.csr.n <= 0 || c.csr.n > RF_PRE_ROWS || c.csr.nnz > RF_PRE_EDGES || c.csr.n_child > PUSH_SMEM_BITS) continue;
+                P.pre = c.csr;
+                f.publish_op = c.publish_op;
+                f.acct_bytes += c.acct_bytes;
+                q->ops.erase(q->ops.begin() + k);
+                for (Op& o : q->ops)
+                    if (o.publish_op > (int)k) o.publish_op -= 1;
+                if (f.publish_op > (int)k) f.publish_op -= 1;
+                break;
+            }
+        }
+        if (P.pre.n > 0)
+            for (int g = 0; g < f.ng; ++g)
+                if (P.gather[g].bits == P.pre.out_bits) P.pre_mask |= 1u << g;
+        if (coop_gather) ST(fill_fused_gather(P.pg));
+        f.name = "root_fused";
+        q->ops.push_back(f);
+    } else if (q->opt_fused_compact >= 2 && !coop_gather) {
         // single pass with decoupled look-back: one CTA per tile, ordinary launch
         const int ng = (int)q->deferred.size();
         const int64_t n_tiles = std::max<int64_t>(1, (n_words + CF_WORDS_PER_TILE - 1) / CF_WORDS_PER_TILE);
@@ -1257,12 +1381,10 @@ colq_status run_pipeline(colq_query* q) {
         f.grid = (int)n_tiles;
         q->ops.push_back(f);
     } else if (q->opt_fused_compact) {
-        // one cooperative launch: per-tile popcount, grid barrier, ordered write
+        // one cooperative launch: per-tile popcount, grid barrier, ordered write (+ the peer-memory final gather:
+        // COLQ_OPT_FUSED_GATHER, default on)
         const int ng = (int)q->deferred.size();
-        // COLQ_OPT_FUSED_GATHER: the final gather becomes phases 3 and 4 of the compaction launch.  Off by default: on
-        // 2, 4 and 8 B200s the two dedicated launches were faster (0.165 vs 0.178 ms per step at N=8) -- the extra grid
-        // barriers serialise on the slowest block, while separate kernels overlap their tails with the peers' stores.
-        const bool fuse_gather = peer_gather && q->opt_fused_gather;
+        const bool fuse_gather = coop_gather;
         const int variant = ng * 2 + (fuse_gather ? 1 : 0);
         if (ctx->compact_grid[variant] == 0) {
             int occ = 0;
@@ -1286,21 +1408,13 @@ colq_status run_pipeline(colq_query* q) {
         f.name = ng ? (fuse_gather ? "compact_fused+chains+gather" : "compact_fused+chains") : (fuse_gather ? "compact_fused+gather" : "compact_fused");
         f.grid = (int)std::min<int64_t>(n_tiles, ctx->compact_grid[variant]);
         if (fuse_gather) {
-            if (!q->ginfo_buf.ptr) ST(dev_alloc(ctx, q->ginfo_buf, 64));
-            const int64_t cap = std::min<int64_t>(q->idx_capacity, ctx->peer.slot_cap);
-            if (q->gout_buf.bytes < (size_t)cap * 4 * ctx->n_ranks) ST(dev_alloc(ctx, q->gout_buf, (size_t)cap * 4 * ctx->n_ranks));
-            PeerGatherParams& G = P.pg;
-            G.count = q->d_total; G.idx = q->d_idx; G.idx_capacity = q->idx_capacity; G.slot_cap = ctx->peer.slot_cap;
-            G.slot_bytes = ctx->peer.slot_bytes; G.n_ranks = ctx->n_ranks; G.rank = ctx->rank; G.peers = ctx->peer.d_peers;
-            G.done = ctx->peer.d_done; G.blocks_per_peer = 0; G.status = ctx->peer.d_status;
-            G.out = (int32_t*)q->gout_buf.ptr; G.info = (u64*)q->ginfo_buf.ptr;
+            ST(fill_fused_gather(P.pg));
             f.gather = true;
-            f.capacity = cap;
-            q->gather_is_peer = true;
-            q->gather_block_cap = cap;
+            f.capacity = q->gather_block_cap;
         }
         q->ops.push_back(f);
     } else {
+        coop_gather = false;
         Op p{};
         p.kind = K_POPC; p.node = 0; p.src = root.bits; p.n_words = n_words; p.n_blocks = n_blocks; p.block_counts = (u32*)bc;
         p.name = "popc_blocks"; p.acct_rows = n; p.acct_bytes = n_words * 4;
@@ -1317,7 +1431,7 @@ colq_status run_pipeline(colq_query* q) {
         q->ops.push_back(c);
     }
     if (q->gathered && !coop_gather) {
-        // final gather of matched indices, entirely on the device
+        // final gather of matched indices as launches of its own, entirely on the device
         if (!q->ginfo_buf.ptr) ST(dev_alloc(ctx, q->ginfo_buf, 64));
         if (peer_gather) {
             // own kernels over NVLink peer memory: every rank stores its indices into every peer's mailbox slot
@@ -1327,7 +1441,7 @@ colq_status run_pipeline(colq_query* q) {
             Op g{};
             g.kind = K_PEER_GATHER; g.node = 0; g.name = "peer_gather_indices"; g.capacity = cap;
             PeerGatherParams& P = g.pgather;
-            P.count = q->d_total; P.idx = q->d_idx; P.idx_capacity = q->idx_capacity; P.slot_cap = ctx->peer.slot_cap;
+            P.count = q->d_total; P.idx = q->d_idx; P.idx_capacity = q->idx_capacity; P.slot_cap = cap;
             P.slot_bytes = ctx->peer.slot_bytes; P.n_ranks = ctx->n_ranks; P.rank = ctx->rank; P.peers = ctx->peer.d_peers;
             P.done = ctx->peer.d_done; P.blocks_per_peer = std::max(1, std::min(32, 2 * ctx->sm_count / ctx->n_ranks)); P.status = ctx->peer.d_status;
             P.out = (int32_t*)q->gout_buf.ptr; P.info = (u64*)q->ginfo_buf.ptr;
@@ -1444,7 +1558,10 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
         u32 status = 0;
         CU(ctx, cudaMemcpyAsync(&status, ctx->peer.d_status, 4, cudaMemcpyDeviceToHost, s));
         CU(ctx, cudaStreamSynchronize(s));
-        if (status != 0) return fail(ctx, COLQ_ERR_DEVICE, "peer-memory exchange timed out waiting for another rank");
+        if (status != 0) {
+            cudaMemsetAsync(ctx->peer.d_status, 0, 4, s);  // report once; later fetches on this context start clean
+            return fail(ctx, COLQ_ERR_DEVICE, "peer-memory exchange timed out waiting for another rank");
+        }
     }
     int64_t count = (int64_t)local;
     const int32_t* src_idx = q->d_idx;
@@ -1461,6 +1578,12 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
         }
         count = (int64_t)ginfo[2];
         src_idx = (const int32_t*)q->gout_buf.ptr;
+        if (q->gather_lazy && out_idx && count > 0 && idx_cap >= count) {
+            // the ranks' indices sit in this rank's mailbox slots: concatenate their valid prefixes in rank order now
+            peer_gather_recv_kernel<<<grid_for(block_cap * ctx->n_ranks / 4 + 1, 256, ctx->sm_count, 2), 256, 0, s>>>(q->lazy_pg);
+            CU(ctx, cudaGetLastError());
+            q->timing.kernel_launches++;
+        }
     } else if ((int64_t)local > q->idx_capacity) {
         // index buffer was too small: grow it and run again (happens once per query, the capacity sticks)
         q->want_idx_capacity = (int64_t)local + (int64_t)local / 8 + 1024;
@@ -1648,6 +1771,11 @@ void destroy_peerbox(colq_ctx* ctx) {
 extern "C" {
 
 int colq_abi_version(void) { return COLQ_ABI_VERSION; }
+
+#ifndef COLQ_BUILD_ID
+#define COLQ_BUILD_ID "unknown"
+#endif
+const char* colq_build_id(void) { return COLQ_BUILD_ID; }
 
 colq_status colq_create(int device, colq_ctx** out_ctx) {
     if (!out_ctx) return COLQ_THROW_NULL;
@@ -2217,7 +2345,6 @@ colq_status colq_query_destroy(colq_query* q) {
     live.erase(std::remove(live.begin(), live.end(), q), live.end());
     cudaSetDevice(q->ctx->device);
     cudaStreamSynchronize(q->ctx->stream);
-    if (q->graph_exec) cudaGraphExecDestroy(q->graph_exec);
     if (q->ev_start) cudaEventDestroy(q->ev_start);
     if (q->ev_stop) cudaEventDestroy(q->ev_stop);
     for (cudaEvent_t e : q->stage_ev) cudaEventDestroy(e);
@@ -2288,13 +2415,13 @@ colq_status colq_query_set_option(colq_query* q, colq_option option, int value) 
     switch (option) {
         case COLQ_OPT_LAZY_FK: q->opt_lazy = value; break;
         case COLQ_OPT_PROFILE: q->opt_profile = value; break;
-        case COLQ_OPT_GRAPH: q->opt_graph = value; break;
         case COLQ_OPT_PEER_EXCHANGE: q->opt_peer = value; break;
         case COLQ_OPT_FUSED_COMPACT: q->opt_fused_compact = value; break;
         case COLQ_OPT_DEFER_CHAINS: q->opt_defer = value; break;
         case COLQ_OPT_PROMOTE: q->opt_promote = value; break;
         case COLQ_OPT_FUSED_GATHER: q->opt_fused_gather = value; break;
         case COLQ_OPT_TAIL_PUBLISH: q->opt_tail_publish = value; break;
+        case COLQ_OPT_ROOT_FUSED: q->opt_root_fused = value; break;
         default: return fail(q->ctx, COLQ_THROW_ILLEGAL_ARG, "unknown option %d", (int)option);
     }
     return COLQ_OK;

@@ -80,6 +80,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
 
 __device__ __forceinline__ bool bit_test(const u32* bits, int64_t i) { return (bits[i >> 5] >> (i & 31)) & 1u; }
 
+__device__ __forceinline__ u64 ld_volatile_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(u64* p, u64 v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // push epilogue: ExecutionContext.Node.filterParent for a to-one association (E/ExecutionContext.java:100-122,
 // Association.One branch :114).  A matching child row sets the bit of its parent row in `reach`.
@@ -724,8 +733,10 @@ __device__ __forceinline__ bool bytes_equal(const W& hay, u32 pos, const u32* ne
 }
 
 // String.compareTo sign (UTF-16 code-unit order on UTF-8 bytes; a supplementary code point, lead byte >= 0xF0, sorts
-// below U+E000..U+FFFF, lead bytes 0xEE/0xEF; a differing continuation byte implies equal lead bytes)
-__device__ __forceinline__ int utf16_key(u32 b) { return b >= 0xF0u ? 0xED * 2 + 1 : (int)b * 2; }
+// below U+E000..U+FFFF, lead bytes 0xEE/0xEF, and above everything with a lead byte <= 0xED; two supplementary code
+// points keep their byte order = code-point order = surrogate order; a differing continuation byte implies equal lead
+// bytes)
+__device__ __forceinline__ int utf16_key(u32 b) { return b >= 0xF0u ? 0xED * 512 + 256 + (int)(b - 0xF0u) : (int)b * 512; }
 template <class W>
 __device__ __forceinline__ int compare_to(const W& hay, u32 pos, int len, const u32* needle_w, int nlen) {
     int m = len < nlen ? len : nlen;
@@ -1323,7 +1334,8 @@ struct PeerGatherParams {
     const u64* count;       // this rank's match count (device)
     const int32_t* idx;     // this rank's ascending global row indices
     int64_t idx_capacity;   // how many of them were actually written
-    int64_t slot_cap;       // indices one mailbox slot can hold
+    int64_t slot_cap;       // EFFECTIVE per-rank cap: min(index capacity, indices one mailbox slot can hold) -- the same
+                            // number on the sending and on the receiving side
     size_t slot_bytes;
     int n_ranks, rank;
     uint8_t* const* peers;
@@ -1408,6 +1420,55 @@ __global__ void __launch_bounds__(256) peer_gather_recv_kernel(const PeerGatherP
     }
 }
 
+// ---- final gather fused into the kernel that writes the indices (compact_fused<.., true>, root_fused) --------------
+// The writer of result position `pos` stores the index straight into slot [parity][my rank] of EVERY rank's mailbox
+// (plain 4-byte stores over NVLink, coalesced per warp because neighbouring threads hold neighbouring positions); no
+// separate send launch, no second pass over the index list.  P.slot_cap is the EFFECTIVE per-rank cap
+// min(index capacity, mailbox slot capacity): sender and receiver clamp to the same number.
+__device__ __forceinline__ void gather_store(const PeerGatherParams& P, int64_t pos, int32_t v) {
+    if (pos >= P.slot_cap) return;
+    const size_t off = PEER_GATHER_AREA_OFFSET + ((size_t)(P.epoch & 1) * P.n_ranks + P.rank) * P.slot_bytes + GATHER_SLOT_HEADER + (size_t)pos * 4;
+    for (int r = 0; r < P.n_ranks; ++r) *reinterpret_cast<int32_t*>(P.peers[r] + off) = v;
+}
+
+// Run by ONE block (all of its threads) after every block of the launch has issued its gather_store()s and fenced:
+// publishes this rank's true count and the epoch flag in every rank's slot header, then waits until every rank's flag
+// has arrived here and summarises the counts: info[0] = rows present in the slots (sum of min(count, cap)), info[1] =
+// largest per-rank count (the host's overflow check), info[2] = true total.  The wait is also what keeps ranks in step:
+// nobody starts the next execution (and overwrites the other slot parity) before all peers finished this one.  The
+// concatenation of the slots into one contiguous list is done only when the host asks for the indices
+// (peer_gather_recv_kernel at colq_fetch).
+__device__ __forceinline__ void gather_tail(const PeerGatherParams& P, const u64* total) {
+    __shared__ int s_gt_ok;
+    const size_t area = PEER_GATHER_AREA_OFFSET + (size_t)(P.epoch & 1) * P.n_ranks * P.slot_bytes;
+    const u64 true_count = *reinterpret_cast<const volatile u64*>(total);
+    if (threadIdx.x == 0) s_gt_ok = 1;
+    if ((int)threadIdx.x < P.n_ranks) {
+        u64* slot = reinterpret_cast<u64*>(P.peers[threadIdx.x] + area + (size_t)P.rank * P.slot_bytes);
+        slot[1] = true_count;
+        __threadfence_system();
+        st_release_sys(slot, P.epoch);
+    }
+    __syncthreads();
+    const uint8_t* mine = P.peers[P.rank] + area;
+    if ((int)threadIdx.x < P.n_ranks) {
+        if (!peer_wait(reinterpret_cast<const u64*>(mine + (size_t)threadIdx.x * P.slot_bytes), P.epoch, P.status)) s_gt_ok = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_gt_ok) {
+        u64 rows = 0, maxc = 0, sum = 0;
+        for (int r = 0; r < P.n_ranks; ++r) {
+            const u64 c = __ldcg(reinterpret_cast<const u64*>(mine + (size_t)r * P.slot_bytes) + 1);
+            rows += c < (u64)P.slot_cap ? c : (u64)P.slot_cap;
+            maxc = c > maxc ? c : maxc;
+            sum += c;
+        }
+        P.info[0] = rows;
+        P.info[1] = maxc;
+        P.info[2] = sum;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3'  single-launch compaction (cooperative): per-tile popcount, grid barrier, every block scans the tile counts it
 // needs and writes its indices.  Same result as popc_blocks + scan_counts + compact with one launch instead of three;
@@ -1473,9 +1534,10 @@ __device__ __forceinline__ u32 cf_load(const CompactFusedParams& P, int64_t tile
 // thread of the grid (all walks in flight at once) instead of stalling the streaming warps of the scan.
 constexpr int CF_LIST_CAP = 4096;  // survivors of one 131072-row tile that are resolved block-wide (3 % selectivity)
 
-// GATHER (multi-GPU, sharded root): after the ordered write the same launch stores this rank's indices into every
-// peer's mailbox slot over NVLink (phase 3: coalesced 128-bit stores, then the epoch flags), waits for all ranks'
-// flags and concatenates the valid prefixes in rank order (phase 4) -- the former peer_gather_send / _recv launches.
+// GATHER (multi-GPU, sharded root): the ordered write of phase 2 also stores every index into all ranks' mailbox slots
+// over NVLink (gather_store) and the last block to finish publishes the flags and waits for the peers (gather_tail):
+// no extra grid barrier, no send / receive launches (r01 ran the gather as two more barrier-separated phases of this
+// kernel, which was slower than separate launches; writing from phase 2 is not).
 template <int NG, bool GATHER = false>
 __global__ void __launch_bounds__(CP_THREADS) compact_fused_kernel(const CompactFusedParams P) {
     __shared__ u32 s_warp[33];
@@ -1586,6 +1648,7 @@ __global__ void __launch_bounds__(CP_THREADS) compact_fused_kernel(const Compact
                         int b = __ffs(m) - 1;
                         m &= m - 1;
                         if (pos < P.capacity) P.out_idx[pos] = (int32_t)(rb + b);
+                        if (GATHER) gather_store(P.pg, pos, (int32_t)(rb + b));
                         ++pos;
                     }
                 }
@@ -1597,73 +1660,400 @@ __global__ void __launch_bounds__(CP_THREADS) compact_fused_kernel(const Compact
     if ((P.n_tiles - 1) % gridDim.x == blockIdx.x && threadIdx.x == 0) *P.total = running + P.tile_counts[P.n_tiles - 1];
 
     if (GATHER) {
+        // the indices already went to every rank's mailbox slot in phase 2; the last block to finish publishes the count
+        // and the epoch flags, then waits for every peer's flag (gather_tail)
         const PeerGatherParams& G = P.pg;
-        grid_barrier(P.barrier);  // every index and the total are in HBM
-        // ---- phase 3: my slice of the index list goes to every rank's mailbox (my own included)
-        const size_t area = PEER_GATHER_AREA_OFFSET + (size_t)(G.epoch & 1) * G.n_ranks * G.slot_bytes;
-        const u64 true_count = *reinterpret_cast<const volatile u64*>(P.total);
-        int64_t n = (int64_t)true_count;
-        if (n > P.capacity) n = P.capacity;
-        if (n > G.slot_cap) n = G.slot_cap;
-        const int64_t n4 = n >> 2;  // whole 128-bit lines; block 0 adds the 0..3 tail elements
-        const int4* src4 = reinterpret_cast<const int4*>(P.out_idx);
-        for (int r = 0; r < G.n_ranks; ++r) {
-            int32_t* dst = reinterpret_cast<int32_t*>(G.peers[r] + area + (size_t)G.rank * G.slot_bytes + GATHER_SLOT_HEADER);
-            int4* dst4 = reinterpret_cast<int4*>(dst);
-            for (int64_t i = (int64_t)blockIdx.x * CP_THREADS + threadIdx.x; i < n4; i += (int64_t)gridDim.x * CP_THREADS) dst4[i] = __ldcg(src4 + i);
-            if (blockIdx.x == 0 && (int64_t)threadIdx.x < n - (n4 << 2)) dst[(n4 << 2) + threadIdx.x] = __ldcg(P.out_idx + (n4 << 2) + threadIdx.x);
-        }
+        __shared__ u32 s_last;
         __threadfence_system();
         __syncthreads();
-        if (threadIdx.x == 0) {
-            const u32 prev = atomicAdd(&G.done[0], 1u);
-            if (prev == gridDim.x - 1) {  // every block's stores are out: publish count + flag everywhere
-                G.done[0] = 0;
-                __threadfence_system();
-                for (int r = 0; r < G.n_ranks; ++r) {
-                    u64* slot = reinterpret_cast<u64*>(G.peers[r] + area + (size_t)G.rank * G.slot_bytes);
-                    slot[1] = true_count;
+        if (threadIdx.x == 0) s_last = (atomicAdd(&G.done[0], 1u) == gridDim.x - 1) ? 1u : 0u;
+        __syncthreads();
+        if (s_last) {
+            if (threadIdx.x == 0) G.done[0] = 0;
+            gather_tail(G, P.total);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1+K4+K3  root_fused: the whole ROOT node in one persistent launch
+//
+//   filterSelf of the root (E/ExecutionContext.java:79-94, int predicates as in scan_rows)
+//   + the root's deferred to-one chains (filterParent One branch, :114, pull form)
+//   + (optional) a tiny to-many hop feeding such a chain, e.g. the 51-row / 219-edge state adjacency (:111-113), with the
+//     multi-GPU mask COLLECT in front of it
+//   + the ascending index half of Table.subset (M/InMemoryTable.java:121-131)
+//   + (multi-GPU) the final gather of the matched indices into every rank's mailbox.
+//
+// r01 ran these as scan_rows -> csr_pull -> compact_fused -> peer_gather_send -> peer_gather_recv: the compaction
+// re-read the dense root mask twice across a grid barrier (57 us at 38 % of DRAM bandwidth for 0.17 GB) and the
+// launch-latency-class kernels were a third of the 8-GPU step.  Here:
+//
+// Phase A (bandwidth): every WARP owns a contiguous range of 512-row chunks (virtual warp id = CTA ticket * 8 + warp,
+//   tickets handed out in CTA start order).  It streams the predicate columns with the same 128-bit streaming loads as
+//   scan_rows, stores the mask words (the root BitSet stays available to the host), and appends the surviving rows --
+//   0.16 % for the population predicate -- to its own ordered candidate list in global memory (ballot + warp prefix, no
+//   block synchronisation anywhere in the streaming loop).  Ascending warp id == ascending row order.
+// Phase B (latency, ~400 candidates per CTA): (1) collect the exchanged mask and redo the tiny to-many hop into shared
+//   memory -- every CTA does it redundantly, it is 219 edges; (2) walk the chains of all candidates of the CTA at once,
+//   one thread per candidate, clearing failed bits in the mask with atomicAnd; (3) publish the CTA's survivor count and
+//   sum the counts of all lower tickets (decoupled look-back: a CTA only waits for CTAs that started before it, so an
+//   ordinary launch cannot deadlock); (4) ordered write of the indices, locally and (multi-GPU) into all peers' slots.
+//   The last CTA to finish re-arms the counters and runs gather_tail.
+// A CTA whose candidate list overflowed (selectivity above ~3 %) falls back, for its own row range only, to the dense
+//   per-word walk over the mask it just wrote (same as compact_fused's dense tiles).
+// ---------------------------------------------------------------------------------------------
+
+constexpr int RF_THREADS = 256;
+constexpr int RF_WARPS = RF_THREADS / 32;
+constexpr int RF_PRE_ROWS = PUSH_SMEM_BITS;   // a folded to-many hop has at most this many parent / child rows ...
+constexpr int RF_PRE_EDGES = CSR_SMEM_EDGES;  // ... and this many edges
+
+struct RootFusedParams {
+    int64_t n;                   // root rows
+    IntPredD pred[SR_MAX_PRED];  // NP of them (promote pointers unused: the planner does not fuse a promoting scan)
+    const u32* in_bits;          // nullable: bits the root already has from other launches
+    u32* bits;                   // root mask, always written
+    int64_t n_chunks;            // ceil(n / 512)
+    int64_t chunks_per_warp;
+    u32* lists;                  // [gridDim.x * RF_WARPS][list_cap] candidate rows (bit 31: chain failed)
+    int list_cap;
+    u32* counters;               // [0] CTA tickets, [1] finished CTAs; both are zero between launches
+    u64* cta_state;              // [gridDim.x]  epoch << 32 | survivors of that ticket
+    u32 epoch;                   // differs from the previous launch on the same cta_state (host resets at wrap)
+    int ng;
+    GatherD gather[CF_MAX_GATHER];
+    u32 pre_mask;                // bit g: gather[g].bits is the output of `pre` (held in shared memory)
+    CsrPullParams pre;           // pre.n > 0: folded tiny to-many hop (pm.n_words > 0: collect the mask exchange first)
+    u64* total;
+    int32_t* out_idx;
+    int64_t capacity;
+    int64_t row_base;
+    PeerGatherParams pg;         // pg.n_ranks > 0: final gather fused in
+};
+
+__device__ __forceinline__ bool rf_chain(const GatherD& g, const u32* bits, int64_t r) {
+    for (int d = 0; d < g.depth; ++d) {
+        const int32_t t = g.fk[d][r];
+        if (t < 0 || t >= g.n[d]) {
+            if (t != -1 && g.oob != nullptr) *g.oob = 1u;
+            return false;
+        }
+        r = t;
+    }
+    return bits == nullptr ? true : bit_test(bits, r);
+}
+
+template <int NP>
+__global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFusedParams P) {
+    __shared__ u32 s_warp[33];
+    __shared__ u32 s_ticket, s_last, s_overflow;
+    __shared__ u32 s_wcnt[RF_WARPS], s_woff[RF_WARPS + 1];
+    __shared__ u64 s_base;
+    __shared__ u32 s_pre[PUSH_SMEM_WORDS];     // output bits of the folded hop
+    __shared__ u32 s_child[PUSH_SMEM_WORDS];   // its child mask
+    __shared__ int32_t s_tgt[RF_PRE_EDGES];    // its targets
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        s_ticket = atomicAdd(&P.counters[0], 1u);
+        s_overflow = 0;
+    }
+    __syncthreads();
+    const u32 vcta = s_ticket;
+
+    // ======================= phase A: stream, test, store mask words, list the survivors =======================
+    const int64_t vwarp = (int64_t)vcta * RF_WARPS + warp;
+    const int64_t c_lo = vwarp * P.chunks_per_warp;
+    const int64_t c_hi = (c_lo + P.chunks_per_warp) < P.n_chunks ? (c_lo + P.chunks_per_warp) : P.n_chunks;
+    u32* my_list = P.lists + (size_t)vwarp * P.list_cap;
+    u32 cnt = 0;
+    for (int64_t c = c_lo; c < c_hi; ++c) {
+        const int64_t wbase = c * SR_WARP_ROWS;
+        u32 nib[SR_V];
+        if (wbase + SR_WARP_ROWS <= P.n) {
+            int4 v[NP][SR_V];
+#pragma unroll
+            for (int p = 0; p < NP; ++p)
+#pragma unroll
+                for (int j = 0; j < SR_V; ++j) v[p][j] = ldg_stream_v4(P.pred[p].col + wbase + j * 128 + lane * 4);
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) {
+                u32 m = 0xFu;
+#pragma unroll
+                for (int p = 0; p < NP; ++p) m &= range4(v[p][j], P.pred[p].lo, P.pred[p].span);
+                nib[j] = m;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) {
+                u32 m = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int64_t r = wbase + j * 128 + lane * 4 + e;
+                    bool ok = r < P.n;
+#pragma unroll
+                    for (int p = 0; p < NP; ++p)
+                        if (r < P.n) ok = ok && (u32)(P.pred[p].col[r] - P.pred[p].lo) <= P.pred[p].span;
+                    m |= ok ? (1u << e) : 0u;
                 }
-                __threadfence_system();
-                for (int r = 0; r < G.n_ranks; ++r)
-                    st_release_sys(reinterpret_cast<u64*>(G.peers[r] + area + (size_t)G.rank * G.slot_bytes), G.epoch);
+                nib[j] = m;
             }
         }
-        // ---- phase 4: wait for every rank's flag in my own memory, then concatenate in rank order
-        __shared__ int64_t s_off[MAX_RANKS + 1];
-        __shared__ int s_ok;
-        const uint8_t* mine = G.peers[G.rank] + area;
-        if (threadIdx.x == 0) s_ok = 1;
-        __syncthreads();
-        if ((int)threadIdx.x < G.n_ranks) {
-            if (!peer_wait(reinterpret_cast<const u64*>(mine + (size_t)threadIdx.x * G.slot_bytes), G.epoch, G.status)) s_ok = 0;
-        }
-        __syncthreads();
-        if (!s_ok) return;
-        if (threadIdx.x == 0) {
-            int64_t off = 0;
-            u64 maxc = 0, total = 0;
-            for (int r = 0; r < G.n_ranks; ++r) {
-                const u64 c = __ldcg(reinterpret_cast<const u64*>(mine + (size_t)r * G.slot_bytes) + 1);
-                s_off[r] = off;
-                off += (int64_t)(c < (u64)G.slot_cap ? c : (u64)G.slot_cap);
-                maxc = c > maxc ? c : maxc;
-                total += c;
-            }
-            s_off[G.n_ranks] = off;
-            if (blockIdx.x == 0) {
-                G.info[0] = (u64)off;
-                G.info[1] = maxc;
-                G.info[2] = total;
+        if (P.in_bits != nullptr) {
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) {
+                const u32 w = P.in_bits[((wbase + j * 128) >> 5) + (lane >> 3)];
+                nib[j] &= (w >> ((lane & 7) * 4)) & 0xFu;
             }
         }
-        __syncthreads();
-        const int64_t m = s_off[G.n_ranks];
-        for (int64_t i = (int64_t)blockIdx.x * CP_THREADS + threadIdx.x; i < m; i += (int64_t)gridDim.x * CP_THREADS) {
-            int r = 0;
-            while (r + 1 < G.n_ranks && i >= s_off[r + 1]) ++r;
-            G.out[i] = __ldcg(reinterpret_cast<const int32_t*>(mine + (size_t)r * G.slot_bytes + GATHER_SLOT_HEADER) + (i - s_off[r]));
+        // mask words: same packing as scan_rows (64 B per warp and chunk)
+        {
+            u32 y[SR_V];
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) {
+                u32 x = nib[j] << ((lane & 7) * 4);
+                x |= __shfl_xor_sync(FULL_MASK, x, 1);
+                x |= __shfl_xor_sync(FULL_MASK, x, 2);
+                x |= __shfl_xor_sync(FULL_MASK, x, 4);
+                y[j] = __shfl_sync(FULL_MASK, x, (lane & 3) * 8);
+            }
+            u32 out = y[0];
+#pragma unroll
+            for (int j = 1; j < SR_V; ++j) out = ((lane >> 2) == j) ? y[j] : out;
+            if (lane < 4 * SR_V) P.bits[(wbase >> 5) + lane] = out;
         }
+        // survivors, in row order: vector j, then lane, then element
+        if (__ballot_sync(FULL_MASK, (nib[0] | nib[1] | nib[2] | nib[3]) != 0) == 0) continue;
+#pragma unroll
+        for (int j = 0; j < SR_V; ++j) {
+            const u32 m = nib[j];
+            const u32 mine = __popc(m);
+            if (__ballot_sync(FULL_MASK, mine != 0) == 0) continue;
+            u32 incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 t = __shfl_up_sync(FULL_MASK, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const u32 tot = __shfl_sync(FULL_MASK, incl, 31);
+            if (cnt + tot <= (u32)P.list_cap) {
+                u32 pos = cnt + incl - mine, mm = m;
+                while (mm) {
+                    const int e = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    my_list[pos++] = (u32)(wbase + j * 128 + lane * 4 + e);
+                }
+            }
+            cnt += tot;  // keeps counting past the cap: cnt > list_cap marks the overflow
+        }
+    }
+    if (lane == 0) {
+        s_wcnt[warp] = cnt;
+        if (cnt > (u32)P.list_cap) s_overflow = 1;
+    }
+
+    // ======================= phase B =======================
+    // ---- (1) the folded tiny to-many hop (and the mask exchange in front of it) into shared memory
+    if (P.pre.n > 0) {
+        const CsrPullParams& C = P.pre;
+        const int cw = (int)((C.n_child + 31) >> 5);
+        if (C.pm.n_words > 0) {
+            // COLLECT half of the OR-exchange, straight into shared memory (every CTA polls its own rank's mailbox)
+            const PeerMaskParams& M = C.pm;
+            const size_t area = (size_t)(M.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
+            const uint8_t* mine = M.peers[M.rank] + area;
+            if (tid < M.n_ranks) peer_wait(reinterpret_cast<const u64*>(mine + (size_t)tid * MASK_SLOT_BYTES), M.epoch, M.status);
+            __syncthreads();
+            for (int w = tid; w < cw; w += RF_THREADS) {
+                u32 v = 0;
+                for (int r = 0; r < M.n_ranks; ++r) v |= __ldcg(reinterpret_cast<const u32*>(mine + (size_t)r * MASK_SLOT_BYTES + 16) + w);
+                s_child[w] = v;
+                if (vcta == 0) M.reach[w] = v;  // the reduced mask stays readable (node cardinalities)
+            }
+        } else {
+            for (int w = tid; w < cw; w += RF_THREADS) s_child[w] = C.child_bits != nullptr ? __ldcg(C.child_bits + w) : 0xffffffffu;
+        }
+        for (int i = tid; i < (int)C.nnz; i += RF_THREADS) s_tgt[i] = C.targets[i];
+        __syncthreads();
+        const int rows_pad = (int)((C.n + 31) & ~(int64_t)31);
+        for (int r = tid; r < rows_pad; r += RF_THREADS) {
+            bool ok = false;
+            if (r < C.n) {
+                const int64_t e0 = C.offsets[r], e1 = C.offsets[r + 1];
+                for (int64_t e = e0; e < e1 && !ok; ++e) {
+                    const int32_t t = s_tgt[e];
+                    if (t >= 0 && t < C.n_child) ok = (s_child[t >> 5] >> (t & 31)) & 1u;
+                }
+            }
+            u32 word = __ballot_sync(FULL_MASK, ok);
+            if (C.in_bits != nullptr) word &= C.in_bits[r >> 5];
+            if (lane == 0) {
+                s_pre[r >> 5] = word;
+                if (vcta == 0 && C.out_bits != nullptr) C.out_bits[r >> 5] = word;
+            }
+        }
+    }
+    __syncthreads();  // s_wcnt, s_overflow, s_pre
+    if (tid == 0) {
+        u32 o = 0;
+        for (int w = 0; w < RF_WARPS; ++w) {
+            s_woff[w] = o;
+            o += s_wcnt[w];
+        }
+        s_woff[RF_WARPS] = o;
+    }
+    __syncthreads();
+    const bool dense = s_overflow != 0;
+    const u32 n_c = s_woff[RF_WARPS];
+    const int64_t w_lo = (int64_t)vcta * RF_WARPS * P.chunks_per_warp * (SR_WARP_ROWS / 32);  // this CTA's mask words
+    const int64_t w_end = ((int64_t)vcta + 1) * RF_WARPS * P.chunks_per_warp * (SR_WARP_ROWS / 32);
+    const int64_t n_words = (P.n + 31) >> 5;
+    const int64_t w_hi = w_end < n_words ? w_end : n_words;
+    const u32* gbits[CF_MAX_GATHER];
+#pragma unroll
+    for (int g = 0; g < CF_MAX_GATHER; ++g) gbits[g] = ((P.pre_mask >> g) & 1u) ? s_pre : P.gather[g].bits;
+
+    // ---- (2) chains of the surviving rows; count what is left
+    u32 kept = 0;
+    if (!dense) {
+        if (P.ng == 0) {
+            kept = tid == 0 ? n_c : 0;
+        } else {
+            for (u32 i = tid; i < n_c; i += RF_THREADS) {
+                int w = 0;
+#pragma unroll
+                for (int k = 1; k < RF_WARPS; ++k) w += (i >= s_woff[k]) ? 1 : 0;
+                u32* e = P.lists + ((size_t)vcta * RF_WARPS + w) * P.list_cap + (i - s_woff[w]);
+                const u32 row = *e;
+                bool ok = true;
+                for (int g = 0; g < P.ng; ++g) ok = ok && rf_chain(P.gather[g], gbits[g], row);
+                if (ok) ++kept;
+                else {
+                    atomicAnd(&P.bits[row >> 5], ~(1u << (row & 31)));
+                    *e = row | 0x80000000u;
+                }
+            }
+        }
+    } else {
+        for (int64_t w0 = w_lo + (int64_t)tid * 4; w0 < w_hi; w0 += RF_THREADS * 4) {
+            uint4 v = __ldcg(reinterpret_cast<const uint4*>(P.bits + w0));
+            u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (w0 + j >= w_hi) { w[j] = 0; continue; }
+                u32 m = w[j], keep = w[j];
+                if (P.ng > 0) {
+                    const int64_t rb = (w0 + j) << 5;
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        bool ok = true;
+                        for (int g = 0; g < P.ng; ++g) ok = ok && rf_chain(P.gather[g], gbits[g], rb + b);
+                        if (!ok) keep &= ~(1u << b);
+                    }
+                    if (keep != w[j]) P.bits[w0 + j] = keep;
+                }
+                kept += __popc(keep);
+            }
+        }
+    }
+    u32 cta_count;
+    block_exclusive_scan(kept, s_warp, cta_count);
+
+    // ---- (3) publish, then sum the counts of every lower ticket
+    if (tid == 0) st_volatile_u64(P.cta_state + vcta, ((u64)P.epoch << 32) | cta_count);
+    u64 part = 0;
+    for (u32 j = tid; j < vcta; j += RF_THREADS) {
+        u64 st;
+        do { st = ld_volatile_u64(P.cta_state + j); } while ((u32)(st >> 32) != P.epoch);
+        part += (u32)st;
+    }
+    // block reduction of a u64 (the grand total of a 2^31-row table fits, a u32 lane sum might not)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL_MASK, part, d);
+    __shared__ u64 s_part[RF_WARPS];
+    __syncthreads();  // block_exclusive_scan's readers of s_warp are done; s_part is fresh
+    if (lane == 0) s_part[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+        u64 b = 0;
+        for (int w = 0; w < RF_WARPS; ++w) b += s_part[w];
+        s_base = b;
+    }
+    __syncthreads();
+    const u64 base = s_base;
+
+    // ---- (4) ordered write
+    const bool gather = P.pg.n_ranks > 0;
+    if (!dense) {
+        u64 running = base;
+        for (u32 i0 = 0; i0 < n_c; i0 += RF_THREADS) {
+            const u32 i = i0 + tid;
+            u32 row = 0x80000000u;
+            if (i < n_c) {
+                int w = 0;
+#pragma unroll
+                for (int k = 1; k < RF_WARPS; ++k) w += (i >= s_woff[k]) ? 1 : 0;
+                row = __ldcg(P.lists + ((size_t)vcta * RF_WARPS + w) * P.list_cap + (i - s_woff[w]));
+            }
+            const u32 valid = (row & 0x80000000u) ? 0u : 1u;
+            u32 tot;
+            const u32 ex = block_exclusive_scan(valid, s_warp, tot);
+            if (valid) {
+                const int64_t pos = (int64_t)(running + ex);
+                const int32_t v = (int32_t)(P.row_base + row);
+                if (pos < P.capacity) P.out_idx[pos] = v;
+                if (gather) gather_store(P.pg, pos, v);
+            }
+            running += tot;
+            __syncthreads();
+        }
+    } else {
+        u64 running = base;
+        for (int64_t t0 = w_lo; t0 < w_hi; t0 += RF_THREADS * 4) {
+            const int64_t w0 = t0 + (int64_t)tid * 4;
+            u32 w[4] = {0, 0, 0, 0};
+            if (w0 < w_hi) {
+                const uint4 v = __ldcg(reinterpret_cast<const uint4*>(P.bits + w0));
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (w0 + j >= w_hi) w[j] = 0;
+            }
+            const u32 c = __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
+            u32 tot;
+            const u32 ex = block_exclusive_scan(c, s_warp, tot);
+            int64_t pos = (int64_t)(running + ex);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                u32 m = w[j];
+                const int64_t rb = P.row_base + ((w0 + j) << 5);
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (pos < P.capacity) P.out_idx[pos] = (int32_t)(rb + b);
+                    if (gather) gather_store(P.pg, pos, (int32_t)(rb + b));
+                    ++pos;
+                }
+            }
+            running += tot;
+            __syncthreads();
+        }
+    }
+
+    // ---- tail: the highest ticket knows the grand total; the last CTA to finish re-arms the counters
+    if (tid == 0 && vcta == gridDim.x - 1) *P.total = base + cta_count;
+    if (gather) __threadfence_system();
+    else __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&P.counters[1], 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        if (tid == 0) {
+            P.counters[0] = 0;
+            P.counters[1] = 0;
+        }
+        if (gather) gather_tail(P.pg, P.total);
     }
 }
 
@@ -1807,14 +2197,6 @@ struct CompactLookbackParams {
     GatherD gather[CF_MAX_GATHER];
 };
 
-__device__ __forceinline__ u64 ld_volatile_u64(const u64* p) {
-    u64 v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_volatile_u64(u64* p, u64 v) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 template <int NG>
 __global__ void __launch_bounds__(CP_THREADS) compact_lookback_kernel(const CompactLookbackParams P) {

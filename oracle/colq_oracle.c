@@ -315,23 +315,39 @@ void orc_query_add_str(orc_query *q, int node, int ordinal, int op, const uint8_
 /* ------------------------------------------------------------------ predicates */
 
 /*
- * java.lang.String.compareTo compares UTF-16 code units.  On UTF-8 bytes that equals plain byte order
- * except when the first differing code points straddle the surrogate range: a supplementary code point
- * (UTF-8 lead byte 0xF0..0xF4, UTF-16 lead surrogate 0xD800..0xDBFF) sorts BELOW U+E000..U+FFFF (UTF-8
- * lead bytes 0xEE, 0xEF).  A differing continuation byte implies equal lead bytes, hence byte order.
+ * java.lang.String.compareTo compares UTF-16 code units (JDK String.compareTo; called by the reference's lambdas at
+ * QueryTest.java:124-125).  The oracle does it literally: decode one UTF-8 code point from each side (the columns
+ * hold well-formed UTF-8, the encoding the Java shim writes), expand it to its one or two UTF-16 code units and compare
+ * unit by unit -- deliberately NOT the lead-byte key trick the GPU kernel uses, so the two are independent.
  */
-static inline int utf16_key(uint8_t b) { return b >= 0xF0 ? 0xED * 2 + 1 : b * 2; }
+static int utf8_next(const uint8_t *s, int64_t len, int64_t *i, uint16_t out[2]) {
+    uint32_t b = s[*i], cp;
+    int extra = b < 0x80 ? 0 : (b < 0xE0 ? 1 : (b < 0xF0 ? 2 : 3));
+    cp = extra == 0 ? b : (extra == 1 ? (b & 0x1F) : (extra == 2 ? (b & 0x0F) : (b & 0x07)));
+    for (int k = 1; k <= extra; k++) cp = (cp << 6) | ((*i + k < len ? s[*i + k] : 0) & 0x3F);
+    *i += extra + 1;
+    if (cp >= 0x10000) {
+        cp -= 0x10000;
+        out[0] = (uint16_t)(0xD800 + (cp >> 10));
+        out[1] = (uint16_t)(0xDC00 + (cp & 0x3FF));
+        return 2;
+    }
+    out[0] = (uint16_t)cp;
+    return 1;
+}
 
 static int java_compare_to(const uint8_t *a, int64_t la, const uint8_t *b, int64_t lb, int *sign_only) {
     (void)sign_only;
-    int64_t m = la < lb ? la : lb;
-    for (int64_t i = 0; i < m; i++) {
-        if (a[i] != b[i]) {
-            int ka = utf16_key(a[i]), kb = utf16_key(b[i]);
-            return ka < kb ? -1 : 1;
-        }
+    int64_t i = 0, j = 0;
+    uint16_t ua[2], ub[2];
+    int na = 0, nb = 0, pa = 0, pb = 0;  /* pending code units of the current code point on each side */
+    for (;;) {
+        if (pa == na) { if (i >= la) { na = 0; } else { na = utf8_next(a, la, &i, ua); } pa = 0; }
+        if (pb == nb) { if (j >= lb) { nb = 0; } else { nb = utf8_next(b, lb, &j, ub); } pb = 0; }
+        if (na == 0 || nb == 0) return (na == 0 && nb == 0) ? 0 : (na == 0 ? -1 : 1);  /* length difference */
+        if (ua[pa] != ub[pb]) return ua[pa] < ub[pb] ? -1 : 1;
+        pa++; pb++;
     }
-    return la < lb ? -1 : (la > lb ? 1 : 0);
 }
 
 static int bytes_contains(const uint8_t *h, int64_t hl, const uint8_t *n, int64_t nl) {

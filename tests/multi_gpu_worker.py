@@ -46,14 +46,16 @@ def main():
         oracle.close()
 
         geo = G.build_tables(U, n_ranks=world, rank=rank, rename_plymouth_except_last_rank=perturbed)
-        # (peer exchange, lazy FK, deferred chains, fused compaction, gather fused into the compaction)
-        for peer, lazy, defer, fused, fgather, tail in ((1, True, 1, 1, 0, 1), (1, True, 1, 1, 0, 0), (1, True, 1, 2, 0, 1), (1, True, 1, 1, 1, 1),
-                                                       (1, True, 0, 1, 1, 0), (1, False, 1, 1, 0, 1), (1, True, 1, 0, 0, 1), (0, True, 1, 1, 0, 1),
-                                                       (0, False, 1, 2, 0, 1)):
+        # (peer exchange, lazy FK, deferred chains, fused compaction, gather fused into the index writer, tail publish, fused root)
+        for peer, lazy, defer, fused, fgather, tail, rootf in ((1, True, 1, 1, 1, 1, 1), (1, True, 1, 1, 1, 0, 1), (1, True, 1, 1, 0, 1, 1),
+                                                              (1, True, 1, 1, 0, 1, 0), (1, True, 1, 1, 0, 0, 0), (1, True, 1, 2, 0, 1, 1),
+                                                              (1, True, 1, 1, 1, 1, 0), (1, True, 0, 1, 1, 0, 1), (1, False, 1, 1, 1, 1, 1),
+                                                              (1, False, 1, 1, 0, 1, 0), (1, True, 1, 0, 0, 1, 1), (0, True, 1, 1, 0, 1, 1),
+                                                              (0, True, 1, 1, 0, 1, 0), (0, False, 1, 2, 0, 1, 1)):
             if True:
                 ds = DataSystemColq(context=ctx, lazy_fk=lazy, options={_ffi.OPT_PEER_EXCHANGE: peer, _ffi.OPT_DEFER_CHAINS: defer,
                                                                         _ffi.OPT_FUSED_COMPACT: fused, _ffi.OPT_FUSED_GATHER: fgather,
-                                                                        _ffi.OPT_TAIL_PUBLISH: tail})
+                                                                        _ffi.OPT_TAIL_PUBLISH: tail, _ffi.OPT_ROOT_FUSED: rootf})
                 ds._tables.clear()
                 G.register_geography(ds, geo, sharded=True)
                 ds._sync_tables()
@@ -62,16 +64,26 @@ def main():
                 res = cq.execute(want_indices=True, index_capacity=64)   # small on purpose: exercises the regrow path
                 assert res.count == want.shape[0], (rank, perturbed, peer, lazy, res.count, want.shape[0])
                 assert np.array_equal(res.indices, want), (rank, perturbed, peer, lazy)
+                # a second execution of the same query (other slot parity), count only, then the indices through fetch
+                cq.execute_async()
+                res = cq.fetch(want_indices=True, index_capacity=want.shape[0] + 8)
+                assert np.array_equal(res.indices, want), (rank, perturbed, "second execution")
                 names = [n for n, *_ in cq.profile()]
+                root_fused = rootf and fused == 1 and lazy and defer   # (eager plans end in a scan with the gathers inside)
+                assert any(n.startswith("root_fused") for n in names) == bool(root_fused), names
                 if peer and os.environ.get("COLQ_PEER", "1") != "0":
                     pub = [i for i, n in enumerate(names) if n.endswith("publish")]   # own launch, or the scan's last CTA
-                    assert len(pub) == 1 and "peer_mask_collect+csr_pull" in names, names
+                    assert len(pub) == 1, names
                     assert (names[pub[0]] == "peer_mask_publish") == (not tail), names
-                    if fused == 1 and fgather:    # the final gather runs inside the cooperative compaction launch
-                        assert any(n.startswith("compact_fused") and n.endswith("+gather") for n in names), names
+                    if root_fused:       # the COLLECT and the 51-row adjacency hop run inside the root's launch
+                        assert any("+collect+csr" in n for n in names) and "peer_mask_collect+csr_pull" not in names, names
+                    else:
+                        assert "peer_mask_collect+csr_pull" in names, names
+                    if fused == 1 and fgather:    # the final gather rides on the kernel that writes the indices
+                        assert any(n.endswith("+gather") for n in names) and "peer_gather_indices" not in names, names
                     else:
                         assert "peer_gather_indices" in names, names
-                    if lazy and defer and fused:   # the root's predicate scan sits between the two halves of the mask exchange
+                    if not root_fused and lazy and defer and fused:   # the root's scan sits between the two halves of the mask exchange
                         assert pub[0] < names.index("scan_rows<1,0,lazy>") < names.index("peer_mask_collect+csr_pull"), names
                 else:
                     assert "allgather_or_mask" in names and "allgather_indices" in names, names

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), f"{name} is declared in include/colq.h but not exported by libcolq.so"
     assert set(_ffi.SIGNATURES) == set(declared_symbols()), "colq/_ffi.py and include/colq.h disagree"
-    assert lib.colq_abi_version() == 1
+    assert lib.colq_abi_version() == _ffi.ABI_VERSION
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -37,7 +37,8 @@ DICT_HOST = dict(lazy_fk=True, dictionary=True, residency="host")
 LOOKBACK = dict(lazy_fk=True, options={4: 2})            # COLQ_OPT_FUSED_COMPACT=2: single-pass look-back compaction
 DICT_ALL = dict(lazy_fk=True, dictionary="all")          # integer columns dictionary-encoded too
 DICT_ALL_HOST = dict(lazy_fk=True, dictionary="all", residency="host")
-ALL_VARIANTS = (LAZY, EAGER, NO_DEFER, HOST, HOST_NO_PROMOTE, HOST_KERNEL_PROMOTE, DICT, DICT_HOST, LOOKBACK, DICT_ALL, DICT_ALL_HOST)
+UNFUSED = dict(lazy_fk=True, options={9: 0})             # COLQ_OPT_ROOT_FUSED=0: scan_rows / csr_pull / compact_fused launches (r01 plan)
+ALL_VARIANTS = (LAZY, EAGER, NO_DEFER, HOST, HOST_NO_PROMOTE, HOST_KERNEL_PROMOTE, DICT, DICT_HOST, LOOKBACK, DICT_ALL, DICT_ALL_HOST, UNFUSED)
 
 
 def both(engines, build, queries, lazy_modes=(True, False), variants=None):
@@ -282,8 +283,8 @@ def test_deferred_chains_are_planned_into_the_compaction(engines, base_geography
     """The root's lazy FK chains move from the row scan into the fused compaction kernel (COLQ_OPT_DEFER_CHAINS)."""
     new_gpu, _ = engines
     geo = G.build_tables(2, base=base_geography)
-    for opts, want_names in (({}, ["scan_rows<1,0,lazy>", "compact_fused+chains"]), ({4: 2}, ["scan_rows<1,0,lazy>", "compact_lookback+chains"]),
-                             ({5: 0}, ["scan_rows<1,1,lazy>", "compact_fused"])):
+    for opts, want_names in (({}, ["root_fused<1,1>+csr"]), ({9: 0}, ["scan_rows<1,0,lazy>", "csr_pull", "compact_fused+chains"]),
+                             ({4: 2}, ["scan_rows<1,0,lazy>", "compact_lookback+chains"]), ({5: 0}, ["scan_rows<1,1,lazy>", "compact_fused"])):
         ds = new_gpu(options=opts)
         G.register_geography(ds, geo)
         assert isinstance(ds.execute(G.plymouth_query()), QueryResult.Success)
@@ -379,7 +380,8 @@ def test_three_launch_compaction_path_matches(engines, base_geography):
         got = ds.last_query.fetch(want_indices=True)
         assert np.array_equal(got.indices, oracle.last_indices)
         names = [n for n, *_ in ds.last_query.profile()]
-        assert any(n.startswith("compact_fused") for n in names) == (fused == 1)
+        assert any(n.startswith("root_fused") for n in names) == (fused == 1)   # the root's scan, chains and compaction in one launch
+        assert not any(n.startswith("compact_fused") for n in names)
         assert any(n.startswith("compact_lookback") for n in names) == (fused == 2)
         ds.close()
 

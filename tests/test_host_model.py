@@ -100,7 +100,7 @@ def test_bench_reference_arm_contract(tmp_path):
     import sys
     from pathlib import Path
     root = Path(__file__).resolve().parent.parent
-    cmd = [sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--cpu-universes", "20"]
+    cmd = [sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--reference-universes", "20"]
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -112,6 +112,11 @@ def test_bench_reference_arm_contract(tmp_path):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] == "plymouth_adjacency_query_10k_universes"
+    assert d["same_config_as_gpu_arm"] is False and "20 of 10000 universes" in d["cpu_baseline"]["sample"]
+    # the config dict is exactly the one the GPU arm prints (the driver compares them)
+    assert d["config"] == {"workload": "plymouth_adjacency_query_10k_universes", "source": "BASELINE.json configs[3]; app/.../Runner.java:230-236",
+                           "universes": 10_000, "zip_rows": 293_530_000, "city_rows": 257_010_000, "state_rows": 51,
+                           "l2_policy": "inputs larger than L2 (no flush)"}
     # under torchrun the other ranks print nothing and exit 0
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
     assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]

@@ -88,3 +88,21 @@ def test_compare_to_is_utf16_order():
     got = ds.execute(q).result_set.columns()[0].strings()
     pred = str_compare_lt("")
     assert got == [s for s in strings if pred(s)] == ["\U0001F600", "z", ""]
+
+
+def test_compare_to_supplementary_planes_and_mixed_lengths():
+    """two different supplementary-plane lead bytes (0xF0 vs 0xF4) must not tie.  The oracle decodes to
+    UTF-16 code units; the expectation is Python's own UTF-16-BE byte comparison (colq.data_system._java_compare_to)."""
+    from colq import Criteria, Query, of_columns, of_strings
+    from colq.data_system import StringPredicate
+    strings = ["\U00010000", "\U0010FFFF", "\U0001F600", "\U000F0000a", "\uE000", "\uFFFD", "\uD7FF", "a\U00010400", "a\U0010F400",
+               "a", "", "\U0001F600\U0001F600", "é", "z\uFB01"]
+    for needle in ("\U0001F600", "\U0010FFFF", "\U00010000", "\uE000", "a\U00010400", "", "\U000F0000"):
+        for op in (2, 3, 4, 5):
+            ds = new_oracle()
+            ds.register("s", of_columns(of_strings(*strings)))
+            q = Query("s")
+            pred = StringPredicate(op, needle)
+            q.root_node.add_criteria(Criteria.StringCriteria(0, pred))
+            got = ds.execute(q).result_set.columns()[0].strings()
+            assert got == [s for s in strings if pred(s)], (op, needle)
