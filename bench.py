@@ -312,8 +312,9 @@ def run_colq(args, rank, local_rank, world):
     if res.count != 31 * U or not np.array_equal(res.indices.astype(np.int64), want):
         raise SystemExit(f"rank {rank}: GPU result differs from the oracle-derived expectation (count {res.count} vs {31 * U})")
     gate["exact"] = True
-    launches_per_step = int(res.timing.kernel_launches)
-    collectives_per_step = int(res.timing.collectives)
+    r_plain = q.execute(want_indices=False)   # what one timed step launches (fetching the indices adds the gather's concatenation at N > 1)
+    launches_per_step = int(r_plain.timing.kernel_launches)
+    collectives_per_step = int(r_plain.timing.collectives)
 
     # ---- value: K steps, resident tables, CUDA events on the launching stream, max over ranks
     sampler = ClockSampler(local_rank)

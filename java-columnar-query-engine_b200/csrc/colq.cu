@@ -254,6 +254,7 @@ struct colq_ctx {
     void* h_stage = nullptr;
     int compact_grid[2 * (CF_MAX_GATHER + 1)] = {};  // co-resident grid of compact_fused_kernel<NG, GATHER>
     int root_fused_grid[SR_MAX_PRED + 1] = {};       // resident CTAs of root_fused_kernel<NP> on this device
+    u32* d_tile_counters = nullptr;                  // scan_str's tile-claim counter pair (zero between launches)
     std::map<std::pair<int, size_t>, int> str_occupancy;  // (kernel mode, dynamic smem bytes) -> resident CTAs per SM
 };
 
@@ -273,6 +274,8 @@ struct colq_query {
     u32 rf_epoch = 0;
     // the final gather of the last plan left every rank's indices in the mailbox slots (written by the kernel that
     // produced them); the concatenation into one list runs when the host fetches the indices
+    u64* rf_dbg = nullptr;
+    int rf_dbg_ctas = 0;
     bool gather_lazy = false;
     PeerGatherParams lazy_pg{};
     DevBuf lookback_buf;  // [2 counters | pad | tile states] of the single-pass compaction kernel (zeroed once)
@@ -718,6 +721,7 @@ struct Planner {
             }
             P.in_bits = in_bits;
             P.out_bits = out_bits;
+            P.tile_counter = ctx->d_tile_counters;
             o.smem = (size_t)P.stages * st_stage_bytes(P.cap) + st_needle_region(P.needle_len) + 2 * ST_MAX_STAGES * 8 +
                      ST_MAX_STAGES * sizeof(StrTileMeta) + PUSH_SMEM_WORDS * 4;
             o.acct_rows = rows;
@@ -1356,6 +1360,15 @@ colq_status run_pipeline(colq_query* q) {
             for (int g = 0; g < f.ng; ++g)
                 if (P.gather[g].bits == P.pre.out_bits) P.pre_mask |= 1u << g;
         if (coop_gather) ST(fill_fused_gather(P.pg));
+#ifdef COLQ_RF_DEBUG
+        {
+            void* dbg;
+            ST(pool_alloc(q, (size_t)f.grid * 64, &dbg));
+            P.dbg = (u64*)dbg;
+            q->rf_dbg = P.dbg;
+            q->rf_dbg_ctas = f.grid;
+        }
+#endif
         f.name = "root_fused";
         q->ops.push_back(f);
     } else if (q->opt_fused_compact >= 2 && !coop_gather) {
@@ -1800,6 +1813,11 @@ colq_status colq_create(int device, colq_ctx** out_ctx) {
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) return COLQ_ERR_DEVICE;
     ctx->stream = ctx->own_stream;
     {
+        void* p = nullptr;
+        if (cudaMalloc(&p, 64) != cudaSuccess || cudaMemset(p, 0, 64) != cudaSuccess) return COLQ_ERR_DEVICE;
+        ctx->d_tile_counters = (u32*)p;
+    }
+    {
         DeviceCache& cache = device_cache();
         std::lock_guard<std::mutex> g(cache.mu);
         cache.live_contexts++;
@@ -1817,6 +1835,7 @@ colq_status colq_destroy(colq_ctx* ctx) {
     if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
     ctx->tables.clear();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->d_tile_counters) cudaFree(ctx->d_tile_counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     DeviceCache& cache = device_cache();
@@ -2629,3 +2648,14 @@ colq_status colq_node_cardinalities(colq_ctx* ctx, const colq_query* q, int64_t*
 }
 
 }  // extern "C"
+
+#ifdef COLQ_RF_DEBUG
+// debug builds only (not part of include/colq.h): the per-CTA phase timestamps of the last root_fused launch
+extern "C" int colq_debug_rf_times(colq_query* q, uint64_t* out, int cap_ctas) {
+    if (!q || !q->rf_dbg) return 0;
+    cudaStreamSynchronize(q->ctx->stream);
+    const int n = std::min(cap_ctas, q->rf_dbg_ctas);
+    cudaMemcpy(out, q->rf_dbg, (size_t)n * 64, cudaMemcpyDeviceToHost);
+    return n;
+}
+#endif

@@ -690,13 +690,20 @@ struct ScanStrParams {
     uint8_t* promote_bytes;
     PeerMaskParams pub;   // pub.n_words > 0: the last CTA publishes push.reach to the peers (multi-GPU mask exchange)
     u32* pub_done;
+    u32* tile_counter;    // [0] next unclaimed tile, [1] finished CTAs; both are zero between launches
 };
+
+constexpr u32 ST_NO_TILE = 0xffffffffu;  // sentinel stage: the producer has run out of tiles
+#ifndef COLQ_ST_CLAIM
+#define COLQ_ST_CLAIM 2
+#endif
+constexpr int ST_CLAIM = COLQ_ST_CLAIM;   // tiles per claim
 
 struct StrTileMeta {
     u32 a0;    // 16-byte-aligned global byte offset the staged slice starts at (offsets are uint32)
     u32 fast;  // 1: bytes were staged in shared memory, 0: read them from global memory
     u32 sz;    // bytes of the 16-byte-aligned slice [a0, a0 + sz) covering the tile's strings
-    u32 pad;
+    u32 tile;  // which tile this stage holds (tiles are claimed dynamically), or ST_NO_TILE
 };
 
 // ---- word loaders: the same row tests run over the staged slice (ld.shared) or the column itself (ld.global)
@@ -871,28 +878,49 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == -1 || MODE == -2) ? 4 : 3
     }
     __syncthreads();
 
-    const int64_t first_tile = blockIdx.x;
-    const int64_t tile_stride = gridDim.x;
-    const int64_t my_tiles = first_tile < P.n_tiles ? (P.n_tiles - first_tile + tile_stride - 1) / tile_stride : 0;
+    // Tiles are CLAIMED from a device-wide counter (r02): with a static round-robin every CTA got the same number of tiles,
+    // but SMs do not get the same share of HBM bandwidth, so the slowest CTA finished 10-20 us after the median one.
+    const u32 n_tiles = (u32)P.n_tiles;
 
     if (warp == ST_CONSUMER_WARPS) {
         // =========================== producer warp: one lane drives the TMA ring ===========================
         if (lane == 0) {
             u32 nb0 = 0, nb1 = 0;
-            auto tile_bounds = [&](int64_t k, u32& gb0, u32& gb1) {
-                const int64_t r0 = (first_tile + k * tile_stride) * ST_ROWS;
+            auto tile_bounds = [&](u32 t, u32& gb0, u32& gb1) {
+                const int64_t r0 = (int64_t)t * ST_ROWS;
                 const int64_t r1 = (r0 + ST_ROWS) < P.n ? (r0 + ST_ROWS) : P.n;
                 gb0 = __ldg(P.offsets + r0);
                 gb1 = __ldg(P.offsets + r1);
             };
-            if (my_tiles > 0) tile_bounds(0, nb0, nb1);
+            // claims are batches of ST_CLAIM consecutive tiles, and the NEXT batch is claimed while the current one is
+            // being issued: neither the atomic's nor the bounds load's latency sits between two TMA issues
+            u32 batch = atomicAdd(P.tile_counter, (u32)ST_CLAIM);
+            u32 batch_next = atomicAdd(P.tile_counter, (u32)ST_CLAIM);
+            u32 j = 0;
+            u32 next = batch;
+            if (next < n_tiles) tile_bounds(next, nb0, nb1);
             int s = 0;
             u32 round = 0;  // how many times the ring has wrapped
-            for (int64_t k = 0; k < my_tiles; ++k) {
+            while (true) {
+                const u32 cur = next;
                 const u32 gb0 = nb0, gb1 = nb1;
-                if (k + 1 < my_tiles) tile_bounds(k + 1, nb0, nb1);  // in flight while we wait for the slot
+                if (cur < n_tiles) {  // the tile after this one: its bounds are in flight while we wait for the slot
+                    if (++j == ST_CLAIM) {
+                        j = 0;
+                        batch = batch_next;
+                        batch_next = atomicAdd(P.tile_counter, (u32)ST_CLAIM);
+                    }
+                    next = batch + j;
+                    if (next < n_tiles) tile_bounds(next, nb0, nb1);
+                }
                 if (round > 0) mbar_wait(&s_empty[s], (round - 1) & 1);
-                const int64_t r0 = (first_tile + k * tile_stride) * ST_ROWS;
+                if (cur >= n_tiles) {  // out of tiles: tell the consumers
+                    s_meta[s].tile = ST_NO_TILE;
+                    mbar_arrive(&s_full[s]);
+                    break;
+                }
+                s_meta[s].tile = cur;
+                const int64_t r0 = (int64_t)cur * ST_ROWS;
                 const int nr = (int)((P.n - r0) < ST_ROWS ? (P.n - r0) : ST_ROWS);
                 uint8_t* base = smem + (size_t)s * stage_bytes;
                 const u64 a0 = (u64)gb0 & ~(u64)15;
@@ -927,11 +955,11 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == -1 || MODE == -2) ? 4 : 3
         u32* out_bits = P.out_bits;
         const u32 n_words_out = (u32)(((P.n + 63) >> 6) << 1);  // whole 64-row BitSet words, as u32 halves
 
-        const u32 n_my = (u32)my_tiles;
-        u32 tile = (u32)first_tile;  // global tile index; tile * 1024 < 2^31 because n < 2^31
         u32 s = 0, parity = 0;
-        for (u32 k = 0; k < n_my; ++k, tile += (u32)tile_stride) {
+        while (true) {
             mbar_wait(&s_full[s], parity);
+            const u32 tile = s_meta[s].tile;  // global tile index; tile * 1024 < 2^31 because n < 2^31
+            if (tile == ST_NO_TILE) break;
 
             const u32 so = smem_u32(smem) + s * (u32)stage_bytes;
             const u32 r0 = tile * ST_ROWS;
@@ -1040,9 +1068,11 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == -1 || MODE == -2) ? 4 : 3
         }
     }
 
-    if (do_push) {
-        __syncthreads();
-        push_flush(P.push, s_reach);
+    __syncthreads();  // every claim of this CTA has been made
+    if (do_push) push_flush(P.push, s_reach);
+    if (tid == 0 && atomicAdd(P.tile_counter + 1, 1u) == gridDim.x - 1) {  // last CTA: re-arm the claim counter
+        P.tile_counter[0] = 0;
+        P.tile_counter[1] = 0;
     }
     if (P.pub.n_words > 0) peer_mask_publish_tail(P.pub, P.pub_done);
 }
@@ -1706,6 +1736,7 @@ __global__ void __launch_bounds__(CP_THREADS) compact_fused_kernel(const Compact
 
 constexpr int RF_THREADS = 256;
 constexpr int RF_WARPS = RF_THREADS / 32;
+constexpr int RF_ILP = 4;                     // candidates whose chains one thread walks concurrently
 constexpr int RF_PRE_ROWS = PUSH_SMEM_BITS;   // a folded to-many hop has at most this many parent / child rows ...
 constexpr int RF_PRE_EDGES = CSR_SMEM_EDGES;  // ... and this many edges
 
@@ -1730,6 +1761,7 @@ struct RootFusedParams {
     int64_t capacity;
     int64_t row_base;
     PeerGatherParams pg;         // pg.n_ranks > 0: final gather fused in
+    u64* dbg;                    // (COLQ_RF_DEBUG builds) 8 globaltimer stamps per CTA
 };
 
 __device__ __forceinline__ bool rf_chain(const GatherD& g, const u32* bits, int64_t r) {
@@ -1743,6 +1775,12 @@ __device__ __forceinline__ bool rf_chain(const GatherD& g, const u32* bits, int6
     }
     return bits == nullptr ? true : bit_test(bits, r);
 }
+
+#ifdef COLQ_RF_DEBUG
+#define RF_STAMP(k) do { if (threadIdx.x == 0 && P.dbg != nullptr) P.dbg[(size_t)blockIdx.x * 8 + (k)] = global_timer_ns(); } while (0)
+#else
+#define RF_STAMP(k) do { } while (0)
+#endif
 
 template <int NP>
 __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFusedParams P) {
@@ -1760,6 +1798,64 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
     }
     __syncthreads();
     const u32 vcta = s_ticket;
+    RF_STAMP(0);
+
+    // ---- the folded tiny to-many hop (and the mask exchange in front of it) into shared memory.  Block-wide.
+    auto run_pre = [&]() {
+        const CsrPullParams& C = P.pre;
+        const int cw = (int)((C.n_child + 31) >> 5);
+        if (C.pm.n_words > 0) {
+            // COLLECT half of the OR-exchange, straight into shared memory (every CTA polls its own rank's mailbox)
+            const PeerMaskParams& M = C.pm;
+            const size_t area = (size_t)(M.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
+            const uint8_t* mine = M.peers[M.rank] + area;
+            if (tid < M.n_ranks) peer_wait(reinterpret_cast<const u64*>(mine + (size_t)tid * MASK_SLOT_BYTES), M.epoch, M.status);
+            __syncthreads();
+            for (int w = tid; w < cw; w += RF_THREADS) {
+                u32 v = 0;
+                for (int r = 0; r < M.n_ranks; ++r) v |= __ldcg(reinterpret_cast<const u32*>(mine + (size_t)r * MASK_SLOT_BYTES + 16) + w);
+                s_child[w] = v;
+                if (vcta == 0) M.reach[w] = v;  // the reduced mask stays readable (node cardinalities)
+            }
+        } else {
+            for (int w = tid; w < cw; w += RF_THREADS) s_child[w] = C.child_bits != nullptr ? __ldcg(C.child_bits + w) : 0xffffffffu;
+        }
+        for (int i = tid; i < (int)C.nnz; i += RF_THREADS) s_tgt[i] = C.targets[i];
+        __syncthreads();
+        const int rows_pad = (int)((C.n + 31) & ~(int64_t)31);
+        for (int r = tid; r < rows_pad; r += RF_THREADS) {
+            bool ok = false;
+            if (r < C.n) {
+                const int64_t e0 = C.offsets[r], e1 = C.offsets[r + 1];
+                for (int64_t e = e0; e < e1 && !ok; ++e) {
+                    const int32_t t = s_tgt[e];
+                    if (t >= 0 && t < C.n_child) ok = (s_child[t >> 5] >> (t & 31)) & 1u;
+                }
+            }
+            u32 word = __ballot_sync(FULL_MASK, ok);
+            if (C.in_bits != nullptr) word &= C.in_bits[r >> 5];
+            if (lane == 0) {
+                s_pre[r >> 5] = word;
+                if (vcta == 0 && C.out_bits != nullptr) C.out_bits[r >> 5] = word;
+            }
+        }
+    };
+    // Single GPU: the hop's input is final before this launch starts, so it runs first (2 us on an idle memory system
+    // instead of 5-16 us behind the other CTAs' streams, and off the critical tail).  Multi-GPU: if every peer's mask
+    // flag is already here, likewise; otherwise after phase A, so that the wait for the slowest rank hides behind the scan.
+    bool pre_done = false;
+    if (P.pre.n > 0) {
+        int ready = 1;
+        if (P.pre.pm.n_words > 0) {
+            const PeerMaskParams& M = P.pre.pm;
+            const uint8_t* mine = M.peers[M.rank] + (size_t)(M.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
+            if (tid < M.n_ranks) ready = ld_acquire_sys(reinterpret_cast<const u64*>(mine + (size_t)tid * MASK_SLOT_BYTES)) == M.epoch;
+        }
+        if (__syncthreads_and(ready)) {
+            run_pre();
+            pre_done = true;
+        }
+    }
 
     // ======================= phase A: stream, test, store mask words, list the survivors =======================
     const int64_t vwarp = (int64_t)vcta * RF_WARPS + warp;
@@ -1852,48 +1948,12 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
         if (cnt > (u32)P.list_cap) s_overflow = 1;
     }
 
+    RF_STAMP(1);
     // ======================= phase B =======================
-    // ---- (1) the folded tiny to-many hop (and the mask exchange in front of it) into shared memory
-    if (P.pre.n > 0) {
-        const CsrPullParams& C = P.pre;
-        const int cw = (int)((C.n_child + 31) >> 5);
-        if (C.pm.n_words > 0) {
-            // COLLECT half of the OR-exchange, straight into shared memory (every CTA polls its own rank's mailbox)
-            const PeerMaskParams& M = C.pm;
-            const size_t area = (size_t)(M.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
-            const uint8_t* mine = M.peers[M.rank] + area;
-            if (tid < M.n_ranks) peer_wait(reinterpret_cast<const u64*>(mine + (size_t)tid * MASK_SLOT_BYTES), M.epoch, M.status);
-            __syncthreads();
-            for (int w = tid; w < cw; w += RF_THREADS) {
-                u32 v = 0;
-                for (int r = 0; r < M.n_ranks; ++r) v |= __ldcg(reinterpret_cast<const u32*>(mine + (size_t)r * MASK_SLOT_BYTES + 16) + w);
-                s_child[w] = v;
-                if (vcta == 0) M.reach[w] = v;  // the reduced mask stays readable (node cardinalities)
-            }
-        } else {
-            for (int w = tid; w < cw; w += RF_THREADS) s_child[w] = C.child_bits != nullptr ? __ldcg(C.child_bits + w) : 0xffffffffu;
-        }
-        for (int i = tid; i < (int)C.nnz; i += RF_THREADS) s_tgt[i] = C.targets[i];
-        __syncthreads();
-        const int rows_pad = (int)((C.n + 31) & ~(int64_t)31);
-        for (int r = tid; r < rows_pad; r += RF_THREADS) {
-            bool ok = false;
-            if (r < C.n) {
-                const int64_t e0 = C.offsets[r], e1 = C.offsets[r + 1];
-                for (int64_t e = e0; e < e1 && !ok; ++e) {
-                    const int32_t t = s_tgt[e];
-                    if (t >= 0 && t < C.n_child) ok = (s_child[t >> 5] >> (t & 31)) & 1u;
-                }
-            }
-            u32 word = __ballot_sync(FULL_MASK, ok);
-            if (C.in_bits != nullptr) word &= C.in_bits[r >> 5];
-            if (lane == 0) {
-                s_pre[r >> 5] = word;
-                if (vcta == 0 && C.out_bits != nullptr) C.out_bits[r >> 5] = word;
-            }
-        }
-    }
+    // ---- (1) the folded hop, unless it already ran in front of phase A
+    if (P.pre.n > 0 && !pre_done) run_pre();
     __syncthreads();  // s_wcnt, s_overflow, s_pre
+    RF_STAMP(2);
     if (tid == 0) {
         u32 o = 0;
         for (int w = 0; w < RF_WARPS; ++w) {
@@ -1919,18 +1979,55 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
         if (P.ng == 0) {
             kept = tid == 0 ? n_c : 0;
         } else {
-            for (u32 i = tid; i < n_c; i += RF_THREADS) {
-                int w = 0;
+            // RF_ILP candidates per thread at a time, walked level by level: the dependent loads of one chain are
+            // serial, those of different candidates are all in flight together (r02 timeline: 13 us -> 4 us on the
+            // critical CTA)
+            for (u32 i0 = 0; i0 < n_c; i0 += RF_THREADS * RF_ILP) {
+                u32* ep[RF_ILP];
+                u32 row[RF_ILP];
+                bool ok[RF_ILP], pass[RF_ILP];
 #pragma unroll
-                for (int k = 1; k < RF_WARPS; ++k) w += (i >= s_woff[k]) ? 1 : 0;
-                u32* e = P.lists + ((size_t)vcta * RF_WARPS + w) * P.list_cap + (i - s_woff[w]);
-                const u32 row = *e;
-                bool ok = true;
-                for (int g = 0; g < P.ng; ++g) ok = ok && rf_chain(P.gather[g], gbits[g], row);
-                if (ok) ++kept;
-                else {
-                    atomicAnd(&P.bits[row >> 5], ~(1u << (row & 31)));
-                    *e = row | 0x80000000u;
+                for (int k = 0; k < RF_ILP; ++k) {
+                    const u32 i = i0 + k * RF_THREADS + tid;
+                    ok[k] = i < n_c;
+                    int w = 0;
+#pragma unroll
+                    for (int q = 1; q < RF_WARPS; ++q) w += (i >= s_woff[q]) ? 1 : 0;
+                    ep[k] = P.lists + ((size_t)vcta * RF_WARPS + w) * P.list_cap + (i - s_woff[w]);
+                    row[k] = ok[k] ? __ldcg(ep[k]) : 0u;
+                    pass[k] = ok[k];
+                }
+                for (int g = 0; g < P.ng; ++g) {
+                    const GatherD& G = P.gather[g];
+                    int64_t r[RF_ILP];
+#pragma unroll
+                    for (int k = 0; k < RF_ILP; ++k) r[k] = row[k];
+                    for (int d = 0; d < G.depth; ++d) {
+                        int32_t t[RF_ILP];
+#pragma unroll
+                        for (int k = 0; k < RF_ILP; ++k) t[k] = pass[k] ? G.fk[d][r[k]] : 0;
+#pragma unroll
+                        for (int k = 0; k < RF_ILP; ++k) {
+                            if (pass[k] && (t[k] < 0 || t[k] >= G.n[d])) {
+                                if (t[k] != -1 && G.oob != nullptr) *G.oob = 1u;
+                                pass[k] = false;
+                            }
+                            r[k] = t[k];
+                        }
+                    }
+                    if (gbits[g] != nullptr) {
+#pragma unroll
+                        for (int k = 0; k < RF_ILP; ++k) pass[k] = pass[k] && bit_test(gbits[g], pass[k] ? r[k] : 0);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < RF_ILP; ++k) {
+                    if (!ok[k]) continue;
+                    if (pass[k]) ++kept;
+                    else {
+                        atomicAnd(&P.bits[row[k] >> 5], ~(1u << (row[k] & 31)));
+                        *ep[k] = row[k] | 0x80000000u;
+                    }
                 }
             }
         }
@@ -1959,6 +2056,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
     }
     u32 cta_count;
     block_exclusive_scan(kept, s_warp, cta_count);
+    RF_STAMP(3);
 
     // ---- (3) publish, then sum the counts of every lower ticket
     if (tid == 0) st_volatile_u64(P.cta_state + vcta, ((u64)P.epoch << 32) | cta_count);
@@ -1982,6 +2080,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
     }
     __syncthreads();
     const u64 base = s_base;
+    RF_STAMP(4);
 
     // ---- (4) ordered write
     const bool gather = P.pg.n_ranks > 0;
@@ -2041,6 +2140,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
         }
     }
 
+    RF_STAMP(5);
     // ---- tail: the highest ticket knows the grand total; the last CTA to finish re-arms the counters
     if (tid == 0 && vcta == gridDim.x - 1) *P.total = base + cta_count;
     if (gather) __threadfence_system();
@@ -2048,6 +2148,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(&P.counters[1], 1u) == gridDim.x - 1) ? 1u : 0u;
     __syncthreads();
+    RF_STAMP(6);
     if (s_last) {
         if (tid == 0) {
             P.counters[0] = 0;
@@ -2055,6 +2156,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
         }
         if (gather) gather_tail(P.pg, P.total);
     }
+    RF_STAMP(7);
 }
 
 // ---------------------------------------------------------------------------------------------
