@@ -160,6 +160,24 @@ colq_status colq_trim(colq_ctx *ctx);
 colq_status colq_comm_unique_id(colq_ctx *ctx, uint8_t out_id[128]);
 colq_status colq_comm_init(colq_ctx *ctx, const uint8_t id[128], int n_ranks, int rank);
 colq_status colq_comm_info(const colq_ctx *ctx, int *out_n_ranks, int *out_rank);
+/*
+ * The same communicator for ONE host process that drives all GPUs -- the shape of the reference, where the engine is a
+ * single object in a single JVM (E/DataSystemSerialIndices.java:14-22; app/.../Runner.java:40): ctxs[i] (one context per
+ * GPU, created with colq_create on distinct devices) becomes rank i of n_ranks.  The mailboxes are made mutually
+ * reachable with cudaDeviceEnablePeerAccess instead of CUDA IPC, NCCL is not involved at all, and the exchange kernels
+ * are the same.  Because those kernels wait for one another ACROSS GPUs, the host must enqueue the work of every rank
+ * before it fetches any rank's result: call colq_execute_group (or colq_execute_async on every context), then
+ * colq_fetch per context.  A plain colq_execute on one context of a local group would wait for peers that were never
+ * launched (the kernels give up after 4 s: COLQ_ERR_DEVICE).
+ */
+colq_status colq_comm_init_local(colq_ctx **ctxs, int n_ranks);
+/* colq_execute_async(ctxs[i], queries[i]) for i in [0, n); stops at the first non-OK status and returns it */
+colq_status colq_execute_group(colq_ctx **ctxs, colq_query **queries, int n);
+/* Waits for every rank and writes the match counts (global count for a sharded root) to out_counts[n] (nullable).  If a
+   rank's result block was too small, the query is first re-run on ALL ranks with a larger block -- the step a
+   one-process-per-GPU host performs inside colq_fetch on every rank at once.  Afterwards colq_fetch(ctxs[i], ...) copies
+   rank i's bitmask / indices out without waiting for anybody. */
+colq_status colq_fetch_group(colq_ctx **ctxs, colq_query **queries, int n, int64_t *out_counts);
 
 /* ---- tables and columns: InMemoryTable.ofColumns / associateTo (M/InMemoryTable.java:32-35,44-90) --- */
 

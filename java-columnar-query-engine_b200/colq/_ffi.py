@@ -47,6 +47,9 @@ SIGNATURES = {
     "colq_comm_unique_id": (_int, [_p, _p]),
     "colq_comm_init": (_int, [_p, _p, _int, _int]),
     "colq_comm_info": (_int, [_p, C.POINTER(_int), C.POINTER(_int)]),
+    "colq_comm_init_local": (_int, [C.POINTER(_p), _int]),
+    "colq_execute_group": (_int, [C.POINTER(_p), C.POINTER(_p), _int]),
+    "colq_fetch_group": (_int, [C.POINTER(_p), C.POINTER(_p), _int, C.POINTER(_i64)]),
     "colq_table_create": (_int, [_p, _i64, _int, _i64, C.POINTER(_i32)]),
     "colq_register": (_int, [_p, C.c_char_p, _i32]),
     "colq_col_i32": (_int, [_p, _i32, _int, _p, _i64]),

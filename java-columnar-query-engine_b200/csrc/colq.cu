@@ -239,6 +239,8 @@ struct colq_ctx {
     // peer-memory mailboxes (CUDA IPC over NVLink); ok == false -> NCCL collectives on the data path
     struct PeerBox {
         bool ok = false;
+        bool ipc = true;   // peer pointers come from cudaIpcOpenMemHandle (one process per GPU); false: one process drives
+                           // all GPUs and the pointers are the peers' own allocations (colq_comm_init_local)
         void* local = nullptr;
         size_t bytes = 0;
         void* peer_ptr[MAX_RANKS] = {};
@@ -652,7 +654,11 @@ struct Planner {
                     // the only data-path collective: OR-allreduce of the replicated parent's mask
                     Op g{};
                     g.node = xi; g.dst = reach; g.n_words = bitmap_words(n);
-                    if (ctx->peer.ok && q->opt_peer && g.n_words <= MASK_WORDS_MAX) {
+                    const bool local_group = ctx->comm == nullptr;   // one process, no NCCL: peer memory is the only exchange
+                    if (local_group && g.n_words > MASK_WORDS_MAX)
+                        return fail(ctx, COLQ_FAILURE, "a replicated table of %lld rows is too large for the peer-memory mask exchange of a local communicator (limit %d rows)",
+                                    (long long)n, MASK_WORDS_MAX * 32);
+                    if (ctx->peer.ok && (q->opt_peer || local_group) && g.n_words <= MASK_WORDS_MAX) {
                         g.kind = K_PEER_MASK_PUBLISH; g.name = "peer_mask_publish";
                         PeerMaskParams& P = g.pmask;
                         P.reach = reach; P.n_words = (int)g.n_words; P.n_ranks = ctx->n_ranks; P.rank = ctx->rank;
@@ -1195,7 +1201,8 @@ colq_status run_pipeline(colq_query* q) {
     const Table& RT = ctx->tables[q->root_table];
     const int64_t n = RT.n_rows;
     q->gathered = ctx->n_ranks > 1 && RT.placement == COLQ_SHARDED;
-    const bool peer_gather = q->gathered && ctx->peer.ok && q->opt_peer;
+    const bool local_group = ctx->n_ranks > 1 && ctx->comm == nullptr;
+    const bool peer_gather = q->gathered && ctx->peer.ok && (q->opt_peer || local_group);
     if (q->want_idx_capacity <= 0) q->want_idx_capacity = (q->gathered && !peer_gather) ? (1 << 16) : (1 << 20);
     ST(ensure_idx_capacity(q, q->want_idx_capacity));
     Planner pl{q, ctx};
@@ -1534,6 +1541,10 @@ colq_status run_pipeline(colq_query* q) {
     return COLQ_OK;
 }
 
+// internal: a rank of a LOCAL communicator needs a larger result block; its peers' kernels wait for it across GPUs, so the
+// re-run has to be enqueued on every rank before anybody fetches again (colq_fetch_group does that)
+constexpr colq_status RERUN_GROUP = (colq_status)100;
+
 // count D2H, (multi-GPU) final gather to rank 0, result copies. Synchronises the stream.
 colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_cap, int32_t* out_idx, int64_t idx_cap,
                           int64_t* out_count, colq_timing* out_timing) {
@@ -1585,7 +1596,13 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
             // some rank found more rows than a result block holds: every rank sees the same gathered counts, so all
             // of them grow the block (or leave the fixed-size mailbox path) and run the query again
             q->want_idx_capacity = (int64_t)ginfo[1] + (int64_t)ginfo[1] / 4 + 1024;
-            if (peer_gather && q->want_idx_capacity > ctx->peer.slot_cap) q->opt_peer = 0;
+            if (ctx->comm == nullptr && q->want_idx_capacity <= ctx->peer.slot_cap) return RERUN_GROUP;  // all ranks re-run together (colq_fetch_group)
+            if (peer_gather && q->want_idx_capacity > ctx->peer.slot_cap) {
+                if (ctx->comm == nullptr)
+                    return fail(ctx, COLQ_ERR_CAPACITY, "a rank matched %llu rows but a mailbox slot holds %lld; a local communicator has no NCCL path: raise COLQ_PEER_SLOT_CAP",
+                                (unsigned long long)ginfo[1], (long long)ctx->peer.slot_cap);
+                q->opt_peer = 0;
+            }
             ST(run_pipeline(q));
             return fetch_results(q, out_bitmask, bitmask_cap, out_idx, idx_cap, out_count, out_timing);
         }
@@ -1600,6 +1617,7 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
     } else if ((int64_t)local > q->idx_capacity) {
         // index buffer was too small: grow it and run again (happens once per query, the capacity sticks)
         q->want_idx_capacity = (int64_t)local + (int64_t)local / 8 + 1024;
+        if (ctx->n_ranks > 1 && ctx->comm == nullptr) return RERUN_GROUP;
         ST(run_pipeline(q));
         return fetch_results(q, out_bitmask, bitmask_cap, out_idx, idx_cap, out_count, out_timing);
     }
@@ -1768,7 +1786,7 @@ colq_status setup_peerbox(colq_ctx* ctx) {
 void destroy_peerbox(colq_ctx* ctx) {
     auto& pb = ctx->peer;
     for (int r = 0; r < ctx->n_ranks; ++r)
-        if (r != ctx->rank && pb.peer_ptr[r]) cudaIpcCloseMemHandle(pb.peer_ptr[r]);
+        if (pb.ipc && r != ctx->rank && pb.peer_ptr[r]) cudaIpcCloseMemHandle(pb.peer_ptr[r]);
     if (pb.local) cudaFree(pb.local);
     if (pb.d_peers) cudaFree(pb.d_peers);
     if (pb.d_done) cudaFree(pb.d_done);
@@ -1903,6 +1921,105 @@ colq_status colq_comm_init(colq_ctx* ctx, const uint8_t id_bytes[128], int n_ran
     ctx->n_ranks = n_ranks;
     ctx->rank = rank;
     return setup_peerbox(ctx);
+}
+
+// One host process (the reference is ONE DataSystemSerialIndices object in one JVM, E/DataSystemSerialIndices.java:14-22)
+// driving one context per GPU: the mailboxes are plain cudaMalloc allocations made reachable with
+// cudaDeviceEnablePeerAccess, the exchange kernels are the same as in the one-process-per-GPU mode.
+colq_status colq_comm_init_local(colq_ctx** ctxs, int n_ranks) {
+    if (!ctxs) return COLQ_THROW_NULL;
+    if (n_ranks < 1 || n_ranks > MAX_RANKS) return COLQ_THROW_ILLEGAL_ARG;
+    for (int i = 0; i < n_ranks; ++i) {
+        if (!ctxs[i]) return COLQ_THROW_NULL;
+        if (ctxs[i]->comm || ctxs[i]->n_ranks != 1) return fail(ctxs[i], COLQ_THROW_ILLEGAL_STATE, "communicator already initialised");
+        for (int j = 0; j < i; ++j)
+            if (ctxs[j]->device == ctxs[i]->device) return fail(ctxs[i], COLQ_THROW_ILLEGAL_ARG, "contexts %d and %d are on the same GPU %d", j, i, ctxs[i]->device);
+    }
+    if (n_ranks == 1) return COLQ_OK;
+    colq_ctx* c0 = ctxs[0];
+    const char* cap_env = getenv("COLQ_PEER_SLOT_CAP");
+    const int64_t slot_cap = cap_env ? std::max<int64_t>(1024, atoll(cap_env)) : ((int64_t)1 << 20);
+    const size_t slot_bytes = (size_t)GATHER_SLOT_HEADER + (size_t)slot_cap * 4;
+    const size_t bytes = PEER_GATHER_AREA_OFFSET + (size_t)2 * n_ranks * slot_bytes;
+    for (int i = 0; i < n_ranks; ++i) {
+        colq_ctx* c = ctxs[i];
+        CU(c, cudaSetDevice(c->device));
+        for (int j = 0; j < n_ranks; ++j) {
+            if (j == i) continue;
+            int can = 0;
+            CU(c, cudaDeviceCanAccessPeer(&can, c->device, ctxs[j]->device));
+            if (!can) return fail(c0, COLQ_ERR_DEVICE, "GPU %d cannot access GPU %d's memory (no NVLink / P2P path)", c->device, ctxs[j]->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(c0, COLQ_ERR_DEVICE, "cudaDeviceEnablePeerAccess(%d -> %d): %s", c->device, ctxs[j]->device, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        auto& pb = c->peer;
+        pb.slot_cap = slot_cap; pb.slot_bytes = slot_bytes; pb.bytes = bytes; pb.ipc = false;
+        CU(c, cudaMalloc(&pb.local, bytes));
+        CU(c, cudaMemset(pb.local, 0, bytes));
+    }
+    for (int i = 0; i < n_ranks; ++i) {
+        colq_ctx* c = ctxs[i];
+        CU(c, cudaSetDevice(c->device));
+        auto& pb = c->peer;
+        for (int r = 0; r < n_ranks; ++r) pb.peer_ptr[r] = ctxs[r]->peer.local;
+        void* p;
+        CU(c, cudaMalloc(&p, sizeof(void*) * MAX_RANKS));
+        pb.d_peers = (uint8_t**)p;
+        CU(c, cudaMemcpy(pb.d_peers, pb.peer_ptr, sizeof(void*) * MAX_RANKS, cudaMemcpyHostToDevice));
+        CU(c, cudaMalloc(&p, sizeof(u32) * (MAX_RANKS + 16)));
+        CU(c, cudaMemset(p, 0, sizeof(u32) * (MAX_RANKS + 16)));
+        pb.d_done = (u32*)p;
+        pb.d_status = pb.d_done + MAX_RANKS;
+        pb.ok = true;
+        c->n_ranks = n_ranks;
+        c->rank = i;
+        CU(c, cudaDeviceSynchronize());
+    }
+    return COLQ_OK;
+}
+
+// colq_execute_async on every context of a group (a local communicator's kernels wait for one another across GPUs, so
+// every rank's work must be enqueued before any rank's result is fetched)
+colq_status colq_execute_group(colq_ctx** ctxs, colq_query** queries, int n) {
+    if (!ctxs || !queries) return COLQ_THROW_NULL;
+    for (int i = 0; i < n; ++i) {
+        if (!ctxs[i] || !queries[i]) return COLQ_THROW_NULL;
+        if (queries[i]->ctx != ctxs[i]) return fail(ctxs[i], COLQ_THROW_ILLEGAL_ARG, "query %d belongs to another context", i);
+    }
+    colq_status first = COLQ_OK;
+    for (int i = 0; i < n; ++i) {
+        // a Failure is the same on every rank (same schema, same query); a rank that failed to enqueue must not leave its
+        // peers spinning, so stop at the first one
+        colq_status st = run_pipeline(queries[i]);
+        if (st != COLQ_OK) { first = st; break; }
+    }
+    return first;
+}
+
+// Waits for every rank's execution and reports the match counts; if a rank's result block turned out too small, the
+// query is re-run on ALL ranks with a larger block first (the ranks decide alike: they all see the gathered counts).
+colq_status colq_fetch_group(colq_ctx** ctxs, colq_query** queries, int n, int64_t* out_counts) {
+    if (!ctxs || !queries) return COLQ_THROW_NULL;
+    for (int i = 0; i < n; ++i)
+        if (!ctxs[i] || !queries[i] || queries[i]->ctx != ctxs[i]) return COLQ_THROW_ILLEGAL_ARG;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        bool rerun = false;
+        int64_t want = 0;
+        for (int i = 0; i < n; ++i) {
+            int64_t count = 0;
+            colq_status st = fetch_results(queries[i], nullptr, 0, nullptr, 0, &count, nullptr);
+            if (st == RERUN_GROUP) rerun = true;
+            else if (st != COLQ_OK) return st;
+            else if (out_counts) out_counts[i] = count;
+            want = std::max(want, queries[i]->want_idx_capacity);
+        }
+        if (!rerun) return COLQ_OK;
+        for (int i = 0; i < n; ++i) queries[i]->want_idx_capacity = want;
+        ST(colq_execute_group(ctxs, queries, n));
+    }
+    return fail(ctxs[0], COLQ_ERR_CAPACITY, "result block still too small after re-running the group");
 }
 
 colq_status colq_comm_info(const colq_ctx* ctx, int* out_n_ranks, int* out_rank) {
@@ -2456,7 +2573,10 @@ colq_status colq_fetch(colq_ctx* ctx, colq_query* q, uint64_t* out_bitmask, int6
                        int64_t indices_capacity, int64_t* out_count, colq_timing* out_timing) {
     if (!ctx || !q) return COLQ_THROW_NULL;
     if (q->ctx != ctx) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "query belongs to another context");
-    return fetch_results(q, out_bitmask, bitmask_capacity_words, out_indices, indices_capacity, out_count, out_timing);
+    colq_status st = fetch_results(q, out_bitmask, bitmask_capacity_words, out_indices, indices_capacity, out_count, out_timing);
+    if (st == RERUN_GROUP)
+        return fail(ctx, COLQ_ERR_CAPACITY, "the result block of this rank is too small and the query must be re-run on every rank of the local communicator: use colq_fetch_group");
+    return st;
 }
 
 colq_status colq_execute(colq_ctx* ctx, colq_query* q, uint64_t* out_bitmask, int64_t bitmask_capacity_words, int32_t* out_indices,
@@ -2466,7 +2586,10 @@ colq_status colq_execute(colq_ctx* ctx, colq_query* q, uint64_t* out_bitmask, in
     if (indices_capacity > q->want_idx_capacity && out_indices && !(ctx->n_ranks > 1))
         q->want_idx_capacity = std::min<int64_t>(indices_capacity, (int64_t)1 << 28);
     ST(run_pipeline(q));
-    return fetch_results(q, out_bitmask, bitmask_capacity_words, out_indices, indices_capacity, out_count, out_timing);
+    colq_status st = fetch_results(q, out_bitmask, bitmask_capacity_words, out_indices, indices_capacity, out_count, out_timing);
+    if (st == RERUN_GROUP)
+        return fail(ctx, COLQ_ERR_CAPACITY, "the result block of this rank is too small and the query must be re-run on every rank of the local communicator: use colq_execute_group + colq_fetch_group");
+    return st;
 }
 
 colq_status colq_profile(const colq_query* q, colq_stage* out_stages, int capacity, int* out_n_stages) {
