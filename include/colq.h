@@ -274,6 +274,25 @@ colq_status colq_associate_fk_device(colq_ctx *ctx, colq_table x, int x_ordinal,
 colq_status colq_associate_fk_host(colq_ctx *ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal,
                                    const int32_t *fk_pinned, int64_t capacity_bytes, int64_t n);
 
+/*
+ * Cross-shard associations: the general case of filterParent (E/ExecutionContext.java:100-122), where
+ * an association between two tables that are BOTH sharded -- or from a replicated table into a sharded one -- points at
+ * rows of other ranks.  The targets are then GLOBAL row indices of the associated table:
+ *   colq_table_partition   declares how a COLQ_SHARDED table is split: bounds[r] .. bounds[r+1] are rank r's global rows
+ *                          (bounds[0] = 0, every bound below the total a multiple of 64 so that a shard is whole BitSet
+ *                          words; this rank's entry must match its colq_table_create).  Same array on every rank.
+ *   colq_associate_*_global  like colq_associate_fk / _csr with targets in [0, global rows of y) (-1 = None for _fk).
+ * A hop through such a column exchanges a bitmap over y's (or x's) GLOBAL rows through the peer-mapped heap behind the
+ * mailboxes: all-gather of the child's bits for a pull, OR-reduce-scatter of the reach bits for a push (own kernels over
+ * NVLink; needs the peer-memory exchange -- there is no NCCL path for these).  On a single rank they are ordinary
+ * associations.  Heap size per execution parity: COLQ_PEER_HEAP_MB (default 128 MB = 1 G rows of bitmap).
+ */
+colq_status colq_table_partition(colq_ctx *ctx, colq_table table, const int64_t *bounds, int n_ranks);
+colq_status colq_associate_fk_global(colq_ctx *ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal,
+                                     const int32_t *fk_global, int64_t n);
+colq_status colq_associate_csr_global(colq_ctx *ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal,
+                                      const int64_t *offsets, const int32_t *targets_global, int64_t n, int64_t nnz);
+
 /* Release a table's device memory and its registrations (the reference leaves this to the garbage collector).
    Association columns of other tables that pointed at it become unset. The handle stays reserved. */
 colq_status colq_table_destroy(colq_ctx *ctx, colq_table table);

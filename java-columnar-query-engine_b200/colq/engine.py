@@ -379,6 +379,20 @@ class ColqContext:
         self._check(self.lib.colq_associate_csr(self.handle, x, x_ordinal, y, y_ordinal, _ptr(o), _ptr(t), o.shape[0] - 1,
                                                 t.shape[0]))
 
+    # -- cross-shard associations: global targets into a sharded table (include/colq.h)
+    def table_partition(self, table: int, bounds: Sequence[int]) -> None:
+        b = np.ascontiguousarray(bounds, dtype=np.int64)
+        self._check(self.lib.colq_table_partition(self.handle, table, _ptr(b), b.shape[0] - 1))
+
+    def associate_fk_global(self, x: int, x_ordinal: int, y: int, y_ordinal: int, fk: np.ndarray) -> None:
+        f = np.ascontiguousarray(fk, dtype=np.int32)
+        self._check(self.lib.colq_associate_fk_global(self.handle, x, x_ordinal, y, y_ordinal, _ptr(f), f.shape[0]))
+
+    def associate_csr_global(self, x: int, x_ordinal: int, y: int, y_ordinal: int, offsets: np.ndarray, targets: np.ndarray) -> None:
+        o = np.ascontiguousarray(offsets, dtype=np.int64)
+        t = np.ascontiguousarray(targets, dtype=np.int32)
+        self._check(self.lib.colq_associate_csr_global(self.handle, x, x_ordinal, y, y_ordinal, _ptr(o), _ptr(t), o.shape[0] - 1, t.shape[0]))
+
     def query(self, table_name: str) -> ColqQuery:
         return ColqQuery(self, table_name)
 

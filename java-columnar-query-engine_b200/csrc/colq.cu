@@ -132,6 +132,7 @@ struct Column {
     // dictionary-encoded string column (colq_col_str_dict): `data` holds int32 codes, the n_dict DISTINCT values live
     // in an ordinary (offsets, bytes) string column of their own.  A predicate is evaluated once per distinct value.
     std::unique_ptr<Column> dict;
+    bool global_targets = false;  // association targets are GLOBAL rows of a sharded target table (cross-shard hops)
     bool host_resident = false;
     bool fk_validated = true;  // false: to-one targets are range-checked on the rows a query walks, not at ingest
     DevBuf promoted, promoted_offsets;
@@ -141,7 +142,9 @@ struct Table {
     int64_t n_rows = 0;
     colq_placement placement = COLQ_REPLICATED;
     int64_t row_base = 0;
+    std::vector<int64_t> part;  // colq_table_partition: global row bounds of every rank's shard (n_ranks + 1 entries)
     std::vector<Column> cols;
+    int64_t global_rows() const { return part.empty() ? n_rows : part.back(); }
 };
 
 struct Crit {
@@ -163,7 +166,7 @@ struct QNode {
 };
 
 // one kernel launch (or collective / memset) of a planned query
-enum OpKind { K_SCAN_ROWS, K_SCAN_CODES, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER, K_COMPACT_FUSED, K_COMPACT_LOOKBACK, K_ROOT_FUSED, K_PEER_MASK_PUBLISH, K_PEER_MASK_COLLECT, K_PEER_GATHER };
+enum OpKind { K_SCAN_ROWS, K_SCAN_CODES, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER, K_COMPACT_FUSED, K_COMPACT_LOOKBACK, K_ROOT_FUSED, K_PEER_BITS_ALLGATHER, K_PEER_BITS_REDUCE, K_PEER_MASK_PUBLISH, K_PEER_MASK_COLLECT, K_PEER_GATHER };
 
 struct Op {
     OpKind kind;
@@ -189,6 +192,7 @@ struct Op {
     CompactFusedParams cfused{};
     CompactLookbackParams clook{};
     RootFusedParams rfused{};
+    PeerBitsParams pbits{};
     PeerMaskParams pmask{};
     PeerGatherParams pgather{};
     bool tail_publish = false;  // K_SCAN_STR / K_SCAN_CODES: the last CTA publishes the pushed mask to the peers
@@ -250,6 +254,10 @@ struct colq_ctx {
         u64 mask_epoch = 0, gather_epoch = 0;
         int64_t slot_cap = 0;
         size_t slot_bytes = 0;
+        // peer-mapped heap behind the mailbox: global bitmaps of cross-shard hops, two halves used alternately by
+        // successive executions (a rank can be at most one execution ahead of a peer)
+        size_t heap_off = 0, heap_half = 0;
+        u64 heap_step = 0;
     } peer;
     // pinned [header | first FETCH_SPEC indices] staging of colq_fetch: small results come back with ONE sync.  Owned by
     // the context, allocated once: cudaHostAlloc / cudaFreeHost per query cost up to hundreds of ms on some hosts
@@ -269,6 +277,9 @@ struct colq_query {
     int own_begin = -1, own_end = -1;  // root-node scan ops that depend on no child (hoistable behind a mask publish)
     std::vector<Column*> pending_promotions;  // host-resident columns whose HBM copy this execution fills
     bool lazy_oob = false;  // the plan walks a to-one column that was not range-checked at ingest
+    size_t heap_cursor = 0;  // bytes of the peer heap half this plan uses
+    bool heap_used = false;
+    int heap_parity = 0;
     int64_t promoted_bytes = 0;
     DevBuf barrier_buf;  // {arrival count, generation} of the cooperative compaction kernel
     DevBuf rf_state_buf;  // root_fused_kernel: [ticket, finished counters | pad to 64 B | one u64 state per CTA]
@@ -590,7 +601,37 @@ struct Planner {
         if (!(col.forward && col.is_fk)) return false;
         const Table& ct = ctx->tables[col.peer_table];
         if (!sharded(t) && sharded(ct)) return false;
+        if (col.global_targets && sharded(ct)) return false;  // the hop leaves the shard: its child is materialised and exchanged
         return true;
+    }
+
+    // a bitmap over the GLOBAL rows of a sharded table, at the same offset of the peer-mapped heap on every rank
+    colq_status heap_bitmap(int64_t global_rows, u32** local, size_t* off) {
+        auto& pb = ctx->peer;
+        if (!pb.ok || pb.heap_half == 0)
+            return fail(ctx, COLQ_FAILURE, "unsupported placement: an association hop between shards needs the peer-memory exchange (NVLink P2P mailboxes), which is not available on this communicator");
+        const size_t bytes = (size_t)round_up(bitmap_words(std::max<int64_t>(global_rows, 1)) * 4 + 16, 256);
+        if (!q->heap_used) {
+            q->heap_used = true;
+            q->heap_parity = (int)(pb.heap_step++ & 1);
+        }
+        if (q->heap_cursor + bytes > pb.heap_half)
+            return fail(ctx, COLQ_ERR_CAPACITY, "the global bitmaps of this query's cross-shard hops need %zu bytes of peer heap but a half holds %zu: raise COLQ_PEER_HEAP_MB",
+                        q->heap_cursor + bytes, pb.heap_half);
+        *off = pb.heap_off + (size_t)q->heap_parity * pb.heap_half + q->heap_cursor;
+        *local = (u32*)((char*)pb.local + *off);
+        q->heap_cursor += bytes;
+        return COLQ_OK;
+    }
+
+    PeerBitsParams peer_bits(const Table& owner, size_t heap_off) const {
+        PeerBitsParams P{};
+        P.heap_off = heap_off;
+        P.word_base = owner.part[ctx->rank] / 32;
+        P.n_words = bitmap_words(owner.n_rows);
+        P.n_ranks = ctx->n_ranks; P.rank = ctx->rank; P.n_src = ctx->n_ranks;
+        P.peers = ctx->peer.d_peers; P.status = ctx->peer.d_status; P.done = ctx->peer.d_done + MAX_RANKS + 9;
+        return P;
     }
 
     colq_status eval(int xi, const Consume& consume, NodeBits* out) {
@@ -608,8 +649,40 @@ struct Planner {
             const Column& col = T.cols[ordinal];
             const Table& CT = ctx->tables[col.peer_table];
             if (col.forward) {
-                if (!sharded(T) && sharded(CT))
-                    return fail(ctx, COLQ_FAILURE, "unsupported placement: a replicated table holds an association into a sharded table");
+                const bool xs = col.global_targets && sharded(CT);  // the keys are GLOBAL rows of a sharded table
+                if (!sharded(T) && sharded(CT) && !xs)
+                    return fail(ctx, COLQ_FAILURE, "unsupported placement: a replicated table holds an association with shard-local targets into a sharded table (register it with colq_associate_*_global)");
+                if (xs) {
+                    // cross-shard PULL: materialise the child on its owners, all-gather its bits into a global bitmap on
+                    // every rank, then test bit [global key] like any local one
+                    if (CT.part.empty()) return fail(ctx, COLQ_THROW_ILLEGAL_STATE, "the sharded target table has no partition (colq_table_partition)");
+                    NodeBits nb;
+                    ST(eval(ci, Consume{}, &nb));
+                    const int64_t gy = CT.global_rows();
+                    u32* gbits = nullptr;
+                    if (!nb.all_ones) {
+                        size_t off = 0;
+                        ST(heap_bitmap(gy, &gbits, &off));
+                        Op ag{};
+                        ag.kind = K_PEER_BITS_ALLGATHER; ag.node = xi; ag.name = "peer_bits_allgather";
+                        ag.pbits = peer_bits(CT, off);
+                        ag.pbits.src = nb.bits;
+                        ag.acct_rows = CT.n_rows; ag.acct_bytes = ag.pbits.n_words * 4 * (ctx->n_ranks + 1);
+                        q->ops.push_back(ag);
+                    }
+                    if (col.is_fk) {
+                        GatherD g{};
+                        g.fk[0] = (const int32_t*)col.data.ptr;
+                        g.n[0] = gy;
+                        g.depth = 1;
+                        g.oob = oob_for(col);
+                        g.bits = gbits;
+                        gathers.push_back(g);
+                    } else {
+                        csrs.push_back({&col, NodeBits{gbits, gbits == nullptr}, gy});
+                    }
+                    continue;
+                }
                 if (col.is_fk) {
                     GatherD g{};
                     g.fk[0] = (const int32_t*)col.data.ptr;
@@ -639,10 +712,42 @@ struct Planner {
             } else {
                 // reverse side: the data is the child's forward column; the child pushes into `reach`
                 const Column& f = CT.cols[col.peer_ordinal];
-                if (sharded(T) && !sharded(CT))
-                    return fail(ctx, COLQ_FAILURE, "unsupported placement: a replicated table holds an association into a sharded table");
+                const bool xs = f.global_targets && sharded(T);  // the child's keys are GLOBAL rows of this sharded table
+                if (sharded(T) && !sharded(CT) && !xs)
+                    return fail(ctx, COLQ_FAILURE, "unsupported placement: a replicated table holds an association with shard-local targets into a sharded table (register it with colq_associate_*_global)");
                 u32* reach;
                 ST(alloc_bitmap(n, &reach));
+                if (xs) {
+                    // cross-shard PUSH: the child sets bits in this rank's own GLOBAL-sized reach bitmap; every rank then
+                    // ORs all ranks' copies of its own slice (OR-reduce-scatter by remote loads)
+                    if (T.part.empty()) return fail(ctx, COLQ_THROW_ILLEGAL_STATE, "the sharded table has no partition (colq_table_partition)");
+                    const int64_t gt = T.global_rows();
+                    u32* reach_g = nullptr;
+                    size_t off = 0;
+                    ST(heap_bitmap(gt, &reach_g, &off));
+                    Op z{};
+                    z.kind = K_ZERO; z.node = xi; z.dst = reach_g; z.n_alloc_words = bitmap_words(std::max<int64_t>(gt, 1)) + 4; z.name = "memset_reach";
+                    q->ops.push_back(z);
+                    Consume cc;
+                    cc.push = true; cc.fwd = &f; cc.reach = reach_g; cc.n_parent = gt;
+                    NodeBits nb;
+                    ST(eval(ci, cc, &nb));
+                    Op rd{};
+                    rd.kind = K_PEER_BITS_REDUCE; rd.node = xi; rd.name = "peer_bits_reduce";
+                    rd.pbits = peer_bits(T, off);
+                    rd.pbits.dst = reach;
+                    rd.pbits.n_src = sharded(CT) ? ctx->n_ranks : 1;  // a replicated child pushed the same bits on every rank
+                    rd.acct_rows = n; rd.acct_bytes = rd.pbits.n_words * 4 * (rd.pbits.n_src + 1);
+                    q->ops.push_back(rd);
+                    if (cur == nullptr) cur = reach;
+                    else {
+                        Op a{};
+                        a.kind = K_AND; a.node = xi; a.dst = cur; a.src = reach; a.n_words = bitmap_words(n); a.name = "and_words";
+                        a.acct_rows = n; a.acct_bytes = a.n_words * 12;
+                        q->ops.push_back(a);
+                    }
+                    continue;
+                }
                 Op z{};
                 z.kind = K_ZERO; z.node = xi; z.dst = reach; z.n_alloc_words = bitmap_alloc_words(n); z.name = "memset_reach";
                 q->ops.push_back(z);
@@ -1140,6 +1245,16 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
             q->timing.kernel_launches++;
             break;
         }
+        case K_PEER_BITS_ALLGATHER:
+            o.pbits.epoch = ++ctx->peer.mask_epoch;
+            peer_bits_allgather_kernel<<<grid_for(std::max<int64_t>(o.pbits.n_words, 1), 256, ctx->sm_count, 2), 256, 0, s>>>(o.pbits);
+            q->timing.kernel_launches++;
+            break;
+        case K_PEER_BITS_REDUCE:
+            if (o.pbits.n_src > 1) o.pbits.epoch = ++ctx->peer.mask_epoch;
+            peer_bits_reduce_kernel<<<grid_for(std::max<int64_t>(o.pbits.n_words, 1), 256, ctx->sm_count, 2), 256, 0, s>>>(o.pbits);
+            q->timing.kernel_launches++;
+            break;
         case K_PEER_MASK_PUBLISH:
             o.pmask.epoch = ++ctx->peer.mask_epoch;
             peer_mask_publish_kernel<<<1, 256, 0, s>>>(o.pmask);
@@ -1196,6 +1311,8 @@ colq_status run_pipeline(colq_query* q) {
     q->own_begin = q->own_end = -1;
     q->pending_promotions.clear();
     q->lazy_oob = false;
+    q->heap_cursor = 0;
+    q->heap_used = false;
     q->promoted_bytes = 0;
     // the result block first: the planner hands its flags word to kernels that range-check lazily
     const Table& RT = ctx->tables[q->root_table];
@@ -1714,6 +1831,13 @@ void unlink_assoc(colq_ctx* ctx, colq_table x, int xo, colq_table y, int yo) {
     ctx->tables[y].cols[yo] = Column();
 }
 
+// size of one half of the peer heap (global bitmaps of cross-shard hops): COLQ_PEER_HEAP_MB, default 128 MB = 1 G rows of bitmap
+size_t peer_heap_half_bytes() {
+    const char* e = getenv("COLQ_PEER_HEAP_MB");
+    const double mb = e ? atof(e) : 128.0;
+    return (size_t)round_up((int64_t)(std::max(mb, 1.0) * 1048576.0), 256);
+}
+
 // CUDA-IPC mailboxes for the peer-memory exchange kernels.  Collective over the freshly created NCCL communicator
 // (used here only to ship the 64-byte IPC handles and to agree on success).  Any failure leaves peer.ok == false and
 // the data path falls back to NCCL all-gathers.
@@ -1725,7 +1849,9 @@ colq_status setup_peerbox(colq_ctx* ctx) {
     const char* cap_env = getenv("COLQ_PEER_SLOT_CAP");
     pb.slot_cap = cap_env ? std::max<int64_t>(1024, atoll(cap_env)) : ((int64_t)1 << 20);
     pb.slot_bytes = (size_t)GATHER_SLOT_HEADER + (size_t)pb.slot_cap * 4;
-    pb.bytes = PEER_GATHER_AREA_OFFSET + (size_t)2 * ctx->n_ranks * pb.slot_bytes;
+    pb.heap_off = (size_t)round_up((int64_t)(PEER_GATHER_AREA_OFFSET + (size_t)2 * ctx->n_ranks * pb.slot_bytes), 256);
+    pb.heap_half = peer_heap_half_bytes();
+    pb.bytes = pb.heap_off + 2 * pb.heap_half;
     struct Msg { cudaIpcMemHandle_t handle; int ok; int pad[15]; };
     static_assert(sizeof(Msg) == 128, "message layout");
     Msg mine{};
@@ -1940,7 +2066,9 @@ colq_status colq_comm_init_local(colq_ctx** ctxs, int n_ranks) {
     const char* cap_env = getenv("COLQ_PEER_SLOT_CAP");
     const int64_t slot_cap = cap_env ? std::max<int64_t>(1024, atoll(cap_env)) : ((int64_t)1 << 20);
     const size_t slot_bytes = (size_t)GATHER_SLOT_HEADER + (size_t)slot_cap * 4;
-    const size_t bytes = PEER_GATHER_AREA_OFFSET + (size_t)2 * n_ranks * slot_bytes;
+    const size_t heap_off = (size_t)round_up((int64_t)(PEER_GATHER_AREA_OFFSET + (size_t)2 * n_ranks * slot_bytes), 256);
+    const size_t heap_half = peer_heap_half_bytes();
+    const size_t bytes = heap_off + 2 * heap_half;
     for (int i = 0; i < n_ranks; ++i) {
         colq_ctx* c = ctxs[i];
         CU(c, cudaSetDevice(c->device));
@@ -1956,6 +2084,7 @@ colq_status colq_comm_init_local(colq_ctx** ctxs, int n_ranks) {
         }
         auto& pb = c->peer;
         pb.slot_cap = slot_cap; pb.slot_bytes = slot_bytes; pb.bytes = bytes; pb.ipc = false;
+        pb.heap_off = heap_off; pb.heap_half = heap_half;
         CU(c, cudaMalloc(&pb.local, bytes));
         CU(c, cudaMemset(pb.local, 0, bytes));
     }
@@ -2432,6 +2561,72 @@ colq_status colq_associate_csr(colq_ctx* ctx, colq_table x, int x_ordinal, colq_
     return st;
 }
 
+colq_status colq_table_partition(colq_ctx* ctx, colq_table table, const int64_t* bounds, int n_ranks) {
+    if (!ctx || !bounds) return COLQ_THROW_NULL;
+    Table* t = get_table(ctx, table);
+    if (!t) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "unknown table handle %d", table);
+    if (t->placement != COLQ_SHARDED) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "only a COLQ_SHARDED table has a partition");
+    if (n_ranks != ctx->n_ranks) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "partition has %d ranks but the communicator has %d", n_ranks, ctx->n_ranks);
+    if (bounds[0] != 0) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "partition bounds must start at 0");
+    for (int r = 0; r < n_ranks; ++r) {
+        if (bounds[r + 1] < bounds[r]) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "partition bounds must be non-decreasing");
+        if (r > 0 && bounds[r] % 64 != 0 && bounds[r] != bounds[n_ranks])  // (a bound at the very end only closes empty shards)
+            return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "partition bound %lld of rank %d is not a multiple of 64 rows (shards must be whole BitSet words)", (long long)bounds[r], r);
+    }
+    if (bounds[n_ranks] > (int64_t)INT32_MAX) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "global row count exceeds the int32 row-index range");
+    if (bounds[ctx->rank] != t->row_base || bounds[ctx->rank + 1] - bounds[ctx->rank] != t->n_rows)
+        return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "this rank's shard is rows [%lld, %lld) but the partition says [%lld, %lld)", (long long)t->row_base,
+                    (long long)(t->row_base + t->n_rows), (long long)bounds[ctx->rank], (long long)bounds[ctx->rank + 1]);
+    t->part.assign(bounds, bounds + n_ranks + 1);
+    return COLQ_OK;
+}
+
+// the row count association targets are checked against: all ranks' rows when the keys are global
+static int64_t target_rows(const Table& y, bool global) { return global ? y.global_rows() : y.n_rows; }
+
+colq_status colq_associate_fk_global(colq_ctx* ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal, const int32_t* fk, int64_t n) {
+    if (!ctx || (!fk && n > 0)) return COLQ_THROW_NULL;
+    CU(ctx, cudaSetDevice(ctx->device));
+    Table* Y = get_table(ctx, y);
+    if (!Y) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "unknown table handle %d", y);
+    if (Y->placement == COLQ_SHARDED && ctx->n_ranks > 1 && Y->part.empty())
+        return fail(ctx, COLQ_THROW_ILLEGAL_STATE, "declare the target table's partition first (colq_table_partition)");
+    Column* f;
+    ST(link_assoc(ctx, x, x_ordinal, y, y_ordinal, true, &f));
+    if (n != f->n) { unlink_assoc(ctx, x, x_ordinal, y, y_ordinal); return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "association height %lld != table rows", (long long)n); }
+    colq_status st = upload(ctx, f->data, fk, (size_t)n * 4, (size_t)round_up(n * 4 + 16, 16));
+    if (st == COLQ_OK) st = check_fk_range(ctx, (const int32_t*)f->data.ptr, n, target_rows(ctx->tables[y], true));
+    if (st != COLQ_OK) { unlink_assoc(ctx, x, x_ordinal, y, y_ordinal); return st; }
+    ctx->tables[x].cols[x_ordinal].global_targets = true;
+    return COLQ_OK;
+}
+
+colq_status colq_associate_csr_global(colq_ctx* ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal, const int64_t* offsets,
+                                      const int32_t* targets, int64_t n, int64_t nnz) {
+    if (!ctx || !offsets || (!targets && nnz > 0)) return COLQ_THROW_NULL;
+    CU(ctx, cudaSetDevice(ctx->device));
+    Table* Y = get_table(ctx, y);
+    if (!Y) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "unknown table handle %d", y);
+    if (Y->placement == COLQ_SHARDED && ctx->n_ranks > 1 && Y->part.empty())
+        return fail(ctx, COLQ_THROW_ILLEGAL_STATE, "declare the target table's partition first (colq_table_partition)");
+    if (offsets[0] != 0 || offsets[n] != nnz) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "CSR offsets must start at 0 and end at nnz");
+    for (int64_t i = 0; i < n; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "CSR offsets must be non-decreasing");
+    const int64_t gy = Y->global_rows();
+    for (int64_t e = 0; e < nnz; ++e)  // M/InMemoryTable.java:70-71
+        if (targets[e] < 0 || targets[e] >= gy)
+            return fail(ctx, COLQ_THROW_NULL, "association target %d outside the associated table (global size %lld)", targets[e], (long long)gy);
+    Column* f;
+    ST(link_assoc(ctx, x, x_ordinal, y, y_ordinal, false, &f));
+    if (n != f->n) { unlink_assoc(ctx, x, x_ordinal, y, y_ordinal); return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "association height %lld != table rows", (long long)n); }
+    f->nnz = nnz;
+    colq_status st = upload(ctx, f->offsets, offsets, (size_t)(n + 1) * 8, (size_t)(n + 1) * 8 + 16);
+    if (st == COLQ_OK) st = upload(ctx, f->targets, targets, (size_t)nnz * 4, (size_t)nnz * 4 + 16);
+    if (st != COLQ_OK) { unlink_assoc(ctx, x, x_ordinal, y, y_ordinal); return st; }
+    ctx->tables[x].cols[x_ordinal].global_targets = true;
+    return COLQ_OK;
+}
+
 colq_status colq_table_destroy(colq_ctx* ctx, colq_table table) {
     if (!ctx) return COLQ_THROW_NULL;
     Table* t = get_table(ctx, table);
@@ -2445,6 +2640,7 @@ colq_status colq_table_destroy(colq_ctx* ctx, colq_table table) {
         for (Column& c : o.cols)
             if (c.kind == COL_ASSOC && c.peer_table == table && &o != t) c = Column();
     t->cols.clear();
+    t->part.clear();
     t->n_rows = 0;
     return COLQ_OK;
 }

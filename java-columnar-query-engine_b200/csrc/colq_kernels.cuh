@@ -470,6 +470,90 @@ __device__ __forceinline__ void peer_mask_collect(const PeerMaskParams& P) {
 __global__ void __launch_bounds__(256) peer_mask_collect_kernel(const PeerMaskParams P) { peer_mask_collect(P); }
 
 // ---------------------------------------------------------------------------------------------
+// Cross-shard association hops (SURVEY.md 8e "not supported" / 8f4: sharded <-> sharded hops whose targets leave the
+// rank's shard; ExecutionContext.Node.filterParent, E/ExecutionContext.java:100-122, for ANY table pair).
+//
+// The association column holds GLOBAL row indices of the sharded target table.  Every rank keeps a bitmap over the
+// target's GLOBAL rows in the peer-mapped HEAP behind its mailbox (same offset on every rank, double-buffered by the
+// parity of the execution so that a rank one step ahead never overwrites what a peer still reads):
+//   pull (parent holds the key):  the child's local bits are ALL-GATHERED into every rank's global bitmap
+//        (peer_bits_allgather: plain stores over NVLink into each peer's copy, then the epoch flags of the mask
+//        mailbox), and the parent's gather / csr_pull kernels test bit [global key] exactly as they test a local one;
+//   push (child holds the key):   the child's kernels set bits in the rank's OWN global-sized reach bitmap with the
+//        usual local atomics; peer_bits_reduce then ORs, for this rank's slice only, the copies of all ranks (remote
+//        loads over NVLink) into the parent's local reach mask -- an OR-reduce-scatter without remote atomics.
+// Partition bounds are multiples of 64 rows (except the last), so slices are whole BitSet words and never share one.
+// ---------------------------------------------------------------------------------------------
+struct PeerBitsParams {
+    const u32* src;        // allgather: this rank's local bits
+    u32* dst;              // reduce: this rank's local reach mask
+    size_t heap_off;       // byte offset of the global bitmap inside every rank's mailbox allocation
+    int64_t word_base;     // first u32 word of this rank's slice in the global bitmap
+    int64_t n_words;       // u32 words of this rank's slice
+    int n_ranks, rank;
+    int n_src;             // reduce: how many ranks' copies are OR-ed (n_ranks; 1 = only this rank's own: replicated child)
+    uint8_t* const* peers;
+    u64 epoch;
+    u32* status;
+    u32* done;
+};
+
+__device__ __forceinline__ u32 ld_volatile_u32(const u32* p) {
+    u32 v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) peer_bits_allgather_kernel(const PeerBitsParams P) {
+    __shared__ u32 s_last;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < P.n_ranks; ++r) {
+        u32* dst = reinterpret_cast<u32*>(P.peers[r] + P.heap_off) + P.word_base;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_words; i += stride) dst[i] = __ldcg(P.src + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(P.done, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) *P.done = 0;
+    __threadfence_system();
+    const size_t area = (size_t)(P.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
+    if ((int)threadIdx.x < P.n_ranks)
+        st_release_sys(reinterpret_cast<u64*>(P.peers[threadIdx.x] + area + (size_t)P.rank * MASK_SLOT_BYTES), P.epoch);
+    // the launch ends only when every rank's slice has arrived here: the consumers are ordinary later launches
+    const uint8_t* mine = P.peers[P.rank] + area;
+    if ((int)threadIdx.x < P.n_ranks)
+        peer_wait(reinterpret_cast<const u64*>(mine + (size_t)threadIdx.x * MASK_SLOT_BYTES), P.epoch, P.status);
+}
+
+__global__ void __launch_bounds__(256) peer_bits_reduce_kernel(const PeerBitsParams P) {
+    const size_t area = (size_t)(P.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
+    if (P.n_src > 1) {
+        // every push into this rank's copy was made by earlier launches of this stream: tell the peers it is complete,
+        // then wait until theirs are
+        if (blockIdx.x == 0 && (int)threadIdx.x < P.n_ranks) {
+            __threadfence_system();
+            st_release_sys(reinterpret_cast<u64*>(P.peers[threadIdx.x] + area + (size_t)P.rank * MASK_SLOT_BYTES), P.epoch);
+        }
+        const uint8_t* mine = P.peers[P.rank] + area;
+        if ((int)threadIdx.x < P.n_ranks)
+            peer_wait(reinterpret_cast<const u64*>(mine + (size_t)threadIdx.x * MASK_SLOT_BYTES), P.epoch, P.status);
+        __syncthreads();
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_words; i += stride) {
+        u32 v = 0;
+        if (P.n_src > 1) {
+            for (int r = 0; r < P.n_ranks; ++r) v |= ld_volatile_u32(reinterpret_cast<const u32*>(P.peers[r] + P.heap_off) + P.word_base + i);
+        } else {
+            v = __ldcg(reinterpret_cast<const u32*>(P.peers[P.rank] + P.heap_off) + P.word_base + i);
+        }
+        P.dst[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2'  scan_codes: string predicate over a DICTIONARY-ENCODED column -> bitmask
 //
 // Replaces ExecutionContext.Node.filterSelf (E/ExecutionContext.java:79-94) over StringColumn.where
