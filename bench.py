@@ -294,7 +294,8 @@ def run_colq(args, rank, local_rank, world):
         gate["perturbed"] = perturbed_gate(ctx, rank, world, base)   # raises on any mismatch
         gate["perturbed_what"] = ("4*N+1 universes, every PLYMOUTH renamed except in the LAST rank's universes (the state mask exists on "
                                   "one rank only before the OR-exchange); sharded result == unsharded oracle, peer-memory and NCCL "
-                                  "exchanges, raw C ABI and DataSystemColq.execute")
+                                  "exchanges, raw C ABI and DataSystemColq.execute; then the same query with cities / zips split by plain row "
+                                  "ranges and GLOBAL zip -> city keys (cross-shard bitmap all-gather)")
     geo = build_geography_on_device(ctx, U, world, rank, base=base, device=dev, sharded=world > 1, dict_names=args.dict_names)
     if args.dict_names:
         args.no_e2e = True
@@ -557,6 +558,17 @@ def perturbed_gate(ctx, rank, world, base):
         ds.last_query = None
         for h in set(ds._handles.values()):
             ctx.table_destroy(h)
+    # cross-shard hops: cities / zips split by plain row ranges, zip -> city keys global
+    from colq.device_data import plymouth_colq_query, register_cross_shard_geography
+    handles = register_cross_shard_geography(ctx, G.build_tables(Ug, base=base), world, rank, base=base)
+    cq = plymouth_colq_query(ctx)
+    for _ in range(2):
+        res = cq.execute(want_indices=True, index_capacity=want.shape[0] + 8)
+        if res.count != want.shape[0] or not np.array_equal(res.indices, want):
+            raise SystemExit(f"rank {rank}: cross-shard multi-GPU gate FAILED: {res.count} rows vs {want.shape[0]}")
+    cq.close()
+    for h in handles:
+        ctx.table_destroy(h)
     return True
 
 

@@ -201,3 +201,34 @@ def build_name_scan_on_device(ctx: ColqContext, n_rows: int, base=None, seed: in
     ctx.col_str_device(t, 0, off32.data_ptr(), off32.numel() * 4, data.data_ptr(), data.numel(), n_rows, total, keepalive=(off32, data))
     ctx.register("names", t)
     return t, off32, data, idx, total
+
+
+# ------------------------------------------------------------------------------------------------ cross-shard variant
+def register_cross_shard_geography(ctx: ColqContext, geo, n_ranks: int, rank: int, base=None):
+    """The workload of SURVEY.md 8f4 / 8e: ``geo`` (``geography.build_tables(U)``, all universes) with the city and ZIP
+    tables split by PLAIN ROW RANGES -- not by universe -- so that the zip -> city keys, kept GLOBAL
+    (``colq_associate_fk_global``), leave the shard at every range boundary; states replicated.  Registers this rank's
+    shards under the usual names and returns their handles."""
+    from .local_group import even_partition
+    base = base or load_base()
+    name_col = geo.cities.columns()[0]
+    city_state, zip_city = geo.cities.columns()[1].fk(), geo.zips.columns()[2].fk()
+    bc, bz = even_partition(geo.cities.size(), n_ranks), even_partition(geo.zips.size(), n_ranks)
+    c0, c1, z0, z1 = int(bc[rank]), int(bc[rank + 1]), int(bz[rank]), int(bz[rank + 1])
+    states = ctx.table_create(N_STATES, _ffi.REPLICATED, 0)
+    cities = ctx.table_create(c1 - c0, _ffi.SHARDED, c0)
+    zips = ctx.table_create(z1 - z0, _ffi.SHARDED, z0)
+    ctx.table_partition(cities, bc)
+    ctx.table_partition(zips, bz)
+    ctx.col_str(states, 0, base["state_code_offsets"], base["state_code_bytes"])
+    ctx.col_str(states, 1, base["state_name_offsets"], base["state_name_bytes"])
+    off = name_col.offsets[c0:c1 + 1].astype(np.int64)
+    ctx.col_str(cities, 0, (off - off[0]).astype(np.uint32), name_col.data[int(off[0]):int(off[-1])])
+    ctx.associate_fk(cities, 1, states, 2, city_state[c0:c1])
+    ctx.col_i32(zips, 0, geo.zips.columns()[0].ints()[z0:z1])
+    ctx.col_i32(zips, 1, geo.zips.columns()[1].ints()[z0:z1])
+    ctx.associate_fk_global(zips, 2, cities, 2, zip_city[z0:z1])
+    ctx.associate_csr(states, 3, states, 4, base["adj_offsets"].astype(np.int64), base["adj_targets"])
+    for name, tb in (("states", states), ("cities", cities), ("zips", zips)):
+        ctx.register(name, tb)
+    return states, cities, zips

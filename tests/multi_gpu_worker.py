@@ -97,6 +97,25 @@ def main():
                 for h in set(ds._handles.values()):
                     ctx.table_destroy(h)
                 checked += 1
+    # ---- cross-shard hops over the CUDA-IPC mapped heap: cities and zips split by plain row ranges (not by universe), the
+    #      zip -> city keys GLOBAL, so the pull hop leaves the shard; states replicated (small-mask exchange in the same plan)
+    from colq.device_data import plymouth_colq_query, register_cross_shard_geography
+    geo = G.build_tables(U)
+    oracle = OracleDataSystem()
+    G.register_geography(oracle, geo)
+    oracle.execute(G.plymouth_query())
+    want = oracle.last_indices.copy()
+    oracle.close()
+    register_cross_shard_geography(ctx, geo, world, rank)
+    for lazy in (True, False):
+        q = plymouth_colq_query(ctx, lazy_fk=lazy)
+        for _ in range(3):   # both heap parities
+            res = q.execute(want_indices=True, index_capacity=want.shape[0] + 8)
+            assert res.count == want.shape[0] and np.array_equal(res.indices, want), (rank, "cross-shard", lazy)
+        names = [n for n, *_ in q.profile()]
+        assert "peer_bits_allgather" in names, names
+        q.close()
+    checked += 2
     dist.barrier()
     if rank == 0:
         print(f"MULTI_GPU_OK world={world} variants={checked}")
