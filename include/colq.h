@@ -275,6 +275,30 @@ colq_status colq_associate_fk_host(colq_ctx *ctx, colq_table x, int x_ordinal, c
                                    const int32_t *fk_pinned, int64_t capacity_bytes, int64_t n);
 
 /*
+ * Ingest on the device.  The reference classifies and transposes Association[] objects and copies
+ * String[] columns on the host at load time (M/InMemoryTable.java:44-90, app/.../Runner.java:89-196); here the flat arrays
+ * are shipped as they are and kernels do the rest:
+ *   colq_associate       x.associateTo(y, associations) from a CSR (row i -> targets[offsets[i] .. offsets[i+1])): offsets
+ *                        order, target range (COLQ_THROW_NULL like :70-71) and the largest degree are computed in one pass
+ *                        on the GPU; when every row is Association.None or Association.One the column is stored as the
+ *                        dense to-one form (-1 = None), otherwise as the CSR.  *out_is_fk (nullable) says which.
+ *   colq_col_str_encode  turns an already registered plain string column (colq_col_str / _device / _host) into a
+ *                        dictionary-encoded one IN PLACE: hash insert with the first row of each distinct value as its
+ *                        representative, byte-exact verification, codes in first-appearance order.  Afterwards the column
+ *                        behaves exactly like one registered with colq_col_str_dict.  COLQ_ERR_CAPACITY when the column has
+ *                        more than ~45 M distinct values (the column is left unchanged).
+ *   colq_col_dict_str    reads the distinct values of a dictionary-encoded column back (n_dict + 1 offsets + UTF-8 bytes):
+ *                        the host evaluates an opaque Predicate<String> lambda on these (colq_query_criteria_str_accept).
+ */
+colq_status colq_associate(colq_ctx *ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal, const int64_t *offsets,
+                           const int32_t *targets, int64_t n, int64_t nnz, int *out_is_fk);
+colq_status colq_associate_device(colq_ctx *ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal,
+                                  const void *offsets_device, const void *targets_device, int64_t n, int64_t nnz, int *out_is_fk);
+colq_status colq_col_str_encode(colq_ctx *ctx, colq_table table, int ordinal, int64_t *out_n_dict);
+colq_status colq_col_dict_str(colq_ctx *ctx, colq_table table, int ordinal, uint32_t *out_offsets, int64_t offsets_capacity,
+                              uint8_t *out_bytes, int64_t bytes_capacity, int64_t *out_n_dict, int64_t *out_n_bytes);
+
+/*
  * Cross-shard associations: the general case of filterParent (E/ExecutionContext.java:100-122), where
  * an association between two tables that are BOTH sharded -- or from a replicated table into a sharded one -- points at
  * rows of other ranks.  The targets are then GLOBAL row indices of the associated table:

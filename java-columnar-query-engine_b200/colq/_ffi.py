@@ -72,6 +72,10 @@ SIGNATURES = {
     "colq_associate_fk": (_int, [_p, _i32, _int, _i32, _int, _p, _i64]),
     "colq_associate_csr": (_int, [_p, _i32, _int, _i32, _int, _p, _p, _i64, _i64]),
     "colq_associate_fk_device": (_int, [_p, _i32, _int, _i32, _int, _p, _i64]),
+    "colq_associate": (_int, [_p, _i32, _int, _i32, _int, _p, _p, _i64, _i64, C.POINTER(_int)]),
+    "colq_associate_device": (_int, [_p, _i32, _int, _i32, _int, _p, _p, _i64, _i64, C.POINTER(_int)]),
+    "colq_col_str_encode": (_int, [_p, _i32, _int, C.POINTER(_i64)]),
+    "colq_col_dict_str": (_int, [_p, _i32, _int, _p, _i64, _p, _i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "colq_table_partition": (_int, [_p, _i32, _p, _int]),
     "colq_associate_fk_global": (_int, [_p, _i32, _int, _i32, _int, _p, _i64]),
     "colq_associate_csr_global": (_int, [_p, _i32, _int, _i32, _int, _p, _p, _i64, _i64]),

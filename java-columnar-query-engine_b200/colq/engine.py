@@ -379,6 +379,39 @@ class ColqContext:
         self._check(self.lib.colq_associate_csr(self.handle, x, x_ordinal, y, y_ordinal, _ptr(o), _ptr(t), o.shape[0] - 1,
                                                 t.shape[0]))
 
+    # -- ingest on the device (include/colq.h "Ingest on the device")
+    def associate(self, x: int, x_ordinal: int, y: int, y_ordinal: int, offsets: np.ndarray, targets: np.ndarray) -> bool:
+        """``x.associateTo(y, ...)`` from a CSR; the GPU validates it and picks dense to-one vs CSR.  Returns True when the
+        column was stored as the dense to-one form."""
+        o = np.ascontiguousarray(offsets, dtype=np.int64)
+        t = np.ascontiguousarray(targets, dtype=np.int32)
+        is_fk = C.c_int()
+        self._check(self.lib.colq_associate(self.handle, x, x_ordinal, y, y_ordinal, _ptr(o), _ptr(t), o.shape[0] - 1, t.shape[0], C.byref(is_fk)))
+        return bool(is_fk.value)
+
+    def associate_device(self, x: int, x_ordinal: int, y: int, y_ordinal: int, off_ptr: int, tgt_ptr: int, n: int, nnz: int, keepalive=None) -> bool:
+        self._keepalive.append(keepalive)
+        is_fk = C.c_int()
+        self._check(self.lib.colq_associate_device(self.handle, x, x_ordinal, y, y_ordinal, C.c_void_p(off_ptr), C.c_void_p(tgt_ptr), n, nnz, C.byref(is_fk)))
+        return bool(is_fk.value)
+
+    def col_str_encode(self, table: int, ordinal: int) -> int:
+        """Dictionary-encode a registered plain string column in place, on the GPU; returns the number of distinct values."""
+        n = C.c_int64()
+        self._check(self.lib.colq_col_str_encode(self.handle, table, ordinal, C.byref(n)))
+        return n.value
+
+    def col_dict_str(self, table: int, ordinal: int) -> Tuple[np.ndarray, np.ndarray]:
+        """(offsets uint32[n_dict+1], bytes) of a dictionary-encoded column's distinct values."""
+        n, nb = C.c_int64(), C.c_int64()
+        st = self.lib.colq_col_dict_str(self.handle, table, ordinal, None, 0, None, 0, C.byref(n), C.byref(nb))
+        if st not in (_ffi.OK, _ffi.ERR_CAPACITY):
+            self._check(st)
+        off = np.zeros(n.value + 1, dtype=np.uint32)
+        data = np.zeros(max(nb.value, 1), dtype=np.uint8)
+        self._check(self.lib.colq_col_dict_str(self.handle, table, ordinal, _ptr(off), n.value + 1, _ptr(data), nb.value, C.byref(n), C.byref(nb)))
+        return off, data[: nb.value]
+
     # -- cross-shard associations: global targets into a sharded table (include/colq.h)
     def table_partition(self, table: int, bounds: Sequence[int]) -> None:
         b = np.ascontiguousarray(bounds, dtype=np.int64)
@@ -448,7 +481,7 @@ class DataSystemColq(DataSystem):
 
     def __init__(self, device: int = 0, lazy_fk: bool = True, context: Optional[ColqContext] = None,
                  options: Optional[Dict[int, int]] = None, residency: str = "device", dictionary: bool = False,
-                 materialize: str = "host"):
+                 materialize: str = "host", ingest: str = "host"):
         """``residency``: "device" copies every column to HBM at the first ``execute`` (default); "host" keeps int,
         string and to-one association columns in pinned off-heap buffers that the kernels stream in place over PCIe
         (only what a query touches moves; fully scanned columns are promoted to HBM by that first scan)."""
@@ -466,6 +499,12 @@ class DataSystemColq(DataSystem):
         if materialize not in ("host", "device"):
             raise ValueError(materialize)
         self.materialize = materialize
+        # ingest="device": the shim ships flat arrays only -- string columns are dictionary-encoded by the GPU
+        # (colq_col_str_encode, when dictionary is set) and every association goes up as a CSR that the GPU validates and
+        # classifies into dense to-one vs to-many (colq_associate); ingest="host": the round-1 host loops
+        if ingest not in ("host", "device"):
+            raise ValueError(ingest)
+        self.ingest = ingest
         self._dict_values: Dict[Tuple[int, int], List[str]] = {}   # (id(table), ordinal) -> distinct values
         self.ctx = context or ColqContext(device)
         self.lazy_fk = lazy_fk
@@ -525,6 +564,16 @@ class DataSystemColq(DataSystem):
                         self.ctx.col_i32_host(h, ordinal, self.ctx.host_column(c.ints(), np.int32))
                     else:
                         self.ctx.col_i32(h, ordinal, c.ints())
+                elif isinstance(c, StringColumn) and self.dictionary and self.ingest == "device":
+                    if host:
+                        off = self.ctx.host_column(c.offsets, np.uint32)
+                        dat = self.ctx.host_column(c.data, np.uint8)
+                        self.ctx.col_str_host(h, ordinal, off, dat, t.size(), int(c.data.shape[0]))
+                    else:
+                        self.ctx.col_str(h, ordinal, c.offsets, c.data)
+                    self.ctx.col_str_encode(h, ordinal)
+                    d_off, d_bytes = self.ctx.col_dict_str(h, ordinal)
+                    self._dict_values[(tid, ordinal)] = StringColumn(offsets=d_off, data=d_bytes).strings()
                 elif isinstance(c, StringColumn) and self.dictionary:
                     codes, d_off, d_bytes, values = encode_dictionary(c)
                     self._dict_values[(tid, ordinal)] = values
@@ -550,6 +599,10 @@ class DataSystemColq(DataSystem):
                     y = c.associated_entity
                     rev = c.reverse_associated_column()
                     y_ordinal = next(i for i, yc in enumerate(y.columns()) if yc is rev)
+                    if self.ingest == "device":
+                        _kind, offsets, targets = c.csr()
+                        self.ctx.associate(h, ordinal, self._handles[id(y)], y_ordinal, offsets, targets)
+                        continue
                     fk = c.fk()
                     if fk is not None and self.residency == "host" and t.size() > 0:
                         self.ctx.associate_fk_host(h, ordinal, self._handles[id(y)], y_ordinal, self.ctx.host_column(fk, np.int32))

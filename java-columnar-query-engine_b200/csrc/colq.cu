@@ -34,6 +34,7 @@
 #include <vector>
 
 #include "colq_kernels.cuh"
+#include "colq_ingest.cuh"
 #include "colq_nccl.h"
 
 using namespace colq;
@@ -1809,6 +1810,27 @@ colq_status check_fk_range(colq_ctx* ctx, const int32_t* d_fk, int64_t n, int64_
     return COLQ_OK;
 }
 
+// degree / order / range statistics of a CSR that already sits in device memory (one pass, no host loop)
+colq_status assoc_stats(colq_ctx* ctx, const int64_t* d_offsets, const int32_t* d_targets, int64_t n, int64_t nnz, AssocStats* out) {
+    DevBuf st;
+    ST(dev_alloc(ctx, st, sizeof(AssocStats)));
+    AssocStats init{0, 0, INT32_MAX, INT32_MIN};
+    CU(ctx, cudaMemcpyAsync(st.ptr, &init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    assoc_stats_kernel<<<grid_for(std::max<int64_t>(std::max(n, nnz), 1), 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(d_offsets, d_targets, n, nnz, (AssocStats*)st.ptr);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(out, st.ptr, sizeof init, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return COLQ_OK;
+}
+
+colq_status check_csr(colq_ctx* ctx, const AssocStats& a, int64_t nnz, int64_t n_target) {
+    if (a.bad_offsets) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "CSR offsets must be non-decreasing");
+    if (nnz > 0 && (a.min_target < 0 || a.max_target >= n_target))  // M/InMemoryTable.java:70-71
+        return fail(ctx, COLQ_THROW_NULL, "association target outside the associated table (min %d, max %d, size %lld)", a.min_target, a.max_target,
+                    (long long)n_target);
+    return COLQ_OK;
+}
+
 colq_status link_assoc(colq_ctx* ctx, colq_table x, int xo, colq_table y, int yo, bool is_fk, Column** fwd_out) {
     Table* X = get_table(ctx, x);
     Table* Y = get_table(ctx, y);
@@ -2546,19 +2568,198 @@ colq_status colq_associate_csr(colq_ctx* ctx, colq_table x, int x_ordinal, colq_
     Table* Y = get_table(ctx, y);
     if (!Y) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "unknown table handle %d", y);
     if (offsets[0] != 0 || offsets[n] != nnz) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "CSR offsets must start at 0 and end at nnz");
-    for (int64_t i = 0; i < n; ++i)
-        if (offsets[i + 1] < offsets[i]) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "CSR offsets must be non-decreasing");
-    for (int64_t e = 0; e < nnz; ++e)  // M/InMemoryTable.java:70-71
-        if (targets[e] < 0 || targets[e] >= Y->n_rows)
-            return fail(ctx, COLQ_THROW_NULL, "association target %d outside the associated table (size %lld)", targets[e], (long long)Y->n_rows);
+    const int64_t n_target = Y->n_rows;
     Column* f;
     ST(link_assoc(ctx, x, x_ordinal, y, y_ordinal, false, &f));
     if (n != f->n) { unlink_assoc(ctx, x, x_ordinal, y, y_ordinal); return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "association height %lld != table rows", (long long)n); }
     f->nnz = nnz;
     colq_status st = upload(ctx, f->offsets, offsets, (size_t)(n + 1) * 8, (size_t)(n + 1) * 8 + 16);
     if (st == COLQ_OK) st = upload(ctx, f->targets, targets, (size_t)nnz * 4, (size_t)nnz * 4 + 16);
+    AssocStats a{};
+    if (st == COLQ_OK) st = assoc_stats(ctx, (const int64_t*)f->offsets.ptr, (const int32_t*)f->targets.ptr, n, nnz, &a);  // validated on the device
+    if (st == COLQ_OK) st = check_csr(ctx, a, nnz, n_target);
     if (st != COLQ_OK) unlink_assoc(ctx, x, x_ordinal, y, y_ordinal);
     return st;
+}
+
+// x.associateTo(y, Association[]) with the representation chosen on the device
+static colq_status associate_auto(colq_ctx* ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal, DevBuf&& d_off, DevBuf&& d_tgt,
+                                  int64_t n, int64_t nnz, int* out_is_fk) {
+    Table* Y = get_table(ctx, y);
+    if (!Y) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "unknown table handle %d", y);
+    const int64_t n_target = Y->n_rows;
+    AssocStats a{};
+    ST(assoc_stats(ctx, (const int64_t*)d_off.ptr, (const int32_t*)d_tgt.ptr, n, nnz, &a));
+    ST(check_csr(ctx, a, nnz, n_target));
+    const bool to_one = a.max_degree <= 1;   // every row is Association.None or Association.One (DS/Association.java:27-43)
+    Column* f;
+    ST(link_assoc(ctx, x, x_ordinal, y, y_ordinal, to_one, &f));
+    if (n != f->n) { unlink_assoc(ctx, x, x_ordinal, y, y_ordinal); return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "association height %lld != table rows", (long long)n); }
+    if (to_one) {
+        colq_status st = dev_alloc(ctx, f->data, (size_t)round_up(n * 4 + 16, 16));
+        if (st != COLQ_OK) { unlink_assoc(ctx, x, x_ordinal, y, y_ordinal); return st; }
+        cudaMemsetAsync((char*)f->data.ptr + n * 4, 0, f->data.bytes - (size_t)n * 4 < 64 ? f->data.bytes - (size_t)n * 4 : 64, ctx->stream);
+        if (n > 0) csr_to_fk_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>((const int64_t*)d_off.ptr, (const int32_t*)d_tgt.ptr, n, (int32_t*)f->data.ptr);
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaStreamSynchronize(ctx->stream));  // the CSR scratch goes back to the buffer cache when this returns
+    } else {
+        f->nnz = nnz;
+        f->offsets = std::move(d_off);
+        f->targets = std::move(d_tgt);
+    }
+    if (out_is_fk) *out_is_fk = to_one ? 1 : 0;
+    return COLQ_OK;
+}
+
+colq_status colq_associate(colq_ctx* ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal, const int64_t* offsets, const int32_t* targets,
+                           int64_t n, int64_t nnz, int* out_is_fk) {
+    if (!ctx || !offsets || (!targets && nnz > 0)) return COLQ_THROW_NULL;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (offsets[0] != 0 || offsets[n] != nnz) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "CSR offsets must start at 0 and end at nnz");
+    DevBuf d_off, d_tgt;
+    ST(upload(ctx, d_off, offsets, (size_t)(n + 1) * 8, (size_t)(n + 1) * 8 + 16));
+    ST(upload(ctx, d_tgt, targets, (size_t)nnz * 4, (size_t)nnz * 4 + 16));
+    return associate_auto(ctx, x, x_ordinal, y, y_ordinal, std::move(d_off), std::move(d_tgt), n, nnz, out_is_fk);
+}
+
+colq_status colq_associate_device(colq_ctx* ctx, colq_table x, int x_ordinal, colq_table y, int y_ordinal, const void* offsets_device,
+                                  const void* targets_device, int64_t n, int64_t nnz, int* out_is_fk) {
+    if (!ctx || !offsets_device || (!targets_device && nnz > 0)) return COLQ_THROW_NULL;
+    if (((uintptr_t)offsets_device & 7) || ((uintptr_t)targets_device & 3)) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "device CSR buffers must be naturally aligned");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int64_t ends[2] = {0, 0};
+    CU(ctx, cudaMemcpyAsync(&ends[0], offsets_device, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(&ends[1], (const int64_t*)offsets_device + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ends[0] != 0 || ends[1] != nnz) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "CSR offsets must start at 0 and end at nnz");
+    // adopted buffers (the caller keeps them alive when the column stays a CSR)
+    DevBuf d_off, d_tgt;
+    d_off.ptr = const_cast<void*>(offsets_device); d_off.bytes = (size_t)(n + 1) * 8; d_off.owned = false;
+    d_tgt.ptr = const_cast<void*>(targets_device); d_tgt.bytes = (size_t)nnz * 4; d_tgt.owned = false;
+    return associate_auto(ctx, x, x_ordinal, y, y_ordinal, std::move(d_off), std::move(d_tgt), n, nnz, out_is_fk);
+}
+
+// ---- dictionary encoding on the device ------------------------------------------------------------------------------
+
+colq_status colq_col_str_encode(colq_ctx* ctx, colq_table table, int ordinal, int64_t* out_n_dict) {
+    if (!ctx) return COLQ_THROW_NULL;
+    Table* t = get_table(ctx, table);
+    if (!t) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "unknown table handle %d", table);
+    if (ordinal < 0 || (size_t)ordinal >= t->cols.size()) return fail(ctx, COLQ_THROW_INDEX_OOB, "Index %d out of bounds for length %d", ordinal, (int)t->cols.size());
+    Column& c = t->cols[ordinal];
+    if (c.kind != COL_STR) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "column %d is not a string column", ordinal);
+    if (c.dict) { if (out_n_dict) *out_n_dict = c.dict->n; return COLQ_OK; }
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int64_t n = c.n;
+    std::unique_ptr<Column> d(new Column());
+    DevBuf codes;
+    ST(dev_alloc(ctx, codes, (size_t)round_up(n * 4 + 16, 16)));
+    CU(ctx, cudaMemsetAsync((char*)codes.ptr + n * 4, 0, std::min<size_t>(codes.bytes - (size_t)n * 4, 64), s));
+    int64_t n_dict = 0;
+    if (n > 0) {
+        // scratch hash table: twice the rows, capped at 64 M slots (1 GB) -- beyond ~45 M distinct values dictionary
+        // encoding is pointless and the call fails instead
+        int64_t n_slots = 1024;
+        while (n_slots < 2 * n && n_slots < ((int64_t)1 << 26)) n_slots <<= 1;
+        DevBuf slots, first_bits, first_rows, counts, offs, status;
+        ST(dev_alloc(ctx, slots, (size_t)n_slots * sizeof(DictSlot)));
+        ST(dev_alloc(ctx, first_bits, (size_t)bitmap_alloc_words(n) * 4));
+        ST(dev_alloc(ctx, status, 16));
+        const int64_t n_words = bitmap_words(n);
+        const int64_t n_blocks = std::max<int64_t>(1, (n_words + CP_WORDS_PER_BLOCK - 1) / CP_WORDS_PER_BLOCK);
+        ST(dev_alloc(ctx, counts, (size_t)n_blocks * 4));
+        ST(dev_alloc(ctx, offs, (size_t)n_blocks * 8 + 8));
+        const u32* off = (const u32*)c.offsets.ptr;
+        const uint8_t* bytes = (const uint8_t*)c.data.ptr;
+        u32 st_host[2] = {0, 0};
+        for (int attempt = 0;; ++attempt) {
+            const u64 seed = 0x5DEECE66Dull * (u64)(attempt + 1);
+            CU(ctx, cudaMemsetAsync(status.ptr, 0, 16, s));
+            dict_init_kernel<<<grid_for(n_slots, 256, ctx->sm_count, 8), 256, 0, s>>>((DictSlot*)slots.ptr, n_slots);
+            dict_insert_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, s>>>(off, bytes, n, (DictSlot*)slots.ptr, (u32)(n_slots - 1), seed, (int32_t*)codes.ptr,
+                                                                                  (u32*)status.ptr);
+            CU(ctx, cudaMemsetAsync(first_bits.ptr, 0, first_bits.bytes, s));
+            dict_verify_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, s>>>(off, bytes, n, (const DictSlot*)slots.ptr, (const int32_t*)codes.ptr,
+                                                                                  (u32*)first_bits.ptr, (u32*)status.ptr);
+            CU(ctx, cudaGetLastError());
+            CU(ctx, cudaMemcpyAsync(st_host, status.ptr, 8, cudaMemcpyDeviceToHost, s));
+            CU(ctx, cudaStreamSynchronize(s));
+            if (st_host[0]) return fail(ctx, COLQ_ERR_CAPACITY, "too many distinct values for dictionary encoding (scratch table of %lld slots is full)", (long long)n_slots);
+            if (!st_host[1]) break;
+            if (attempt == 3) return fail(ctx, COLQ_ERR_DEVICE, "dictionary encoding: 64-bit hash collisions with four different seeds");
+        }
+        // representatives in ascending row order = first-appearance order (the three-launch compaction)
+        popc_blocks_kernel<<<(int)n_blocks, CP_THREADS, 0, s>>>((const u32*)first_bits.ptr, n_words, (u32*)counts.ptr);
+        scan_counts_kernel<<<1, 1024, 0, s>>>((const u32*)counts.ptr, n_blocks, (u64*)offs.ptr, (u64*)offs.ptr + n_blocks);
+        CU(ctx, cudaGetLastError());
+        u64 total = 0;
+        CU(ctx, cudaMemcpyAsync(&total, (u64*)offs.ptr + n_blocks, 8, cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaStreamSynchronize(s));
+        n_dict = (int64_t)total;
+        ST(dev_alloc(ctx, first_rows, (size_t)n_dict * 4 + 16));
+        compact_kernel<<<(int)n_blocks, CP_THREADS, 0, s>>>((const u32*)first_bits.ptr, n_words, (const u64*)offs.ptr, (int32_t*)first_rows.ptr, n_dict, 0);
+        dict_assign_kernel<<<grid_for(n_dict, 256, ctx->sm_count, 8), 256, 0, s>>>((const int32_t*)first_rows.ptr, n_dict, (const int32_t*)codes.ptr, (DictSlot*)slots.ptr);
+        // the distinct values themselves: lengths -> offsets -> bytes at the representative rows
+        DevBuf off64;
+        ST(dev_alloc(ctx, off64, (size_t)(n_dict + 1) * 8));
+        GatherVarParams<u32> G{off, nullptr, (const int32_t*)first_rows.ptr, 0, n_dict, (u64*)off64.ptr};
+        gather_var_lens_kernel<u32><<<grid_for(n_dict, 256, ctx->sm_count, 8), 256, 0, s>>>(G);
+        scan_u64_inplace_kernel<<<1, 1024, 0, s>>>(G.out_off, n_dict);
+        CU(ctx, cudaGetLastError());
+        u64 dict_bytes = 0;
+        CU(ctx, cudaMemcpyAsync(&dict_bytes, G.out_off + n_dict, 8, cudaMemcpyDeviceToHost, s));
+        CU(ctx, cudaStreamSynchronize(s));
+        ST(dev_alloc(ctx, d->offsets, (size_t)round_up((n_dict + 1) * 4, 16) + 16));
+        CU(ctx, cudaMemsetAsync(d->offsets.ptr, 0, d->offsets.bytes, s));
+        narrow_offsets_kernel<<<grid_for(n_dict + 1, 256, ctx->sm_count, 8), 256, 0, s>>>(G.out_off, (u32*)d->offsets.ptr, n_dict + 1);
+        const size_t cap = (size_t)round_up((int64_t)dict_bytes, 16) + ST_SLACK;
+        ST(dev_alloc(ctx, d->data, cap));
+        CU(ctx, cudaMemsetAsync(d->data.ptr, 0, d->data.bytes, s));
+        if (dict_bytes > 0)
+            gather_var_copy_kernel<u32, uint8_t><<<grid_for((n_dict + 31) / 32 * 32, 256, ctx->sm_count, 8), 256, 0, s>>>(G, bytes, (uint8_t*)d->data.ptr);
+        dict_codes_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, s>>>((int32_t*)codes.ptr, n, (const DictSlot*)slots.ptr);
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaStreamSynchronize(s));
+        d->bytes_capacity = (int64_t)cap;
+        ST(finish_str(ctx, d.get(), n_dict, (int64_t)dict_bytes));
+    } else {
+        ST(dev_alloc(ctx, d->offsets, 32));
+        CU(ctx, cudaMemsetAsync(d->offsets.ptr, 0, 32, s));
+        ST(dev_alloc(ctx, d->data, 16 + ST_SLACK));
+        d->bytes_capacity = 16 + ST_SLACK;
+        ST(finish_str(ctx, d.get(), 0, 0));
+    }
+    // the column becomes a dictionary-encoded one in place: codes + distinct values; the plain buffers are dropped
+    c.data = std::move(codes);
+    c.offsets = DevBuf();
+    c.promoted = DevBuf();
+    c.promoted_offsets = DevBuf();
+    c.host_resident = false;
+    c.n_bytes = 0;
+    c.dict = std::move(d);
+    if (out_n_dict) *out_n_dict = n_dict;
+    return COLQ_OK;
+}
+
+colq_status colq_col_dict_str(colq_ctx* ctx, colq_table table, int ordinal, uint32_t* out_offsets, int64_t offsets_capacity, uint8_t* out_bytes,
+                              int64_t bytes_capacity, int64_t* out_n_dict, int64_t* out_n_bytes) {
+    if (!ctx) return COLQ_THROW_NULL;
+    Table* t = get_table(ctx, table);
+    if (!t) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "unknown table handle %d", table);
+    if (ordinal < 0 || (size_t)ordinal >= t->cols.size()) return fail(ctx, COLQ_THROW_INDEX_OOB, "Index %d out of bounds for length %d", ordinal, (int)t->cols.size());
+    const Column& c = t->cols[ordinal];
+    if (c.kind != COL_STR || !c.dict) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "column %d is not a dictionary-encoded string column", ordinal);
+    const Column& d = *c.dict;
+    if (out_n_dict) *out_n_dict = d.n;
+    if (out_n_bytes) *out_n_bytes = d.n_bytes;
+    if (!out_offsets || offsets_capacity < d.n + 1 || (d.n_bytes > 0 && (!out_bytes || bytes_capacity < d.n_bytes)))
+        return fail(ctx, COLQ_ERR_CAPACITY, "dictionary needs %lld offsets and %lld bytes", (long long)(d.n + 1), (long long)d.n_bytes);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpyAsync(out_offsets, d.offsets.ptr, (size_t)(d.n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d.n_bytes > 0) CU(ctx, cudaMemcpyAsync(out_bytes, d.data.ptr, (size_t)d.n_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return COLQ_OK;
 }
 
 colq_status colq_table_partition(colq_ctx* ctx, colq_table table, const int64_t* bounds, int n_ranks) {
@@ -2873,7 +3074,7 @@ colq_status colq_result_count(colq_ctx* ctx, colq_query* q, int64_t* out_rows) {
 
 colq_status colq_result_i32(colq_ctx* ctx, colq_query* q, int ordinal, int32_t* out_values, int64_t capacity, int64_t* out_count) {
     if (!ctx || !q) return COLQ_THROW_NULL;
-    const Table* T; const Column* c;
+    const Table* T = nullptr; const Column* c = nullptr;
     ST(result_prologue(ctx, q, ordinal, &T, &c));
     const bool to_one = c->kind == COL_ASSOC && c->forward && c->is_fk;
     if (c->kind != COL_I32 && !to_one)
@@ -2896,7 +3097,7 @@ colq_status colq_result_i32(colq_ctx* ctx, colq_query* q, int ordinal, int32_t* 
 
 colq_status colq_result_bool(colq_ctx* ctx, colq_query* q, int ordinal, uint8_t* out_values, int64_t capacity, int64_t* out_count) {
     if (!ctx || !q) return COLQ_THROW_NULL;
-    const Table* T; const Column* c;
+    const Table* T = nullptr; const Column* c = nullptr;
     ST(result_prologue(ctx, q, ordinal, &T, &c));
     if (c->kind != COL_BOOL) return fail(ctx, COLQ_FAILURE, "column %d is not a boolean column", ordinal);
     return result_fixed<uint8_t>(ctx, q, *T, c->data.ptr, out_values, capacity, out_count);
@@ -2905,7 +3106,7 @@ colq_status colq_result_bool(colq_ctx* ctx, colq_query* q, int ordinal, uint8_t*
 colq_status colq_result_str(colq_ctx* ctx, colq_query* q, int ordinal, uint32_t* out_offsets, int64_t offsets_capacity, uint8_t* out_bytes,
                             int64_t bytes_capacity, int64_t* out_count, int64_t* out_n_bytes) {
     if (!ctx || !q) return COLQ_THROW_NULL;
-    const Table* T; const Column* c;
+    const Table* T = nullptr; const Column* c = nullptr;
     ST(result_prologue(ctx, q, ordinal, &T, &c));
     if (c->kind != COL_STR) return fail(ctx, COLQ_FAILURE, "column %d is not a string column", ordinal);
     const Column* payload = c->dict ? c->dict.get() : c;
@@ -2917,7 +3118,7 @@ colq_status colq_result_str(colq_ctx* ctx, colq_query* q, int ordinal, uint32_t*
 colq_status colq_result_csr(colq_ctx* ctx, colq_query* q, int ordinal, int64_t* out_offsets, int64_t offsets_capacity, int32_t* out_targets,
                             int64_t targets_capacity, int64_t* out_count, int64_t* out_nnz) {
     if (!ctx || !q) return COLQ_THROW_NULL;
-    const Table* T; const Column* c;
+    const Table* T = nullptr; const Column* c = nullptr;
     ST(result_prologue(ctx, q, ordinal, &T, &c));
     if (!(c->kind == COL_ASSOC && c->forward && !c->is_fk))
         return fail(ctx, COLQ_FAILURE, "column %d is not a stored to-many association column", ordinal);

@@ -37,8 +37,11 @@ DICT_HOST = dict(lazy_fk=True, dictionary=True, residency="host")
 LOOKBACK = dict(lazy_fk=True, options={4: 2})            # COLQ_OPT_FUSED_COMPACT=2: single-pass look-back compaction
 DICT_ALL = dict(lazy_fk=True, dictionary="all")          # integer columns dictionary-encoded too
 DICT_ALL_HOST = dict(lazy_fk=True, dictionary="all", residency="host")
+INGEST_DEVICE = dict(lazy_fk=True, ingest="device")     # associations go up as CSRs, the GPU validates and classifies them
+INGEST_DEVICE_DICT = dict(lazy_fk=True, ingest="device", dictionary=True)   # + string columns dictionary-encoded by the GPU
+INGEST_DEVICE_DICT_HOST = dict(lazy_fk=True, ingest="device", dictionary=True, residency="host")
 UNFUSED = dict(lazy_fk=True, options={9: 0})             # COLQ_OPT_ROOT_FUSED=0: scan_rows / csr_pull / compact_fused launches (r01 plan)
-ALL_VARIANTS = (LAZY, EAGER, NO_DEFER, HOST, HOST_NO_PROMOTE, HOST_KERNEL_PROMOTE, DICT, DICT_HOST, LOOKBACK, DICT_ALL, DICT_ALL_HOST, UNFUSED)
+ALL_VARIANTS = (LAZY, EAGER, NO_DEFER, HOST, HOST_NO_PROMOTE, HOST_KERNEL_PROMOTE, DICT, DICT_HOST, LOOKBACK, DICT_ALL, DICT_ALL_HOST, UNFUSED, INGEST_DEVICE, INGEST_DEVICE_DICT, INGEST_DEVICE_DICT_HOST)
 
 
 def both(engines, build, queries, lazy_modes=(True, False), variants=None):
@@ -656,4 +659,92 @@ def test_global_row_indices_must_fit_int32():
     ctx.table_create(1000, _ffi.SHARDED, 2 ** 31 - 1 - 1000)
     with pytest.raises(ValueError, match="int32 row-index range"):
         ctx.table_create(1000, _ffi.SHARDED, 2 ** 31 - 1000)
+    ctx.close()
+
+
+# ------------------------------------------------------------------ ingest on the device
+@pytest.mark.parametrize("n,alphabet,max_len", [(0, "ab", 3), (1, "ab", 3), (33, "ab", 2), (5000, "abc", 3), (200_000, "abcdefgh", 4),
+                                                (70_000, "xy", 12), (3000, "é😀a", 3)])
+def test_device_dictionary_equals_host_dictionary(n, alphabet, max_len):
+    """colq_col_str_encode: codes in first-appearance order and the distinct values, bit for bit what the host's
+    encode_dictionary produces (the loop the Java shim ran in round 1)."""
+    from colq.engine import ColqContext, encode_dictionary
+    rng = np.random.default_rng(n + max_len)
+    strings = random_strings(rng, n, max_len, np.array(list(alphabet)))
+    col = StringColumn(strings)
+    want_codes, want_off, want_bytes, _values = encode_dictionary(col)
+    ctx = ColqContext(0)
+    t = ctx.table_create(n)
+    ctx.col_str(t, 0, col.offsets, col.data)
+    n_dict = ctx.col_str_encode(t, 0)
+    assert n_dict == want_off.shape[0] - 1
+    off, data = ctx.col_dict_str(t, 0)
+    assert np.array_equal(off, want_off) and np.array_equal(data, want_bytes)
+    ctx.register("s", t)
+    # the codes themselves: an equality query per distinct value returns exactly the rows the host codes say (a few values)
+    for code in list(range(min(n_dict, 3))) + ([n_dict - 1] if n_dict > 3 else []):
+        needle = bytes(want_bytes[want_off[code]:want_off[code + 1]])
+        q = ctx.query("s")
+        q.criteria_str(0, 0, 0, needle)
+        res = q.execute(want_indices=True, index_capacity=n + 1)
+        assert np.array_equal(res.indices, np.flatnonzero(want_codes == code).astype(np.int32)), code
+        assert any(nm.startswith("scan_codes") for nm, *_ in q.profile())
+        q.close()
+    assert ctx.col_str_encode(t, 0) == n_dict     # idempotent
+    ctx.close()
+
+
+def test_device_dictionary_of_the_city_names(base_geography):
+    from colq.engine import ColqContext, encode_dictionary
+    geo = G.build_tables(40, base=base_geography)
+    col = geo.cities.columns()[0]
+    want_codes, want_off, want_bytes, _ = encode_dictionary(col)
+    ctx = ColqContext(0)
+    t = ctx.table_create(col.height())
+    ctx.col_str(t, 0, col.offsets, col.data)
+    assert ctx.col_str_encode(t, 0) == want_off.shape[0] - 1 == 16_584
+    off, data = ctx.col_dict_str(t, 0)
+    assert np.array_equal(off, want_off) and np.array_equal(data, want_bytes)
+    ctx.close()
+
+
+def test_device_association_classification():
+    """colq_associate: None / One rows -> dense to-one, any Many row -> CSR; bad input is rejected by the GPU's own pass."""
+    from colq.engine import ColqContext
+    rng = np.random.default_rng(11)
+    ctx = ColqContext(0)
+    nx, ny = 10_000, 333
+    x, y = ctx.table_create(nx), ctx.table_create(ny)
+    ctx.col_i32(x, 0, np.arange(nx, dtype=np.int32))
+    ctx.col_i32(y, 0, np.arange(ny, dtype=np.int32))
+    fk = rng.integers(-1, ny, size=nx, dtype=np.int32)
+    deg = (fk >= 0).astype(np.int64)
+    off = np.zeros(nx + 1, dtype=np.int64); np.cumsum(deg, out=off[1:])
+    assert ctx.associate(x, 1, y, 1, off, fk[fk >= 0]) is True            # all None / One
+    ctx.register("x", x); ctx.register("y", y)
+    q = ctx.query("x")
+    c = q.child(0, 1)
+    q.criteria_i32_range(c, 0, 10, 20)
+    res = q.execute(want_indices=True, index_capacity=nx)
+    assert np.array_equal(res.indices, np.flatnonzero((fk >= 10) & (fk <= 20)).astype(np.int32))
+    assert np.array_equal(q.result_i32(1), fk[res.indices])              # the stored dense form, Nones as -1
+    q.close()
+    deg = rng.integers(0, 4, size=nx)
+    off = np.zeros(nx + 1, dtype=np.int64); np.cumsum(deg, out=off[1:])
+    tg = rng.integers(0, ny, size=int(off[-1]), dtype=np.int32)
+    assert ctx.associate(x, 2, y, 2, off, tg) is False                   # some Many rows: stays a CSR
+    q = ctx.query("x")
+    c = q.child(0, 2)
+    q.criteria_i32_range(c, 0, 0, 5)
+    res = q.execute(want_indices=True, index_capacity=nx)
+    want = np.array([i for i in range(nx) if np.any(tg[off[i]:off[i + 1]] <= 5)], dtype=np.int32)
+    assert np.array_equal(res.indices, want)
+    q.close()
+    bad = tg.copy(); bad[7] = ny
+    with pytest.raises(TypeError, match="NullPointerException"):           # M/InMemoryTable.java:70-71
+        ctx.associate(x, 3, y, 3, off, bad)
+    off_bad = off.copy(); off_bad[5], off_bad[6] = off_bad[6] + 1, off_bad[5]
+    with pytest.raises(ValueError):
+        ctx.associate(x, 3, y, 3, off_bad, tg)
+    assert ctx.associate(x, 3, y, 3, off, tg) is False                   # the ordinals were released by the failed calls
     ctx.close()
