@@ -64,6 +64,7 @@ def parse_args():
                          "(a bounded sample for hosts with little RAM: the full 10k-universe tables need ~30 GB)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the load-time (ingest) kernel measurements")
     ap.add_argument("--no-small-queries", action="store_true", help="skip the 1-universe latency measurements (keeps ncu launch lists clean)")
     ap.add_argument("--eager", action="store_true", help="disable the lazy FK chain (materialise every node)")
     ap.add_argument("--weak", action="store_true",
@@ -377,6 +378,14 @@ def run_colq(args, rank, local_rank, world):
         dist.all_reduce(t)
         algo_total = float(t.item())
     query_gbs = algo_total / (ms_step * 1e-3) / 1e9
+    # bytes the launches really touch: the lazy chains skip all but a few sectors of the two FK columns (2.2 GB of the 6.58 GB
+    # "every column read once" figure), so the physical rate is this one -- the algorithmic-equivalent above can exceed any peak
+    touched = float(sum(v["algorithmic_bytes"] for v in stages.values()))
+    if world > 1:
+        t = torch.tensor([touched], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        touched = float(t.item())
+    touched_gbs = touched / (ms_step * 1e-3) / 1e9
 
     # ---- e2e_resident: the public call with resident tables, matched indices read back every step
     barrier()
@@ -393,7 +402,10 @@ def run_colq(args, rank, local_rank, world):
     small = small_query_latency(base) if (world == 1 and not args.no_small_queries) else None
 
     # ---- e2e: HOST buffers in, matched indices out, every step (columns re-uploaded from pinned memory)
-    e2e = e2e_upload = None
+    e2e = e2e_upload = e2e_dict = None
+    ingest = None
+    if world == 1 and not args.no_ingest and not args.dict_names:
+        ingest = measure_ingest(ctx, geo, base)
     if not args.no_e2e:
         host = {}
         for k, t in geo.tensors.items():
@@ -415,10 +427,20 @@ def run_colq(args, rank, local_rank, world):
 
         small_h2d = int(base["state_code_bytes"].size + base["state_name_bytes"].size) + 4 * 104 + 8 * 52 + 4 * 219
 
-        def e2e_step(upload: bool):
+        # dictionary-encoded city names held by the host (what the shim keeps once the column has been encoded at load time)
+        from colq.engine import encode_dictionary
+        from colq.in_memory import StringColumn
+        codes1, d_off, d_bytes, _vals = encode_dictionary(StringColumn(offsets=base["city_name_offsets"], data=base["city_name_bytes"]))
+        hc = torch.empty(nc + 16, dtype=torch.int32, pin_memory=True)
+        hc[:nc].copy_(torch.from_numpy(codes1).repeat(geo.n_universes))
+        hc[nc:] = 0
+        host["city_name_codes"] = hc.numpy()
+
+        def e2e_step(upload: bool, dict_names: bool = False):
             """upload=False (the product's host path): the big columns stay in the pinned host buffers and are
             registered in place (colq_*_host); the query moves only what it touches over PCIe.
-            upload=True: every column is copied to HBM first (colq_col_* / colq_associate_fk), then the query runs."""
+            upload=True: every column is copied to HBM first (colq_col_* / colq_associate_fk), then the query runs.
+            dict_names: the host holds the city names dictionary-encoded (int32 codes + 16,584 distinct values)."""
             states = ctx.table_create(51, _ffi.REPLICATED, 0)
             cities = ctx.table_create(nc, place, geo.u0 * N_CITIES)
             zips = ctx.table_create(nz, place, geo.u0 * N_ZIPS)
@@ -431,7 +453,10 @@ def run_colq(args, rank, local_rank, world):
                 ctx.col_i32(zips, 1, host["zip_pop"][:nz])
                 ctx.associate_fk(zips, 2, cities, 2, host["zip_city"][:nz])
             else:
-                ctx.col_str_host(cities, 0, host["city_name_offsets"].view(np.uint32), host["city_name_bytes"], nc, nb)
+                if dict_names:
+                    ctx.col_str_dict_host(cities, 0, host["city_name_codes"], d_off, d_bytes, n=nc)
+                else:
+                    ctx.col_str_host(cities, 0, host["city_name_offsets"].view(np.uint32), host["city_name_bytes"], nc, nb)
                 ctx.associate_fk_host(cities, 1, states, 2, host["city_state"], n=nc)
                 ctx.col_i32_host(zips, 0, host["zip_code"], n=nz)
                 ctx.col_i32_host(zips, 1, host["zip_pop"], n=nz)
@@ -447,9 +472,9 @@ def run_colq(args, rank, local_rank, world):
             ctx._keepalive.clear()
             return r
 
-        def time_e2e(upload: bool):
+        def time_e2e(upload: bool, dict_names: bool = False):
             for _ in range(2):  # warm-up: first touch of the pinned pages, and the device-buffer cache reaches its fixed point
-                r3 = e2e_step(upload)
+                r3 = e2e_step(upload, dict_names)
             assert r3.count == 31 * U and np.array_equal(r3.indices.astype(np.int64), want)
             barrier()
             t0 = time.perf_counter()
@@ -458,7 +483,7 @@ def run_colq(args, rank, local_rank, world):
                 e0.record(stream)
                 for _ in range(args.e2e_steps):
                     t1 = time.perf_counter()
-                    r3 = e2e_step(upload)
+                    r3 = e2e_step(upload, dict_names)
                     per_step.append((time.perf_counter() - t1) * 1e3)
                 e1.record(stream)
                 stream.synchronize()
@@ -478,6 +503,11 @@ def run_colq(args, rank, local_rank, world):
                        "ahead of their kernels, the lazily walked FK columns are read in place, single sectors over PCIe -- "
                        "matched indices read back, colq_table_destroy. h2d_bytes_per_step counts the fully scanned columns; the "
                        "never-touched ZIP-code column and all but ~0.5 M sectors of the FK columns (3.4 GB) do not cross PCIe"}
+        ms_d, r5, steps_d = time_e2e(upload=False, dict_names=True)
+        e2e_dict = {"value": rows / (ms_d * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": int(r5.timing.h2d_bytes) + small_h2d + int(d_off.nbytes + d_bytes.nbytes),
+                    "d2h_bytes_per_step": int(r5.timing.d2h_bytes), "ms_per_step": ms_d, "steps": args.e2e_steps, "ms_each_step_rank0": steps_d,
+                    "what": "the same step when the host holds the city names dictionary-encoded (SURVEY 8f rank 2; int32 codes + 16,584 distinct "
+                            "names, colq_col_str_dict_host): the query scans 4 B of code per city row instead of offsets + bytes"}
         ms_up, r4, steps_up = time_e2e(upload=True)
         e2e_upload = {"value": rows / (ms_up * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": int(h2d),
                       "d2h_bytes_per_step": int(r4.timing.d2h_bytes), "ms_per_step": ms_up, "steps": args.e2e_steps,
@@ -502,9 +532,10 @@ def run_colq(args, rank, local_rank, world):
             "data": "synthetic", "config": dict(workload_config(U), **({"city_names": "dictionary-encoded"} if args.dict_names else {})),
             "sharding": f"universe ranges over {world} rank(s); states replicated",
             "strategy": "lazy_fk_chain" if not args.eager else "materialise_all_nodes", "gate": gate,
+            "hbm_gbs_touched": touched_gbs, "touched_bytes": touched,
             "hbm_gbs_query_algorithmic": query_gbs, "query_algorithmic_bytes": algo_total,
             "roofline": roofline, "stages_ms": {k: round(v["ms"], 5) for k, v in stages.items()},
-            "cpu_baseline": cpu, "e2e": e2e, "e2e_upload_all_columns": e2e_upload,
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_dictionary": e2e_dict, "e2e_upload_all_columns": e2e_upload, "ingest": ingest,
             "e2e_resident": {"value": rows / (ms_res * 1e-3), "unit": "rows/s", "ms_per_step": ms_res, "h2d_bytes_per_step": 0,
                              "d2h_bytes_per_step": d2h_res, "what": "colq_execute with resident tables, matched indices read back into a pinned result buffer every step"},
             "small_query_latency": small,
@@ -515,6 +546,56 @@ def run_colq(args, rank, local_rank, world):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_ingest(ctx, geo, base):
+    """Load-time work done by the GPU instead of host loops, timed on the full-size resident columns:
+    dictionary encoding of the city-name column (colq_col_str_encode) and validation + None/One/Many classification of the
+    zip -> city association shipped as a CSR (colq_associate_device).  Host wall clock around the (synchronous) calls."""
+    import torch
+    from colq import _ffi
+    from colq.engine import encode_dictionary
+    from colq.in_memory import StringColumn
+    nc, nz = geo.n_city_rows, geo.n_zip_rows
+    out = {}
+    tt = geo.tensors["city_name_offsets"], geo.tensors["city_name_bytes"]
+    best = None
+    for _ in range(2):
+        t = ctx.table_create(nc, _ffi.REPLICATED, 0)
+        ctx.col_str_device(t, 0, tt[0].data_ptr(), tt[0].numel() * 4, tt[1].data_ptr(), tt[1].numel(), nc, geo.name_bytes, keepalive=tt)
+        t0 = time.perf_counter()
+        n_dict = ctx.col_str_encode(t, 0)
+        ms = (time.perf_counter() - t0) * 1e3
+        best = ms if best is None else min(best, ms)
+        if _ == 0:   # parity with the host loop of round 1 (one universe's names have the same distinct values in the same order)
+            _c, want_off, want_bytes, _v = encode_dictionary(StringColumn(offsets=base["city_name_offsets"], data=base["city_name_bytes"]))
+            off, data = ctx.col_dict_str(t, 0)
+            assert np.array_equal(off, want_off) and np.array_equal(data, want_bytes), "device dictionary differs from the host dictionary"
+        ctx.table_destroy(t)
+    read_bytes = 4 * (nc + 1) + geo.name_bytes
+    out["dict_encode"] = {"ms": best, "rows": nc, "n_dict": int(n_dict), "bytes_read_per_pass": read_bytes,
+                          "gbs_two_passes": 2 * read_bytes / (best * 1e-3) / 1e9,
+                          "what": "colq_col_str_encode on the resident city-name column: hash insert, byte-exact verification, first-appearance "
+                                  "codes, dictionary gather (reads the column twice, writes 4 B of code per row)"}
+    dev = geo.tensors["zip_city"].device
+    off = torch.arange(nz + 1, dtype=torch.int64, device=dev)          # every ZIP has exactly one city: Association.One
+    torch.cuda.synchronize(dev)                                        # (torch filled it on its own stream)
+    best = None
+    for _ in range(2):
+        x = ctx.table_create(nz, _ffi.REPLICATED, 0)
+        y = ctx.table_create(nc, _ffi.REPLICATED, 0)
+        t0 = time.perf_counter()
+        is_fk = ctx.associate_device(x, 0, y, 0, off.data_ptr(), geo.tensors["zip_city"].data_ptr(), nz, nz, keepalive=(off,))
+        ms = (time.perf_counter() - t0) * 1e3
+        best = ms if best is None else min(best, ms)
+        assert is_fk
+        ctx.table_destroy(x)
+        ctx.table_destroy(y)
+    del off
+    out["assoc_classify"] = {"ms": best, "rows": nz, "edges": nz, "stored_as": "dense to-one",
+                             "what": "colq_associate_device on zip -> city as a CSR: offsets order, target range and max degree in one pass, "
+                                     "then the dense to-one column"}
+    return out
 
 
 def perturbed_gate(ctx, rank, world, base):
