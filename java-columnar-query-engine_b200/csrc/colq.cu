@@ -1231,8 +1231,17 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
                 q->rf_epoch = 1;
             }
             P.epoch = q->rf_epoch;
-            if (o.np == 1) root_fused_kernel<1><<<o.grid, RF_THREADS, 0, s>>>(P);
-            else root_fused_kernel<2><<<o.grid, RF_THREADS, 0, s>>>(P);
+            // programmatic dependent launch: the CTAs may move onto SMs that the kernel in front (the string scan) is
+            // leaving; the kernel orders itself against that kernel with griddepcontrol.wait (pdl_wait)
+            static const bool pdl = !(getenv("COLQ_PDL") && getenv("COLQ_PDL")[0] == '0');
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(o.grid); cfg.blockDim = dim3(RF_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            if (o.np == 1) CU(ctx, cudaLaunchKernelEx(&cfg, root_fused_kernel<1>, P));
+            else CU(ctx, cudaLaunchKernelEx(&cfg, root_fused_kernel<2>, P));
             q->timing.kernel_launches++;
             break;
         }
@@ -1451,7 +1460,7 @@ colq_status run_pipeline(colq_query* q) {
         // candidate lists: room for ~3 % of a warp's rows, at least 128; denser CTAs take the dense path
         P.list_cap = (int)std::max<int64_t>(128, P.chunks_per_warp * (SR_WARP_ROWS / 32));
         void* lists;
-        ST(pool_alloc(q, (size_t)f.grid * RF_WARPS * P.list_cap * 4, &lists));
+        ST(pool_alloc(q, (size_t)f.grid * RF_WARPS * P.list_cap * 4 * (1 + f.ng), &lists));
         P.lists = (u32*)lists;
         if (q->rf_state_ctas < f.grid) {
             ST(dev_alloc(ctx, q->rf_state_buf, 64 + (size_t)f.grid * 8));

@@ -80,6 +80,13 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
 
 __device__ __forceinline__ bool bit_test(const u32* bits, int64_t i) { return (bits[i >> 5] >> (i & 31)) & 1u; }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while the kernel in front of it in the stream is still draining, once every CTA of that kernel has executed
+// pdl_launch_dependents() or exited; it must call pdl_wait() before it touches anything the earlier kernel wrote
+// (pdl_wait returns when that kernel has completed and its writes are visible).  Both are no-ops in ordinary launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ u64 ld_volatile_u64(const u64* p) {
     u64 v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -943,6 +950,8 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == -1 || MODE == -2) ? 4 : 3
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool do_push = P.push.fk != nullptr;
+    // the next kernel of the plan (the root's fused scan) may move onto an SM as soon as this kernel's CTAs leave it
+    pdl_launch_dependents();
 
     for (int i = tid; i < needle_region / 4; i += ST_THREADS) {
         u32 w = 0;
@@ -1820,7 +1829,8 @@ __global__ void __launch_bounds__(CP_THREADS) compact_fused_kernel(const Compact
 
 constexpr int RF_THREADS = 256;
 constexpr int RF_WARPS = RF_THREADS / 32;
-constexpr int RF_ILP = 4;                     // candidates whose chains one thread walks concurrently
+constexpr int RF_ILP = 2;                     // candidates whose chains one lane walks concurrently
+constexpr u32 RF_NO_LEAF = 0xffffffffu;       // a chain that ended in Association.None (or outside its table)
 constexpr int RF_PRE_ROWS = PUSH_SMEM_BITS;   // a folded to-many hop has at most this many parent / child rows ...
 constexpr int RF_PRE_EDGES = CSR_SMEM_EDGES;  // ... and this many edges
 
@@ -1831,7 +1841,7 @@ struct RootFusedParams {
     u32* bits;                   // root mask, always written
     int64_t n_chunks;            // ceil(n / 512)
     int64_t chunks_per_warp;
-    u32* lists;                  // [gridDim.x * RF_WARPS][list_cap] candidate rows (bit 31: chain failed)
+    u32* lists;                  // [gridDim.x * RF_WARPS][list_cap][1 + ng]: candidate row (bit 31: dropped), chain leaf rows
     int list_cap;
     u32* counters;               // [0] CTA tickets, [1] finished CTAs; both are zero between launches
     u64* cta_state;              // [gridDim.x]  epoch << 32 | survivors of that ticket
@@ -1924,28 +1934,18 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
             }
         }
     };
-    // Single GPU: the hop's input is final before this launch starts, so it runs first (2 us on an idle memory system
-    // instead of 5-16 us behind the other CTAs' streams, and off the critical tail).  Multi-GPU: if every peer's mask
-    // flag is already here, likewise; otherwise after phase A, so that the wait for the slowest rank hides behind the scan.
-    bool pre_done = false;
-    if (P.pre.n > 0) {
-        int ready = 1;
-        if (P.pre.pm.n_words > 0) {
-            const PeerMaskParams& M = P.pre.pm;
-            const uint8_t* mine = M.peers[M.rank] + (size_t)(M.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
-            if (tid < M.n_ranks) ready = ld_acquire_sys(reinterpret_cast<const u64*>(mine + (size_t)tid * MASK_SLOT_BYTES)) == M.epoch;
-        }
-        if (__syncthreads_and(ready)) {
-            run_pre();
-            pre_done = true;
-        }
-    }
+    // Ordering against the kernel in front of this one (P.pdl: launched as a programmatic dependent of it, typically the
+    // string scan that produces the mask the folded hop reads): phase A reads only the root's own predicate columns, so
+    // it may run while that kernel drains; everything it produced is touched only after pdl_wait() below.  If the root
+    // already carries bits from earlier launches (in_bits), phase A does depend on them: wait first.
+    if (P.in_bits != nullptr) pdl_wait();
 
     // ======================= phase A: stream, test, store mask words, list the survivors =======================
     const int64_t vwarp = (int64_t)vcta * RF_WARPS + warp;
     const int64_t c_lo = vwarp * P.chunks_per_warp;
     const int64_t c_hi = (c_lo + P.chunks_per_warp) < P.n_chunks ? (c_lo + P.chunks_per_warp) : P.n_chunks;
-    u32* my_list = P.lists + (size_t)vwarp * P.list_cap;
+    const int stride = 1 + P.ng;  // list entry: [row | leaf row of chain 0 | leaf row of chain 1]
+    u32* my_list = P.lists + (size_t)vwarp * P.list_cap * stride;
     u32 cnt = 0;
     for (int64_t c = c_lo; c < c_hi; ++c) {
         const int64_t wbase = c * SR_WARP_ROWS;
@@ -2021,21 +2021,64 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
                 while (mm) {
                     const int e = __ffs(mm) - 1;
                     mm &= mm - 1;
-                    my_list[pos++] = (u32)(wbase + j * 128 + lane * 4 + e);
+                    my_list[(pos++) * stride] = (u32)(wbase + j * 128 + lane * 4 + e);
                 }
             }
             cnt += tot;  // keeps counting past the cap: cnt > list_cap marks the overflow
+        }
+    }
+    // The warp walks the key levels of its OWN candidates' chains right away (RF_ILP candidates per lane, level by level)
+    // and leaves each chain's leaf row next to the candidate: these dependent DRAM reads overlap the other warps' and
+    // CTAs' streaming instead of sitting on the kernel's tail (r02 timeline: 7-13 us on the critical CTA).  Only the
+    // final bit test -- which needs the exchanged mask -- is left for phase B.
+    if (P.ng > 0 && cnt <= (u32)P.list_cap) {
+        __syncwarp();
+        for (u32 i0 = 0; i0 < cnt; i0 += 32 * RF_ILP) {
+            u32 row[RF_ILP];
+            bool ok[RF_ILP];
+#pragma unroll
+            for (int k = 0; k < RF_ILP; ++k) {
+                const u32 i = i0 + k * 32 + lane;
+                ok[k] = i < cnt;
+                row[k] = ok[k] ? my_list[(size_t)i * stride] : 0u;
+            }
+            for (int g = 0; g < P.ng; ++g) {
+                const GatherD& G = P.gather[g];
+                int64_t r[RF_ILP];
+                bool pass[RF_ILP];
+#pragma unroll
+                for (int k = 0; k < RF_ILP; ++k) { r[k] = row[k]; pass[k] = ok[k]; }
+                for (int d = 0; d < G.depth; ++d) {
+                    int32_t t[RF_ILP];
+#pragma unroll
+                    for (int k = 0; k < RF_ILP; ++k) t[k] = pass[k] ? G.fk[d][r[k]] : 0;
+#pragma unroll
+                    for (int k = 0; k < RF_ILP; ++k) {
+                        if (pass[k] && (t[k] < 0 || t[k] >= G.n[d])) {
+                            if (t[k] != -1 && G.oob != nullptr) *G.oob = 1u;
+                            pass[k] = false;
+                        }
+                        r[k] = t[k];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < RF_ILP; ++k)
+                    if (ok[k]) my_list[(size_t)(i0 + k * 32 + lane) * stride + 1 + g] = pass[k] ? (u32)r[k] : RF_NO_LEAF;
+            }
         }
     }
     if (lane == 0) {
         s_wcnt[warp] = cnt;
         if (cnt > (u32)P.list_cap) s_overflow = 1;
     }
+    // from here on the kernel reads what earlier launches produced (the mask behind the folded hop, chain bitmaps)
+    pdl_wait();
 
     RF_STAMP(1);
     // ======================= phase B =======================
-    // ---- (1) the folded hop, unless it already ran in front of phase A
-    if (P.pre.n > 0 && !pre_done) run_pre();
+    // ---- (1) the folded hop (multi-GPU: the COLLECT of the mask exchange first -- the wait for the slowest rank has been
+    //      hiding behind phase A)
+    if (P.pre.n > 0) run_pre();
     __syncthreads();  // s_wcnt, s_overflow, s_pre
     RF_STAMP(2);
     if (tid == 0) {
@@ -2063,55 +2106,22 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
         if (P.ng == 0) {
             kept = tid == 0 ? n_c : 0;
         } else {
-            // RF_ILP candidates per thread at a time, walked level by level: the dependent loads of one chain are
-            // serial, those of different candidates are all in flight together (r02 timeline: 13 us -> 4 us on the
-            // critical CTA)
-            for (u32 i0 = 0; i0 < n_c; i0 += RF_THREADS * RF_ILP) {
-                u32* ep[RF_ILP];
-                u32 row[RF_ILP];
-                bool ok[RF_ILP], pass[RF_ILP];
+            // the key levels were walked in phase A: test the leaf bits (shared memory for a folded hop)
+            for (u32 i = tid; i < n_c; i += RF_THREADS) {
+                int w = 0;
 #pragma unroll
-                for (int k = 0; k < RF_ILP; ++k) {
-                    const u32 i = i0 + k * RF_THREADS + tid;
-                    ok[k] = i < n_c;
-                    int w = 0;
-#pragma unroll
-                    for (int q = 1; q < RF_WARPS; ++q) w += (i >= s_woff[q]) ? 1 : 0;
-                    ep[k] = P.lists + ((size_t)vcta * RF_WARPS + w) * P.list_cap + (i - s_woff[w]);
-                    row[k] = ok[k] ? __ldcg(ep[k]) : 0u;
-                    pass[k] = ok[k];
-                }
+                for (int k = 1; k < RF_WARPS; ++k) w += (i >= s_woff[k]) ? 1 : 0;
+                u32* e = P.lists + (((size_t)vcta * RF_WARPS + w) * P.list_cap + (i - s_woff[w])) * stride;
+                bool ok = true;
                 for (int g = 0; g < P.ng; ++g) {
-                    const GatherD& G = P.gather[g];
-                    int64_t r[RF_ILP];
-#pragma unroll
-                    for (int k = 0; k < RF_ILP; ++k) r[k] = row[k];
-                    for (int d = 0; d < G.depth; ++d) {
-                        int32_t t[RF_ILP];
-#pragma unroll
-                        for (int k = 0; k < RF_ILP; ++k) t[k] = pass[k] ? G.fk[d][r[k]] : 0;
-#pragma unroll
-                        for (int k = 0; k < RF_ILP; ++k) {
-                            if (pass[k] && (t[k] < 0 || t[k] >= G.n[d])) {
-                                if (t[k] != -1 && G.oob != nullptr) *G.oob = 1u;
-                                pass[k] = false;
-                            }
-                            r[k] = t[k];
-                        }
-                    }
-                    if (gbits[g] != nullptr) {
-#pragma unroll
-                        for (int k = 0; k < RF_ILP; ++k) pass[k] = pass[k] && bit_test(gbits[g], pass[k] ? r[k] : 0);
-                    }
+                    const u32 leaf = __ldcg(e + 1 + g);
+                    ok = ok && leaf != RF_NO_LEAF && (gbits[g] == nullptr || bit_test(gbits[g], leaf));
                 }
-#pragma unroll
-                for (int k = 0; k < RF_ILP; ++k) {
-                    if (!ok[k]) continue;
-                    if (pass[k]) ++kept;
-                    else {
-                        atomicAnd(&P.bits[row[k] >> 5], ~(1u << (row[k] & 31)));
-                        *ep[k] = row[k] | 0x80000000u;
-                    }
+                if (ok) ++kept;
+                else {
+                    const u32 row = __ldcg(e);
+                    atomicAnd(&P.bits[row >> 5], ~(1u << (row & 31)));
+                    *e = row | 0x80000000u;
                 }
             }
         }
@@ -2177,7 +2187,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
                 int w = 0;
 #pragma unroll
                 for (int k = 1; k < RF_WARPS; ++k) w += (i >= s_woff[k]) ? 1 : 0;
-                row = __ldcg(P.lists + ((size_t)vcta * RF_WARPS + w) * P.list_cap + (i - s_woff[w]));
+                row = __ldcg(P.lists + (((size_t)vcta * RF_WARPS + w) * P.list_cap + (i - s_woff[w])) * stride);
             }
             const u32 valid = (row & 0x80000000u) ? 0u : 1u;
             u32 tot;
