@@ -112,7 +112,11 @@ typedef enum colq_option {
        to-one chains, a tiny to-many hop feeding them (e.g. the 51-row state adjacency, with the multi-GPU mask COLLECT),
        ordered compaction and the final gather (root_fused_kernel); 0: scan_rows / csr_pull / compact_fused launches.
        Needs COLQ_OPT_FUSED_COMPACT == 1. */
-    COLQ_OPT_ROOT_FUSED = 9
+    COLQ_OPT_ROOT_FUSED = 9,
+    /* 1 (default): a fused final gather whose plan already synchronises the ranks once per execution (a mask or bitmap
+       exchange) only PUBLISHES its flags; they are awaited when the host fetches the result.  0: every execution ends with
+       a wait for all ranks' flags. */
+    COLQ_OPT_LAZY_GATHER_WAIT = 10
 } colq_option;
 
 typedef struct colq_ctx colq_ctx;       /* one DataSystem instance  (E/DataSystemSerialIndices.java:14-22) */

@@ -273,7 +273,7 @@ struct colq_query {
     colq_ctx* ctx = nullptr;
     std::string table_name;
     std::vector<QNode> nodes;
-    int opt_lazy = 1, opt_profile = 0, opt_peer = 1, opt_fused_compact = 1, opt_defer = 1, opt_promote = 2, opt_fused_gather = 1, opt_tail_publish = 1, opt_root_fused = 1;
+    int opt_lazy = 1, opt_profile = 0, opt_peer = 1, opt_fused_compact = 1, opt_defer = 1, opt_promote = 2, opt_fused_gather = 1, opt_tail_publish = 1, opt_root_fused = 1, opt_lazy_gather_wait = 1;
     std::vector<GatherD> deferred;  // root-node FK chains resolved by the compaction kernel instead of the row scan
     int own_begin = -1, own_end = -1;  // root-node scan ops that depend on no child (hoistable behind a mask publish)
     std::vector<Column*> pending_promotions;  // host-resident columns whose HBM copy this execution fills
@@ -1153,7 +1153,10 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
                     if (occ < 1) return fail(ctx, COLQ_ERR_DEVICE, "scan_str_kernel does not fit on an SM (smem %zu)", o.smem);
                     it = ctx->str_occupancy.emplace(key, occ).first;
                 }
-                o.grid = (int)std::min<int64_t>(o.str.n_tiles, (int64_t)ctx->sm_count * it->second);
+                // (COLQ_STR_CTAS, experiment knob: resident CTAs per SM to use -- tiles are claimed dynamically, so any grid works)
+                static const int ctas_env = getenv("COLQ_STR_CTAS") ? atoi(getenv("COLQ_STR_CTAS")) : 0;
+                const int per_sm = ctas_env > 0 ? std::min(ctas_env, it->second) : it->second;
+                o.grid = (int)std::min<int64_t>(o.str.n_tiles, (int64_t)ctx->sm_count * per_sm);
             }
             if (o.tail_publish) o.pmask.epoch = o.str.pub.epoch = ++ctx->peer.mask_epoch;
             kern<<<o.grid, ST_THREADS, o.smem, s>>>(o.str);
@@ -1431,6 +1434,15 @@ colq_status run_pipeline(colq_query* q) {
         q->gather_is_peer = true;
         q->gather_block_cap = cap;
         q->gather_lazy = true;
+        // The last block normally waits for every peer's flag before the launch ends: that keeps the ranks within one
+        // execution of each other (slot parity).  A plan that already synchronises the ranks once per execution -- a mask
+        // or bitmap exchange -- does not need a second all-rank wait per step: the flags are then awaited only when the
+        // host fetches the result (peer_gather_recv_kernel).
+        bool synced = false;
+        for (const Op& o : q->ops)
+            synced = synced || o.kind == K_PEER_MASK_PUBLISH || o.kind == K_PEER_MASK_COLLECT || o.kind == K_PEER_BITS_ALLGATHER ||
+                     (o.kind == K_PEER_BITS_REDUCE && o.pbits.n_src > 1) || o.tail_publish || (o.kind == K_CSR_PULL && o.csr.pm.n_words > 0);
+        G.wait = (synced && q->opt_lazy_gather_wait) ? 0 : 1;
         return COLQ_OK;
     };
     bool coop_gather = peer_gather && q->opt_fused_gather && q->opt_fused_compact == 1;  // the gather rides on the index writer
@@ -1693,6 +1705,13 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
         CU(ctx, cudaStreamSynchronize(s));
         memcpy(header, ctx->h_stage, 16);
     } else {
+        if (gather && q->gather_lazy) {
+            // the ranks' indices sit in this rank's mailbox slots: wait for every rank's flag (if the launch itself did
+            // not), summarise the counts and concatenate the valid prefixes in rank order
+            peer_gather_recv_kernel<<<grid_for(q->gather_block_cap * ctx->n_ranks / 4 + 1, 256, ctx->sm_count, 2), 256, 0, s>>>(q->lazy_pg);
+            CU(ctx, cudaGetLastError());
+            q->timing.kernel_launches++;
+        }
         CU(ctx, cudaMemcpyAsync(header, q->d_total, 16, cudaMemcpyDeviceToHost, s));
         if (gather) CU(ctx, cudaMemcpyAsync(ginfo, q->ginfo_buf.ptr, 32, cudaMemcpyDeviceToHost, s));
         CU(ctx, cudaStreamSynchronize(s));
@@ -1735,12 +1754,7 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
         }
         count = (int64_t)ginfo[2];
         src_idx = (const int32_t*)q->gout_buf.ptr;
-        if (q->gather_lazy && out_idx && count > 0 && idx_cap >= count) {
-            // the ranks' indices sit in this rank's mailbox slots: concatenate their valid prefixes in rank order now
-            peer_gather_recv_kernel<<<grid_for(block_cap * ctx->n_ranks / 4 + 1, 256, ctx->sm_count, 2), 256, 0, s>>>(q->lazy_pg);
-            CU(ctx, cudaGetLastError());
-            q->timing.kernel_launches++;
-        }
+
     } else if ((int64_t)local > q->idx_capacity) {
         // index buffer was too small: grow it and run again (happens once per query, the capacity sticks)
         q->want_idx_capacity = (int64_t)local + (int64_t)local / 8 + 1024;
@@ -2964,6 +2978,7 @@ colq_status colq_query_set_option(colq_query* q, colq_option option, int value) 
         case COLQ_OPT_FUSED_GATHER: q->opt_fused_gather = value; break;
         case COLQ_OPT_TAIL_PUBLISH: q->opt_tail_publish = value; break;
         case COLQ_OPT_ROOT_FUSED: q->opt_root_fused = value; break;
+        case COLQ_OPT_LAZY_GATHER_WAIT: q->opt_lazy_gather_wait = value; break;
         default: return fail(q->ctx, COLQ_THROW_ILLEGAL_ARG, "unknown option %d", (int)option);
     }
     return COLQ_OK;

@@ -1468,6 +1468,8 @@ struct PeerGatherParams {
     u32* status;
     int32_t* out;           // concatenation of all ranks' indices in rank order
     u64* info;              // [0] rows written, [1] largest per-rank count, [2] true total
+    int wait;               // fused gather: 1 = the launch ends only when every peer's flag has arrived (gather_tail);
+                            // 0 = publish only, the flags are awaited when the host fetches (peer_gather_recv_kernel)
 };
 
 // final gather, send half: every rank stores its indices into every peer's mailbox slot, the last block per peer
@@ -1573,6 +1575,7 @@ __device__ __forceinline__ void gather_tail(const PeerGatherParams& P, const u64
         st_release_sys(slot, P.epoch);
     }
     __syncthreads();
+    if (!P.wait) return;
     const uint8_t* mine = P.peers[P.rank] + area;
     if ((int)threadIdx.x < P.n_ranks) {
         if (!peer_wait(reinterpret_cast<const u64*>(mine + (size_t)threadIdx.x * P.slot_bytes), P.epoch, P.status)) s_gt_ok = 0;

@@ -47,15 +47,18 @@ def main():
 
         geo = G.build_tables(U, n_ranks=world, rank=rank, rename_plymouth_except_last_rank=perturbed)
         # (peer exchange, lazy FK, deferred chains, fused compaction, gather fused into the index writer, tail publish, fused root)
-        for peer, lazy, defer, fused, fgather, tail, rootf in ((1, True, 1, 1, 1, 1, 1), (1, True, 1, 1, 1, 0, 1), (1, True, 1, 1, 0, 1, 1),
+        for variant in ((1, True, 1, 1, 1, 1, 1), (1, True, 1, 1, 1, 0, 1), (1, True, 1, 1, 0, 1, 1),
                                                               (1, True, 1, 1, 0, 1, 0), (1, True, 1, 1, 0, 0, 0), (1, True, 1, 2, 0, 1, 1),
                                                               (1, True, 1, 1, 1, 1, 0), (1, True, 0, 1, 1, 0, 1), (1, False, 1, 1, 1, 1, 1),
                                                               (1, False, 1, 1, 0, 1, 0), (1, True, 1, 0, 0, 1, 1), (0, True, 1, 1, 0, 1, 1),
-                                                              (0, True, 1, 1, 0, 1, 0), (0, False, 1, 2, 0, 1, 1)):
+                                                              (0, True, 1, 1, 0, 1, 0), (0, False, 1, 2, 0, 1, 1), (1, True, 1, 1, 1, 1, 1, 0)):
+            peer, lazy, defer, fused, fgather, tail, rootf = variant[:7]
+            lazy_wait = variant[7] if len(variant) > 7 else 1   # COLQ_OPT_LAZY_GATHER_WAIT
             if True:
                 ds = DataSystemColq(context=ctx, lazy_fk=lazy, options={_ffi.OPT_PEER_EXCHANGE: peer, _ffi.OPT_DEFER_CHAINS: defer,
                                                                         _ffi.OPT_FUSED_COMPACT: fused, _ffi.OPT_FUSED_GATHER: fgather,
-                                                                        _ffi.OPT_TAIL_PUBLISH: tail, _ffi.OPT_ROOT_FUSED: rootf})
+                                                                        _ffi.OPT_TAIL_PUBLISH: tail, _ffi.OPT_ROOT_FUSED: rootf,
+                                                                        _ffi.OPT_LAZY_GATHER_WAIT: lazy_wait})
                 ds._tables.clear()
                 G.register_geography(ds, geo, sharded=True)
                 ds._sync_tables()
