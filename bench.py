@@ -78,6 +78,7 @@ def parse_args():
                          "compaction); str_eq = configs[4] (city-name equality, one GPU's 62.5M-row shard). The last two are "
                          "single-GPU kernel benchmarks for DESIGN.md, not the driver's bench line.")
     ap.add_argument("--rows", type=int, default=0, help="row count override for int_scan / str_eq")
+    ap.add_argument("--unfused-root", action="store_true", help="COLQ_OPT_ROOT_FUSED=0: scan_rows / csr_pull / compact_fused launches (A/B runs)")
     return ap.parse_args()
 
 
@@ -301,6 +302,8 @@ def run_colq(args, rank, local_rank, world):
     if args.dict_names:
         args.no_e2e = True
     q = plymouth_colq_query(ctx, lazy_fk=not args.eager)
+    if args.unfused_root:
+        q.set_option(_ffi.OPT_ROOT_FUSED, 0)
 
     # ---- correctness gate before any number: the result must be exactly {u * 29353 + r}
     from oracle_system import OracleDataSystem
@@ -743,6 +746,8 @@ def run_single_table(args, rank=0, local_rank=0, world=1):
                     "sharding": f"contiguous row ranges over {world} rank(s), final index gather over NVLink peer memory" if world > 1 else "none"}
         metric = "string_equality_scan_rows_per_sec"
         algo = lambda m: 4 * (n + 1) + total + n // 8  # noqa: E731  
+    if args.unfused_root:
+        q.set_option(_ffi.OPT_ROOT_FUSED, 0)
     res = q.execute(want_indices=True, index_capacity=max(expect, 1) + 16)
     if res.count != expect or (res.indices.shape[0] > 1 and not np.all(np.diff(res.indices.astype(np.int64)) > 0)):
         raise SystemExit(f"GPU count {res.count} != independent expectation {expect} (or indices not ascending)")

@@ -1096,7 +1096,26 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
                 if (o.rows.out_bits)
                     CU(ctx, cudaMemsetAsync(o.rows.out_bits, 0, (size_t)bitmap_alloc_words(o.rows.n) * 4, s));
             } else {
-                launch_scan_rows(o, s);
+                // A/B variant (COLQ_SCAN_ROWS_TMA=1): the plain single-predicate scan staged through shared memory with TMA bulk
+                // copies instead of per-lane LDG.128 (measured slower or equal on B200: profiles/r02_scan_rows_tma_ab.txt)
+                static const bool tma_env = getenv("COLQ_SCAN_ROWS_TMA") && getenv("COLQ_SCAN_ROWS_TMA")[0] == '1';
+                const bool plain = o.np == 1 && o.ng == 0 && !o.eager && o.rows.in_bits == nullptr && o.rows.push.fk == nullptr &&
+                                   o.rows.pred[0].promote == nullptr && o.rows.out_bits != nullptr && o.rows.n > 0;
+                if (tma_env && plain) {
+                    static bool attr_set = false;
+                    const size_t smem = (size_t)SRT_STAGES * SRT_TILE_BYTES;
+                    if (!attr_set) {
+                        CU(ctx, cudaFuncSetAttribute(scan_rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        attr_set = true;
+                    }
+                    int occ = 0;
+                    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_rows_tma_kernel, SRT_THREADS, smem));
+                    const int64_t n_tiles = (o.rows.n + SR_BLOCK_ROWS - 1) / SR_BLOCK_ROWS;
+                    ScanRowsTmaParams T{o.rows.n, o.rows.pred[0].col, o.rows.pred[0].lo, o.rows.pred[0].span, o.rows.out_bits, ctx->d_tile_counters};
+                    scan_rows_tma_kernel<<<(int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * std::max(1, occ)), SRT_THREADS, smem, s>>>(T);
+                } else {
+                    launch_scan_rows(o, s);
+                }
                 q->timing.kernel_launches++;
             }
             break;

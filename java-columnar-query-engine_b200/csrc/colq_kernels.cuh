@@ -21,6 +21,7 @@ typedef uint32_t u32;
 typedef uint64_t u64;
 
 constexpr u32 FULL_MASK = 0xffffffffu;
+constexpr u32 ST_NO_TILE = 0xffffffffu;  // sentinel stage of the TMA rings: the producer has run out of tiles
 
 // ---------------------------------------------------------------------------------------------
 // small device helpers
@@ -366,6 +367,124 @@ __global__ void __launch_bounds__(SR_THREADS) scan_rows_kernel(const ScanRowsPar
     if (do_push) {
         __syncthreads();
         push_flush(P.push, s_reach);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1-TMA  scan_rows_tma: the single-predicate scan with cp.async.bulk staging (north_star: "128-bit vectorised coalesced
+// loads and TMA/shared-memory staging").  A/B variant of scan_rows<1, 0>, selected with COLQ_SCAN_ROWS_TMA=1: persistent
+// CTAs, one producer lane claims 4096-row tiles from the device-wide counter and copies each (16 KB) into a ring of
+// SRT_STAGES shared-memory slots with one bulk copy; eight consumer warps read their 512 rows with conflict-free LDS.128
+// and do the same compare / pack / 64-byte mask store as scan_rows.  Measured against the LDG.128 kernel in
+// profiles/r02_scan_rows_tma_ab.txt; the faster one is the default.
+// ---------------------------------------------------------------------------------------------
+constexpr int SRT_STAGES = 4;
+constexpr int SRT_THREADS = SR_THREADS + 32;
+constexpr int SRT_TILE_BYTES = SR_BLOCK_ROWS * 4;  // 16 KB
+
+struct ScanRowsTmaParams {
+    int64_t n;
+    const int32_t* col;
+    int32_t lo;
+    u32 span;
+    u32* out_bits;
+    u32* tile_counter;  // [0] next unclaimed tile, [1] finished CTAs (zero between launches)
+};
+
+__global__ void __launch_bounds__(SRT_THREADS) scan_rows_tma_kernel(const ScanRowsTmaParams P) {
+    extern __shared__ __align__(128) uint8_t srt_smem[];
+    __shared__ u64 s_full[SRT_STAGES], s_empty[SRT_STAGES];
+    __shared__ u32 s_tile[SRT_STAGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 n_tiles = (u32)((P.n + SR_BLOCK_ROWS - 1) / SR_BLOCK_ROWS);
+    if (tid == 0) {
+        for (int s = 0; s < SRT_STAGES; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], SR_THREADS / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == SR_THREADS / 32) {
+        if (lane == 0) {
+            u32 batch = atomicAdd(P.tile_counter, 2u), batch_next = atomicAdd(P.tile_counter, 2u), j = 0;
+            int s = 0;
+            u32 round = 0;
+            while (true) {
+                const u32 cur = batch + j;
+                if (round > 0) mbar_wait(&s_empty[s], (round - 1) & 1);
+                if (cur >= n_tiles) {
+                    s_tile[s] = ST_NO_TILE;
+                    mbar_arrive(&s_full[s]);
+                    break;
+                }
+                s_tile[s] = cur;
+                const int64_t r0 = (int64_t)cur * SR_BLOCK_ROWS;
+                const int64_t rows = (P.n - r0) < SR_BLOCK_ROWS ? (P.n - r0) : SR_BLOCK_ROWS;
+                const u32 bytes = (u32)((rows * 4 + 15) & ~(int64_t)15);
+                mbar_arrive_expect_tx(&s_full[s], bytes);
+                tma_bulk_g2s(srt_smem + (size_t)s * SRT_TILE_BYTES, P.col + r0, bytes, &s_full[s]);
+                if (++j == 2) {
+                    j = 0;
+                    batch = batch_next;
+                    batch_next = atomicAdd(P.tile_counter, 2u);
+                }
+                if (++s == SRT_STAGES) {
+                    s = 0;
+                    ++round;
+                }
+            }
+        }
+    } else {
+        u32 s = 0, parity = 0;
+        while (true) {
+            mbar_wait(&s_full[s], parity);
+            const u32 tile = s_tile[s];
+            if (tile == ST_NO_TILE) break;
+            const int64_t wbase = (int64_t)tile * SR_BLOCK_ROWS + (int64_t)warp * SR_WARP_ROWS;
+            const u32 sbase = smem_u32(srt_smem) + s * SRT_TILE_BYTES + (u32)warp * SR_WARP_ROWS * 4;
+            u32 nib[SR_V];
+#pragma unroll
+            for (int j = 0; j < SR_V; ++j) {
+                int4 v;
+                asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sbase + (j * 128 + lane * 4) * 4));
+                u32 m = range4(v, P.lo, P.span);
+                const int64_t r = wbase + j * 128 + lane * 4;
+                if (r + 3 >= P.n) {  // the table's last rows
+                    u32 valid = 0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) valid |= (r + e < P.n) ? (1u << e) : 0u;
+                    m &= valid;
+                }
+                nib[j] = m;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[s]);
+            if (wbase < P.n) {
+                u32 y[SR_V];
+#pragma unroll
+                for (int j = 0; j < SR_V; ++j) {
+                    u32 x = nib[j] << ((lane & 7) * 4);
+                    x |= __shfl_xor_sync(FULL_MASK, x, 1);
+                    x |= __shfl_xor_sync(FULL_MASK, x, 2);
+                    x |= __shfl_xor_sync(FULL_MASK, x, 4);
+                    y[j] = __shfl_sync(FULL_MASK, x, (lane & 3) * 8);
+                }
+                u32 out = y[0];
+#pragma unroll
+                for (int j = 1; j < SR_V; ++j) out = ((lane >> 2) == j) ? y[j] : out;
+                if (lane < 4 * SR_V) P.out_bits[(wbase >> 5) + lane] = out;
+            }
+            if (++s == SRT_STAGES) {
+                s = 0;
+                parity ^= 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && atomicAdd(P.tile_counter + 1, 1u) == gridDim.x - 1) {
+        P.tile_counter[0] = 0;
+        P.tile_counter[1] = 0;
     }
 }
 
@@ -784,7 +903,6 @@ struct ScanStrParams {
     u32* tile_counter;    // [0] next unclaimed tile, [1] finished CTAs; both are zero between launches
 };
 
-constexpr u32 ST_NO_TILE = 0xffffffffu;  // sentinel stage: the producer has run out of tiles
 #ifndef COLQ_ST_CLAIM
 #define COLQ_ST_CLAIM 2
 #endif
