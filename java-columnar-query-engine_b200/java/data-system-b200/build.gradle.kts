@@ -9,6 +9,8 @@ dependencies {
     api(project(":data-system"))
     // the shim reads column arrays through the InMemoryColumn record accessors (Column exposes no raw accessor)
     implementation(project(":data-model-in-memory"))
+    // the TCK also runs against the reference's own engine (QueryTckTest.ReferenceSerialIndices)
+    testImplementation(project(":data-system-serial-indices-arrays"))
     testImplementation(libs.junit.jupiter.api)
     testImplementation(libs.assertj)
     testRuntimeOnly(libs.junit.jupiter.engine)
@@ -17,5 +19,6 @@ dependencies {
 tasks.withType<Test> {
     // where lib/libcolq.so was built
     systemProperty("colq.library", System.getProperty("colq.library") ?: "libcolq.so")
+    systemProperty("colq.gpus", System.getProperty("colq.gpus") ?: "2")   // GPUs QueryTckTest.AllGpusOneJvm drives from this JVM
     jvmArgs("--enable-native-access=dgroomes.data_system_b200")
 }

@@ -57,9 +57,16 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
      * values, and ANY Predicate&lt;String&gt; -- including the app's unchanged lambdas (Runner.java:236,255-259) -- is
      * evaluated once per distinct value here and applied on the GPU as a code lookup.
      */
-    public record Layout(boolean hostResident, boolean dictionary) {
+    public record Layout(boolean hostResident, boolean dictionary, boolean deviceIngest) {
+        public Layout(boolean hostResident, boolean dictionary) { this(hostResident, dictionary, false); }
         /** Everything the unchanged app needs: pinned off-heap columns, string AND integer columns dictionary-encoded. */
-        public static Layout forUnchangedLambdas() { return new Layout(true, true); }
+        public static Layout forUnchangedLambdas() { return new Layout(true, true, false); }
+        /**
+         * The same, with the load-time work done by the GPU (include/colq.h "Ingest on the device"): string columns are
+         * shipped as plain offsets + bytes and dictionary-encoded by colq_col_str_encode, every association goes up as one
+         * CSR that colq_associate validates and classifies into dense to-one vs to-many.
+         */
+        public static Layout deviceIngest() { return new Layout(false, true, true); }
     }
 
     private final Layout layout;
@@ -79,6 +86,7 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
         this.layout = layout;
         try (Arena a = Arena.ofConfined()) {
             MemorySegment out = a.allocate(ADDRESS);
+            if ((int) colq_abi_version.invokeExact() != ABI_VERSION) throw new IllegalStateException("libcolq.so ABI version mismatch");
             int st = (int) colq_create.invokeExact(device, out);
             if (st != OK) throw new IllegalStateException("colq_create failed (" + st + "): no usable sm_100 GPU; libcolq has no CPU fallback");
             ctx = out.get(ADDRESS, 0);
@@ -234,6 +242,36 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
                             check((int) colq_col_i32.invokeExact(ctx, h, ordinal, seg, (long) ints.length));
                         }
                     }
+                    case InMemoryColumn.StringColumn(String[] strings) when layout.dictionary() && layout.deviceIngest() -> {
+                        // plain offsets + UTF-8 bytes go up once; the GPU builds the dictionary (first-appearance order) and
+                        // the distinct values come back for the opaque-lambda path
+                        byte[][] enc = new byte[strings.length][];
+                        long total = 0;
+                        for (int i = 0; i < strings.length; i++) { enc[i] = strings[i].getBytes(StandardCharsets.UTF_8); total += enc[i].length; }
+                        MemorySegment off = call.allocate(JAVA_INT, strings.length + 1L);
+                        MemorySegment bytes = call.allocate(Math.max(total, 1));
+                        long pos = 0;
+                        for (int i = 0; i < strings.length; i++) {
+                            off.setAtIndex(JAVA_INT, i, (int) pos);
+                            MemorySegment.copy(enc[i], 0, bytes, JAVA_BYTE, pos, enc[i].length);
+                            pos += enc[i].length;
+                        }
+                        off.setAtIndex(JAVA_INT, strings.length, (int) pos);
+                        check((int) colq_col_str.invokeExact(ctx, h, ordinal, off, bytes, (long) strings.length, total));
+                        MemorySegment nDict = call.allocate(JAVA_LONG), nBytes = call.allocate(JAVA_LONG);
+                        check((int) colq_col_str_encode.invokeExact(ctx, h, ordinal, nDict));
+                        int sizeQuery = (int) colq_col_dict_str.invokeExact(ctx, h, ordinal, MemorySegment.NULL, 0L, MemorySegment.NULL, 0L, nDict, nBytes);
+                        if (sizeQuery != OK && sizeQuery != ERR_CAPACITY) check(sizeQuery);
+                        long d = nDict.get(JAVA_LONG, 0), db = nBytes.get(JAVA_LONG, 0);
+                        MemorySegment dOff = call.allocate(JAVA_INT, d + 1), dBytes = call.allocate(Math.max(db, 1));
+                        check((int) colq_col_dict_str.invokeExact(ctx, h, ordinal, dOff, d + 1, dBytes, db, nDict, nBytes));
+                        String[] distinct = new String[(int) d];
+                        for (int i = 0; i < d; i++) {
+                            int a = dOff.getAtIndex(JAVA_INT, i), b = dOff.getAtIndex(JAVA_INT, i + 1);
+                            distinct[i] = new String(dBytes.asSlice(a, b - a).toArray(JAVA_BYTE), StandardCharsets.UTF_8);
+                        }
+                        dictionaryValues.computeIfAbsent(t, k -> new HashMap<>()).put(ordinal, distinct);
+                    }
                     case InMemoryColumn.StringColumn(String[] strings) when layout.dictionary() -> {
                         // dictionary-encode while copying off-heap: distinct values in first-appearance order
                         var index = new HashMap<String, Integer>();
@@ -326,6 +364,7 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
             if (a instanceof Association.Many(int[] idx)) { toOne = false; nnz += idx.length; }
             else if (a instanceof Association.One) nnz++;
         }
+        if (layout.deviceIngest()) toOne = false;   // always ship the CSR: the GPU validates it and picks the representation
         if (toOne) {
             boolean host = layout.hostResident() && assoc.length > 0;
             MemorySegment fk = host ? pinned(4L * assoc.length) : call.allocate(JAVA_INT, Math.max(assoc.length, 1));
@@ -345,7 +384,8 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
                 }
             }
             off.setAtIndex(JAVA_LONG, assoc.length, pos);
-            check((int) colq_associate_csr.invokeExact(ctx, x, xOrdinal, y, yOrdinal, off, tgt, (long) assoc.length, nnz));
+            if (layout.deviceIngest()) check((int) colq_associate.invokeExact(ctx, x, xOrdinal, y, yOrdinal, off, tgt, (long) assoc.length, nnz, MemorySegment.NULL));
+            else check((int) colq_associate_csr.invokeExact(ctx, x, xOrdinal, y, yOrdinal, off, tgt, (long) assoc.length, nnz));
         }
     }
 
@@ -380,6 +420,24 @@ public final class DataSystemColq implements DataSystem, AutoCloseable {
             case THROW_NULL -> throw new NullPointerException(lastError());
             case THROW_ILLEGAL_ARG -> throw new IllegalArgumentException(lastError());
             default -> throw new IllegalStateException("libcolq status " + status + ": " + lastError());
+        }
+    }
+
+    /** Forget a registered table and release its device memory (the reference leaves this to the garbage collector). */
+    public synchronized void unregister(String tableName) {
+        Table t = tables.remove(tableName);
+        registeredHandle.remove(tableName);
+        if (t == null || tables.containsValue(t)) return;
+        Integer h = handles.remove(t);
+        uploadedColumns.remove(t);
+        dictionaryValues.remove(t);
+        intDictionaryValues.remove(t);
+        try {
+            if (h != null) check((int) colq_table_destroy.invokeExact(ctx, (int) h));
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable e) {
+            throw new IllegalStateException(e);
         }
     }
 

@@ -1,61 +1,87 @@
 package dgroomes.data_system_b200;
 
-import dgroomes.data_system.Association;
 import dgroomes.data_system.Criteria;
+import dgroomes.data_system.DataSystem;
 import dgroomes.data_system.Query;
 import dgroomes.data_system.QueryResult;
-import dgroomes.in_memory.InMemoryColumn;
-import org.junit.jupiter.api.AfterEach;
-import org.junit.jupiter.api.BeforeEach;
+import dgroomes.data_system.Table;
+import dgroomes.data_system_serial_indices_arrays.DataSystemSerialIndices;
 import org.junit.jupiter.api.Test;
 
 import static dgroomes.in_memory.InMemoryColumn.ofInts;
-import static dgroomes.in_memory.InMemoryColumn.ofStrings;
 import static dgroomes.in_memory.InMemoryTable.ofColumns;
 import static org.assertj.core.api.Assertions.assertThat;
 
 /**
- * The reference's QueryTest (data-system-serial-indices-arrays/src/test/java/dgroomes/queryengine/QueryTest.java)
- * against DataSystemColq, lambdas replaced by structured predicates. The same cases run in this repository through
- * the ctypes twin (tests/tck.py); this JUnit class is for a machine that has JDK 22 and a B200.
+ * The TCK (AbstractQueryTck) against every engine and physical layout: the B200 engine with columns copied to HBM, with
+ * pinned host-resident + dictionary-encoded columns ({@code Layout.forUnchangedLambdas()}), with the load-time work done
+ * by the GPU ({@code Layout.deviceIngest()}), sharded over every visible GPU from this one JVM (DataSystemColqGroup) --
+ * and against the reference's own serial engine, which must pass the very same cases.
  */
-class QueryTckTest {
+final class QueryTckTest {
 
-    DataSystemColq dataSystem;
-
-    @BeforeEach
-    void setUp() { dataSystem = new DataSystemColq(); }
-
-    @AfterEach
-    void tearDown() { dataSystem.close(); }
-
-    @Test
-    void intQuery_oneColumnTable() {   // QueryTest.java:37-73
-        dataSystem.register("ints", ofColumns(ofInts(-1, 0, 1, 2, 3)));
-        var query = new Query("ints");
-        query.rootNode.addCriteria(new Criteria.IntCriteria(0, Predicates.intGreaterThan(0)));
-        var result = (QueryResult.Success) dataSystem.execute(query);
-        assertThat(((InMemoryColumn.IntegerColumn) result.resultSet().columns().get(0)).ints()).containsExactly(1, 2, 3);
+    private static AbstractQueryTck.Engine colq(DataSystemColq.Layout layout) {
+        var ds = new DataSystemColq(0, layout);
+        return new AbstractQueryTck.Engine() {
+            public DataSystem system() { return ds; }
+            public void register(String name, Table table) { ds.register(name, table); }
+            public void close() { ds.close(); }
+        };
     }
 
-    @Test
-    void queryOnAssociationProperty() {   // QueryTest.java:150-229
-        var cities = ofColumns(ofStrings("Minneapolis", "Pierre", "Duluth"));
-        dataSystem.register("cities", cities);
-        var states = ofColumns(ofStrings("Minnesota", "South Dakota"));
-        dataSystem.register("states", states);
-        cities.associateTo(states, Association.toOne(0), Association.toOne(1), Association.toOne(0));
-        var query = new Query("cities");
-        query.rootNode.createChild(1).addCriteria(new Criteria.StringCriteria(0, Predicates.strEquals("Minnesota")));
-        var result = (QueryResult.Success) dataSystem.execute(query);
-        assertThat(((InMemoryColumn.StringColumn) result.resultSet().columns().getFirst()).strings()).containsExactly("Minneapolis", "Duluth");
+    static final class DefaultLayout extends AbstractQueryTck {
+        @Override Engine newEngine() { return colq(new DataSystemColq.Layout(false, false)); }
+
+        @Test
+        void opaqueLambdaIsAFailureNotAFallback() {
+            engine.register("ints", ofColumns(ofInts(1, 2, 3)));
+            var query = new Query("ints");
+            query.rootNode.addCriteria(new Criteria.IntCriteria(0, i -> i > 1));
+            assertThat(engine.system().execute(query)).isInstanceOf(QueryResult.Failure.class);
+        }
     }
 
-    @Test
-    void opaqueLambdaIsAFailure() {
-        dataSystem.register("ints", ofColumns(ofInts(1, 2, 3)));
-        var query = new Query("ints");
-        query.rootNode.addCriteria(new Criteria.IntCriteria(0, i -> i > 1));
-        assertThat(dataSystem.execute(query)).isInstanceOf(QueryResult.Failure.class);
+    static final class HostResidentDictionary extends AbstractQueryTck {
+        @Override Engine newEngine() { return colq(DataSystemColq.Layout.forUnchangedLambdas()); }
+
+        @Test
+        void theReferencesOwnLambdasRunPerDistinctValue() {   // Runner.java:231,236: opaque lambdas over dictionary-encoded columns
+            engine.register("ints", ofColumns(ofInts(5, 10_050, 7, 10_050, 99_999)));
+            var query = new Query("ints");
+            query.rootNode.addCriteria(new Criteria.IntCriteria(0, i -> i >= 10_000 && i < 10_100));
+            var result = (QueryResult.Success) engine.system().execute(query);
+            assertThat(result.resultSet().size()).isEqualTo(2);
+        }
+    }
+
+    static final class DeviceIngest extends AbstractQueryTck {
+        @Override Engine newEngine() { return colq(DataSystemColq.Layout.deviceIngest()); }
+    }
+
+    /** Every table split over all visible GPUs, association keys global, driven from this one JVM. */
+    static final class AllGpusOneJvm extends AbstractQueryTck {
+        @Override Engine newEngine() {
+            int n = Integer.getInteger("colq.gpus", 2);
+            int[] devices = new int[n];
+            for (int i = 0; i < n; i++) devices[i] = i;
+            var ds = new DataSystemColqGroup(devices);
+            return new Engine() {
+                public DataSystem system() { return ds; }
+                public void register(String name, Table table) { ds.register(name, table); }
+                public void close() { ds.close(); }
+            };
+        }
+    }
+
+    /** The reference's own engine passes the same suite (structured predicates are ordinary IntPredicate / Predicate). */
+    static final class ReferenceSerialIndices extends AbstractQueryTck {
+        @Override Engine newEngine() {
+            var ds = new DataSystemSerialIndices();
+            return new Engine() {
+                public DataSystem system() { return ds; }
+                public void register(String name, Table table) { ds.register(name, table); }
+                public void close() { }
+            };
+        }
     }
 }
