@@ -110,7 +110,9 @@ typedef enum colq_option {
     COLQ_OPT_TAIL_PUBLISH = 8,
     /* 1 (default): a root node that ends in an int-predicate scan runs as ONE persistent launch -- predicate scan, deferred
        to-one chains, a tiny to-many hop feeding them (e.g. the 51-row state adjacency, with the multi-GPU mask COLLECT),
-       ordered compaction and the final gather (root_fused_kernel); 0: scan_rows / csr_pull / compact_fused launches.
+       ordered compaction and the final gather (root_fused_kernel); 0: scan_rows / csr_pull / compact_fused launches;
+       2: two launches -- the ordinary non-persistent scan_rows, which additionally lists every 512-row chunk's
+       survivors, then root_finish_kernel (chains, hop, ordered write, gather) over those lists.
        Needs COLQ_OPT_FUSED_COMPACT == 1. */
     COLQ_OPT_ROOT_FUSED = 9,
     /* 1 (default): a fused final gather whose plan already synchronises the ranks once per execution (a mask or bitmap

@@ -167,7 +167,7 @@ struct QNode {
 };
 
 // one kernel launch (or collective / memset) of a planned query
-enum OpKind { K_SCAN_ROWS, K_SCAN_CODES, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER, K_COMPACT_FUSED, K_COMPACT_LOOKBACK, K_ROOT_FUSED, K_PEER_BITS_ALLGATHER, K_PEER_BITS_REDUCE, K_PEER_MASK_PUBLISH, K_PEER_MASK_COLLECT, K_PEER_GATHER };
+enum OpKind { K_SCAN_ROWS, K_SCAN_CODES, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER, K_COMPACT_FUSED, K_COMPACT_LOOKBACK, K_ROOT_FUSED, K_ROOT_FINISH, K_PEER_BITS_ALLGATHER, K_PEER_BITS_REDUCE, K_PEER_MASK_PUBLISH, K_PEER_MASK_COLLECT, K_PEER_GATHER };
 
 struct Op {
     OpKind kind;
@@ -198,6 +198,7 @@ struct Op {
     PeerGatherParams pgather{};
     bool tail_publish = false;  // K_SCAN_STR / K_SCAN_CODES: the last CTA publishes the pushed mask to the peers
     bool dict_scan = false;  // K_SCAN_ROWS over the distinct values of a dictionary-encoded int column
+    bool list = false;       // K_SCAN_ROWS: the LIST instantiation in front of a K_ROOT_FINISH (per-chunk survivor lists)
     bool gather = false;  // K_COMPACT_FUSED: the peer-memory final gather is fused into this launch
     int publish_op = -1;  // K_PEER_MASK_COLLECT / a csr_pull with a fused collect: index of the matching publish
     // launch shape for scan_str
@@ -265,6 +266,7 @@ struct colq_ctx {
     void* h_stage = nullptr;
     int compact_grid[2 * (CF_MAX_GATHER + 1)] = {};  // co-resident grid of compact_fused_kernel<NG, GATHER>
     int root_fused_grid[SR_MAX_PRED + 1] = {};       // resident CTAs of root_fused_kernel<NP> on this device
+    int root_finish_grid = 0;                        // resident CTAs of root_finish_kernel
     u32* d_tile_counters = nullptr;                  // scan_str's tile-claim counter pair (zero between launches)
     std::map<std::pair<int, size_t>, int> str_occupancy;  // (kernel mode, dynamic smem bytes) -> resident CTAs per SM
 };
@@ -1063,8 +1065,12 @@ void launch_scan_rows(const Op& o, cudaStream_t s) {
 void stage_name(const Op& o, char* out, size_t cap) {
     if (o.kind == K_SCAN_CODES) snprintf(out, cap, "scan_codes%s%s", o.codes.push.fk ? "+push" : "", o.tail_publish ? "+publish" : "");
     else if (o.kind == K_SCAN_ROWS && o.dict_scan) snprintf(out, cap, "scan_rows_dictionary");
+    else if (o.kind == K_SCAN_ROWS && o.list) snprintf(out, cap, "scan_rows<%d,%d,list>", o.np, o.ng);
     else if (o.kind == K_SCAN_ROWS) snprintf(out, cap, "scan_rows<%d,%d,%s>%s", o.np, o.ng, o.eager ? "eager" : "lazy", o.rows.push.fk ? "+push" : "");
     else if (o.kind == K_SCAN_STR) snprintf(out, cap, "%s<op%d>%s%s", o.name, o.str.op, o.str.push.fk ? "+push" : "", o.tail_publish ? "+publish" : "");
+    else if (o.kind == K_ROOT_FINISH)
+        snprintf(out, cap, "root_finish<%d>%s%s", o.ng, o.rfused.pre.n > 0 ? (o.rfused.pre.pm.n_words > 0 ? "+collect+csr" : "+csr") : "",
+                 o.rfused.pg.n_ranks > 0 ? "+gather" : "");
     else if (o.kind == K_ROOT_FUSED)
         snprintf(out, cap, "root_fused<%d,%d>%s%s%s", o.np, o.ng, o.rfused.pre.n > 0 ? (o.rfused.pre.pm.n_words > 0 ? "+collect+csr" : "+csr") : "",
                  o.rfused.pg.n_ranks > 0 ? "+gather" : "", "");
@@ -1098,6 +1104,23 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
             } else {
                 // A/B variant (COLQ_SCAN_ROWS_TMA=1): the plain single-predicate scan staged through shared memory with TMA bulk
                 // copies instead of per-lane LDG.128 (measured slower or equal on B200: profiles/r02_scan_rows_tma_ab.txt)
+                if (o.list) {
+                    // the root's scan in front of root_finish_kernel; a programmatic dependent of the string scan when it reads
+                    // nothing an earlier launch wrote
+                    static const bool pdl = !(getenv("COLQ_PDL") && getenv("COLQ_PDL")[0] == '0');
+                    cudaLaunchConfig_t cfg{};
+                    cfg.gridDim = dim3((unsigned)((o.rows.n + SR_BLOCK_ROWS - 1) / SR_BLOCK_ROWS)); cfg.blockDim = dim3(SR_THREADS); cfg.stream = s;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    at[0].val.programmaticStreamSerializationAllowed = (pdl && o.rows.in_bits == nullptr) ? 1 : 0;
+                    cfg.attrs = at; cfg.numAttrs = 1;
+                    if (cfg.gridDim.x > 0) {
+                        if (o.np == 1) CU(ctx, cudaLaunchKernelEx(&cfg, scan_rows_kernel<1, 0, false, true>, o.rows));
+                        else CU(ctx, cudaLaunchKernelEx(&cfg, scan_rows_kernel<2, 0, false, true>, o.rows));
+                        q->timing.kernel_launches++;
+                    }
+                    break;
+                }
                 static const bool tma_env = getenv("COLQ_SCAN_ROWS_TMA") && getenv("COLQ_SCAN_ROWS_TMA")[0] == '1';
                 const bool plain = o.np == 1 && o.ng == 0 && !o.eager && o.rows.in_bits == nullptr && o.rows.push.fk == nullptr &&
                                    o.rows.pred[0].promote == nullptr && o.rows.out_bits != nullptr && o.rows.n > 0;
@@ -1238,6 +1261,28 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
                 case 1: compact_lookback_kernel<1><<<o.grid, CP_THREADS, 0, s>>>(o.clook); break;
                 default: compact_lookback_kernel<2><<<o.grid, CP_THREADS, 0, s>>>(o.clook); break;
             }
+            q->timing.kernel_launches++;
+            break;
+        }
+        case K_ROOT_FINISH: {
+            RootFusedParams& P = o.rfused;
+            if (P.pre.pm.n_words > 0) P.pre.pm.epoch = q->ops[o.publish_op].pmask.epoch;
+            if (P.pg.n_ranks > 0) {
+                P.pg.epoch = ++ctx->peer.gather_epoch;
+                q->lazy_pg = P.pg;
+            }
+            if (++q->rf_epoch == 0xffffffffu) {
+                CU(ctx, cudaMemsetAsync(q->rf_state_buf.ptr, 0, q->rf_state_buf.bytes, s));
+                q->rf_epoch = 1;
+            }
+            P.epoch = q->rf_epoch;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(o.grid); cfg.blockDim = dim3(RF_THREADS); cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CU(ctx, cudaLaunchKernelEx(&cfg, root_finish_kernel, P));
             q->timing.kernel_launches++;
             break;
         }
@@ -1465,7 +1510,72 @@ colq_status run_pipeline(colq_query* q) {
         return COLQ_OK;
     };
     bool coop_gather = peer_gather && q->opt_fused_gather && q->opt_fused_compact == 1;  // the gather rides on the index writer
-    if (fuse_root) {
+    // COLQ_OPT_ROOT_FUSED == 2: the bandwidth half stays the ordinary non-persistent scan_rows (LIST instantiation: it also
+    // lists every chunk's survivors), the latency half is root_finish_kernel; tables too large for its per-CTA prefix
+    // array use the single persistent kernel
+    bool split_root = false;
+    if (fuse_root && q->opt_root_fused == 2) {
+        if (ctx->root_finish_grid == 0) {
+            int occ = 0;
+            CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)root_finish_kernel, RF_THREADS, 0));
+            ctx->root_finish_grid = ctx->sm_count * std::max(1, occ);
+        }
+        const int64_t n_chunks = (n + SR_WARP_ROWS - 1) / SR_WARP_ROWS;
+        split_root = n_chunks <= (int64_t)ctx->root_finish_grid * RF_MAX_UPC;
+    }
+    if (fuse_root && split_root) {
+        Op& sc = q->ops.back();
+        const int64_t n_chunks = (n + SR_WARP_ROWS - 1) / SR_WARP_ROWS;
+        void *lists, *ucount;
+        ST(pool_alloc(q, (size_t)std::max<int64_t>(n_chunks, 1) * (SR_WARP_ROWS / 32) * 4, &lists));
+        ST(pool_alloc(q, (size_t)std::max<int64_t>(n_chunks, 1) * 4 + 16, &ucount));
+        sc.list = true;
+        sc.rows.lists = (u32*)lists; sc.rows.ucount = (u32*)ucount; sc.rows.list_cap = SR_WARP_ROWS / 32;
+        sc.acct_bytes += n_chunks * 4;
+        Op f{};
+        f.kind = K_ROOT_FINISH; f.node = 0; f.np = sc.np; f.ng = (int)q->deferred.size();
+        f.acct_rows = n; f.acct_bytes = n_chunks * 4;
+        RootFusedParams& P = f.rfused;
+        P.n = n;
+        P.bits = root.bits;
+        P.n_chunks = n_chunks;
+        P.lists = (u32*)lists; P.ucount = (u32*)ucount; P.list_cap = SR_WARP_ROWS / 32;
+        f.grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_chunks + 31) / 32, ctx->root_finish_grid));
+        P.units_per_cta = std::max<int64_t>(1, (n_chunks + f.grid - 1) / f.grid);
+        if (q->rf_state_ctas < f.grid) {
+            ST(dev_alloc(ctx, q->rf_state_buf, 64 + (size_t)f.grid * 8));
+            CU(ctx, cudaMemsetAsync(q->rf_state_buf.ptr, 0, q->rf_state_buf.bytes, ctx->stream));
+            q->rf_state_ctas = f.grid;
+            q->rf_epoch = 0;
+        }
+        P.counters = (u32*)q->rf_state_buf.ptr;
+        P.cta_state = (u64*)((char*)q->rf_state_buf.ptr + 64);
+        P.ng = f.ng;
+        for (int g = 0; g < f.ng; ++g) P.gather[g] = q->deferred[g];
+        P.total = q->d_total; P.out_idx = q->d_idx; P.capacity = q->idx_capacity; P.row_base = RT.row_base;
+        for (int g = 0; g < f.ng && P.pre.n == 0; ++g) {
+            if (!P.gather[g].bits) continue;
+            for (size_t k = 0; k < q->ops.size(); ++k) {
+                const Op& c = q->ops[k];
+                if (c.kind != K_CSR_PULL || c.csr.out_bits != P.gather[g].bits || c.csr.push.fk != nullptr) continue;
+                if (c.csr.n <= 0 || c.csr.n > RF_PRE_ROWS || c.csr.nnz > RF_PRE_EDGES || c.csr.n_child > PUSH_SMEM_BITS) continue;
+                P.pre = c.csr;
+                f.publish_op = c.publish_op;
+                f.acct_bytes += c.acct_bytes;
+                q->ops.erase(q->ops.begin() + k);
+                for (Op& o : q->ops)
+                    if (o.publish_op > (int)k) o.publish_op -= 1;
+                if (f.publish_op > (int)k) f.publish_op -= 1;
+                break;
+            }
+        }
+        if (P.pre.n > 0)
+            for (int g = 0; g < f.ng; ++g)
+                if (P.gather[g].bits == P.pre.out_bits) P.pre_mask |= 1u << g;
+        if (coop_gather) ST(fill_fused_gather(P.pg));
+        f.name = "root_finish";
+        q->ops.push_back(f);
+    } else if (fuse_root) {
         // ---- the root's scan + chains + (tiny to-many hop) + compaction + gather as one persistent launch
         Op sc = q->ops.back();
         q->ops.pop_back();
@@ -2906,6 +3016,7 @@ colq_status colq_query_create(colq_ctx* ctx, const char* table_name, colq_query*
     if (!ctx || !table_name || !out_query) return COLQ_THROW_NULL;
     colq_query* q = new colq_query();
     if (const char* e = getenv("COLQ_COMPACT")) q->opt_fused_compact = atoi(e);  // experiment knob: default compaction kernel
+    if (const char* e = getenv("COLQ_ROOT_FUSED")) q->opt_root_fused = atoi(e);   // experiment knob: default root plan (0, 1, 2)
     q->ctx = ctx;
     q->table_name = table_name;
     q->nodes.emplace_back();  // rootNode (DS/Query.java:22-25)

@@ -190,6 +190,11 @@ struct ScanRowsParams {
     IntPredD pred[SR_MAX_PRED];
     GatherD gather[SR_MAX_GATHER];
     PushD push;
+    // LIST instantiations (the root's scan in front of root_finish_kernel): every warp also leaves the surviving rows of
+    // its 512-row chunk, in row order, in lists[chunk][list_cap] and their number in ucount[chunk] (> list_cap: overflow)
+    u32* lists;
+    u32* ucount;
+    int list_cap;
 };
 
 __device__ __forceinline__ bool gather_eval(const GatherD& g, int64_t r, int level) {
@@ -216,7 +221,7 @@ __device__ __forceinline__ u32 range4(const int4& v, int32_t lo, u32 span) {
 // NP predicates, NG gather chains.  EAGER: the first hop of every chain is loaded with coalesced 128-bit loads
 // for all rows (right when no selective predicate precedes it); otherwise chains are walked lazily, only for rows
 // that survived the predicates (the 0.16 %-selective population filter skips almost every FK sector).
-template <int NP, int NG, bool EAGER>
+template <int NP, int NG, bool EAGER, bool LIST = false>
 __global__ void __launch_bounds__(SR_THREADS) scan_rows_kernel(const ScanRowsParams P) {
     __shared__ u32 s_reach[PUSH_SMEM_WORDS];
     const int lane = threadIdx.x & 31;
@@ -362,7 +367,43 @@ __global__ void __launch_bounds__(SR_THREADS) scan_rows_kernel(const ScanRowsPar
             for (int j = 1; j < SR_V; ++j) out = ((lane >> 2) == j) ? y[j] : out;
             if (lane < 4 * SR_V) P.out_bits[(wbase >> 5) + lane] = out;
         }
+
+        // ---- LIST: the chunk's survivors, in row order (vector j, then lane, then element), for root_finish_kernel
+        if (LIST) {
+            const int64_t chunk = wbase / SR_WARP_ROWS;
+            u32* my_list = P.lists + (size_t)chunk * P.list_cap;
+            u32 cnt = 0;
+            if (__ballot_sync(FULL_MASK, (nib[0] | nib[1] | nib[2] | nib[3]) != 0) != 0) {
+#pragma unroll
+                for (int j = 0; j < SR_V; ++j) {
+                    const u32 m = nib[j];
+                    const u32 mine = __popc(m);
+                    if (__ballot_sync(FULL_MASK, mine != 0) == 0) continue;
+                    u32 incl = mine;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const u32 t = __shfl_up_sync(FULL_MASK, incl, d);
+                        if (lane >= d) incl += t;
+                    }
+                    const u32 tot = __shfl_sync(FULL_MASK, incl, 31);
+                    if (cnt + tot <= (u32)P.list_cap) {
+                        u32 pos = cnt + incl - mine, mm = m;
+                        while (mm) {
+                            const int e = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            my_list[pos++] = (u32)(wbase + j * 128 + lane * 4 + e);
+                        }
+                    }
+                    cnt += tot;  // keeps counting past the cap: cnt > list_cap marks the overflow
+                }
+            }
+            if (lane == 0) P.ucount[chunk] = cnt;
+        }
     }
+    // LIST launches sit between the string scan (whose programmatic dependent they are: they read nothing of it) and
+    // root_finish_kernel, which does: this launch must not COMPLETE before that scan has, so that the finish kernel's
+    // own dependency wait covers both.  A no-op in ordinary launches.
+    if (LIST) pdl_wait();
 
     if (do_push) {
         __syncthreads();
@@ -1960,6 +2001,9 @@ struct RootFusedParams {
     int64_t row_base;
     PeerGatherParams pg;         // pg.n_ranks > 0: final gather fused in
     u64* dbg;                    // (COLQ_RF_DEBUG builds) 8 globaltimer stamps per CTA
+    // root_finish_kernel only (the candidates were listed per 512-row chunk by scan_rows<.., LIST>):
+    u32* ucount;                 // [n_chunks] candidates of the chunk (> list_cap: its list overflowed)
+    int64_t units_per_cta;       // ticket v finishes the chunks [v * units_per_cta, (v + 1) * units_per_cta); <= RF_MAX_UPC
 };
 
 __device__ __forceinline__ bool rf_chain(const GatherD& g, const u32* bits, int64_t r) {
@@ -1972,6 +2016,46 @@ __device__ __forceinline__ bool rf_chain(const GatherD& g, const u32* bits, int6
         r = t;
     }
     return bits == nullptr ? true : bit_test(bits, r);
+}
+
+// The folded tiny to-many hop of root_fused / root_finish (and the COLLECT of the mask exchange in front of it) into shared
+// memory: s_pre receives the hop's output bits.  Block-wide (RF_THREADS threads); every CTA runs it redundantly.
+__device__ __forceinline__ void rf_run_pre(const CsrPullParams& C, u32 vcta, u32* s_pre, u32* s_child, int32_t* s_tgt) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cw = (int)((C.n_child + 31) >> 5);
+    if (C.pm.n_words > 0) {
+        // COLLECT half of the OR-exchange, straight into shared memory (every CTA polls its own rank's mailbox)
+        const PeerMaskParams& M = C.pm;
+        const size_t area = (size_t)(M.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
+        const uint8_t* mine = M.peers[M.rank] + area;
+        for (int w = tid; w < cw; w += RF_THREADS) {
+            u32 v = 0;
+            for (int r = 0; r < M.n_ranks; ++r) v |= ll_load(reinterpret_cast<const u64*>(mine + (size_t)r * MASK_SLOT_BYTES + 16) + w, M.epoch, M.status);
+            s_child[w] = v;
+            if (vcta == 0) M.reach[w] = v;  // the reduced mask stays readable (node cardinalities)
+        }
+    } else {
+        for (int w = tid; w < cw; w += RF_THREADS) s_child[w] = C.child_bits != nullptr ? __ldcg(C.child_bits + w) : 0xffffffffu;
+    }
+    for (int i = tid; i < (int)C.nnz; i += RF_THREADS) s_tgt[i] = C.targets[i];
+    __syncthreads();
+    const int rows_pad = (int)((C.n + 31) & ~(int64_t)31);
+    for (int r = tid; r < rows_pad; r += RF_THREADS) {
+        bool ok = false;
+        if (r < C.n) {
+            const int64_t e0 = C.offsets[r], e1 = C.offsets[r + 1];
+            for (int64_t e = e0; e < e1 && !ok; ++e) {
+                const int32_t t = s_tgt[e];
+                if (t >= 0 && t < C.n_child) ok = (s_child[t >> 5] >> (t & 31)) & 1u;
+            }
+        }
+        u32 word = __ballot_sync(FULL_MASK, ok);
+        if (C.in_bits != nullptr) word &= C.in_bits[r >> 5];
+        if (lane == 0) {
+            s_pre[r >> 5] = word;
+            if (vcta == 0 && C.out_bits != nullptr) C.out_bits[r >> 5] = word;
+        }
+    }
 }
 
 #ifdef COLQ_RF_DEBUG
@@ -1998,44 +2082,6 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
     const u32 vcta = s_ticket;
     RF_STAMP(0);
 
-    // ---- the folded tiny to-many hop (and the mask exchange in front of it) into shared memory.  Block-wide.
-    auto run_pre = [&]() {
-        const CsrPullParams& C = P.pre;
-        const int cw = (int)((C.n_child + 31) >> 5);
-        if (C.pm.n_words > 0) {
-            // COLLECT half of the OR-exchange, straight into shared memory (every CTA polls its own rank's mailbox)
-            const PeerMaskParams& M = C.pm;
-            const size_t area = (size_t)(M.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
-            const uint8_t* mine = M.peers[M.rank] + area;
-            for (int w = tid; w < cw; w += RF_THREADS) {
-                u32 v = 0;
-                for (int r = 0; r < M.n_ranks; ++r) v |= ll_load(reinterpret_cast<const u64*>(mine + (size_t)r * MASK_SLOT_BYTES + 16) + w, M.epoch, M.status);
-                s_child[w] = v;
-                if (vcta == 0) M.reach[w] = v;  // the reduced mask stays readable (node cardinalities)
-            }
-        } else {
-            for (int w = tid; w < cw; w += RF_THREADS) s_child[w] = C.child_bits != nullptr ? __ldcg(C.child_bits + w) : 0xffffffffu;
-        }
-        for (int i = tid; i < (int)C.nnz; i += RF_THREADS) s_tgt[i] = C.targets[i];
-        __syncthreads();
-        const int rows_pad = (int)((C.n + 31) & ~(int64_t)31);
-        for (int r = tid; r < rows_pad; r += RF_THREADS) {
-            bool ok = false;
-            if (r < C.n) {
-                const int64_t e0 = C.offsets[r], e1 = C.offsets[r + 1];
-                for (int64_t e = e0; e < e1 && !ok; ++e) {
-                    const int32_t t = s_tgt[e];
-                    if (t >= 0 && t < C.n_child) ok = (s_child[t >> 5] >> (t & 31)) & 1u;
-                }
-            }
-            u32 word = __ballot_sync(FULL_MASK, ok);
-            if (C.in_bits != nullptr) word &= C.in_bits[r >> 5];
-            if (lane == 0) {
-                s_pre[r >> 5] = word;
-                if (vcta == 0 && C.out_bits != nullptr) C.out_bits[r >> 5] = word;
-            }
-        }
-    };
     // Ordering against the kernel in front of this one (P.pdl: launched as a programmatic dependent of it, typically the
     // string scan that produces the mask the folded hop reads): phase A reads only the root's own predicate columns, so
     // it may run while that kernel drains; everything it produced is touched only after pdl_wait() below.  If the root
@@ -2180,7 +2226,7 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
     // ======================= phase B =======================
     // ---- (1) the folded hop (multi-GPU: the COLLECT of the mask exchange first -- the wait for the slowest rank has been
     //      hiding behind phase A)
-    if (P.pre.n > 0) run_pre();
+    if (P.pre.n > 0) rf_run_pre(P.pre, vcta, s_pre, s_child, s_tgt);
     __syncthreads();  // s_wcnt, s_overflow, s_pre
     RF_STAMP(2);
     if (tid == 0) {
@@ -2344,6 +2390,267 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
     __syncthreads();
     if (tid == 0) __threadfence();
     if (tid == 0) s_last = (atomicAdd(&P.counters[1], 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    RF_STAMP(6);
+    if (s_last) {
+        if (tid == 0) {
+            P.counters[0] = 0;
+            P.counters[1] = 0;
+        }
+        if (gather) gather_tail(P.pg, P.total);
+    }
+    RF_STAMP(7);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4+K3  root_finish: the latency half of the root node as a launch of its own (COLQ_OPT_ROOT_FUSED=2).
+//
+// The bandwidth half is the ordinary NON-persistent scan_rows<NP, 0, false, LIST> -- 71 k short-lived CTAs walking the
+// column in address order at 8 CTAs/SM and 32 registers, the access pattern that reaches 7.0 TB/s, where the persistent
+// root_fused_kernel's phase A reaches 6.4 (r02 timelines) -- which additionally leaves every 512-row chunk's survivors in
+// lists[chunk][list_cap] and their number in ucount[chunk].  This kernel is the rest: ticket v takes the chunks
+// [v * units_per_cta, ...), builds the exclusive prefix of their counts in shared memory, walks the chains of its ~800
+// candidates RF_ILP per thread (failed bits cleared in the mask with atomicAnd), publishes its survivor count, sums the counts
+// of all lower tickets (decoupled look-back), and writes the indices in order -- locally and, multi-GPU, as flag-in-data
+// words into every peer's slot.  The folded to-many hop, the mask COLLECT, the dense fallback (a chunk whose list
+// overflowed: this CTA walks its part of the mask word by word) and the tail are those of root_fused_kernel.
+// r01's compact_fused did this work in 57.6 us by reading the dense 37 MB mask twice across a grid barrier.
+// ---------------------------------------------------------------------------------------------
+constexpr int RF_MAX_UPC = 2048;  // chunks one CTA finishes (shared-memory prefix array)
+
+__global__ void __launch_bounds__(RF_THREADS, 4) root_finish_kernel(const RootFusedParams P) {
+    __shared__ u32 s_warp[33];
+    __shared__ u32 s_ticket, s_last, s_overflow;
+    __shared__ u32 s_uoff[RF_MAX_UPC + 1];     // exclusive prefix of this CTA's chunk counts
+    __shared__ u64 s_base;
+    __shared__ u64 s_part[RF_WARPS];
+    __shared__ u32 s_pre[PUSH_SMEM_WORDS];
+    __shared__ u32 s_child[PUSH_SMEM_WORDS];
+    __shared__ int32_t s_tgt[RF_PRE_EDGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        s_ticket = atomicAdd(&P.counters[0], 1u);
+        s_overflow = 0;
+    }
+    pdl_wait();  // everything below was produced by earlier launches (lists, counts, mask words, the exchanged mask)
+    __syncthreads();
+    const u32 vcta = s_ticket;
+    RF_STAMP(0);
+    if (P.pre.n > 0) rf_run_pre(P.pre, vcta, s_pre, s_child, s_tgt);
+    RF_STAMP(1);
+
+    // ---- this CTA's chunks and the exclusive prefix of their candidate counts
+    const int64_t u_lo = (int64_t)vcta * P.units_per_cta;
+    const int64_t u_end = u_lo + P.units_per_cta;
+    const int64_t u_hi = u_end < P.n_chunks ? u_end : P.n_chunks;
+    const int nu = u_hi > u_lo ? (int)(u_hi - u_lo) : 0;
+    {
+        u32 carry = 0;
+        for (int i0 = 0; i0 < nu; i0 += RF_THREADS) {
+            const int i = i0 + tid;
+            u32 c = 0;
+            if (i < nu) {
+                c = __ldcg(P.ucount + u_lo + i);
+                if (c > (u32)P.list_cap) {
+                    s_overflow = 1;
+                    c = 0;
+                }
+            }
+            u32 tot;
+            const u32 ex = block_exclusive_scan(c, s_warp, tot);
+            if (i < nu) s_uoff[i] = carry + ex;
+            carry += tot;
+            __syncthreads();
+        }
+        if (tid == 0) s_uoff[nu] = carry;
+    }
+    __syncthreads();  // s_uoff, s_overflow, s_pre
+    RF_STAMP(2);
+    const bool dense = s_overflow != 0;
+    const u32 n_c = s_uoff[nu];
+    const int64_t words_per_unit = SR_WARP_ROWS / 32;
+    const int64_t n_words = (P.n + 31) >> 5;
+    const int64_t w_lo = u_lo * words_per_unit;  // this CTA's mask words
+    const int64_t w_end = u_end * words_per_unit;
+    const int64_t w_hi = w_end < n_words ? w_end : n_words;
+    const u32* gbits[CF_MAX_GATHER];
+#pragma unroll
+    for (int g = 0; g < CF_MAX_GATHER; ++g) gbits[g] = ((P.pre_mask >> g) & 1u) ? s_pre : P.gather[g].bits;
+    // candidate i of this CTA -> its list entry (the chunk is found by bisection of the shared prefix array)
+    auto entry = [&](u32 i) -> u32* {
+        int lo = 0, hi = nu;  // s_uoff[lo] <= i < s_uoff[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_uoff[mid] <= i) lo = mid;
+            else hi = mid;
+        }
+        return P.lists + ((size_t)u_lo + lo) * P.list_cap + (i - s_uoff[lo]);
+    };
+
+    // ---- chains of the candidates; count what is left
+    u32 kept = 0;
+    if (!dense) {
+        if (P.ng == 0) {
+            kept = tid == 0 ? n_c : 0;
+        } else {
+            // RF_ILP candidates per thread at a time, walked level by level: the dependent loads of one chain are
+            // serial, those of different candidates are all in flight together
+            for (u32 i0 = 0; i0 < n_c; i0 += RF_THREADS * RF_ILP) {
+                u32* ep[RF_ILP];
+                u32 row[RF_ILP];
+                bool ok[RF_ILP], pass[RF_ILP];
+#pragma unroll
+                for (int k = 0; k < RF_ILP; ++k) {
+                    const u32 i = i0 + k * RF_THREADS + tid;
+                    ok[k] = i < n_c;
+                    ep[k] = ok[k] ? entry(i) : P.lists;
+                    row[k] = ok[k] ? __ldcg(ep[k]) : 0u;
+                    pass[k] = ok[k];
+                }
+                for (int g = 0; g < P.ng; ++g) {
+                    const GatherD& G = P.gather[g];
+                    int64_t r[RF_ILP];
+#pragma unroll
+                    for (int k = 0; k < RF_ILP; ++k) r[k] = row[k];
+                    for (int d = 0; d < G.depth; ++d) {
+                        int32_t t[RF_ILP];
+#pragma unroll
+                        for (int k = 0; k < RF_ILP; ++k) t[k] = pass[k] ? G.fk[d][r[k]] : 0;
+#pragma unroll
+                        for (int k = 0; k < RF_ILP; ++k) {
+                            if (pass[k] && (t[k] < 0 || t[k] >= G.n[d])) {
+                                if (t[k] != -1 && G.oob != nullptr) *G.oob = 1u;
+                                pass[k] = false;
+                            }
+                            r[k] = t[k];
+                        }
+                    }
+                    if (gbits[g] != nullptr) {
+#pragma unroll
+                        for (int k = 0; k < RF_ILP; ++k) pass[k] = pass[k] && bit_test(gbits[g], pass[k] ? r[k] : 0);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < RF_ILP; ++k) {
+                    if (!ok[k]) continue;
+                    if (pass[k]) ++kept;
+                    else {
+                        atomicAnd(&P.bits[row[k] >> 5], ~(1u << (row[k] & 31)));
+                        *ep[k] = row[k] | 0x80000000u;
+                    }
+                }
+            }
+        }
+    } else {
+        for (int64_t w0 = w_lo + (int64_t)tid * 4; w0 < w_hi; w0 += RF_THREADS * 4) {
+            uint4 v = __ldcg(reinterpret_cast<const uint4*>(P.bits + w0));
+            u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (w0 + j >= w_hi) { w[j] = 0; continue; }
+                u32 m = w[j], keep = w[j];
+                if (P.ng > 0) {
+                    const int64_t rb = (w0 + j) << 5;
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        bool ok = true;
+                        for (int g = 0; g < P.ng; ++g) ok = ok && rf_chain(P.gather[g], gbits[g], rb + b);
+                        if (!ok) keep &= ~(1u << b);
+                    }
+                    if (keep != w[j]) P.bits[w0 + j] = keep;
+                }
+                kept += __popc(keep);
+            }
+        }
+    }
+    u32 cta_count;
+    block_exclusive_scan(kept, s_warp, cta_count);
+    RF_STAMP(3);
+
+    // ---- publish, then sum the counts of every lower ticket
+    if (tid == 0) st_volatile_u64(P.cta_state + vcta, ((u64)P.epoch << 32) | cta_count);
+    u64 part = 0;
+    for (u32 j = tid; j < vcta; j += RF_THREADS) {
+        u64 st;
+        do { st = ld_volatile_u64(P.cta_state + j); } while ((u32)(st >> 32) != P.epoch);
+        part += (u32)st;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL_MASK, part, d);
+    __syncthreads();
+    if (lane == 0) s_part[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+        u64 b = 0;
+        for (int w = 0; w < RF_WARPS; ++w) b += s_part[w];
+        s_base = b;
+    }
+    __syncthreads();
+    const u64 base = s_base;
+    RF_STAMP(4);
+
+    // ---- ordered write
+    const bool gather = P.pg.n_ranks > 0;
+    if (!dense) {
+        u64 running = base;
+        for (u32 i0 = 0; i0 < n_c; i0 += RF_THREADS) {
+            const u32 i = i0 + tid;
+            u32 row = 0x80000000u;
+            if (i < n_c) row = __ldcg(entry(i));
+            const u32 valid = (row & 0x80000000u) ? 0u : 1u;
+            u32 tot;
+            const u32 ex = block_exclusive_scan(valid, s_warp, tot);
+            if (valid) {
+                const int64_t pos = (int64_t)(running + ex);
+                const int32_t v = (int32_t)(P.row_base + row);
+                if (pos < P.capacity) P.out_idx[pos] = v;
+                if (gather) gather_store(P.pg, pos, v);
+            }
+            running += tot;
+            __syncthreads();
+        }
+    } else {
+        u64 running = base;
+        for (int64_t t0 = w_lo; t0 < w_hi; t0 += RF_THREADS * 4) {
+            const int64_t w0 = t0 + (int64_t)tid * 4;
+            u32 w[4] = {0, 0, 0, 0};
+            if (w0 < w_hi) {
+                const uint4 v = __ldcg(reinterpret_cast<const uint4*>(P.bits + w0));
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (w0 + j >= w_hi) w[j] = 0;
+            }
+            const u32 c = __popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3]);
+            u32 tot;
+            const u32 ex = block_exclusive_scan(c, s_warp, tot);
+            int64_t pos = (int64_t)(running + ex);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                u32 m = w[j];
+                const int64_t rb = P.row_base + ((w0 + j) << 5);
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (pos < P.capacity) P.out_idx[pos] = (int32_t)(rb + b);
+                    if (gather) gather_store(P.pg, pos, (int32_t)(rb + b));
+                    ++pos;
+                }
+            }
+            running += tot;
+            __syncthreads();
+        }
+    }
+    RF_STAMP(5);
+
+    // ---- tail: the highest ticket knows the grand total; the last CTA to finish re-arms the counters
+    if (tid == 0 && vcta == gridDim.x - 1) *P.total = base + cta_count;
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&P.counters[1], 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
     __syncthreads();
     RF_STAMP(6);
     if (s_last) {

@@ -51,7 +51,8 @@ def main():
                                                               (1, True, 1, 1, 0, 1, 0), (1, True, 1, 1, 0, 0, 0), (1, True, 1, 2, 0, 1, 1),
                                                               (1, True, 1, 1, 1, 1, 0), (1, True, 0, 1, 1, 0, 1), (1, False, 1, 1, 1, 1, 1),
                                                               (1, False, 1, 1, 0, 1, 0), (1, True, 1, 0, 0, 1, 1), (0, True, 1, 1, 0, 1, 1),
-                                                              (0, True, 1, 1, 0, 1, 0), (0, False, 1, 2, 0, 1, 1), (1, True, 1, 1, 1, 1, 1, 0)):
+                                                              (0, True, 1, 1, 0, 1, 0), (0, False, 1, 2, 0, 1, 1), (1, True, 1, 1, 1, 1, 1, 0),
+                        (1, True, 1, 1, 1, 1, 2), (1, True, 1, 1, 0, 1, 2), (0, True, 1, 1, 0, 1, 2), (1, True, 1, 1, 1, 0, 2, 0)):
             peer, lazy, defer, fused, fgather, tail, rootf = variant[:7]
             lazy_wait = variant[7] if len(variant) > 7 else 1   # COLQ_OPT_LAZY_GATHER_WAIT
             if True:
@@ -73,7 +74,8 @@ def main():
                 assert np.array_equal(res.indices, want), (rank, perturbed, "second execution")
                 names = [n for n, *_ in cq.profile()]
                 root_fused = rootf and fused == 1 and lazy and defer   # (eager plans end in a scan with the gathers inside)
-                assert any(n.startswith("root_fused") for n in names) == bool(root_fused), names
+                assert any(n.startswith("root_fused") for n in names) == bool(root_fused and rootf == 1), names
+                assert any(n.startswith("root_finish") for n in names) == bool(root_fused and rootf == 2), names
                 if peer and os.environ.get("COLQ_PEER", "1") != "0":
                     pub = [i for i, n in enumerate(names) if n.endswith("publish")]   # own launch, or the scan's last CTA
                     assert len(pub) == 1, names

@@ -40,8 +40,10 @@ DICT_ALL_HOST = dict(lazy_fk=True, dictionary="all", residency="host")
 INGEST_DEVICE = dict(lazy_fk=True, ingest="device")     # associations go up as CSRs, the GPU validates and classifies them
 INGEST_DEVICE_DICT = dict(lazy_fk=True, ingest="device", dictionary=True)   # + string columns dictionary-encoded by the GPU
 INGEST_DEVICE_DICT_HOST = dict(lazy_fk=True, ingest="device", dictionary=True, residency="host")
+SPLIT_ROOT = dict(lazy_fk=True, options={9: 2})          # COLQ_OPT_ROOT_FUSED=2: scan_rows<..,list> + root_finish launches
+SPLIT_ROOT_HOST = dict(lazy_fk=True, residency="host", options={9: 2})
 UNFUSED = dict(lazy_fk=True, options={9: 0})             # COLQ_OPT_ROOT_FUSED=0: scan_rows / csr_pull / compact_fused launches (r01 plan)
-ALL_VARIANTS = (LAZY, EAGER, NO_DEFER, HOST, HOST_NO_PROMOTE, HOST_KERNEL_PROMOTE, DICT, DICT_HOST, LOOKBACK, DICT_ALL, DICT_ALL_HOST, UNFUSED, INGEST_DEVICE, INGEST_DEVICE_DICT, INGEST_DEVICE_DICT_HOST)
+ALL_VARIANTS = (LAZY, EAGER, NO_DEFER, HOST, HOST_NO_PROMOTE, HOST_KERNEL_PROMOTE, DICT, DICT_HOST, LOOKBACK, DICT_ALL, DICT_ALL_HOST, UNFUSED, SPLIT_ROOT, SPLIT_ROOT_HOST, INGEST_DEVICE, INGEST_DEVICE_DICT, INGEST_DEVICE_DICT_HOST)
 
 
 def both(engines, build, queries, lazy_modes=(True, False), variants=None):
@@ -286,7 +288,7 @@ def test_deferred_chains_are_planned_into_the_compaction(engines, base_geography
     """The root's lazy FK chains move from the row scan into the fused compaction kernel (COLQ_OPT_DEFER_CHAINS)."""
     new_gpu, _ = engines
     geo = G.build_tables(2, base=base_geography)
-    for opts, want_names in (({}, ["root_fused<1,1>+csr"]), ({9: 0}, ["scan_rows<1,0,lazy>", "csr_pull", "compact_fused+chains"]),
+    for opts, want_names in (({9: 1}, ["root_fused<1,1>+csr"]), ({9: 2}, ["scan_rows<1,0,list>", "root_finish<1>+csr"]), ({9: 0}, ["scan_rows<1,0,lazy>", "csr_pull", "compact_fused+chains"]),
                              ({4: 2}, ["scan_rows<1,0,lazy>", "compact_lookback+chains"]), ({5: 0}, ["scan_rows<1,1,lazy>", "compact_fused"])):
         ds = new_gpu(options=opts)
         G.register_geography(ds, geo)
@@ -383,7 +385,7 @@ def test_three_launch_compaction_path_matches(engines, base_geography):
         got = ds.last_query.fetch(want_indices=True)
         assert np.array_equal(got.indices, oracle.last_indices)
         names = [n for n, *_ in ds.last_query.profile()]
-        assert any(n.startswith("root_fused") for n in names) == (fused == 1)   # the root's scan, chains and compaction in one launch
+        assert any(n.startswith("root_f") for n in names) == (fused == 1)   # root_fused / root_finish: the root's chains and compaction fused
         assert not any(n.startswith("compact_fused") for n in names)
         assert any(n.startswith("compact_lookback") for n in names) == (fused == 2)
         ds.close()
