@@ -6,14 +6,20 @@
 // but evaluates the node tree bottom-up in ONE post-order pass (the reference's repeated leaf-to-root walks reach
 // the same fixed point because every step is a monotone AND), and fuses work across nodes:
 //   * a hop through a forward to-one column is PULLED (parent row tests its child's bit) inside the parent's scan,
-//   * chains of criteria-free to-one hops are walked lazily only for rows that survived the parent's predicates -- for
-//     the root node inside the compaction kernel, so that the root's row scan stays a pure coalesced stream,
+//   * chains of criteria-free to-one hops are walked lazily only for rows that survived the parent's predicates,
 //   * a hop through a reverse column is PUSHED by the epilogue of the child's own scan kernel,
-//   * in a multi-GPU communicator a push from a sharded child into a replicated parent is followed by the only
-//     data-path exchange besides the final gather: an OR of the (tiny) parent mask over NVLink peer memory, split
-//     into publish / collect halves with the root's independent predicate scan scheduled between them.
-// Columns may live in HBM or stay in pinned host memory (colq_*_host; moved on first touch only), and string / int
-// columns may be dictionary-encoded (predicates evaluated per distinct value, rows tested by code lookup).
+//   * the ROOT node -- predicate scan, its chains, a tiny to-many hop feeding them, the ordered compaction and the
+//     multi-GPU gather -- runs as one persistent launch (root_fused_kernel), started as a programmatic dependent of the
+//     kernel in front of it,
+//   * in a multi-GPU communicator (one process per GPU over CUDA IPC, or ONE process driving all GPUs over peer access) a
+//     push from a sharded child into a replicated parent is followed by an OR of the (tiny) parent mask over NVLink peer
+//     memory: published by the last CTA of the producing scan, collected inside the root's launch, as fence-free
+//     flag-in-data words; hops between tables that are both sharded exchange whole bitmaps (all-gather / OR-reduce-scatter)
+//     through a peer-mapped heap; the matched indices are written straight into every rank's mailbox by the kernel that
+//     produces them.
+// Columns may live in HBM or stay in pinned host memory (colq_*_host; moved on first touch only), string / int columns
+// may be dictionary-encoded (predicates evaluated per distinct value, rows tested by code lookup), and the load-time work
+// (dictionary building, association classification and validation) runs on the device too (colq_ingest.cuh).
 // There is no CPU fallback anywhere in this file.
 //
 // E = data-system-serial-indices-arrays/src/main/java/dgroomes/data_system_serial_indices_arrays
