@@ -23,11 +23,33 @@ struct DictSlot {
     u32 code;     // dictionary code = rank of min_row among all representatives
 };
 
-__device__ __forceinline__ u64 hash_bytes(const uint8_t* p, u32 len, u64 seed) {
+// The strings are read as little-endian 32-bit words of the (16-byte aligned, padded) bytes buffer and re-aligned with a
+// funnel shift -- 2-3 loads per city name instead of 8.5 single-byte loads.
+struct StrWords {
+    const u32* words;
+    u32 wi, sh, cur;
+    __device__ __forceinline__ StrWords(const uint8_t* bytes, u32 o0) : words(reinterpret_cast<const u32*>(bytes)), wi(o0 >> 2), sh((o0 & 3) * 8) {
+        cur = words[wi];
+    }
+    // the next 4 bytes of the string (bytes past `remaining` are zeroed)
+    __device__ __forceinline__ u32 next(u32 remaining) {
+        const u32 nxt = words[++wi];  // at most 4 bytes past the string: inside the buffer's slack
+        u32 w = __funnelshift_r(cur, nxt, sh);
+        cur = nxt;
+        if (remaining < 4) w &= (1u << (remaining * 8)) - 1u;
+        return w;
+    }
+};
+
+__device__ __forceinline__ u64 hash_bytes(const uint8_t* bytes, u32 o0, u32 len, u64 seed) {
     u64 h = 0xcbf29ce484222325ull ^ seed;
-    for (u32 i = 0; i < len; ++i) {
-        h ^= p[i];
-        h *= 0x100000001b3ull;
+    if (len > 0) {
+        StrWords sw(bytes, o0);
+        for (u32 c = 0; c < len; c += 4) {
+            h ^= sw.next(len - c);
+            h *= 0x100000001b3ull;
+            h ^= h >> 29;
+        }
     }
     h ^= (u64)len * 0x9E3779B97F4A7C15ull;
     h = (h ^ (h >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -52,7 +74,7 @@ __global__ void __launch_bounds__(256) dict_insert_kernel(const u32* offsets, co
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const u32 o0 = offsets[i], len = offsets[i + 1] - o0;
-        const u64 h = hash_bytes(bytes + o0, len, seed);
+        const u64 h = hash_bytes(bytes, o0, len, seed);
         u32 s = (u32)(h >> 7) & mask;
         u32 probes = 0;
         while (true) {
@@ -93,7 +115,10 @@ __global__ void __launch_bounds__(256) dict_verify_kernel(const u32* offsets, co
                 const u32 a0 = offsets[i], la = offsets[i + 1] - a0;
                 const u32 b0 = offsets[rep], lb = offsets[rep + 1] - b0;
                 bool same = la == lb;
-                for (u32 k = 0; same && k < la; ++k) same = bytes[a0 + k] == bytes[b0 + k];
+                if (same && la > 0) {
+                    StrWords wa(bytes, a0), wb(bytes, b0);
+                    for (u32 k = 0; same && k < la; k += 4) same = wa.next(la - k) == wb.next(la - k);
+                }
                 if (!same) status[1] = 1;
             }
         }

@@ -637,11 +637,14 @@ __device__ __forceinline__ void peer_mask_publish_tail(const PeerMaskParams& P, 
 __device__ __forceinline__ void peer_mask_collect(const PeerMaskParams& P) {
     const size_t area = (size_t)(P.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
     const uint8_t* mine = P.peers[P.rank] + area;
-    for (int w = threadIdx.x; w < P.n_words; w += blockDim.x) {
-        u32 v = 0;
-        for (int r = 0; r < P.n_ranks; ++r) v |= ll_load(reinterpret_cast<const u64*>(mine + (size_t)r * MASK_SLOT_BYTES + 16) + w, P.epoch, P.status);
-        P.reach[w] = v;
+    for (int w = threadIdx.x; w < P.n_words; w += blockDim.x) P.reach[w] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.n_words * P.n_ranks; i += blockDim.x) {  // one thread per (rank, word): all polls in flight at once
+        const int r = i / P.n_words, w = i - r * P.n_words;
+        const u32 v = ll_load(reinterpret_cast<const u64*>(mine + (size_t)r * MASK_SLOT_BYTES + 16) + w, P.epoch, P.status);
+        if (v) atomicOr(&P.reach[w], v);
     }
+    __threadfence_block();
     __syncthreads();
 }
 
@@ -1157,11 +1160,13 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == -1 || MODE == -2) ? 4 : 3
             };
             // claims are batches of ST_CLAIM consecutive tiles, and the NEXT batch is claimed while the current one is
             // being issued: neither the atomic's nor the bounds load's latency sits between two TMA issues
-            u32 batch = atomicAdd(P.tile_counter, (u32)ST_CLAIM);
-            u32 batch_next = atomicAdd(P.tile_counter, (u32)ST_CLAIM);
-            u32 j = 0;
-            u32 next = batch;
-            if (next < n_tiles) tile_bounds(next, nb0, nb1);
+            // (the first tile of every CTA is static -- tile blockIdx.x, the grid never exceeds the tile count -- so the first
+            // copy leaves without waiting for an atomic; the counter hands out the tiles from gridDim.x on)
+            u32 next = blockIdx.x;
+            tile_bounds(next, nb0, nb1);
+            u32 batch = gridDim.x + atomicAdd(P.tile_counter, (u32)ST_CLAIM);
+            u32 batch_next = gridDim.x + atomicAdd(P.tile_counter, (u32)ST_CLAIM);
+            u32 j = ST_CLAIM - 1;  // the static tile counts as the last of a (virtual) batch: the next one is batch + 0
             int s = 0;
             u32 round = 0;  // how many times the ring has wrapped
             while (true) {
@@ -1170,8 +1175,10 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == -1 || MODE == -2) ? 4 : 3
                 if (cur < n_tiles) {  // the tile after this one: its bounds are in flight while we wait for the slot
                     if (++j == ST_CLAIM) {
                         j = 0;
-                        batch = batch_next;
-                        batch_next = atomicAdd(P.tile_counter, (u32)ST_CLAIM);
+                        if (cur >= gridDim.x) {   // (not right after the static tile: `batch` is still unused then)
+                            batch = batch_next;
+                            batch_next = gridDim.x + atomicAdd(P.tile_counter, (u32)ST_CLAIM);
+                        }
                     }
                     next = batch + j;
                     if (next < n_tiles) tile_bounds(next, nb0, nb1);
@@ -2028,12 +2035,18 @@ __device__ __forceinline__ void rf_run_pre(const CsrPullParams& C, u32 vcta, u32
         const PeerMaskParams& M = C.pm;
         const size_t area = (size_t)(M.epoch & 1) * MAX_RANKS * MASK_SLOT_BYTES;
         const uint8_t* mine = M.peers[M.rank] + area;
-        for (int w = tid; w < cw; w += RF_THREADS) {
-            u32 v = 0;
-            for (int r = 0; r < M.n_ranks; ++r) v |= ll_load(reinterpret_cast<const u64*>(mine + (size_t)r * MASK_SLOT_BYTES + 16) + w, M.epoch, M.status);
-            s_child[w] = v;
-            if (vcta == 0) M.reach[w] = v;  // the reduced mask stays readable (node cardinalities)
+        // one thread per (rank, word): all polls are in flight at once -- eight ranks polled one after the other by the
+        // same thread put 5 us of L2 round trips on the critical path of every step
+        for (int w = tid; w < cw; w += RF_THREADS) s_child[w] = 0;
+        __syncthreads();
+        for (int i = tid; i < cw * M.n_ranks; i += RF_THREADS) {
+            const int r = i / cw, w = i - r * cw;
+            const u32 v = ll_load(reinterpret_cast<const u64*>(mine + (size_t)r * MASK_SLOT_BYTES + 16) + w, M.epoch, M.status);
+            if (v) atomicOr(&s_child[w], v);
         }
+        __syncthreads();
+        if (vcta == 0)
+            for (int w = tid; w < cw; w += RF_THREADS) M.reach[w] = s_child[w];  // the reduced mask stays readable (node cardinalities)
     } else {
         for (int w = tid; w < cw; w += RF_THREADS) s_child[w] = C.child_bits != nullptr ? __ldcg(C.child_bits + w) : 0xffffffffu;
     }
