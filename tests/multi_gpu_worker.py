@@ -72,6 +72,13 @@ def main():
                 cq.execute_async()
                 res = cq.fetch(want_indices=True, index_capacity=want.shape[0] + 8)
                 assert np.array_equal(res.indices, want), (rank, perturbed, "second execution")
+                # the public call: this rank's rows of the result table (the gathered list holds ALL ranks' rows)
+                got = ds.execute(G.plymouth_query())
+                mine = want[(want >= geo.zip_row_base) & (want < geo.zip_row_base + geo.zips.size())]
+                assert got.result_set.size() == mine.shape[0], (rank, got.result_set.size(), mine.shape[0])
+                assert np.array_equal(got.result_set.columns()[0].ints(), geo.zips.columns()[0].ints()[mine - geo.zip_row_base])
+                ds.last_query.close()
+                ds.last_query = None
                 names = [n for n, *_ in cq.profile()]
                 root_fused = rootf and fused == 1 and lazy and defer   # (eager plans end in a scan with the gathers inside)
                 assert any(n.startswith("root_fused") for n in names) == bool(root_fused and rootf == 1), names

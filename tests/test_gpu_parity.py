@@ -750,3 +750,51 @@ def test_device_association_classification():
         ctx.associate(x, 3, y, 3, off_bad, tg)
     assert ctx.associate(x, 3, y, 3, off, tg) is False                   # the ordinals were released by the failed calls
     ctx.close()
+
+
+# ------------------------------------------------------------------ regressions for the round-1 advisor findings
+def test_compare_to_between_supplementary_planes(engines):
+    """Two different supplementary-plane lead bytes (0xF0 vs 0xF4) must not tie: String.compareTo orders them by surrogate
+    value = code-point order.  Every comparison operator, needles on both planes, device and dictionary layouts."""
+    strings = ["\U00010000", "\U0010FFFF", "\U0001F600", "\U000F0000a", "\uE000", "\uFFFD", "\uD7FF", "a\U00010400", "a\U0010F400",
+               "a", "", "\U0001F600\U0001F600", "é", "z\uFB01"] * 3
+    col = StringColumn(strings)
+
+    def build(ds):
+        ds.register("s", InMemoryTable.of_columns(col))
+
+    queries = []
+    for needle in ("\U0001F600", "\U0010FFFF", "\U00010000", "\uE000", "a\U00010400", "", "\U000F0000"):
+        for op in (2, 3, 4, 5):
+            def mk(op=op, needle=needle):
+                q = Query("s")
+                q.root_node.add_criteria(Criteria.StringCriteria(0, StringPredicate(op, needle)))
+                return q
+            queries.append(mk)
+    both(engines, build, queries, variants=(LAZY, DICT))
+
+
+def test_empty_interval_does_not_promote_a_host_column(engines):
+    """COLQ_OPT_PROMOTE=1 with a valid and an EMPTY int interval on one node: the launch degenerates to clearing the mask,
+    so the host-resident column must not be switched to a never-filled HBM copy -- the next query reads real data."""
+    rng = np.random.default_rng(77)
+    n = 50_000
+    a = IntegerColumn(rng.integers(0, 1000, size=n, dtype=np.int32))
+    b = IntegerColumn(rng.integers(0, 1000, size=n, dtype=np.int32))
+
+    def build(ds):
+        ds.register("t", InMemoryTable.of_columns(a, b))
+
+    def empty_and_valid():
+        q = Query("t")
+        q.root_node.add_criteria(Criteria.IntCriteria(0, int_range(10, 500)))
+        q.root_node.add_criteria(Criteria.IntCriteria(1, int_range(7, 3)))      # lo > hi: matches nothing
+        return q
+
+    def valid_only():
+        q = Query("t")
+        q.root_node.add_criteria(Criteria.IntCriteria(0, int_range(10, 500)))
+        q.root_node.add_criteria(Criteria.IntCriteria(1, int_range(3, 700)))
+        return q
+
+    both(engines, build, [empty_and_valid, valid_only, empty_and_valid, valid_only], variants=(HOST_KERNEL_PROMOTE, HOST, HOST_NO_PROMOTE))
