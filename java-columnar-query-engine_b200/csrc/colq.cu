@@ -2816,10 +2816,13 @@ colq_status colq_col_str_encode(colq_ctx* ctx, colq_table table, int ordinal, in
     CU(ctx, cudaMemsetAsync((char*)codes.ptr + n * 4, 0, std::min<size_t>(codes.bytes - (size_t)n * 4, 64), s));
     int64_t n_dict = 0;
     if (n > 0) {
-        // scratch hash table: twice the rows, capped at 64 M slots (1 GB) -- beyond ~45 M distinct values dictionary
-        // encoding is pointless and the call fails instead
+        // scratch hash table, at most half full.  It starts SMALL -- 1 M slots, 16 MB, L2-resident: a column worth
+        // dictionary-encoding has few distinct values, and probes into a table sized for the row count were TLB and L2
+        // misses -- and grows 16x whenever the distinct values exceed half of it, up to 64 M slots (1 GB, 32 M distinct
+        // values); beyond that dictionary encoding is pointless and the call fails
+        const int64_t max_slots = (int64_t)1 << 26;
         int64_t n_slots = 1024;
-        while (n_slots < 2 * n && n_slots < ((int64_t)1 << 26)) n_slots <<= 1;
+        while (n_slots < 2 * n && n_slots < ((int64_t)1 << 20)) n_slots <<= 1;
         DevBuf slots, first_bits, first_rows, counts, offs, status;
         ST(dev_alloc(ctx, slots, (size_t)n_slots * sizeof(DictSlot)));
         ST(dev_alloc(ctx, first_bits, (size_t)bitmap_alloc_words(n) * 4));
@@ -2843,7 +2846,14 @@ colq_status colq_col_str_encode(colq_ctx* ctx, colq_table table, int ordinal, in
             CU(ctx, cudaGetLastError());
             CU(ctx, cudaMemcpyAsync(st_host, status.ptr, 8, cudaMemcpyDeviceToHost, s));
             CU(ctx, cudaStreamSynchronize(s));
-            if (st_host[0]) return fail(ctx, COLQ_ERR_CAPACITY, "too many distinct values for dictionary encoding (scratch table of %lld slots is full)", (long long)n_slots);
+            if (st_host[0]) {  // more distinct values than half the table: a larger table, same seed
+                if (n_slots >= max_slots || n_slots >= 4 * n)
+                    return fail(ctx, COLQ_ERR_CAPACITY, "too many distinct values for dictionary encoding (more than %lld)", (long long)(n_slots / 2));
+                n_slots = std::min<int64_t>(n_slots * 16, max_slots);
+                ST(dev_alloc(ctx, slots, (size_t)n_slots * sizeof(DictSlot)));
+                --attempt;
+                continue;
+            }
             if (!st_host[1]) break;
             if (attempt == 3) return fail(ctx, COLQ_ERR_DEVICE, "dictionary encoding: 64-bit hash collisions with four different seeds");
         }

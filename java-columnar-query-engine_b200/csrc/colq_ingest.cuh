@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(256) dict_init_kernel(DictSlot* slots, int64_t
     }
 }
 
-// status[0]: 1 = table full (too many distinct values for the scratch table), status[1]: 1 = hash collision found
-// by the verification pass.  slot_of_row[i] receives the slot that represents row i's value.
+// status[0]: 1 = table more than half full (the host retries with a larger one), status[1]: 1 = hash collision found
+// by the verification pass, status[2]: distinct values inserted so far.  slot_of_row[i] receives the slot that represents row i's value.
 __global__ void __launch_bounds__(256) dict_insert_kernel(const u32* offsets, const uint8_t* bytes, int64_t n, DictSlot* slots, u32 mask,
                                                          u64 seed, int32_t* slot_of_row, u32* status) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(256) dict_insert_kernel(const u32* offsets, co
             if (k == 0) {
                 const u64 prev = atomicCAS((unsigned long long*)&slots[s].key, 0ull, (unsigned long long)h);
                 k = prev == 0 ? h : prev;
+                // a new distinct value: keep the table at most half full (the host retries with a larger one)
+                if (prev == 0 && atomicAdd(&status[2], 1u) >= (mask >> 1)) status[0] = 1;
             }
             if (k == h) {
                 // the value's representative is its FIRST row; rows arrive roughly in order, so after the first few
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(256) dict_insert_kernel(const u32* offsets, co
                 break;
             }
             s = (s + 1) & mask;
-            if (++probes > mask) {
+            if (++probes > mask || ld_volatile_u32(&status[0]) != 0) {
                 status[0] = 1;
                 slot_of_row[i] = 0;
                 break;
@@ -104,6 +106,7 @@ __global__ void __launch_bounds__(256) dict_insert_kernel(const u32* offsets, co
 // the representatives raise their first-occurrence flag; one bitmask word per warp
 __global__ void __launch_bounds__(256) dict_verify_kernel(const u32* offsets, const uint8_t* bytes, int64_t n, const DictSlot* slots,
                                                          const int32_t* slot_of_row, u32* first_bits, u32* status) {
+    if (ld_volatile_u32(&status[0]) != 0) return;  // the insert pass gave up (table too small): slot_of_row is not meaningful
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n_pad = (n + 31) & ~(int64_t)31;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
