@@ -349,6 +349,13 @@ colq_status colq_query_criteria_str_accept(colq_query *query, int node, int ordi
 /* addCriteria(new Criteria.IntCriteria(ordinal, <any IntPredicate>)) over a dictionary-encoded int column (DS/Criteria.java:19) */
 colq_status colq_query_criteria_i32_accept(colq_query *query, int node, int ordinal, const uint64_t *accept_words,
                                            int64_t n_dict);
+/* A criterion over a BooleanColumn (M/InMemoryColumn.java:28-44).  The reference declares the column kind and its
+   BooleanColumnFilterable.where(Predicate<Boolean>) (DS/ColumnFilterable.java:20-22) but its Verifier answers Failure
+   for it (E/Verifier.java:82-84, "not supported yet") and Criteria has no boolean member (DS/Criteria.java:10-20): this
+   is the SURVEY.md 8(f4) extension.  A Predicate<Boolean> has a two-entry truth table, so the host evaluates the lambda
+   on FALSE and on TRUE and passes both answers; a row matches when accept_{its value} != 0 (a byte != 0 is TRUE).
+   Int / string criteria on a boolean column keep the reference's Failure. */
+colq_status colq_query_criteria_bool(colq_query *query, int node, int ordinal, int accept_false, int accept_true);
 colq_status colq_query_set_option(colq_query *query, colq_option option, int value);
 
 /*

@@ -89,6 +89,7 @@ SIGNATURES = {
     "colq_query_criteria_str": (_int, [_p, _int, _int, _int, _p, _i32]),
     "colq_query_criteria_str_accept": (_int, [_p, _int, _int, _p, _i64]),
     "colq_query_criteria_i32_accept": (_int, [_p, _int, _int, _p, _i64]),
+    "colq_query_criteria_bool": (_int, [_p, _int, _int, _int, _int]),
     "colq_query_set_option": (_int, [_p, _int, _int]),
     "colq_execute": (_int, [_p, _p, _p, _i64, _p, _i64, C.POINTER(_i64), C.POINTER(Timing)]),
     "colq_execute_async": (_int, [_p, _p]),

@@ -206,7 +206,11 @@ def str_ends_with(x: str) -> StringPredicate:
 
 # --------------------------------------------------------------------------------------- Criteria / Query / QueryResult
 class Criteria:
-    """DS/Criteria.java:10-20 (sealed: IntCriteria | StringCriteria)."""
+    """DS/Criteria.java:10-20 (sealed: IntCriteria | StringCriteria).
+
+    BooleanCriteria is the SURVEY.md 8(f4) extension: the reference declares BooleanColumnFilterable.where(Predicate<Boolean>)
+    (DS/ColumnFilterable.java:20-22) but has no criterion for it and its Verifier refuses boolean columns
+    (E/Verifier.java:82-84).  Int / string criteria on a boolean column still answer that Failure."""
 
     @dataclass(frozen=True)
     class StringCriteria:
@@ -217,6 +221,11 @@ class Criteria:
     class IntCriteria:
         ordinal: int
         integer_predicate: Callable[[int], bool]
+
+    @dataclass(frozen=True)
+    class BooleanCriteria:
+        ordinal: int
+        boolean_predicate: Callable[[bool], bool]
 
 
 class Query:

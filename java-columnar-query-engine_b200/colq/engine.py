@@ -108,6 +108,9 @@ class ColqQuery:
         w = np.ascontiguousarray(words, dtype=np.uint64)
         self.ctx._check(self.ctx.lib.colq_query_criteria_str_accept(self.handle, node, ordinal, _ptr(w), n_dict))
 
+    def criteria_bool(self, node: int, ordinal: int, accept_false: bool, accept_true: bool) -> None:
+        self.ctx._check(self.ctx.lib.colq_query_criteria_bool(self.handle, node, ordinal, int(bool(accept_false)), int(bool(accept_true))))
+
     def criteria_i32_accept(self, node: int, ordinal: int, words: np.ndarray, n_dict: int) -> None:
         w = np.ascontiguousarray(words, dtype=np.uint64)
         self.ctx._check(self.ctx.lib.colq_query_criteria_i32_accept(self.handle, node, ordinal, _ptr(w), n_dict))
@@ -654,6 +657,10 @@ class DataSystemColq(DataSystem):
                                       "structured predicates (colq.data_system.str_equals & co.) over plain string columns and has no CPU "
                                       "fallback; construct DataSystemColq(dictionary=True) to run opaque string predicates per distinct value." % crit.ordinal)
                     cq.criteria_str(nid, crit.ordinal, p.op, p.needle)
+                elif isinstance(crit, Criteria.BooleanCriteria):
+                    # a Predicate<Boolean> has two inputs: evaluate the lambda on both, the GPU tests the truth table
+                    p = crit.boolean_predicate
+                    cq.criteria_bool(nid, crit.ordinal, bool(p(False)), bool(p(True)))
                 else:
                     raise TypeError(f"not a Criteria: {crit!r}")
             for ordinal, child in node.get_children_by_ordinal().items():

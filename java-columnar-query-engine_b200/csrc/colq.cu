@@ -165,6 +165,9 @@ struct Crit {
     bool is_accept = false;
     int64_t accept_n = 0;
     DevBuf accept_dev;
+    // a Predicate<Boolean>: its truth table (colq_query_criteria_bool)
+    bool is_bool = false;
+    bool accept_false = false, accept_true = false;
 };
 
 struct QNode {
@@ -173,7 +176,7 @@ struct QNode {
 };
 
 // one kernel launch (or collective / memset) of a planned query
-enum OpKind { K_SCAN_ROWS, K_SCAN_CODES, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER, K_COMPACT_FUSED, K_COMPACT_LOOKBACK, K_ROOT_FUSED, K_ROOT_FINISH, K_PEER_BITS_ALLGATHER, K_PEER_BITS_REDUCE, K_PEER_MASK_PUBLISH, K_PEER_MASK_COLLECT, K_PEER_GATHER };
+enum OpKind { K_SCAN_ROWS, K_SCAN_CODES, K_SCAN_STR, K_CSR_PULL, K_PUSH_BITS, K_AND, K_FILL, K_ZERO, K_ALLGATHER_OR, K_POPC, K_SCAN_COUNTS, K_COMPACT, K_GATHER, K_COMPACT_FUSED, K_COMPACT_LOOKBACK, K_ROOT_FUSED, K_ROOT_FINISH, K_PEER_BITS_ALLGATHER, K_PEER_BITS_REDUCE, K_PEER_MASK_PUBLISH, K_PEER_MASK_COLLECT, K_PEER_GATHER, K_SCAN_BOOL };
 
 struct Op {
     OpKind kind;
@@ -181,6 +184,7 @@ struct Op {
     int np = 0, ng = 0;
     bool eager = false;
     ScanCodesParams codes{};
+    ScanBoolParams boolp{};
     bool never = false;  // an empty int interval: the launch degenerates to clearing the mask
     ScanRowsParams rows{};
     ScanStrParams str{};
@@ -468,7 +472,7 @@ colq_status verify(colq_query* q) {
             const Column& col = tb.cols[c.ordinal];
             switch (col.kind) {  // switch (column.filterableType()) (:71-90)
                 case COL_STR:
-                    if (!c.is_str)
+                    if (!c.is_str || c.is_bool)
                         return fail(ctx, COLQ_FAILURE, "The column is a string column but the criterion is not a string predicate.");
                     if (c.is_accept && !col.dict)
                         return fail(ctx, COLQ_FAILURE, "An opaque string predicate can only run over a dictionary-encoded column (colq_col_str_dict): it is evaluated per distinct value on the host; there is no CPU fallback for the row scan.");
@@ -476,7 +480,7 @@ colq_status verify(colq_query* q) {
                         return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "accept set has %lld entries but the column's dictionary has %lld", (long long)c.accept_n, (long long)col.dict->n);
                     break;
                 case COL_I32:
-                    if (c.is_str)
+                    if (c.is_str || c.is_bool)
                         return fail(ctx, COLQ_FAILURE, "The column is an integer column but the criterion is not an integer predicate.");
                     if (c.is_accept && !col.dict)
                         return fail(ctx, COLQ_FAILURE, "An opaque integer predicate can only run over a dictionary-encoded column (colq_col_i32_dict): it is evaluated per distinct value on the host; there is no CPU fallback for the row scan.");
@@ -484,7 +488,11 @@ colq_status verify(colq_query* q) {
                         return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "accept set has %lld entries but the column's dictionary has %lld", (long long)c.accept_n, (long long)col.dict->n);
                     break;
                 case COL_BOOL:
-                    return fail(ctx, COLQ_FAILURE, "Boolean columns are not supported yet.");
+                    // the reference stops here for every criterion (:82-84); Criteria has no boolean member, so an int
+                    // or string criterion on a boolean column is all it can be asked.  colq_query_criteria_bool is the
+                    // 8(f4) extension.
+                    if (!c.is_bool) return fail(ctx, COLQ_FAILURE, "Boolean columns are not supported yet.");
+                    break;
                 case COL_ASSOC:
                     return fail(ctx, COLQ_FAILURE, "Association columns can't be matched on with a scalar criteria.");
                 default:
@@ -850,6 +858,24 @@ struct Planner {
         };
         for (const Crit* c : xr.preds) {
             const Column& col = T.cols[c->ordinal];
+            if (c->is_bool) {  // one byte per row against the predicate's truth table
+                u32* ob;
+                ST(out_buf(&ob));
+                Op o{};
+                o.kind = K_SCAN_BOOL; o.node = xi; o.name = "scan_bool";
+                o.boolp.n = n;
+                o.boolp.n_alloc_words = bitmap_alloc_words(n);
+                o.boolp.values = (const uint8_t*)col.data.ptr;
+                o.boolp.accept_false = c->accept_false;
+                o.boolp.accept_true = c->accept_true;
+                o.boolp.in_bits = cur;
+                o.boolp.out_bits = ob;
+                o.acct_rows = n;
+                o.acct_bytes = n + bitmap_words(n) * 4;
+                q->ops.push_back(o);
+                cur = ob;
+                continue;
+            }
             if (!c->is_str && !col.dict) continue;  // plain int columns: fused row scans below
             u32* ob;
             ST(out_buf(&ob));
@@ -912,7 +938,7 @@ struct Planner {
         // ---- int criteria + forward to-one hops: fused row scans, at most 2 predicates and 2 chains per launch
         std::vector<const Crit*> ints;
         for (const Crit* c : xr.preds)
-            if (!c->is_str && !T.cols[c->ordinal].dict) ints.push_back(c);
+            if (!c->is_str && !c->is_bool && !T.cols[c->ordinal].dict) ints.push_back(c);
         size_t pi = 0, gi = 0;
         // The root's criteria-free to-one chains need not stall the streaming scan: when a predicate (or an earlier
         // mask) already thins the rows out, hand the chains to the fused compaction, which walks them for the
@@ -1159,6 +1185,12 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
             const size_t smem = (size_t)(PUSH_SMEM_WORDS + o.codes.mask_words) * 4;
             if (o.codes.mask_words > 0) scan_codes_kernel<true><<<grid, SR_THREADS, smem, s>>>(o.codes);
             else scan_codes_kernel<false><<<grid, SR_THREADS, smem, s>>>(o.codes);
+            q->timing.kernel_launches++;
+            break;
+        }
+        case K_SCAN_BOOL: {
+            const int grid = (int)((o.boolp.n_alloc_words * 32 + SB_BLOCK_ROWS - 1) / SB_BLOCK_ROWS);
+            scan_bool_kernel<<<grid, SB_THREADS, 0, s>>>(o.boolp);
             q->timing.kernel_launches++;
             break;
         }
@@ -3110,6 +3142,15 @@ colq_status colq_query_criteria_i32_accept(colq_query* q, int node, int ordinal,
     colq_status st = colq_query_criteria_str_accept(q, node, ordinal, accept_words, n_dict);
     if (st == COLQ_OK) q->nodes[node].crit.back().is_str = false;
     return st;
+}
+
+colq_status colq_query_criteria_bool(colq_query* q, int node, int ordinal, int accept_false, int accept_true) {
+    if (!q) return COLQ_THROW_NULL;
+    if (node < 0 || (size_t)node >= q->nodes.size()) return fail(q->ctx, COLQ_THROW_ILLEGAL_ARG, "unknown query node %d", node);
+    Crit c;
+    c.ordinal = ordinal; c.is_bool = true; c.accept_false = accept_false != 0; c.accept_true = accept_true != 0;
+    q->nodes[node].crit.push_back(std::move(c));
+    return COLQ_OK;
 }
 
 colq_status colq_query_set_option(colq_query* q, colq_option option, int value) {

@@ -898,6 +898,82 @@ __global__ void __launch_bounds__(SR_THREADS) scan_codes_kernel(const ScanCodesP
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1c  scan_bool: Predicate<Boolean> over a BooleanColumn (M/InMemoryColumn.java:28-44; the where() the reference
+// declares in DS/ColumnFilterable.java:20-22 and never implements, E/Verifier.java:82-84).  One byte per row; the
+// predicate is its two-entry truth table.  A thread takes 16 consecutive rows with one 128-bit streaming load (a warp
+// reads 512 contiguous bytes), turns them into 16 bits with a SIMD byte compare, and lane pairs assemble the BitSet
+// word.  1 byte per row in, 1 bit out: HBM-bound.  The grid covers the whole padded bitmap, words past n are zeroed.
+// ---------------------------------------------------------------------------------------------
+
+struct ScanBoolParams {
+    int64_t n;
+    int64_t n_alloc_words;  // words of out_bits (a multiple of 16)
+    const uint8_t* values;  // allocation padded to whole 16-byte lines
+    u32 accept_false, accept_true;
+    const u32* in_bits;
+    u32* out_bits;
+};
+
+constexpr int SB_THREADS = 256;
+constexpr int SB_V = 4;                            // 16-byte loads in flight per thread
+constexpr int SB_WARP_ROWS = 32 * 16 * SB_V;       // 2048
+constexpr int SB_BLOCK_ROWS = (SB_THREADS / 32) * SB_WARP_ROWS;
+
+// 16 bytes -> 16 bits (bit k: byte k != 0).  Per 32-bit word: the SWAR nonzero-byte test leaves bit 7 of every nonzero
+// byte set, and one multiply gathers bits 7 / 15 / 23 / 31 into four adjacent bits (the partial products land on
+// distinct bit positions, so nothing carries).
+__device__ __forceinline__ u32 sb_truth16(const int4 v) {
+    const u32 w[4] = {(u32)v.x, (u32)v.y, (u32)v.z, (u32)v.w};
+    u32 truth = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const u32 nz = ((((w[e] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w[e]) & 0x80808080u) >> 7;  // bits 0 / 8 / 16 / 24
+        truth |= (((nz * 0x00204081u) >> 21) & 0xFu) << (4 * e);
+    }
+    return truth;
+}
+
+__global__ void __launch_bounds__(SB_THREADS) scan_bool_kernel(const ScanBoolParams P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wbase = ((int64_t)blockIdx.x * (SB_THREADS / 32) + (threadIdx.x >> 5)) * SB_WARP_ROWS;
+    const u32 flip = P.accept_false ? 0xFFFFu : 0u;          // m = (truth ^ flip) & keep covers the four truth tables
+    const u32 keep = P.accept_false != P.accept_true ? 0xFFFFu : (P.accept_true ? 0xFFFFu : 0u);
+    const bool constant = (P.accept_false != 0) == (P.accept_true != 0);
+    u32 m[SB_V];
+    if (wbase + SB_WARP_ROWS <= P.n) {
+        int4 v[SB_V];
+#pragma unroll
+        for (int j = 0; j < SB_V; ++j) v[j] = ldg_stream_v4(reinterpret_cast<const int32_t*>(P.values + wbase + j * 512 + lane * 16));
+#pragma unroll
+        for (int j = 0; j < SB_V; ++j) m[j] = constant ? keep : ((sb_truth16(v[j]) ^ flip) & 0xFFFFu);
+    } else {
+#pragma unroll
+        for (int j = 0; j < SB_V; ++j) {
+            const int64_t r0 = wbase + j * 512 + lane * 16;
+            const int64_t left = P.n - r0;
+            m[j] = 0;
+            if (left > 0) {
+                const int4 v = ldg_stream_v4(reinterpret_cast<const int32_t*>(P.values + r0));
+                m[j] = constant ? keep : ((sb_truth16(v) ^ flip) & 0xFFFFu);
+                if (left < 16) m[j] &= (1u << (int)left) - 1u;
+            }
+        }
+    }
+    u32* out_words = P.out_bits + (wbase >> 5) + (lane >> 1);
+    const u32* in_words = P.in_bits != nullptr ? P.in_bits + (wbase >> 5) + (lane >> 1) : nullptr;
+    const bool in_range = (wbase >> 5) + SB_WARP_ROWS / 32 <= P.n_alloc_words;  // whole-warp tile inside the padded bitmap
+#pragma unroll
+    for (int j = 0; j < SB_V; ++j) {
+        const u32 hi = __shfl_down_sync(FULL_MASK, m[j], 1);
+        if ((lane & 1) == 0 && (in_range || (wbase >> 5) + j * 16 + (lane >> 1) < P.n_alloc_words)) {
+            u32 out = m[j] | (hi << 16);
+            if (in_words != nullptr && out != 0) out &= in_words[j * 16];
+            out_words[j * 16] = out;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2  scan_str: string predicate over an (offsets, bytes) column -> bitmask, TMA-staged, warp-specialised
 //
 // Replaces ExecutionContext.Node.filterSelf (E/ExecutionContext.java:79-94) over StringColumn.where

@@ -60,6 +60,9 @@ typedef struct {
     int op;
     uint8_t *needle;
     int32_t nlen;
+    /* 8(f4) extension: a Predicate<Boolean> as its truth table -- the where() the reference declares
+       (DS/ColumnFilterable.java:20-22) and its Verifier refuses (E/Verifier.java:82-84) */
+    int is_bool, accept_false, accept_true;
 } criterion;
 
 typedef struct {
@@ -312,6 +315,11 @@ void orc_query_add_str(orc_query *q, int node, int ordinal, int op, const uint8_
     c->needle = (uint8_t *)xdup(needle, (size_t)len);
 }
 
+void orc_query_add_bool(orc_query *q, int node, int ordinal, int accept_false, int accept_true) {
+    criterion *c = push_criterion(q, node);
+    c->ordinal = ordinal; c->is_bool = 1; c->accept_false = accept_false != 0; c->accept_true = accept_true != 0;
+}
+
 /* ------------------------------------------------------------------ predicates */
 
 /*
@@ -376,6 +384,7 @@ static inline int str_test(const criterion *c, const uint8_t *s, int64_t len) {
 /* idx -> predicate.test(ints[idx]) / predicate.test(strings[idx])  (M/InMemoryColumn.java:53-56,71-74) */
 static inline int pred_test(const orc_system *s, const xnode *n, const criterion *c, int64_t i) {
     const column *col = &s->tables[n->table].cols[c->ordinal];
+    if (c->is_bool) return col->bools[i] ? c->accept_true : c->accept_false;
     if (c->is_str) {
         uint32_t a = col->soff[i], b = col->soff[i + 1];
         return str_test(c, col->sbytes + a, (int64_t)b - a);
@@ -444,18 +453,19 @@ static int verify(orc_system *s, const orc_query *q, int root_table, xctx *x) {
             const column *col = &tb->cols[c->ordinal];
             switch (col->kind) {   /* switch (column.filterableType()) (:71-90) */
                 case COL_STR:
-                    if (!c->is_str) {
+                    if (!c->is_str || c->is_bool) {
                         snprintf(s->msg, sizeof s->msg, "The column is a string column but the criterion is not a string predicate.");
                         rc = ORC_FAILURE; goto done;
                     }
                     break;
                 case COL_INT:
-                    if (c->is_str) {
+                    if (c->is_str || c->is_bool) {
                         snprintf(s->msg, sizeof s->msg, "The column is an integer column but the criterion is not an integer predicate.");
                         rc = ORC_FAILURE; goto done;
                     }
                     break;
                 case COL_BOOL:
+                    if (c->is_bool) break;   /* the extension; every criterion the reference can express fails (:82-84) */
                     snprintf(s->msg, sizeof s->msg, "Boolean columns are not supported yet.");
                     rc = ORC_FAILURE; goto done;
                 default:

@@ -58,6 +58,7 @@ def load() -> C.CDLL:
         "orc_query_create_child": (C.c_int, [p, C.c_int, C.c_int]),
         "orc_query_add_int_range": (None, [p, C.c_int, C.c_int, i32, i32]),
         "orc_query_add_str": (None, [p, C.c_int, C.c_int, C.c_int, p, i32]),
+        "orc_query_add_bool": (None, [p, C.c_int, C.c_int, C.c_int, C.c_int]),
         "orc_execute": (C.c_int, [p, p, C.c_int, C.POINTER(p), C.POINTER(i64), C.POINTER(p), C.POINTER(i64)]),
         "orc_last_node_cardinalities": (C.c_int, [p, C.POINTER(i64), C.c_int]),
         "orc_free": (None, [p]),
@@ -172,6 +173,9 @@ class OracleDataSystem:
                     p = crit.integer_predicate
                     assert isinstance(p, IntPredicate), "the C oracle evaluates structured predicates"
                     self.lib.orc_query_add_int_range(q, nid, crit.ordinal, p.lo, p.hi)
+                elif isinstance(crit, Criteria.BooleanCriteria):
+                    p = crit.boolean_predicate
+                    self.lib.orc_query_add_bool(q, nid, crit.ordinal, int(bool(p(False))), int(bool(p(True))))
                 else:
                     p = crit.string_predicate
                     assert isinstance(p, StringPredicate), "the C oracle evaluates structured predicates"

@@ -232,4 +232,45 @@ def two_children_on_one_node(new_system):
     assert success_columns(ds.execute(q))[0].strings() == ["p2"]
 
 
-EXTRA_TESTS = [none_and_mixed_reverse, two_children_on_one_node]
+def boolean_criteria(new_system):
+    """predicates over a BooleanColumn (M/InMemoryColumn.java:28-44) -- the
+    BooleanColumnFilterable.where(Predicate<Boolean>) the reference declares (DS/ColumnFilterable.java:20-22) and
+    never reaches (E/Verifier.java:82-84).  All four truth tables, the AND with other criteria, and a boolean
+    criterion on a child pruning its parent."""
+    flags = [True, False, False, True, True, False, True]
+    for pred, want in [(lambda b: b, [0, 3, 4, 6]), (lambda b: not b, [1, 2, 5]), (lambda b: True, list(range(7))),
+                       (lambda b: False, [])]:
+        ds = new_system()
+        ds.register("t", of_columns(of_ints(*range(7)), BooleanColumn(flags)))
+        q = Query("t")
+        q.root_node.add_criteria(Criteria.BooleanCriteria(1, pred))
+        assert success_columns(ds.execute(q))[0].ints().tolist() == want
+    ds = new_system()
+    ds.register("t", of_columns(of_ints(*range(7)), BooleanColumn(flags), of_strings("a", "b", "c", "a", "b", "a", "a")))
+    q = Query("t")
+    (q.root_node.add_criteria(Criteria.BooleanCriteria(1, lambda b: b)).add_criteria(Criteria.IntCriteria(0, int_range(1, 6)))
+        .add_criteria(Criteria.StringCriteria(2, str_equals("a"))))
+    assert success_columns(ds.execute(q))[0].ints().tolist() == [3, 6]
+    # a child's boolean criterion prunes the parent, through a to-one and through a to-many column
+    ds = new_system()
+    pets = of_columns(of_strings("p0", "p1", "p2", "p3"), BooleanColumn([False, True, False, False]))
+    owners = of_columns(of_strings("ann", "bob", "cy"))
+    owners.associate_to(pets, Association.to_many(0, 2), Association.to_one(1), Association.to_none())
+    pets.associate_to(owners, Association.to_one(0), Association.to_none(), Association.to_one(2), Association.to_one(0))
+    ds.register("owners", owners)
+    ds.register("pets", pets)
+    q = Query("owners")
+    q.root_node.create_child(1).add_criteria(Criteria.BooleanCriteria(1, lambda b: b))
+    assert success_columns(ds.execute(q))[0].strings() == ["bob"]
+    q = Query("pets")
+    q.root_node.add_criteria(Criteria.BooleanCriteria(1, lambda b: not b))
+    q.root_node.create_child(3).add_criteria(Criteria.StringCriteria(0, str_equals("ann")))
+    assert success_columns(ds.execute(q))[0].strings() == ["p0", "p3"]
+    # a boolean criterion on a column of another kind is a type mismatch, like the reference's other mismatches
+    q = Query("pets")
+    q.root_node.add_criteria(Criteria.BooleanCriteria(0, lambda b: b))
+    r = ds.execute(q)
+    assert isinstance(r, QueryResult.Failure) and r.message == "The column is a string column but the criterion is not a string predicate."
+
+
+EXTRA_TESTS = [none_and_mixed_reverse, two_children_on_one_node, boolean_criteria]

@@ -798,3 +798,50 @@ def test_empty_interval_does_not_promote_a_host_column(engines):
         return q
 
     both(engines, build, [empty_and_valid, valid_only, empty_and_valid, valid_only], variants=(HOST_KERNEL_PROMOTE, HOST, HOST_NO_PROMOTE))
+
+
+# ------------------------------------------------------------------ boolean criteria
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 31, 32, 33, 4095, 4096, 4097, 100_003, (1 << 20) + 5])
+def test_boolean_scan_sizes(engines, n):
+    """scan_bool against the oracle around every word / tile boundary: the four truth tables, bytes other than 0 / 1
+    never reach the column (BooleanColumn holds bools), the AND with a preceding string mask and a following int
+    scan, and a boolean criterion on a child pushed through a to-one column."""
+    from colq.in_memory import BooleanColumn
+    rng = np.random.default_rng(1000 + n)
+    flags = rng.integers(0, 2, size=n).astype(bool)
+    vals = rng.integers(-100, 100, size=n, dtype=np.int32)
+    strings = random_strings(rng, n, 3, np.array(list("ab")))
+    m = max(1, n // 7)
+    fk = rng.integers(-1, n, size=m, dtype=np.int32) if n > 0 else np.full(m, -1, dtype=np.int32)
+
+    def build(ds):
+        t = InMemoryTable.of_columns(BooleanColumn(flags), IntegerColumn(vals), StringColumn(strings))
+        u = InMemoryTable.of_columns(IntegerColumn(np.arange(m, dtype=np.int32)))
+        u.associate_to(t, fk=fk)                      # u.1 to-one into t (with Nones), t.3 reverse
+        ds.register("t", t); ds.register("u", u)
+
+    def truth(f, t):
+        def mk():
+            q = Query("t"); q.root_node.add_criteria(Criteria.BooleanCriteria(0, lambda b: t if b else f)); return q
+        return mk
+
+    def mixed():
+        q = Query("t")
+        q.root_node.add_criteria(Criteria.StringCriteria(2, StringPredicate(1, "a")))
+        q.root_node.add_criteria(Criteria.BooleanCriteria(0, lambda b: not b))
+        q.root_node.add_criteria(Criteria.IntCriteria(1, int_range(-50, 60)))
+        return q
+
+    def child_forward():
+        q = Query("u")
+        q.root_node.create_child(1).add_criteria(Criteria.BooleanCriteria(0, lambda b: b))
+        return q
+
+    def child_reverse():
+        q = Query("t")
+        q.root_node.add_criteria(Criteria.BooleanCriteria(0, lambda b: b))
+        q.root_node.create_child(3).add_criteria(Criteria.IntCriteria(0, int_range(0, m // 2)))
+        return q
+
+    both(engines, build, [truth(False, True), truth(True, False), truth(True, True), truth(False, False), mixed,
+                          child_forward, child_reverse], variants=(LAZY, EAGER, DICT))
