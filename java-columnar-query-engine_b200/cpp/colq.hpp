@@ -159,7 +159,10 @@ inline StringOp strCompareLt(std::string v) { return {COLQ_STR_CMP_LT, std::move
 using StringLambda = std::function<bool(const std::string&)>;
 struct IntCriteria { int ordinal; IntRange integerPredicate; };
 struct StringCriteria { int ordinal; std::variant<StringOp, StringLambda> stringPredicate; };
-using Criteria = std::variant<IntCriteria, StringCriteria>;
+// SURVEY.md 8(f4) extension: BooleanColumnFilterable.where(Predicate<Boolean>) (DS/ColumnFilterable.java:20-22), which the
+// reference declares and its Verifier refuses (E/Verifier.java:82-84); evaluated on false and true by the host
+struct BooleanCriteria { int ordinal; std::function<bool(bool)> booleanPredicate; };
+using Criteria = std::variant<IntCriteria, StringCriteria, BooleanCriteria>;
 
 class Query {
 public:
@@ -238,6 +241,10 @@ private:
         for (const Criteria& c : node.criteria) {
             if (auto* ic = std::get_if<IntCriteria>(&c)) {
                 check(colq_query_criteria_i32_range(q, id, ic->ordinal, ic->integerPredicate.lo, ic->integerPredicate.hi));
+                continue;
+            }
+            if (auto* bc = std::get_if<BooleanCriteria>(&c)) {
+                check(colq_query_criteria_bool(q, id, bc->ordinal, bc->booleanPredicate(false) ? 1 : 0, bc->booleanPredicate(true) ? 1 : 0));
                 continue;
             }
             const auto& sc = std::get<StringCriteria>(c);

@@ -134,6 +134,22 @@ static void opaqueLambdas_onlyOverDictionaryColumns() {
     }
 }
 
+// criteria over a BooleanColumn (declared, never reached by the reference: E/Verifier.java:82-84)
+static void booleanCriteria() {
+    DataSystemColq ds(0, g_options);
+    auto t = InMemoryTable::ofColumns({ofInts({0, 1, 2, 3, 4}), BooleanColumn{{1, 0, 0, 1, 1}}});
+    ds.registerTable("t", t);
+    Query q("t");
+    q.rootNode.addCriteria(BooleanCriteria{1, [](bool b) { return !b; }}).addCriteria(IntCriteria{0, IntRange{0, 1}});
+    EXPECT((std::get<IntegerColumn>(success(ds.execute(q))->columns[0]).ints == std::vector<int32_t>{1}));
+    Query all("t");
+    all.rootNode.addCriteria(BooleanCriteria{1, [](bool) { return true; }});
+    EXPECT(std::get<IntegerColumn>(success(ds.execute(all))->columns[0]).ints.size() == 5);
+    Query bad("t");   // every criterion the reference can express on a boolean column keeps its Failure
+    bad.rootNode.addCriteria(IntCriteria{1, IntRange{0, 1}});
+    EXPECT(std::get<Failure>(ds.execute(bad)).message == "Boolean columns are not supported yet.");
+}
+
 int main() {
     const std::pair<const char*, std::function<void()>> cases[] = {
         {"intQuery_oneColumnTable", intQuery_oneColumnTable},
@@ -143,6 +159,7 @@ int main() {
         {"multiCriteria_includingIntermediateEntity", multiCriteria_includingIntermediateEntity},
         {"failures_followTheVerifier", failures_followTheVerifier},
         {"opaqueLambdas_onlyOverDictionaryColumns", opaqueLambdas_onlyOverDictionaryColumns},
+        {"booleanCriteria", booleanCriteria},
     };
     const std::pair<const char*, Options> layouts[] = {
         {"device", Options{Residency::Device, false}}, {"host-resident", Options{Residency::Host, false}},
