@@ -118,7 +118,14 @@ typedef enum colq_option {
     /* 1 (default): a fused final gather whose plan already synchronises the ranks once per execution (a mask or bitmap
        exchange) only PUBLISHES its flags; they are awaited when the host fetches the result.  0: every execution ends with
        a wait for all ranks' flags. */
-    COLQ_OPT_LAZY_GATHER_WAIT = 10
+    COLQ_OPT_LAZY_GATHER_WAIT = 10,
+    /* 1 (default): back-to-back executions of the same query are pipelined (execute is called over and over on one plan,
+       E/DataSystemSerialIndices.java:53): the root kernel leaves the small push target behind its folded hop zeroed, so
+       the next execution needs no memset, and that execution's first scan is launched as a programmatic dependent of the
+       root kernel -- it streams its (immutable) column while the root kernel drains and touches shared state only after
+       griddepcontrol.wait.  colq_timing.gpu_ms is -1 for an execution that was pipelined this way.  0: every execution
+       starts after the previous one has finished. */
+    COLQ_OPT_PIPELINE = 11
 } colq_option;
 
 typedef struct colq_ctx colq_ctx;       /* one DataSystem instance  (E/DataSystemSerialIndices.java:14-22) */
@@ -126,7 +133,8 @@ typedef struct colq_query colq_query;   /* one Query                (DS/Query.ja
 typedef int32_t colq_table;             /* table handle, valid for the owning context */
 
 typedef struct colq_timing {
-    double gpu_ms;          /* CUDA-event time of the whole kernel(+collective) pipeline of the last execute */
+    double gpu_ms;          /* CUDA-event time of the whole kernel(+collective) pipeline of the last execute
+                               (-1: not measured, the execution overlapped the previous one -- COLQ_OPT_PIPELINE) */
     int32_t kernel_launches;/* kernels of this library launched by the last execute */
     int32_t collectives;    /* NCCL calls issued by the last execute */
     int64_t h2d_bytes;      /* bytes the last execute streamed host->device: host-resident columns it scanned in full */

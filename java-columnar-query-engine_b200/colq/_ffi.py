@@ -17,7 +17,7 @@ OK, FAILURE, THROW_INDEX_OOB, THROW_NULL, THROW_ILLEGAL_STATE, THROW_ILLEGAL_ARG
 # colq_placement
 REPLICATED, SHARDED = 0, 1
 # colq_option
-OPT_LAZY_FK, OPT_PROFILE, OPT_PEER_EXCHANGE, OPT_FUSED_COMPACT, OPT_DEFER_CHAINS, OPT_PROMOTE, OPT_FUSED_GATHER, OPT_TAIL_PUBLISH, OPT_ROOT_FUSED, OPT_LAZY_GATHER_WAIT = 0, 1, 3, 4, 5, 6, 7, 8, 9, 10
+OPT_LAZY_FK, OPT_PROFILE, OPT_PEER_EXCHANGE, OPT_FUSED_COMPACT, OPT_DEFER_CHAINS, OPT_PROMOTE, OPT_FUSED_GATHER, OPT_TAIL_PUBLISH, OPT_ROOT_FUSED, OPT_LAZY_GATHER_WAIT, OPT_PIPELINE = 0, 1, 3, 4, 5, 6, 7, 8, 9, 10, 11
 ABI_VERSION = 2
 
 

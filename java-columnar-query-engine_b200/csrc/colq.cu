@@ -278,6 +278,7 @@ struct colq_ctx {
     int root_fused_grid[SR_MAX_PRED + 1] = {};       // resident CTAs of root_fused_kernel<NP> on this device
     int root_finish_grid = 0;                        // resident CTAs of root_finish_kernel
     u32* d_tile_counters = nullptr;                  // scan_str's tile-claim counter pair (zero between launches)
+    colq_query* chain_query = nullptr;               // the last thing enqueued on the stream was this query's pipelining root kernel
     std::map<std::pair<int, size_t>, int> str_occupancy;  // (kernel mode, dynamic smem bytes) -> resident CTAs per SM
 };
 
@@ -285,7 +286,9 @@ struct colq_query {
     colq_ctx* ctx = nullptr;
     std::string table_name;
     std::vector<QNode> nodes;
-    int opt_lazy = 1, opt_profile = 0, opt_peer = 1, opt_fused_compact = 1, opt_defer = 1, opt_promote = 2, opt_fused_gather = 1, opt_tail_publish = 1, opt_root_fused = 1, opt_lazy_gather_wait = 1;
+    int opt_lazy = 1, opt_profile = 0, opt_peer = 1, opt_fused_compact = 1, opt_defer = 1, opt_promote = 2, opt_fused_gather = 1, opt_tail_publish = 1, opt_root_fused = 1, opt_lazy_gather_wait = 1, opt_pipeline = 1;
+    u32* clean_ready = nullptr;   // the push target the last execution's root kernel left zeroed (COLQ_OPT_PIPELINE)
+    bool timed = true;            // ev_start / ev_stop were recorded for the last execution
     std::vector<GatherD> deferred;  // root-node FK chains resolved by the compaction kernel instead of the row scan
     int own_begin = -1, own_end = -1;  // root-node scan ops that depend on no child (hoistable behind a mask publish)
     std::vector<Column*> pending_promotions;  // host-resident columns whose HBM copy this execution fills
@@ -1239,7 +1242,18 @@ colq_status launch_op(colq_query* q, Op& o, cudaStream_t s, bool count_only = fa
                 o.grid = (int)std::min<int64_t>(o.str.n_tiles, (int64_t)ctx->sm_count * per_sm);
             }
             if (o.tail_publish) o.pmask.epoch = o.str.pub.epoch = ++ctx->peer.mask_epoch;
-            kern<<<o.grid, ST_THREADS, o.smem, s>>>(o.str);
+            if (o.str.early) {
+                // pipelined behind the previous execution's root kernel (COLQ_OPT_PIPELINE): programmatic dependent launch
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(o.grid); cfg.blockDim = dim3(ST_THREADS); cfg.dynamicSmemBytes = o.smem; cfg.stream = s;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                CU(ctx, cudaLaunchKernelEx(&cfg, kern, o.str));
+            } else {
+                kern<<<o.grid, ST_THREADS, o.smem, s>>>(o.str);
+            }
             q->timing.kernel_launches++;
             break;
         }
@@ -1785,6 +1799,46 @@ colq_status run_pipeline(colq_query* q) {
         }
     }
 
+    // ---- pipelining of back-to-back executions (COLQ_OPT_PIPELINE): exactly [memset R][scan_str pushing into R]
+    //      [root_fused whose folded hop reads R (or the exchange of R)] with R small.  The root kernel's last CTA re-zeroes
+    //      R, so the memset is dropped from the second execution on; and when the previous thing on the stream was this
+    //      query's root kernel, the string scan is launched as its programmatic dependent (ScanStrParams::early).
+    static const bool pdl_env = !(getenv("COLQ_PDL") && getenv("COLQ_PDL")[0] == '0');
+    bool pipelined = false, early = false;
+    if (q->opt_pipeline && q->opt_profile != 1 && q->ops.size() == 3 && q->ops[0].kind == K_ZERO && q->ops[1].kind == K_SCAN_STR &&
+        q->ops[2].kind == K_ROOT_FUSED) {
+        const Op& z = q->ops[0];
+        Op& sc = q->ops[1];
+        Op& rf = q->ops[2];
+        u32* R = z.dst;
+        const bool exchanged = rf.rfused.pre.pm.n_words > 0;
+        const bool reads_r = rf.rfused.pre.n > 0 && (exchanged ? (rf.rfused.pre.pm.reach == R && sc.tail_publish && sc.str.pub.reach == R)
+                                                                : rf.rfused.pre.child_bits == R);
+        if (R != nullptr && reads_r && z.n_alloc_words <= 4096 && sc.str.push.fk != nullptr && sc.str.push.reach == R &&
+            sc.str.push.n_parent <= PUSH_SMEM_BITS && sc.str.in_bits == nullptr && sc.str.out_bits == nullptr && sc.str.n_tiles > 0 &&
+            rf.rfused.in_bits != R && rf.rfused.pre.in_bits != R) {
+            pipelined = true;
+            rf.rfused.clean = R;
+            rf.rfused.clean_words = (int)z.n_alloc_words;
+            if (exchanged) rf.rfused.pre.pm.reach = nullptr;  // the reduced mask is not written back into R
+            for (XNode& x : q->xnodes)
+                if (x.bits == R) { x.bits = nullptr; x.fused = true; }  // the mask does not outlive the execution (cardinality -1)
+            const bool was_clean = q->clean_ready == R;
+            // the scan may start early only if it has no side effect in global memory before its wait: no promotion, no
+            // lazy range-check flag, and nothing between it and the root kernel on the stream (events, memsets)
+            early = was_clean && pdl_env && ctx->chain_query == q && q->opt_profile == 0 && !q->lazy_oob && sc.str.push.oob == nullptr &&
+                    sc.str.promote_bytes == nullptr && sc.str.promote_offsets == nullptr;
+            sc.str.early = early ? 1u : 0u;
+            if (was_clean) {
+                q->ops.erase(q->ops.begin());
+                for (Op& o : q->ops)
+                    if (o.publish_op > 0) o.publish_op -= 1;
+            }
+        }
+    }
+    q->clean_ready = nullptr;   // set again below, once everything is enqueued
+    ctx->chain_query = nullptr;
+
     // ---- enqueue
     cudaStream_t s = ctx->stream;
     if (!q->ev_start) {
@@ -1814,7 +1868,10 @@ colq_status run_pipeline(colq_query* q) {
             q->stage_ev.push_back(e);
         }
     }
-    CU(ctx, cudaEventRecord(q->ev_start, s));
+    // (experiment knob COLQ_PIPELINE_EVENTS=1: record the per-execution events even between pipelined executions)
+    static const bool ev_env = getenv("COLQ_PIPELINE_EVENTS") && getenv("COLQ_PIPELINE_EVENTS")[0] == '1';
+    q->timed = !early || ev_env;
+    if (q->timed) CU(ctx, cudaEventRecord(q->ev_start, s));
     if (q->lazy_oob) CU(ctx, cudaMemsetAsync((u32*)q->idx_buf.ptr + RESULT_FLAGS_WORD, 0, 4, s));
     if (prof) CU(ctx, cudaEventRecord(q->stage_ev[0], s));
     for (size_t i = 0; i < q->ops.size(); ++i) {
@@ -1830,7 +1887,14 @@ colq_status run_pipeline(colq_query* q) {
             st.bytes = o.acct_bytes;
         }
     }
-    CU(ctx, cudaEventRecord(q->ev_stop, s));
+    // (an event between two executions would keep the next one from starting early: when this one may be followed by a
+    //  pipelined execution, the stop event is recorded only if this execution itself was timed from its start)
+    if (q->timed && (ev_env || !(pipelined && pdl_env && q->opt_profile == 0))) CU(ctx, cudaEventRecord(q->ev_stop, s));
+    else q->timed = false;
+    if (pipelined) {
+        q->clean_ready = q->ops.back().rfused.clean;
+        if (q->opt_profile == 0) ctx->chain_query = q;
+    }
     // first-touch promotion: the scans enqueued above fill the HBM copies; everything enqueued later on this stream
     // (the next query's plan included) reads those instead of the pinned host memory
     for (Column* c : q->pending_promotions) {
@@ -1852,8 +1916,21 @@ colq_status run_pipeline(colq_query* q) {
 constexpr colq_status RERUN_GROUP = (colq_status)100;
 
 // count D2H, (multi-GPU) final gather to rank 0, result copies. Synchronises the stream.
+colq_status fetch_results_impl(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_cap, int32_t* out_idx, int64_t idx_cap,
+                               int64_t* out_count, colq_timing* out_timing);
+
 colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_cap, int32_t* out_idx, int64_t idx_cap,
                           int64_t* out_count, colq_timing* out_timing) {
+    const colq_status st = fetch_results_impl(q, out_bitmask, bitmask_cap, out_idx, idx_cap, out_count, out_timing);
+    if (st != COLQ_OK) {  // a failed execution may have left the push target dirty: the next one starts from a memset
+        q->clean_ready = nullptr;
+        q->ctx->chain_query = nullptr;
+    }
+    return st;
+}
+
+colq_status fetch_results_impl(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_cap, int32_t* out_idx, int64_t idx_cap,
+                               int64_t* out_count, colq_timing* out_timing) {
     colq_ctx* ctx = q->ctx;
     if (!q->executed) return fail(ctx, COLQ_THROW_ILLEGAL_STATE, "colq_fetch before colq_execute_async");
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1887,8 +1964,8 @@ colq_status fetch_results(colq_query* q, uint64_t* out_bitmask, int64_t bitmask_
     const u64 local = header[0];
     if (q->lazy_oob && (header[1] & 1u))  // M/InMemoryTable.java:70-71 would have thrown at associateTo
         return fail(ctx, COLQ_THROW_NULL, "association target outside the associated table (found while walking a host-resident to-one column)");
-    float ms = 0;
-    CU(ctx, cudaEventElapsedTime(&ms, q->ev_start, q->ev_stop));
+    float ms = -1.f;
+    if (q->timed) CU(ctx, cudaEventElapsedTime(&ms, q->ev_start, q->ev_stop));
     q->timing.gpu_ms = ms;
 
     if (ctx->peer.ok) {
@@ -2220,6 +2297,7 @@ colq_status colq_set_stream(colq_ctx* ctx, void* cuda_stream) {
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->chain_query = nullptr;
     return COLQ_OK;
 }
 
@@ -3065,6 +3143,7 @@ colq_status colq_query_create(colq_ctx* ctx, const char* table_name, colq_query*
     colq_query* q = new colq_query();
     if (const char* e = getenv("COLQ_COMPACT")) q->opt_fused_compact = atoi(e);  // experiment knob: default compaction kernel
     if (const char* e = getenv("COLQ_ROOT_FUSED")) q->opt_root_fused = atoi(e);   // experiment knob: default root plan (0, 1, 2)
+    if (const char* e = getenv("COLQ_PIPELINE")) q->opt_pipeline = atoi(e);       // experiment knob: default COLQ_OPT_PIPELINE
     q->ctx = ctx;
     q->table_name = table_name;
     q->nodes.emplace_back();  // rootNode (DS/Query.java:22-25)
@@ -3077,6 +3156,7 @@ colq_status colq_query_destroy(colq_query* q) {
     if (!q) return COLQ_OK;
     auto& live = q->ctx->queries;
     live.erase(std::remove(live.begin(), live.end(), q), live.end());
+    if (q->ctx->chain_query == q) q->ctx->chain_query = nullptr;
     cudaSetDevice(q->ctx->device);
     cudaStreamSynchronize(q->ctx->stream);
     if (q->ev_start) cudaEventDestroy(q->ev_start);
@@ -3166,6 +3246,7 @@ colq_status colq_query_set_option(colq_query* q, colq_option option, int value) 
         case COLQ_OPT_TAIL_PUBLISH: q->opt_tail_publish = value; break;
         case COLQ_OPT_ROOT_FUSED: q->opt_root_fused = value; break;
         case COLQ_OPT_LAZY_GATHER_WAIT: q->opt_lazy_gather_wait = value; break;
+        case COLQ_OPT_PIPELINE: q->opt_pipeline = value; break;
         default: return fail(q->ctx, COLQ_THROW_ILLEGAL_ARG, "unknown option %d", (int)option);
     }
     return COLQ_OK;

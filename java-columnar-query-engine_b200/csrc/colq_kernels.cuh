@@ -1032,6 +1032,11 @@ struct ScanStrParams {
     PeerMaskParams pub;   // pub.n_words > 0: the last CTA publishes push.reach to the peers (multi-GPU mask exchange)
     u32* pub_done;
     u32* tile_counter;    // [0] next unclaimed tile, [1] finished CTAs; both are zero between launches
+    // 1: pipelined behind the previous execution of the same query (COLQ_OPT_PIPELINE): this launch is a programmatic
+    // dependent of that execution's root kernel and may start while it drains.  Until pdl_wait() it only reads immutable
+    // columns, claims tiles (the previous string scan has completed: the root kernel triggers only after its own wait)
+    // and sets bits in shared memory; the flush, the publish and the trigger for the next kernel come after the wait.
+    u32 early;
 };
 
 #ifndef COLQ_ST_CLAIM
@@ -1200,7 +1205,7 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == -1 || MODE == -2) ? 4 : 3
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool do_push = P.push.fk != nullptr;
     // the next kernel of the plan (the root's fused scan) may move onto an SM as soon as this kernel's CTAs leave it
-    pdl_launch_dependents();
+    if (!P.early) pdl_launch_dependents();
 
     for (int i = tid; i < needle_region / 4; i += ST_THREADS) {
         u32 w = 0;
@@ -1415,6 +1420,10 @@ __global__ void __launch_bounds__(ST_THREADS, (MODE == -1 || MODE == -2) ? 4 : 3
     }
 
     __syncthreads();  // every claim of this CTA has been made
+    if (P.early) {
+        pdl_wait();  // the previous execution's root kernel has completed: it has read and re-zeroed the push target
+        pdl_launch_dependents();
+    }
     if (do_push) push_flush(P.push, s_reach);
     if (tid == 0 && atomicAdd(P.tile_counter + 1, 1u) == gridDim.x - 1) {  // last CTA: re-arm the claim counter
         P.tile_counter[0] = 0;
@@ -2083,6 +2092,8 @@ struct RootFusedParams {
     int64_t capacity;
     int64_t row_base;
     PeerGatherParams pg;         // pg.n_ranks > 0: final gather fused in
+    u32* clean;                  // nullable: the push target behind the folded hop; the last CTA re-zeroes it, so the next
+    int clean_words;             //   execution needs no memset in front of its first scan (COLQ_OPT_PIPELINE)
     u64* dbg;                    // (COLQ_RF_DEBUG builds) 8 globaltimer stamps per CTA
     // root_finish_kernel only (the candidates were listed per 512-row chunk by scan_rows<.., LIST>):
     u32* ucount;                 // [n_chunks] candidates of the chunk (> list_cap: its list overflowed)
@@ -2121,7 +2132,7 @@ __device__ __forceinline__ void rf_run_pre(const CsrPullParams& C, u32 vcta, u32
             if (v) atomicOr(&s_child[w], v);
         }
         __syncthreads();
-        if (vcta == 0)
+        if (vcta == 0 && M.reach != nullptr)
             for (int w = tid; w < cw; w += RF_THREADS) M.reach[w] = s_child[w];  // the reduced mask stays readable (node cardinalities)
     } else {
         for (int w = tid; w < cw; w += RF_THREADS) s_child[w] = C.child_bits != nullptr ? __ldcg(C.child_bits + w) : 0xffffffffu;
@@ -2310,6 +2321,9 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
     }
     // from here on the kernel reads what earlier launches produced (the mask behind the folded hop, chain bitmaps)
     pdl_wait();
+    // the next execution's first scan may move onto the SMs this kernel leaves (it orders itself with its own pdl_wait);
+    // triggering only now keeps the chain simple: whatever starts early starts after the kernel in front of this one is done
+    pdl_launch_dependents();
 
     RF_STAMP(1);
     // ======================= phase B =======================
@@ -2486,6 +2500,9 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_fused_kernel(const RootFus
             P.counters[0] = 0;
             P.counters[1] = 0;
         }
+        // every CTA has read the push target (before its arrival at the counter above): leave it zeroed
+        if (P.clean != nullptr)
+            for (int w = tid; w < P.clean_words; w += RF_THREADS) P.clean[w] = 0;
         if (gather) gather_tail(P.pg, P.total);
     }
     RF_STAMP(7);
@@ -2747,6 +2764,9 @@ __global__ void __launch_bounds__(RF_THREADS, 4) root_finish_kernel(const RootFu
             P.counters[0] = 0;
             P.counters[1] = 0;
         }
+        // every CTA has read the push target (before its arrival at the counter above): leave it zeroed
+        if (P.clean != nullptr)
+            for (int w = tid; w < P.clean_words; w += RF_THREADS) P.clean[w] = 0;
         if (gather) gather_tail(P.pg, P.total);
     }
     RF_STAMP(7);

@@ -72,6 +72,12 @@ def main():
                 cq.execute_async()
                 res = cq.fetch(want_indices=True, index_capacity=want.shape[0] + 8)
                 assert np.array_equal(res.indices, want), (rank, perturbed, "second execution")
+                # a burst of back-to-back executions (COLQ_OPT_PIPELINE: no memset, the string scan starts while the previous
+                # execution's root kernel is still waiting for the peers)
+                for _ in range(6):
+                    cq.execute_async()
+                res = cq.fetch(want_indices=True, index_capacity=want.shape[0] + 8)
+                assert res.count == want.shape[0] and np.array_equal(res.indices, want), (rank, perturbed, "pipelined burst")
                 # the public call: this rank's rows of the result table (the gathered list holds ALL ranks' rows)
                 got = ds.execute(G.plymouth_query())
                 mine = want[(want >= geo.zip_row_base) & (want < geo.zip_row_base + geo.zips.size())]

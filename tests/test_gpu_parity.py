@@ -845,3 +845,56 @@ def test_boolean_scan_sizes(engines, n):
 
     both(engines, build, [truth(False, True), truth(True, False), truth(True, True), truth(False, False), mixed,
                           child_forward, child_reverse], variants=(LAZY, EAGER, DICT))
+
+
+# ------------------------------------------------------------------ pipelined back-to-back executions (COLQ_OPT_PIPELINE)
+@pytest.mark.parametrize("U", [3, 40])
+def test_pipelined_back_to_back_executions(engines, base_geography, U):
+    """execute is called over and over on one plan (E/DataSystemSerialIndices.java:53).  From the second execution on the
+    root kernel has left the push target zeroed (no memset in front of the string scan) and the scan is launched as a
+    programmatic dependent of the previous execution's root kernel.  Every execution must return the oracle's rows: after
+    a run of back-to-back launches, with another query of the same context in between, with the option off, and after
+    the criteria changed."""
+    new_gpu, new_oracle = engines
+    geo = G.build_tables(U, base=base_geography)
+    oracle = new_oracle()
+    G.register_geography(oracle, geo)
+    assert isinstance(oracle.execute(G.plymouth_query()), QueryResult.Success)
+    want = oracle.last_indices.copy()
+    assert isinstance(oracle.execute(G.north_south_north_query()), QueryResult.Success)
+    want_nsn = oracle.last_indices.copy()
+    for opts in ({}, {11: 0}):
+        ds = new_gpu(options=opts)
+        G.register_geography(ds, geo)
+        assert isinstance(ds.execute(G.plymouth_query()), QueryResult.Success)
+        cq = ds.last_query
+        ds.last_query = None   # keep it: the next ds.execute would close it
+        names = [n for n, *_ in cq.profile()]
+        assert any(n.startswith("scan_str") for n in names) and any(n.startswith("root_fused") for n in names), names
+        first = cq.fetch(want_indices=True)
+        assert np.array_equal(first.indices, want)
+        launches = []
+        for _ in range(8):
+            cq.execute_async()
+        got = cq.fetch(want_indices=True)
+        assert got.count == want.shape[0] and np.array_equal(got.indices, want)
+        launches.append(int(got.timing.kernel_launches))
+        assert launches[-1] == 2, launches
+        assert (got.timing.gpu_ms < 0) == (opts == {}), got.timing.gpu_ms   # pipelined executions are not timed one by one
+        # another query of the same context between two executions: the chain is broken, results stay right
+        assert isinstance(ds.execute(G.north_south_north_query()), QueryResult.Success)
+        other = ds.last_query
+        for _ in range(3):
+            cq.execute_async()
+            other.execute_async()
+        assert np.array_equal(other.fetch(want_indices=True).indices, want_nsn)
+        assert np.array_equal(cq.fetch(want_indices=True).indices, want)
+        cq.execute_async()
+        cq.execute_async()
+        assert np.array_equal(cq.fetch(want_indices=True).indices, want)
+        # node cardinalities: the pushed mask does not outlive a pipelined execution (-1), the others are the oracle's
+        assert isinstance(oracle.execute(G.plymouth_query()), QueryResult.Success)
+        for a, b in zip(cq.node_cardinalities(), oracle.node_cardinalities()):
+            assert a == -1 or a == b
+        cq.close()
+        ds.close()
