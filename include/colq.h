@@ -123,8 +123,8 @@ typedef enum colq_option {
        E/DataSystemSerialIndices.java:53): the root kernel leaves the small push target behind its folded hop zeroed, so
        the next execution needs no memset, and that execution's first scan is launched as a programmatic dependent of the
        root kernel -- it streams its (immutable) column while the root kernel drains and touches shared state only after
-       griddepcontrol.wait.  colq_timing.gpu_ms is -1 for an execution that was pipelined this way.  0: every execution
-       starts after the previous one has finished. */
+       griddepcontrol.wait.  An event between two executions would undo the overlap, so executions of such a plan are not
+       timed one by one: colq_timing.gpu_ms is -1 for them.  0: every execution starts after the previous one has finished. */
     COLQ_OPT_PIPELINE = 11
 } colq_option;
 
@@ -134,7 +134,7 @@ typedef int32_t colq_table;             /* table handle, valid for the owning co
 
 typedef struct colq_timing {
     double gpu_ms;          /* CUDA-event time of the whole kernel(+collective) pipeline of the last execute
-                               (-1: not measured, the execution overlapped the previous one -- COLQ_OPT_PIPELINE) */
+                               (-1: not measured, the plan pipelines back-to-back executions -- COLQ_OPT_PIPELINE) */
     int32_t kernel_launches;/* kernels of this library launched by the last execute */
     int32_t collectives;    /* NCCL calls issued by the last execute */
     int64_t h2d_bytes;      /* bytes the last execute streamed host->device: host-resident columns it scanned in full */

@@ -288,6 +288,7 @@ struct colq_query {
     std::vector<QNode> nodes;
     int opt_lazy = 1, opt_profile = 0, opt_peer = 1, opt_fused_compact = 1, opt_defer = 1, opt_promote = 2, opt_fused_gather = 1, opt_tail_publish = 1, opt_root_fused = 1, opt_lazy_gather_wait = 1, opt_pipeline = 1;
     u32* clean_ready = nullptr;   // the push target the last execution's root kernel left zeroed (COLQ_OPT_PIPELINE)
+    int64_t clean_words = 0;      //   ... and how many words of it
     bool timed = true;            // ev_start / ev_stop were recorded for the last execution
     std::vector<GatherD> deferred;  // root-node FK chains resolved by the compaction kernel instead of the row scan
     int own_begin = -1, own_end = -1;  // root-node scan ops that depend on no child (hoistable behind a mask publish)
@@ -1823,7 +1824,7 @@ colq_status run_pipeline(colq_query* q) {
             if (exchanged) rf.rfused.pre.pm.reach = nullptr;  // the reduced mask is not written back into R
             for (XNode& x : q->xnodes)
                 if (x.bits == R) { x.bits = nullptr; x.fused = true; }  // the mask does not outlive the execution (cardinality -1)
-            const bool was_clean = q->clean_ready == R;
+            const bool was_clean = q->clean_ready == R && z.n_alloc_words <= q->clean_words;
             // the scan may start early only if it has no side effect in global memory before its wait: no promotion, no
             // lazy range-check flag, and nothing between it and the root kernel on the stream (events, memsets)
             early = was_clean && pdl_env && ctx->chain_query == q && q->opt_profile == 0 && !q->lazy_oob && sc.str.push.oob == nullptr &&
@@ -1893,6 +1894,7 @@ colq_status run_pipeline(colq_query* q) {
     else q->timed = false;
     if (pipelined) {
         q->clean_ready = q->ops.back().rfused.clean;
+        q->clean_words = q->ops.back().rfused.clean_words;
         if (q->opt_profile == 0) ctx->chain_query = q;
     }
     // first-touch promotion: the scans enqueued above fill the HBM copies; everything enqueued later on this stream
