@@ -120,3 +120,20 @@ def test_bench_reference_arm_contract(tmp_path):
     # under torchrun the other ranks print nothing and exit 0
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
     assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_scan_bool_byte_to_bit_arithmetic():
+    """scan_bool (csrc/colq_kernels.cuh, sb_truth16) turns 4 bytes into 4 bits with a SWAR nonzero-byte test and one
+    gathering multiply.  Restated with numpy uint32 arithmetic and checked against the plain definition for every
+    combination of zero / nonzero bytes and for random words: the partial products never carry into the result bits."""
+    rng = np.random.default_rng(3)
+    specials = np.array([0x00, 0x01, 0x7F, 0x80, 0xFF], dtype=np.uint32)
+    combos = np.array([[a, b, c, d] for a in specials for b in specials for c in specials for d in specials], dtype=np.uint32)
+    words = np.concatenate([combos[:, 0] | combos[:, 1] << 8 | combos[:, 2] << 16 | combos[:, 3] << 24,
+                            rng.integers(0, 2 ** 32, size=200_000, dtype=np.uint64).astype(np.uint32)])
+    nz = ((((words & np.uint32(0x7F7F7F7F)) + np.uint32(0x7F7F7F7F)) | words) & np.uint32(0x80808080)) >> np.uint32(7)
+    got = ((nz * np.uint32(0x00204081)) >> np.uint32(21)) & np.uint32(0xF)      # uint32 multiply wraps like the GPU's
+    want = np.zeros_like(words)
+    for k in range(4):
+        want |= (((words >> np.uint32(8 * k)) & np.uint32(0xFF)) != 0).astype(np.uint32) << np.uint32(k)
+    assert np.array_equal(got, want)
