@@ -13,7 +13,7 @@ import pytest
 import tck
 from colq import QueryResult, geography as G
 from oracle_system import OracleDataSystem
-from test_gpu_fuzz import make_case
+from fuzz_cases import make_case
 
 pytestmark = pytest.mark.gpu
 
