@@ -1626,6 +1626,15 @@ colq_status run_pipeline(colq_query* q) {
             for (int g = 0; g < f.ng; ++g)
                 if (P.gather[g].bits == P.pre.out_bits) P.pre_mask |= 1u << g;
         if (coop_gather) ST(fill_fused_gather(P.pg));
+#ifdef COLQ_RF_DEBUG
+        {
+            void* dbg;
+            ST(pool_alloc(q, (size_t)f.grid * 64, &dbg));
+            P.dbg = (u64*)dbg;
+            q->rf_dbg = P.dbg;
+            q->rf_dbg_ctas = f.grid;
+        }
+#endif
         f.name = "root_finish";
         q->ops.push_back(f);
     } else if (fuse_root) {

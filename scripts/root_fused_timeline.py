@@ -12,6 +12,8 @@ U = int(os.environ.get("U", "10000"))
 ctx = ColqContext(0)
 geo = build_geography_on_device(ctx, U)
 q = plymouth_colq_query(ctx)
+for k, v in (os.environ.get("OPTS", "") and [kv.split("=") for kv in os.environ["OPTS"].split(",")] or []):
+    q.set_option(int(k), int(v))   # e.g. OPTS="9=2": the timeline of root_finish_kernel (stamps: start, pre, prefix, chains, look-back, write, tail, exit)
 for _ in range(5):
     r = q.execute(want_indices=False)
 buf = np.zeros((4096, 8), dtype=np.uint64)
@@ -22,6 +24,8 @@ t = buf[:n].astype(np.int64)
 t0 = t[:, 0].min()
 t = (t - t0) / 1000.0   # us
 names = ["start", "A_end", "pre_end", "chains_end", "lookback_end", "write_end", "tail_atomic", "exit"]
+if "9=2" in os.environ.get("OPTS", ""):
+    names = ["start", "pre_end", "prefix_end", "chains_end", "lookback_end", "write_end", "tail_atomic", "exit"]
 print("ctas", n, "count", r.count)
 for k, nm in enumerate(names):
     c = t[:, k]
