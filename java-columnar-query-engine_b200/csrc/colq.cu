@@ -3100,18 +3100,18 @@ colq_status colq_associate_csr_global(colq_ctx* ctx, colq_table x, int x_ordinal
     if (Y->placement == COLQ_SHARDED && ctx->n_ranks > 1 && Y->part.empty())
         return fail(ctx, COLQ_THROW_ILLEGAL_STATE, "declare the target table's partition first (colq_table_partition)");
     if (offsets[0] != 0 || offsets[n] != nnz) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "CSR offsets must start at 0 and end at nnz");
-    for (int64_t i = 0; i < n; ++i)
-        if (offsets[i + 1] < offsets[i]) return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "CSR offsets must be non-decreasing");
     const int64_t gy = Y->global_rows();
-    for (int64_t e = 0; e < nnz; ++e)  // M/InMemoryTable.java:70-71
-        if (targets[e] < 0 || targets[e] >= gy)
-            return fail(ctx, COLQ_THROW_NULL, "association target %d outside the associated table (global size %lld)", targets[e], (long long)gy);
     Column* f;
     ST(link_assoc(ctx, x, x_ordinal, y, y_ordinal, false, &f));
     if (n != f->n) { unlink_assoc(ctx, x, x_ordinal, y, y_ordinal); return fail(ctx, COLQ_THROW_ILLEGAL_ARG, "association height %lld != table rows", (long long)n); }
     f->nnz = nnz;
     colq_status st = upload(ctx, f->offsets, offsets, (size_t)(n + 1) * 8, (size_t)(n + 1) * 8 + 16);
     if (st == COLQ_OK) st = upload(ctx, f->targets, targets, (size_t)nnz * 4, (size_t)nnz * 4 + 16);
+    // offsets order and target range against the GLOBAL row count, in one pass on the device like colq_associate_csr
+    // (M/InMemoryTable.java:70-71)
+    AssocStats a{};
+    if (st == COLQ_OK) st = assoc_stats(ctx, (const int64_t*)f->offsets.ptr, (const int32_t*)f->targets.ptr, n, nnz, &a);
+    if (st == COLQ_OK) st = check_csr(ctx, a, nnz, gy);
     if (st != COLQ_OK) { unlink_assoc(ctx, x, x_ordinal, y, y_ordinal); return st; }
     ctx->tables[x].cols[x_ordinal].global_targets = true;
     return COLQ_OK;

@@ -710,6 +710,56 @@ def test_device_dictionary_of_the_city_names(base_geography):
     ctx.close()
 
 
+def test_global_key_associations_on_a_single_rank():
+    """colq_associate_fk_global / _csr_global on a context without a communicator: the keys are global rows of the target
+    table, which on one rank are its local rows, so queries behave like the local calls; a target outside the table is the
+    reference's NPE (M/InMemoryTable.java:70-71) and decreasing CSR offsets are refused -- both found by the GPU's own
+    validation pass, and a refused call releases its ordinals."""
+    from colq import _ffi
+    from colq.engine import ColqContext
+    rng = np.random.default_rng(23)
+    ctx = ColqContext(0)
+    nx, ny = 7000, 640
+    x, y = ctx.table_create(nx, _ffi.SHARDED, 0), ctx.table_create(ny, _ffi.SHARDED, 0)
+    ctx.table_partition(x, [0, nx])
+    ctx.table_partition(y, [0, ny])
+    ctx.col_i32(x, 0, np.arange(nx, dtype=np.int32))
+    ctx.col_i32(y, 0, np.arange(ny, dtype=np.int32))
+    fk = rng.integers(-1, ny, size=nx, dtype=np.int32)
+    bad_fk = fk.copy(); bad_fk[100] = ny
+    with pytest.raises(TypeError, match="outside the associated table"):
+        ctx.associate_fk_global(x, 1, y, 1, bad_fk)
+    ctx.associate_fk_global(x, 1, y, 1, fk)
+    deg = rng.integers(0, 4, size=nx)
+    off = np.zeros(nx + 1, dtype=np.int64); np.cumsum(deg, out=off[1:])
+    tg = rng.integers(0, ny, size=int(off[-1]), dtype=np.int32)
+    for bad_value in (ny, -1):
+        bad = tg.copy(); bad[len(bad) // 2] = bad_value
+        with pytest.raises(TypeError, match="outside the associated table"):
+            ctx.associate_csr_global(x, 2, y, 2, off, bad)
+    off_bad = off.copy(); off_bad[5], off_bad[6] = off_bad[6] + 1, off_bad[5]
+    with pytest.raises(ValueError, match="non-decreasing"):
+        ctx.associate_csr_global(x, 2, y, 2, off_bad, tg)
+    ctx.associate_csr_global(x, 2, y, 2, off, tg)
+    ctx.register("x", x); ctx.register("y", y)
+    # forward hops (pull) ...
+    q = ctx.query("x")
+    q.criteria_i32_range(q.child(0, 1), 0, 10, 20)
+    q.criteria_i32_range(q.child(0, 2), 0, 0, 50)
+    res = q.execute(want_indices=True, index_capacity=nx)
+    many = np.array([np.any(tg[off[i]:off[i + 1]] <= 50) for i in range(nx)])
+    assert np.array_equal(res.indices, np.flatnonzero((fk >= 10) & (fk <= 20) & many).astype(np.int32))
+    q.close()
+    # ... and the reverse side (push)
+    q = ctx.query("y")
+    q.criteria_i32_range(q.child(0, 2), 0, 0, 30)
+    res = q.execute(want_indices=True, index_capacity=ny)
+    want = np.unique(tg[: int(off[31])])
+    assert np.array_equal(res.indices, want.astype(np.int32))
+    q.close()
+    ctx.close()
+
+
 def test_device_association_classification():
     """colq_associate: None / One rows -> dense to-one, any Many row -> CSR; bad input is rejected by the GPU's own pass."""
     from colq.engine import ColqContext
