@@ -553,6 +553,11 @@ def run_colq(args, rank, local_rank, world):
             "hbm_gbs_touched": touched_gbs, "touched_bytes": touched,
             "hbm_gbs_query_algorithmic": query_gbs, "query_algorithmic_bytes": algo_total,
             "roofline": roofline, "stages_ms": {k: round(v["ms"], 5) for k, v in stages.items()},
+            # every launch of the step against the same peak (separate profiled steps, one event pair per launch): algorithmic
+            # bytes of the launch / its time.  root_fused additionally issues ~0.94 M random 32-byte key reads that its
+            # algorithmic bytes do not show ("What bounds the root kernel")
+            "stages_roofline": {k: {"algorithmic_bytes": int(v["algorithmic_bytes"]), "gbs": round(v["algorithmic_bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
+                                    "frac": round(v["algorithmic_bytes"] / (v["ms"] * 1e-3) / 1e9 / peak, 4)} for k, v in stages.items() if v["ms"] > 0},
             "cpu_baseline": cpu, "e2e": e2e, "e2e_dictionary": e2e_dict, "e2e_upload_all_columns": e2e_upload, "ingest": ingest,
             "e2e_resident": {"value": rows / (ms_res * 1e-3), "unit": "rows/s", "ms_per_step": ms_res, "h2d_bytes_per_step": 0,
                              "d2h_bytes_per_step": d2h_res, "what": "colq_execute with resident tables, matched indices read back into a pinned result buffer every step"},
