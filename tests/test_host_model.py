@@ -137,3 +137,28 @@ def test_scan_bool_byte_to_bit_arithmetic():
     for k in range(4):
         want |= (((words >> np.uint32(8 * k)) & np.uint32(0xFF)) != 0).astype(np.uint32) << np.uint32(k)
     assert np.array_equal(got, want)
+
+
+def test_committed_bench_lines_keep_the_contract():
+    """The bench lines committed under profiles/ for the final build carry every key the measurement contract names
+    (metric / config.workload / roofline / cpu_baseline / e2e with its copy sizes / clocks / gpu_launches / gate)."""
+    import json
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    for name, n_gpus in (("r02_session2_n1_driver_cmd.json", 1), ("r02_session2_n1.json", 1), ("r02_session2_n2.json", 2), ("r02_session2_n4.json", 4)):
+        d = json.loads((root / "profiles" / name).read_text().strip().splitlines()[-1])
+        assert d["metric"] == "plymouth_query_zip_rows_per_sec" and d["unit"] == "rows/s" and d["higher_is_better"] is True
+        assert d["n_gpus"] == n_gpus and d["steps"] >= 20 and d["warmup"] >= 3 and d["scaling"] == "strong" and d["vs_baseline"] is None
+        assert d["config"]["workload"] == "plymouth_adjacency_query_10k_universes" and d["config"]["universes"] == 10_000
+        assert abs(d["value"] - d["config"]["zip_rows"] / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-9
+        r = d["roofline"]
+        assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["ms_per_launch"] * 1e-3) / 1e9) / r["achieved"] < 1e-9
+        e = d["e2e"]
+        assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
+        assert d["gpu_launches"] == d["gpu_launches_per_step"] * d["steps"] > 0
+        assert d["clocks"]["reasons"] == [] and d["clocks"]["sm_mhz"] == d["clocks"]["sm_max_mhz"]
+        assert d["gate"]["exact"] is True and (d["gate"]["perturbed"] is True) == (n_gpus > 1)
+        if n_gpus == 1 and d["cpu_baseline"] is not None:
+            c = d["cpu_baseline"]
+            assert c["kind"] == "port" and c["cores"] == 1 and c["unit"] == "rows/s" and "universes" in c["sample"]
