@@ -12,6 +12,11 @@ for p in (ROOT, ROOT / "java-columnar-query-engine_b200", ROOT / "oracle", ROOT 
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with `-m gpu` on the GPU box)")
+    # a fresh checkout has no built artefacts (they are git-ignored): build libcolq.so (nvcc cross-compiles sm_100a
+    # without a GPU) and the oracle once, exactly as __graft_entry__.build() does
+    if not (ROOT / "java-columnar-query-engine_b200" / "lib" / "libcolq.so").exists():
+        import subprocess
+        subprocess.run(["make", "-C", str(ROOT / "java-columnar-query-engine_b200")], check=True, capture_output=True)
 
 
 @pytest.fixture(scope="session")
